@@ -1,0 +1,233 @@
+"""ctypes binding of libaudian_b200.so (C ABI: include/audian_b200.h).
+
+Thin by design: argument checks that need numpy (dtype, contiguity), pointer
+extraction, status -> exception.  There is no CPU implementation behind these
+functions; if the shared library is missing or no CUDA device is present the
+calls raise.
+"""
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libaudian_b200.so')
+
+ADN_OK = 0
+ADN_ERR_INVALID = 1
+ADN_ERR_CUDA = 2
+ADN_ERR_UNSUPPORTED = 3
+ADN_ERR_SHORT = 4
+ADN_MAX_SECTIONS = 8
+ADN_MIN_NFFT = 8
+ADN_MAX_NFFT = 16384
+ADN_WINDOW_HANN = 0
+ADN_DETREND_NONE = 0
+ADN_DETREND_CONSTANT = 1
+
+_dp = C.c_void_p
+_i32 = C.c_int32
+_i64 = C.c_int64
+_f64 = C.c_double
+
+# name: (restype, argtypes) -- every symbol include/audian_b200.h declares
+SIGNATURES = {
+    'adn_init': (_i32, [_i32]),
+    'adn_shutdown': (_i32, []),
+    'adn_last_error': (C.c_char_p, []),
+    'adn_version': (_i32, []),
+    'adn_launch_count': (_i64, []),
+    'adn_synchronize': (_i32, []),
+    'adn_host_register': (_i32, [_dp, _i64]),
+    'adn_host_unregister': (_i32, [_dp]),
+    'adn_minmax_f64': (_i32, [_dp, _i64, _i32, _i64, _dp]),
+    'adn_sosfilt_f64': (_i32, [_dp, _i32, _dp, _i64, _i32, _i64, _dp, _i64, _dp]),
+    'adn_envelope_f64': (_i32, [_dp, _i32, _dp, _i64, _i32, _i64, _dp, _i64, _i32]),
+    'adn_spectrogram_f64': (_i32, [_dp, _i64, _i32, _f64, _i32, _i32, _i32, _i32,
+                                   _dp, _i64, _i32, C.POINTER(_i64)]),
+    'adn_decibel_f64': (_i32, [_dp, _i64, _f64, _f64, _dp]),
+    'adn_minmax_f64_dev': (_i32, [_dp, _i64, _i32, _i64, _dp, _dp]),
+    'adn_sosfilt_f64_dev': (_i32, [_dp, _i32, _dp, _i64, _i32, _i64, _dp, _i64,
+                                   _dp, _dp, _dp]),
+    'adn_envelope_f64_dev': (_i32, [_dp, _i32, _dp, _i64, _i32, _i64, _dp, _i64,
+                                    _i32, _dp]),
+    'adn_spectrogram_f64_dev': (_i32, [_dp, _i64, _i32, _f64, _i32, _i32, _i32,
+                                       _i32, _dp, _i64, _i32, C.POINTER(_i64), _dp]),
+    'adn_decibel_f64_dev': (_i32, [_dp, _i64, _f64, _f64, _dp, _dp]),
+    'adn_synth_f64_dev': (_i32, [_dp, _i64, _i64, _i32, _f64, C.c_uint64, _dp]),
+    'adn_sos_state_space': (_i32, [_dp, _i32, _dp, _dp, _i64, _dp]),
+    'adn_sosfiltfilt_edge': (_i32, [_dp, _i32]),
+}
+
+
+class AdnError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f'libaudian_b200 error {code}: {message}')
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library (loaded on first use; raises if absent)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise ImportError(
+                f'{LIB_PATH} is missing: build it with `python -m audian_b200.build` '
+                '(nvcc, sm_100a). audian_b200 has no CPU fallback.')
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(status):
+    if status != ADN_OK:
+        msg = lib().adn_last_error().decode('utf-8', 'replace')
+        if status == ADN_ERR_SHORT:
+            # scipy raises ValueError from sosfiltfilt for too short inputs
+            raise ValueError(msg)
+        raise AdnError(status, msg)
+
+
+def _f64_array(a, name):
+    if not isinstance(a, np.ndarray) or a.dtype != np.float64:
+        raise TypeError(f'{name} must be a float64 ndarray')
+    if not a.flags.c_contiguous:
+        raise ValueError(f'{name} must be C-contiguous')
+    return a
+
+
+def ptr(a):
+    return a.ctypes.data if a.size > 0 else None
+
+
+def sos_array(sos):
+    """(S, 6) float64 C-contiguous, or None -> (None, 0)."""
+    if sos is None:
+        return None, 0
+    sos = np.ascontiguousarray(sos, dtype=np.float64)
+    if sos.ndim != 2 or sos.shape[1] != 6:
+        raise ValueError('sos must have shape (n_sections, 6)')
+    if sos.shape[0] > ADN_MAX_SECTIONS:
+        raise AdnError(ADN_ERR_UNSUPPORTED,
+                       f'{sos.shape[0]} sections (at most {ADN_MAX_SECTIONS})')
+    if not np.all(sos[:, 3] == 1.0):
+        sos = sos/sos[:, 3:4]
+    return sos, sos.shape[0]
+
+
+# ---------------------------------------------------------------- host arrays
+
+def init(device=-1):
+    check(lib().adn_init(device))
+
+
+def launch_count():
+    return int(lib().adn_launch_count())
+
+
+def minmax(src, step, dst=None):
+    """dst (2*ceil(n/step), C): rows 2j / 2j+1 = min / max of source rows
+    [j*step, (j+1)*step).  compresseddata.py:49-52,97-100; traceitem.py:58-61."""
+    src = _f64_array(src, 'src')
+    if src.ndim != 2:
+        raise ValueError('src must be (frames, channels)')
+    n, ch = src.shape
+    nseg = (n + step - 1)//step if n > 0 else 0
+    if dst is None:
+        dst = np.empty((2*nseg, ch))
+    dst = _f64_array(dst, 'dst')
+    if dst.shape != (2*nseg, ch):
+        raise ValueError(f'dst must have shape {(2*nseg, ch)}')
+    check(lib().adn_minmax_f64(ptr(src), n, ch, int(step), ptr(dst)))
+    return dst
+
+
+def sosfilt(sos, src, dst, nbefore=0, zi=None):
+    """dst[i, c] = scipy.signal.sosfilt(sos, src[:, c])[nbefore + i].
+    zi: None or (C, S, 2) float64, updated in place.  bufferedfilter.py:31-36."""
+    src = _f64_array(src, 'src')
+    dst = _f64_array(dst, 'dst')
+    sos, S = sos_array(sos)
+    if src.ndim != 2 or dst.ndim != 2 or src.shape[1] != dst.shape[1]:
+        raise ValueError('src and dst must be (frames, channels) with equal channels')
+    if zi is not None:
+        zi = _f64_array(zi, 'zi')
+        if zi.shape != (src.shape[1], S, 2):
+            raise ValueError('zi must have shape (channels, sections, 2)')
+    check(lib().adn_sosfilt_f64(None if sos is None else sos.ctypes.data, S,
+                                ptr(src), src.shape[0], src.shape[1], int(nbefore),
+                                ptr(dst), dst.shape[0],
+                                None if zi is None else zi.ctypes.data))
+    return dst
+
+
+def envelope(sos, src, dst, nbefore=0, clamp_negative=True):
+    """dst = sosfiltfilt(sos, (pi/2)|src|, axis=0)[nbefore:], negatives clamped.
+    bufferedenvelope.py:34-41."""
+    src = _f64_array(src, 'src')
+    dst = _f64_array(dst, 'dst')
+    sos, S = sos_array(sos)
+    if src.ndim != 2 or dst.ndim != 2 or src.shape[1] != dst.shape[1]:
+        raise ValueError('src and dst must be (frames, channels) with equal channels')
+    check(lib().adn_envelope_f64(None if sos is None else sos.ctypes.data, S,
+                                 ptr(src), src.shape[0], src.shape[1], int(nbefore),
+                                 ptr(dst), dst.shape[0], 1 if clamp_negative else 0))
+    return dst
+
+
+def spectrogram(src, rate, nfft, hop, dst, window=ADN_WINDOW_HANN,
+                detrend=ADN_DETREND_CONSTANT, out_db=False):
+    """Fills dst (n_dst, C, nfft//2+1) like BufferedSpectrogram.process
+    (bufferedspectrogram.py:45-62); returns the number of computed frames."""
+    src = _f64_array(src, 'src')
+    dst = _f64_array(dst, 'dst')
+    if src.ndim != 2 or dst.ndim != 3 or dst.shape[1] != src.shape[1] or \
+       dst.shape[2] != nfft//2 + 1:
+        raise ValueError('src must be (frames, C) and dst (n, C, nfft//2+1)')
+    n = _i64(0)
+    check(lib().adn_spectrogram_f64(ptr(src), src.shape[0], src.shape[1], float(rate),
+                                    int(nfft), int(hop), window, detrend, ptr(dst),
+                                    dst.shape[0], 1 if out_db else 0, C.byref(n)))
+    return n.value
+
+
+def decibel(power, ref_power=1.0, min_power=1e-20):
+    """thunderlab.powerspectrum.decibel on the GPU (specitem.py:36)."""
+    power = np.ascontiguousarray(power, dtype=np.float64)
+    out = np.empty_like(power)
+    check(lib().adn_decibel_f64(ptr(power), power.size, float(ref_power),
+                                float(min_power), ptr(out)))
+    return out
+
+
+def sos_state_space(sos, power=1):
+    """Host-side plan inspection: (A, B, A**power) of the cascade."""
+    sos, S = sos_array(sos)
+    D = 2*S
+    A = np.empty((D, D))
+    B = np.empty(D)
+    P = np.empty((D, D))
+    check(lib().adn_sos_state_space(sos.ctypes.data, S, A.ctypes.data, B.ctypes.data,
+                                    int(power), P.ctypes.data))
+    return A, B, P
+
+
+def sosfiltfilt_edge(sos):
+    sos, S = sos_array(sos)
+    return int(lib().adn_sosfiltfilt_edge(sos.ctypes.data, S))
+
+
+def host_register(a):
+    check(lib().adn_host_register(a.ctypes.data, a.nbytes))
+
+
+def host_unregister(a):
+    check(lib().adn_host_unregister(a.ctypes.data))

@@ -1,0 +1,77 @@
+// Shared declarations of libaudian_b200: context, error handling, scratch memory.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <map>
+#include <atomic>
+#include "../../include/audian_b200.h"
+
+namespace adn {
+
+int32_t fail(int32_t code, const char* fmt, ...);
+int32_t fail_cuda(cudaError_t e, const char* what);
+
+#define ADN_CK(call)                                              \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) return adn::fail_cuda(e__, #call);\
+    } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int32_t reserve(size_t bytes);
+    void release();
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+struct Ctx {
+    bool ready = false;
+    int device = -1;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;     // the library's own stream
+    DevBuf in, out, aux;               // staging of the host-pointer entry points
+    std::atomic<int64_t> launches{0};
+};
+
+Ctx& ctx();
+int32_t ensure_init();
+inline cudaStream_t pick(void* s) { return s ? static_cast<cudaStream_t>(s) : ctx().stream; }
+inline void count_launch(int n = 1) { ctx().launches += n; }
+
+// per-stream scratch that must outlive an asynchronous launch: handed out from a
+// small pool keyed by purpose; grown (never shrunk) under the caller's stream order.
+DevBuf& scratch(int slot);
+enum { SCR_SOS_TILES = 0, SCR_SOS_TABLES, SCR_SOS_MISC, SCR_ENV_FWD, SCR_ENV_MISC,
+       SCR_MINMAX_PART, SCR_SPEC_TABLES, SCR_COUNT };
+
+// ---- kernels' host launchers (device pointers, asynchronous) ----
+int32_t minmax_dev(const double* src, int64_t n, int32_t C, int64_t step, double* dst,
+                   cudaStream_t st);
+int32_t sosfilt_dev(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
+                    int64_t nbefore, double* dst, int64_t n_dst, const double* zi, double* zf,
+                    cudaStream_t st);
+int32_t envelope_dev(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
+                     int64_t nbefore, double* dst, int64_t n_dst, int32_t clamp_negative,
+                     cudaStream_t st);
+int32_t spectrogram_dev(const double* src, int64_t n_src, int32_t C, double rate, int32_t nfft,
+                        int32_t hop, int32_t window_id, int32_t detrend_id, double* dst,
+                        int64_t n_dst, int32_t out_db, int64_t* n_computed, cudaStream_t st);
+int32_t decibel_dev(const double* p, int64_t n, double ref_power, double min_power, double* dst,
+                    cudaStream_t st);
+int32_t synth_dev(double* dst, int64_t t0, int64_t n, int32_t C, double rate, uint64_t seed,
+                  cudaStream_t st);
+
+// number of spectrogram frames the reference computes (bufferedspectrogram.py:46-57)
+inline int64_t spectrogram_frames(int64_t n_src, int64_t n_dst, int32_t nfft, int32_t hop) {
+    if (n_dst <= 0) return 0;
+    int64_t nsource = (n_dst - 1) * (int64_t)hop + nfft;
+    if (nsource > n_src) nsource = n_src;
+    if (nsource < nfft) return 0;
+    return (nsource - (nfft - hop)) / hop;
+}
+
+}  // namespace adn

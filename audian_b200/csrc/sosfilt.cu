@@ -1,0 +1,748 @@
+// SOS biquad cascades over long interleaved traces as a single-pass chunked
+// linear-recurrence scan: BufferedFilter.process (src/audian/bufferedfilter.py:31-36,
+// scipy sosfilt) and BufferedEnvelope.process (src/audian/bufferedenvelope.py:34-41,
+// scipy sosfiltfilt of (pi/2)|x|).
+//
+// The cascade of S direct-form-II-transposed biquads is the linear system
+//     s[t+1] = A s[t] + B x[t],   y[t] = (last section's output)
+// with D = 2S states per channel.  A tile = SOS_NT*SOS_L samples (time x channel
+// group, contiguous rows of the interleaved input) is staged in shared memory
+// (cp.async, 16-byte granules), each thread owns SOS_L consecutive samples of one
+// channel:
+//   pass A   zero-state end state of the sub-chunk: v = sum_i A^(L-1-i) B x_i  (dot
+//            products against a host-made table in the kernel's constant bank)
+//   scan     Kogge-Stone over the sub-chunks of a channel inside a warp with
+//            precomputed A^(L 2^k), then a short serial scan over the warps
+//   carry    decoupled look-back over preceding tiles (aggregate / inclusive
+//            state records + flags in global memory, tickets give the order);
+//            contributions are weighted with (A^T)^j tables and the look-back stops
+//            where the filter has decayed below 1e-30
+//   pass B   the exact DF2T recurrence from the true incoming state, outputs
+//            written in place into the staged tile, tile stored coalesced
+// HBM traffic: 8 B read + 8 B written per sample; state carried in fp64.
+#include "common.cuh"
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+namespace adn {
+
+namespace {
+
+constexpr int SOS_L = 32;          // samples per thread
+constexpr int SOS_NT = 256;        // threads per block
+constexpr int SOS_NW = SOS_NT / 32;
+constexpr int SOS_LOOK = 32;       // look-back window (tiles)
+
+enum { MODE_FWD = 0, MODE_ENVF = 1, MODE_REV = 2 };
+
+// table layout (D x D row-major matrices, DD = D*D doubles each)
+constexpr int TAB_SCAN = 0;        // 5:  A^(L 2^k), k = 0..4
+constexpr int TAB_FIX = 5;         // 32: A^(L j),   j = 0..31
+constexpr int TAB_WARP = 37;       // 1:  A^(L GW)
+constexpr int TAB_TILE = 38;       // 33: (A^T)^j,   j = 0..32
+constexpr int TAB_COUNT = 71;
+
+template <int S>
+struct SosK {                      // lives in the kernel's constant bank
+    double coef[S][5];             // b0 b1 b2 a1 a2
+    double W[2 * S][SOS_L];        // pass-A weights
+};
+
+struct SosRun {
+    const double* src;
+    double* dst;                   // may be null: state only
+    const double* tab;
+    uint32_t* flags;               // per tile: 0 none, 1 aggregate, 2 inclusive
+    double* agg;                   // [tile][CG][D]
+    double* incl;                  // [tile][CG][D]
+    uint32_t* ticket;
+    const double* s0;              // [C][D] initial state or null
+    double* zf;                    // [C][D] final state or null
+    int64_t n;                     // logical length (rows the recurrence runs over)
+    int64_t nx;                    // MODE_ENVF: rows of the raw input
+    int64_t out_skip;              // physical rows dropped before dst row 0
+    int64_t n_dst;
+    int64_t ntt;                   // time tiles
+    int32_t C, CG, ngroups, T;
+    int32_t jdecay;                // (A^T)^j ~ 0 for j >= jdecay
+    int32_t edge;                  // MODE_ENVF: odd-extension length
+    int32_t clamp;                 // negative outputs -> 0
+    int32_t vec_in, vec_out;       // 16-byte granules allowed
+};
+
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* g, int src_bytes) {
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(g), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* g, int src_bytes) {
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(g), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// v += M u, M block lower triangular (section k only sees states of sections <= k)
+template <int D>
+__device__ __forceinline__ void matvec_acc(const double* __restrict__ M, const double (&u)[D],
+                                           double (&v)[D]) {
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+        double a = v[r];
+#pragma unroll
+        for (int c = 0; c <= (r | 1); ++c) a = fma(__ldg(M + r * D + c), u[c], a);
+        v[r] = a;
+    }
+}
+
+template <int S, int MODE>
+__global__ void __launch_bounds__(SOS_NT)
+sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRun R) {
+    constexpr int D = 2 * S;
+    constexpr int DD = D * D;
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = (int)atomicAdd(R.ticket, 1u);
+    __syncthreads();
+    const int64_t tile = s_tile;
+    const int64_t tt = tile / R.ngroups;
+    const int grp = (int)(tile % R.ngroups);
+    const int CG = R.CG, C = R.C;
+    const int c0 = grp * CG;
+    const int Cw = min(CG, C - c0);
+    const int GW = 32 / CG;
+    const int gl = lane / CG, cw = lane % CG;
+    const int g = warp * GW + gl;
+    const bool chan_ok = cw < Cw;
+    const int T = R.T;
+    const int64_t t0 = tt * T;
+    const int pad = CG < 16 ? CG : 0;
+    const int GS = SOS_L * Cw + pad;
+    const int G = SOS_NT / CG;
+
+    double* tile_s = smem;                                   // G * GS
+    double* wagg = smem + (size_t)G * (SOS_L * CG + pad);    // [NW][CG][D]
+    double* wcar = wagg + SOS_NW * CG * D;                   // [NW][CG][D]
+
+    // ---------------------------------------------------------------- load
+    if (MODE == MODE_ENVF) {
+        // (pi/2)|x| with scipy's odd extension by `edge` rows at both ends
+        const int64_t nx = R.nx, edge = R.edge;
+        const int total = T * Cw;
+        for (int q = tid; q < total; q += SOS_NT) {
+            int row = q / Cw, col = q - row * Cw;
+            int64_t e = t0 + row;
+            double val = 0.0;
+            if (e < R.n) {
+                const double* xc = R.src + c0 + col;
+                const double hp = 1.5707963267948966;
+                if (e < edge) {
+                    double r0 = hp * fabs(__ldg(xc));
+                    double rk = hp * fabs(__ldg(xc + (edge - e) * C));
+                    val = 2.0 * r0 - rk;
+                } else if (e < edge + nx) {
+                    val = hp * fabs(__ldcs(xc + (e - edge) * C));
+                } else {
+                    int64_t k = e - edge - nx;
+                    double r1 = hp * fabs(__ldg(xc + (nx - 1) * C));
+                    double rk = hp * fabs(__ldg(xc + (nx - 2 - k) * C));
+                    val = 2.0 * r1 - rk;
+                }
+            }
+            tile_s[(row / SOS_L) * GS + (row % SOS_L) * Cw + col] = val;
+        }
+    } else {
+        const int gw = R.vec_in ? 2 : 1;                 // doubles per granule
+        const int gpr = Cw / gw;                         // granules per row
+        const int total = T * gpr;
+        int row = tid / gpr, col = tid - row * gpr;
+        const int drow = SOS_NT / gpr, dcol = SOS_NT - drow * gpr;
+        for (int q = tid; q < total; q += SOS_NT) {
+            int64_t tau = t0 + row;
+            bool ok = tau < R.n;
+            int64_t phys = MODE == MODE_REV ? R.n - 1 - tau : tau;
+            const double* gp = ok ? R.src + phys * C + c0 + col * gw : R.src;
+            double* sp = tile_s + (row / SOS_L) * GS + (row % SOS_L) * Cw + col * gw;
+            if (gw == 2) cp_async16(sp, gp, ok ? 16 : 0);
+            else cp_async8(sp, gp, ok ? 8 : 0);
+            row += drow;
+            col += dcol;
+            if (col >= gpr) { col -= gpr; ++row; }
+        }
+        cp_async_wait_all();
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------- pass A
+    double* xp = tile_s + g * GS + cw;
+    double v[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) v[d] = 0.0;
+    if (chan_ok) {
+#pragma unroll
+        for (int i = 0; i < SOS_L; ++i) {
+            double x = xp[i * Cw];
+#pragma unroll
+            for (int d = 0; d < D; ++d) v[d] = fma(K.W[d][i], x, v[d]);
+        }
+    }
+
+    // ---------------------------------------------------------------- warp scan over gl
+    {
+        int k = 0;
+        for (int off = CG; off < 32; off <<= 1, ++k) {
+            double u[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) u[d] = __shfl_up_sync(0xffffffffu, v[d], off);
+            if (lane >= off) matvec_acc<D>(R.tab + (TAB_SCAN + k) * DD, u, v);
+        }
+    }
+    double ex[D];                         // exclusive prefix inside the warp
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        double t = __shfl_up_sync(0xffffffffu, v[d], CG & 31);
+        ex[d] = gl == 0 ? 0.0 : t;
+    }
+    if (gl == GW - 1) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) wagg[(warp * CG + cw) * D + d] = v[d];
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------- tile level (warp 0)
+    if (warp == 0) {
+        const double* Mw = R.tab + TAB_WARP * DD;
+        const double* Pt = R.tab + TAB_TILE * DD;
+        const bool ch = lane < CG;                  // one lane per channel of the group
+        const bool ch_real = ch && (c0 + lane < C);
+        double acc[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) acc[d] = 0.0;
+        if (ch) {
+            for (int w = 0; w < SOS_NW; ++w) {
+                double nxt[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    wcar[(w * CG + lane) * D + d] = acc[d];          // prefix before warp w
+                    nxt[d] = wagg[(w * CG + lane) * D + d];
+                }
+                matvec_acc<D>(Mw, acc, nxt);
+#pragma unroll
+                for (int d = 0; d < D; ++d) acc[d] = nxt[d];
+            }
+        }
+        const bool publish = tt + 1 < R.ntt;
+        const size_t rec = (size_t)tile * CG * D + (size_t)lane * D;
+        if (publish) {
+            if (ch) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) __stcg(R.agg + rec + d, acc[d]);
+                __threadfence();
+            }
+            __syncwarp();
+            if (lane == 0) st_release(R.flags + tile, 1u);
+        }
+        // ---- incoming state of the tile
+        double sin[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) sin[d] = 0.0;
+        if (tt == 0) {
+            if (ch_real && R.s0) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) sin[d] = __ldg(R.s0 + (size_t)(c0 + lane) * D + d);
+            }
+        } else {
+            // lane j-1 watches predecessor j (same channel group, j time tiles back)
+            const int j = lane + 1;
+            const int64_t back = tt - j;                 // -1: the virtual tile holding s0
+            const bool decayed = j > R.jdecay;           // weight (A^T)^(j-1) ~ 0
+            const bool real = back >= 0 && !decayed;
+            const uint32_t* fp = R.flags + (real ? tile - (int64_t)j * R.ngroups : tile);
+            uint32_t status = real ? 0u : 2u;
+            int J;
+            unsigned ns = 8;
+            while (true) {
+                if (status != 2u && real) status = ld_acquire(fp);
+                unsigned m2 = __ballot_sync(0xffffffffu, status == 2u);
+                unsigned m0 = __ballot_sync(0xffffffffu, status == 0u);
+                if (m2) {
+                    J = __ffs(m2);                        // nearest inclusive, 1-based
+                    unsigned below = J >= 32 ? 0xffffffffu : ((1u << J) - 1u);
+                    if ((m0 & below) == 0) break;
+                }
+                __nanosleep(ns);
+                if (ns < 256) ns <<= 1;
+            }
+            __threadfence();
+            __syncwarp();
+            if (ch) {
+                for (int jj = 1; jj <= J; ++jj) {
+                    const int64_t b = tt - jj;
+                    double vec[D];
+                    bool zero = false;
+                    if (jj == J) {
+                        if (jj > R.jdecay) zero = true;
+                        else if (b < 0) {
+#pragma unroll
+                            for (int d = 0; d < D; ++d)
+                                vec[d] = (ch_real && R.s0) ? __ldg(R.s0 + (size_t)(c0 + lane) * D + d) : 0.0;
+                        } else {
+                            const double* p = R.incl + (size_t)(tile - (int64_t)jj * R.ngroups) * CG * D + (size_t)lane * D;
+#pragma unroll
+                            for (int d = 0; d < D; ++d) vec[d] = __ldcg(p + d);
+                        }
+                    } else {
+                        const double* p = R.agg + (size_t)(tile - (int64_t)jj * R.ngroups) * CG * D + (size_t)lane * D;
+#pragma unroll
+                        for (int d = 0; d < D; ++d) vec[d] = __ldcg(p + d);
+                    }
+                    if (!zero) matvec_acc<D>(Pt + (jj - 1) * DD, vec, sin);
+                }
+            }
+        }
+        // ---- inclusive state of this tile, for the successors
+        if (publish) {
+            if (ch) {
+                double inc[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) inc[d] = acc[d];
+                matvec_acc<D>(Pt + DD, sin, inc);
+#pragma unroll
+                for (int d = 0; d < D; ++d) __stcg(R.incl + rec + d, inc[d]);
+                __threadfence();
+            }
+            __syncwarp();
+            if (lane == 0) st_release(R.flags + tile, 2u);
+        }
+        // ---- incoming state of every warp chunk
+        if (ch) {
+            double p[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) p[d] = sin[d];
+            for (int w = 0; w < SOS_NW; ++w) {
+                double q[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    wcar[(w * CG + lane) * D + d] += p[d];
+                    q[d] = 0.0;
+                }
+                matvec_acc<D>(Mw, p, q);
+#pragma unroll
+                for (int d = 0; d < D; ++d) p[d] = q[d];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------- pass B
+    const int64_t tau0 = t0 + (int64_t)g * SOS_L;
+    const int64_t last = R.n - 1;
+    const bool want_state = R.zf != nullptr && last >= tau0 && last < tau0 + SOS_L;
+    if (chan_ok && (R.dst != nullptr || want_state)) {
+        double z[D];
+        {
+            double wc[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) { wc[d] = wcar[(warp * CG + cw) * D + d]; z[d] = ex[d]; }
+            if (gl == 0) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) z[d] += wc[d];
+            } else {
+                matvec_acc<D>(R.tab + (TAB_FIX + gl) * DD, wc, z);
+            }
+        }
+        const int ilast = want_state ? (int)(last - tau0) : -1;
+#pragma unroll
+        for (int i = 0; i < SOS_L; ++i) {
+            double x = xp[i * Cw];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                double y = fma(K.coef[s][0], x, z[2 * s]);
+                z[2 * s] = fma(K.coef[s][1], x, z[2 * s + 1]) - K.coef[s][3] * y;
+                z[2 * s + 1] = K.coef[s][2] * x - K.coef[s][4] * y;
+                x = y;
+            }
+            xp[i * Cw] = x;
+            if (i == ilast) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) R.zf[(size_t)(c0 + cw) * D + d] = z[d];
+            }
+        }
+    }
+    if (R.dst == nullptr) return;
+    __syncthreads();
+
+    // ---------------------------------------------------------------- store
+    {
+        const int gw = R.vec_out ? 2 : 1;
+        const int gpr = Cw / gw;
+        const int total = T * gpr;
+        int row = tid / gpr, col = tid - row * gpr;
+        const int drow = SOS_NT / gpr, dcol = SOS_NT - drow * gpr;
+        for (int q = tid; q < total; q += SOS_NT) {
+            int64_t tau = t0 + row;
+            int64_t phys = MODE == MODE_REV ? R.n - 1 - tau : tau;
+            int64_t orow = phys - R.out_skip;
+            if (tau < R.n && orow >= 0 && orow < R.n_dst) {
+                const double* sp = tile_s + (row / SOS_L) * GS + (row % SOS_L) * Cw + col * gw;
+                double* gp = R.dst + orow * C + c0 + col * gw;
+                if (gw == 2) {
+                    double2 o = *reinterpret_cast<const double2*>(sp);
+                    if (R.clamp) { o.x = o.x < 0.0 ? 0.0 : o.x; o.y = o.y < 0.0 ? 0.0 : o.y; }
+                    __stcs(reinterpret_cast<double2*>(gp), o);
+                } else {
+                    double o = *sp;
+                    if (R.clamp) o = o < 0.0 ? 0.0 : o;
+                    __stcs(gp, o);
+                }
+            }
+            row += drow;
+            col += dcol;
+            if (col >= gpr) { col -= gpr; ++row; }
+        }
+    }
+}
+
+// initial states of the two sosfiltfilt sweeps: s0[c][d] = zi[d] * x0[c]
+// which = 0: x0 = ext[0] = 2 r(0) - r(edge) of the raw input;  which = 1: x0 = row[c]
+__global__ void env_s0_kernel(int which, const double* __restrict__ src, int32_t C, int32_t D,
+                              int64_t edge, const double* __restrict__ zi, double* __restrict__ s0) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C * D) return;
+    int c = i / D, d = i - c * D;
+    double x0;
+    if (which == 0) {
+        const double hp = 1.5707963267948966;
+        x0 = 2.0 * (hp * fabs(src[c])) - hp * fabs(src[edge * C + c]);
+    } else {
+        x0 = src[c];
+    }
+    s0[i] = zi[d] * x0;
+}
+
+// ------------------------------------------------------------------ host side plan
+
+typedef long double ld;
+
+struct Mat {                      // D x D, row major
+    int D;
+    std::vector<ld> a;
+    explicit Mat(int D_) : D(D_), a((size_t)D_ * D_, 0.0L) {}
+    ld& at(int r, int c) { return a[(size_t)r * D + c]; }
+    ld at(int r, int c) const { return a[(size_t)r * D + c]; }
+    static Mat eye(int D) { Mat m(D); for (int i = 0; i < D; ++i) m.at(i, i) = 1.0L; return m; }
+};
+
+Mat mul(const Mat& x, const Mat& y) {
+    Mat r(x.D);
+    for (int i = 0; i < x.D; ++i)
+        for (int k = 0; k < x.D; ++k) {
+            ld xv = x.at(i, k);
+            if (xv == 0.0L) continue;
+            for (int j = 0; j < x.D; ++j) r.at(i, j) += xv * y.at(k, j);
+        }
+    return r;
+}
+
+Mat mpow(Mat base, int64_t e) {
+    Mat r = Mat::eye(base.D);
+    while (e > 0) {
+        if (e & 1) r = mul(r, base);
+        e >>= 1;
+        if (e) base = mul(base, base);
+    }
+    return r;
+}
+
+// one step of the cascade (the recurrence of scipy's _sosfilt) in long double
+void step(const double* sos, int S, std::vector<ld>& z, ld x) {
+    for (int s = 0; s < S; ++s) {
+        const double* q = sos + 6 * s;
+        ld y = (ld)q[0] * x + z[2 * s];
+        z[2 * s] = (ld)q[1] * x - (ld)q[4] * y + z[2 * s + 1];
+        z[2 * s + 1] = (ld)q[2] * x - (ld)q[5] * y;
+        x = y;
+    }
+}
+
+void state_space(const double* sos, int S, Mat& A, std::vector<ld>& B) {
+    const int D = 2 * S;
+    for (int j = 0; j < D; ++j) {
+        std::vector<ld> z(D, 0.0L);
+        z[j] = 1.0L;
+        step(sos, S, z, 0.0L);
+        for (int r = 0; r < D; ++r) A.at(r, j) = z[r];
+    }
+    std::vector<ld> z(D, 0.0L);
+    step(sos, S, z, 1.0L);
+    B = z;
+}
+
+struct Plan {
+    std::vector<double> sos;      // key
+    int S = 0, CG = 0;
+    int jdecay = SOS_LOOK + 1;
+    std::vector<double> W;        // [D][L]
+    double* dtab = nullptr;       // device tables
+};
+
+std::vector<Plan> g_plans;
+std::mutex g_plan_mu;
+
+int32_t get_plan(const double* sos, int S, int CG, cudaStream_t st, Plan** out) {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    for (auto& p : g_plans)
+        if (p.S == S && p.CG == CG && memcmp(p.sos.data(), sos, sizeof(double) * 6 * S) == 0) {
+            *out = &p;
+            return ADN_OK;
+        }
+    if (g_plans.size() >= 64) {                 // bounded cache
+        for (auto& p : g_plans) cudaFree(p.dtab);
+        g_plans.clear();
+    }
+    const int D = 2 * S, DD = D * D;
+    Plan p;
+    p.sos.assign(sos, sos + 6 * S);
+    p.S = S;
+    p.CG = CG;
+    Mat A(D);
+    std::vector<ld> B;
+    state_space(sos, S, A, B);
+    // W[d][i] = (A^(L-1-i) B)[d]
+    p.W.assign((size_t)D * SOS_L, 0.0);
+    {
+        std::vector<ld> v = B;
+        for (int i = SOS_L - 1; i >= 0; --i) {
+            for (int d = 0; d < D; ++d) p.W[(size_t)d * SOS_L + i] = (double)v[d];
+            std::vector<ld> nv(D, 0.0L);
+            for (int r = 0; r < D; ++r)
+                for (int c = 0; c < D; ++c) nv[r] += A.at(r, c) * v[c];
+            v = nv;
+        }
+    }
+    std::vector<double> tab((size_t)TAB_COUNT * DD, 0.0);
+    auto put = [&](int slot, const Mat& m) {
+        for (int i = 0; i < DD; ++i) tab[(size_t)slot * DD + i] = (double)m.a[i];
+    };
+    const Mat AL = mpow(A, SOS_L);
+    {
+        Mat m = AL;
+        for (int k = 0; k < 5; ++k) { put(TAB_SCAN + k, m); m = mul(m, m); }
+    }
+    {
+        Mat m = Mat::eye(D);
+        for (int j = 0; j < 32; ++j) { put(TAB_FIX + j, m); m = mul(m, AL); }
+    }
+    const int GW = 32 / CG;
+    put(TAB_WARP, mpow(AL, GW));
+    {
+        const Mat AT = mpow(AL, SOS_NT / CG);         // one tile = NT/CG sub-chunks per channel
+        Mat m = Mat::eye(D);
+        p.jdecay = SOS_LOOK + 1;
+        for (int j = 0; j <= 32; ++j) {
+            put(TAB_TILE + j, m);
+            ld mx = 0.0L;
+            for (auto x : m.a) mx = fmaxl(mx, fabsl(x));
+            if (j >= 1 && mx < 1e-30L && p.jdecay > SOS_LOOK) p.jdecay = j;
+            m = mul(m, AT);
+        }
+    }
+    ADN_CK(cudaMalloc(&p.dtab, tab.size() * sizeof(double)));
+    ADN_CK(cudaMemcpyAsync(p.dtab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    ADN_CK(cudaStreamSynchronize(st));           // `tab` is a stack-lifetime host buffer
+    g_plans.push_back(std::move(p));
+    *out = &g_plans.back();
+    return ADN_OK;
+}
+
+int pick_cg(int C) {
+    int cg = 1;
+    while (cg < C && cg < 32) cg <<= 1;
+    return cg;
+}
+
+template <int S, int MODE>
+int32_t launch_mode(const Plan& plan, SosRun& R, size_t smem_bytes, unsigned grid, cudaStream_t st) {
+    SosK<S> K;
+    for (int s = 0; s < S; ++s) {
+        const double* q = plan.sos.data() + 6 * s;
+        K.coef[s][0] = q[0]; K.coef[s][1] = q[1]; K.coef[s][2] = q[2];
+        K.coef[s][3] = q[4]; K.coef[s][4] = q[5];
+    }
+    memcpy(K.W, plan.W.data(), sizeof(double) * 2 * S * SOS_L);
+    auto kern = sos_scan_kernel<S, MODE>;
+    static bool attr_done = false;               // per instantiation
+    if (!attr_done) {
+        ADN_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done = true;
+    }
+    kern<<<grid, SOS_NT, smem_bytes, st>>>(K, R);
+    count_launch();
+    ADN_CK(cudaGetLastError());
+    return ADN_OK;
+}
+
+template <int S>
+int32_t launch_S(int mode, const Plan& plan, SosRun& R, size_t smem, unsigned grid, cudaStream_t st) {
+    switch (mode) {
+        case MODE_FWD: return launch_mode<S, MODE_FWD>(plan, R, smem, grid, st);
+        case MODE_ENVF: return launch_mode<S, MODE_ENVF>(plan, R, smem, grid, st);
+        default: return launch_mode<S, MODE_REV>(plan, R, smem, grid, st);
+    }
+}
+
+// one sweep of the scan kernel
+int32_t run_scan(int mode, const double* sos, int S, const double* src, int64_t n, int64_t nx,
+                 int edge, int32_t C, double* dst, int64_t out_skip, int64_t n_dst, int clamp,
+                 const double* s0, double* zf, int tile_slot, cudaStream_t st) {
+    const int CG = pick_cg(C);
+    const int D = 2 * S;
+    Plan* plan = nullptr;
+    int32_t rc = get_plan(sos, S, CG, st, &plan);
+    if (rc) return rc;
+    SosRun R;
+    memset(&R, 0, sizeof R);
+    R.src = src; R.dst = dst; R.tab = plan->dtab; R.s0 = s0; R.zf = zf;
+    R.n = n; R.nx = nx; R.out_skip = out_skip; R.n_dst = n_dst;
+    R.C = C; R.CG = CG; R.ngroups = (C + CG - 1) / CG;
+    R.T = (SOS_NT / CG) * SOS_L;
+    R.ntt = (n + R.T - 1) / R.T;
+    R.jdecay = plan->jdecay;
+    R.edge = edge; R.clamp = clamp;
+    const bool even = (C % 2 == 0) && (CG % 2 == 0);
+    R.vec_in = even && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    R.vec_out = even && dst && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    const int64_t ntiles = R.ntt * R.ngroups;
+    if (ntiles > 0x7fffffff) return fail(ADN_ERR_UNSUPPORTED, "sos scan: %lld tiles", (long long)ntiles);
+    // tile records: flags | ticket | agg | incl
+    const size_t nflag = ((size_t)ntiles + 1 + 3) & ~(size_t)3;          // keeps doubles 16B aligned
+    const size_t recs = (size_t)ntiles * CG * D;
+    DevBuf& tb = scratch(tile_slot);
+    if ((rc = tb.reserve(nflag * 4 + recs * 16))) return rc;
+    R.flags = tb.as<uint32_t>();
+    R.ticket = R.flags + ntiles;
+    R.agg = reinterpret_cast<double*>(tb.as<char>() + nflag * 4);
+    R.incl = R.agg + recs;
+    ADN_CK(cudaMemsetAsync(R.flags, 0, nflag * 4, st));
+    const int pad = CG < 16 ? CG : 0;
+    const size_t smem = ((size_t)(SOS_NT / CG) * (SOS_L * CG + pad) + 2 * (size_t)SOS_NW * CG * D) * 8;
+    const unsigned grid = (unsigned)ntiles;
+    switch (S) {
+        case 1: return launch_S<1>(mode, *plan, R, smem, grid, st);
+        case 2: return launch_S<2>(mode, *plan, R, smem, grid, st);
+        case 3: return launch_S<3>(mode, *plan, R, smem, grid, st);
+        case 4: return launch_S<4>(mode, *plan, R, smem, grid, st);
+        case 5: return launch_S<5>(mode, *plan, R, smem, grid, st);
+        case 6: return launch_S<6>(mode, *plan, R, smem, grid, st);
+        case 7: return launch_S<7>(mode, *plan, R, smem, grid, st);
+        case 8: return launch_S<8>(mode, *plan, R, smem, grid, st);
+    }
+    return fail(ADN_ERR_INVALID, "sos scan: S=%d", S);
+}
+
+}  // namespace
+
+int32_t sosfilt_dev(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
+                    int64_t nbefore, double* dst, int64_t n_dst, const double* zi, double* zf,
+                    cudaStream_t st) {
+    if (S == 0) {                                // reference: sos is None -> copy
+        if (dst && n_dst > 0)
+            ADN_CK(cudaMemcpyAsync(dst, src + nbefore * C, (size_t)n_dst * C * 8,
+                                   cudaMemcpyDeviceToDevice, st));
+        return ADN_OK;
+    }
+    // scipy's zi/zf layout (C, S, 2) is the kernel's [C][D] state layout
+    return run_scan(MODE_FWD, sos, S, src, n_src, n_src, 0, C, dst, nbefore, n_dst, 0, zi, zf,
+                    SCR_SOS_TILES, st);
+}
+
+int32_t envelope_dev(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
+                     int64_t nbefore, double* dst, int64_t n_dst, int32_t clamp_negative,
+                     cudaStream_t st) {
+    const int D = 2 * S;
+    const int edge = adn_sosfiltfilt_edge(sos, S);
+    const int64_t next = n_src + 2 * (int64_t)edge;
+    // zi = sosfilt_zi(sos): per section scale * lfilter_zi(b, a), scale *= sum(b)/sum(a)
+    double zi[2 * ADN_MAX_SECTIONS];
+    {
+        double scale = 1.0;
+        for (int s = 0; s < S; ++s) {
+            const double* q = sos + 6 * s;
+            double b0 = q[0], b1 = q[1], b2 = q[2], a0 = q[3], a1 = q[4], a2 = q[5];
+            double B0 = b1 - a1 * b0, B1 = b2 - a2 * b0;
+            double det = 1.0 + a1 + a2;
+            zi[2 * s] = scale * ((B0 + B1) / det);
+            zi[2 * s + 1] = scale * (((1.0 + a1) * B1 - a2 * B0) / det);
+            scale *= (b0 + b1 + b2) / (a0 + a1 + a2);
+        }
+    }
+    DevBuf& fwd = scratch(SCR_ENV_FWD);
+    DevBuf& misc = scratch(SCR_ENV_MISC);
+    int32_t rc;
+    if ((rc = fwd.reserve((size_t)next * C * 8))) return rc;
+    if ((rc = misc.reserve((size_t)(D + 2 * C * D) * 8))) return rc;
+    double* d_zi = misc.as<double>();
+    double* d_s0f = d_zi + D;
+    double* d_s0b = d_s0f + (size_t)C * D;
+    ADN_CK(cudaMemcpyAsync(d_zi, zi, D * 8, cudaMemcpyHostToDevice, st));
+    const int nb = (C * D + 127) / 128;
+    env_s0_kernel<<<nb, 128, 0, st>>>(0, src, C, D, edge, d_zi, d_s0f);
+    count_launch();
+    ADN_CK(cudaGetLastError());
+    double* y1 = fwd.as<double>();
+    if ((rc = run_scan(MODE_ENVF, sos, S, src, next, n_src, edge, C, y1, 0, next, 0, d_s0f, nullptr,
+                       SCR_SOS_TILES, st)))
+        return rc;
+    env_s0_kernel<<<nb, 128, 0, st>>>(1, y1 + (next - 1) * C, C, D, 0, d_zi, d_s0b);
+    count_launch();
+    ADN_CK(cudaGetLastError());
+    return run_scan(MODE_REV, sos, S, y1, next, next, 0, C, dst, edge + nbefore, n_dst,
+                    clamp_negative ? 1 : 0, d_s0b, nullptr, SCR_SOS_MISC, st);
+}
+
+}  // namespace adn
+
+using namespace adn;
+
+extern "C" {
+
+int32_t adn_sos_state_space(const double* sos, int32_t S, double* A, double* B, int64_t power,
+                            double* A_pow) {
+    if (!sos || S < 1 || S > ADN_MAX_SECTIONS || power < 0)
+        return fail(ADN_ERR_INVALID, "adn_sos_state_space: bad arguments");
+    const int D = 2 * S;
+    Mat Am(D);
+    std::vector<ld> Bv;
+    state_space(sos, S, Am, Bv);
+    if (A) for (int i = 0; i < D * D; ++i) A[i] = (double)Am.a[i];
+    if (B) for (int i = 0; i < D; ++i) B[i] = (double)Bv[i];
+    if (A_pow) {
+        Mat P = mpow(Am, power);
+        for (int i = 0; i < D * D; ++i) A_pow[i] = (double)P.a[i];
+    }
+    return ADN_OK;
+}
+
+int32_t adn_sosfiltfilt_edge(const double* sos, int32_t S) {
+    if (!sos || S < 1) return 0;
+    int nb = 0, na = 0;
+    for (int s = 0; s < S; ++s) {
+        if (sos[6 * s + 2] == 0.0) ++nb;
+        if (sos[6 * s + 5] == 0.0) ++na;
+    }
+    int ntaps = 2 * S + 1 - (nb < na ? nb : na);
+    return 3 * ntaps;
+}
+
+}  // extern "C"

@@ -1,0 +1,146 @@
+/* audian_b200.h -- C ABI of libaudian_b200.so
+ *
+ * B200 (sm_100a) implementation of the derived-trace DSP path of
+ * bendalab/audian.  Every entry point is what a ctypes binding on the
+ * reference side would call in place of the numpy/scipy body of one
+ * reference function (paths relative to the reference tree):
+ *
+ *   adn_sosfilt_f64      BufferedFilter.process      src/audian/bufferedfilter.py:31-36
+ *   adn_envelope_f64     BufferedEnvelope.process    src/audian/bufferedenvelope.py:34-41
+ *   adn_spectrogram_f64  BufferedSpectrogram.process src/audian/bufferedspectrogram.py:45-62
+ *   adn_minmax_f64       down_sample_worker / CompressedData.start
+ *                                                    src/audian/compresseddata.py:49-52,97-100
+ *                        TraceItem.update_plot       src/audian/traceitem.py:58-61
+ *   adn_decibel_f64      thunderlab decibel() as used by SpecItem.update_plot
+ *                                                    src/audian/specitem.py:36
+ *
+ * Data layout is the reference's: float64, C-contiguous, time-major, channels
+ * interleaved -- traces are (frames, C), spectrograms (frames, C, nfft/2+1).
+ * Lengths are int64_t, counts int32_t.  Every function returns a status
+ * (ADN_OK == 0); the message of the last failure on the calling thread is
+ * returned by adn_last_error().  There is no CPU fallback: without a CUDA
+ * device every compute entry point fails with ADN_ERR_CUDA.
+ *
+ * Host-pointer entry points copy to and from device memory that the library
+ * owns, on the library's own stream, and block until the result is in `dst`.
+ * The *_dev entry points take device pointers and a cudaStream_t (passed as
+ * void*; NULL = the library's stream), only enqueue work and do not
+ * synchronise.
+ */
+#ifndef AUDIAN_B200_H
+#define AUDIAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADN_OK               0
+#define ADN_ERR_INVALID      1   /* bad argument (shape, NULL pointer, ...) */
+#define ADN_ERR_CUDA         2   /* CUDA runtime error / no device */
+#define ADN_ERR_UNSUPPORTED  3   /* valid in the reference, not built yet */
+#define ADN_ERR_SHORT        4   /* envelope input not longer than the sosfiltfilt pad
+                                    (scipy raises ValueError) */
+
+#define ADN_MAX_SECTIONS     8   /* biquad sections per cascade */
+#define ADN_MIN_NFFT         8
+#define ADN_MAX_NFFT         16384  /* single-kernel shared-memory FFT */
+
+#define ADN_WINDOW_HANN      0   /* periodic Hann == scipy get_window('hann', nfft) */
+#define ADN_DETREND_NONE     0
+#define ADN_DETREND_CONSTANT 1   /* subtract the frame mean */
+
+/* ---- context -------------------------------------------------------- */
+int32_t adn_init(int32_t device);      /* idempotent; selects the device */
+int32_t adn_shutdown(void);
+const char* adn_last_error(void);
+int32_t adn_version(void);
+int64_t adn_launch_count(void);        /* kernels launched by this library so far */
+int32_t adn_synchronize(void);         /* waits for the library's stream */
+/* page-lock a host range so that the host-pointer entry points copy at full
+ * PCIe rate (optional; plain pageable memory works too) */
+int32_t adn_host_register(void* ptr, int64_t bytes);
+int32_t adn_host_unregister(void* ptr);
+
+/* ---- host-pointer entry points (the plugin path) -------------------- */
+
+/* dst (2*ceil(n/step), C): row 2j = min, row 2j+1 = max over source rows
+ * [j*step, min((j+1)*step, n)).  numpy semantics bit for bit: NaN propagates
+ * (the first NaN in time order), equal values resolve to the later row
+ * (signed zeros). */
+int32_t adn_minmax_f64(const double* src, int64_t n, int32_t C, int64_t step,
+                       double* dst);
+
+/* dst[i, c] = sosfilt(sos, src[:, c])[nbefore + i], i < n_dst.
+ * sos: S rows of (b0, b1, b2, a0, a1, a2), a0 == 1 (scipy layout).
+ * n_dst must be <= n_src - nbefore.  zi_inout: NULL = zero initial state,
+ * else (C, S, 2) doubles, read as the initial state and overwritten with the
+ * state after the last source row (streaming, == scipy's zi/zf per channel).
+ * S == 0 copies src[nbefore:] (the reference's `sos is None` branch). */
+int32_t adn_sosfilt_f64(const double* sos, int32_t S,
+                        const double* src, int64_t n_src, int32_t C,
+                        int64_t nbefore, double* dst, int64_t n_dst,
+                        double* zi_inout);
+
+/* dst = sosfiltfilt(sos, (pi/2)*|src|, axis=0)[nbefore:][:n_dst] with scipy's
+ * default odd padding of 3*ntaps rows and sosfilt_zi initial conditions;
+ * clamp_negative != 0 sets negative results to 0.  S == 0 writes zeros. */
+int32_t adn_envelope_f64(const double* sos, int32_t S,
+                         const double* src, int64_t n_src, int32_t C,
+                         int64_t nbefore, double* dst, int64_t n_dst,
+                         int32_t clamp_negative);
+
+/* One-sided power spectral density frames (V**2/Hz), scipy 'density' scaling:
+ * nsource = min((n_dst-1)*hop + nfft, n_src); n = (nsource - (nfft-hop))/hop
+ * frames are computed, dst[n:] is zero-filled (all of dst if nsource < nfft).
+ * dst is (n_dst, C, nfft/2+1).  nfft: power of two in [8, 16384];
+ * 1 <= hop <= nfft.  out_db != 0 stores decibel(P) instead of P.
+ * n_computed (may be NULL) receives n. */
+int32_t adn_spectrogram_f64(const double* src, int64_t n_src, int32_t C,
+                            double rate, int32_t nfft, int32_t hop,
+                            int32_t window_id, int32_t detrend_id,
+                            double* dst, int64_t n_dst, int32_t out_db,
+                            int64_t* n_computed);
+
+/* dst[i] = power[i] > min_power ? 10*log10(power[i]/ref_power) : -inf */
+int32_t adn_decibel_f64(const double* power, int64_t n, double ref_power,
+                        double min_power, double* dst);
+
+/* ---- device-pointer entry points (bench / multi-GPU path) ----------- */
+int32_t adn_minmax_f64_dev(const double* src, int64_t n, int32_t C,
+                           int64_t step, double* dst, void* stream);
+/* sos is a HOST pointer; zi / zf are device pointers to (C, S, 2) or NULL.
+ * dst may be NULL (n_dst ignored): only the final state zf is computed. */
+int32_t adn_sosfilt_f64_dev(const double* sos, int32_t S,
+                            const double* src, int64_t n_src, int32_t C,
+                            int64_t nbefore, double* dst, int64_t n_dst,
+                            const double* zi, double* zf, void* stream);
+int32_t adn_envelope_f64_dev(const double* sos, int32_t S,
+                             const double* src, int64_t n_src, int32_t C,
+                             int64_t nbefore, double* dst, int64_t n_dst,
+                             int32_t clamp_negative, void* stream);
+int32_t adn_spectrogram_f64_dev(const double* src, int64_t n_src, int32_t C,
+                                double rate, int32_t nfft, int32_t hop,
+                                int32_t window_id, int32_t detrend_id,
+                                double* dst, int64_t n_dst, int32_t out_db,
+                                int64_t* n_computed, void* stream);
+int32_t adn_decibel_f64_dev(const double* power, int64_t n, double ref_power,
+                            double min_power, double* dst, void* stream);
+/* rows t0 .. t0+n of the deterministic synthetic recording,
+ * identical to audian_b200.synth.synth() */
+int32_t adn_synth_f64_dev(double* dst, int64_t t0, int64_t n, int32_t C,
+                          double rate, uint64_t seed, void* stream);
+
+/* ---- host-side plan inspection (no GPU needed; used by the CPU tests) -- */
+/* Fills the matrices the scan kernel uses for a cascade: A (D x D state
+ * transition, D = 2*S), B (D), and A^power (D x D), all row-major doubles. */
+int32_t adn_sos_state_space(const double* sos, int32_t S, double* A, double* B,
+                            int64_t power, double* A_pow);
+/* pad length of scipy's sosfiltfilt for this cascade (3*ntaps) */
+int32_t adn_sosfiltfilt_edge(const double* sos, int32_t S);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUDIAN_B200_H */

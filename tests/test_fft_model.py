@@ -1,0 +1,76 @@
+"""Host-side model of the FFT arithmetic in audian_b200/csrc/spectrogram.cu:
+half-size complex FFT of the real frame, radix-2^2 decimation in frequency (two
+stages per pass, optional last radix-2 stage), bit-reversed read-out, split
+step, one-sided density scaling.  Checked against scipy.signal.spectrogram."""
+
+import numpy as np
+import pytest
+from scipy.signal import spectrogram
+
+
+def bitrev(k, bits):
+    r = 0
+    for _ in range(bits):
+        r = (r << 1) | (k & 1)
+        k >>= 1
+    return r
+
+
+def model_frame(x, rate):
+    N = len(x)
+    M = N//2
+    logM = M.bit_length() - 1
+    j = np.arange(N)
+    w = 0.5 - 0.5*np.cos(2*np.pi*j/N)
+    tw = np.exp(-2j*np.pi*np.arange(N//2)/N)
+    xw = (x - x.sum()/N)*w
+    z = xw[0::2] + 1j*xw[1::2]
+    lg = logM
+    while lg >= 2:
+        n = 1 << lg
+        q4 = n >> 2
+        tstep = N >> lg
+        for r in range(M >> 2):
+            blk, k = r >> (lg - 2), r & (q4 - 1)
+            b = (blk << lg) + k
+            a0, a1, a2, a3 = z[b], z[b + q4], z[b + 2*q4], z[b + 3*q4]
+            w1, w2 = tw[k*tstep], tw[2*k*tstep]
+            b0 = a0 + a2
+            b2 = (a0 - a2)*w1
+            b1 = a1 + a3
+            d = a1 - a3
+            b3 = complex(d.imag, -d.real)*w1
+            z[b] = b0 + b1
+            z[b + q4] = (b0 - b1)*w2
+            z[b + 2*q4] = b2 + b3
+            z[b + 3*q4] = (b2 - b3)*w2
+        lg -= 2
+    if lg == 1:
+        for r in range(M >> 1):
+            u, v = z[2*r], z[2*r + 1]
+            z[2*r], z[2*r + 1] = u + v, u - v
+    scale = 1.0/(rate*np.sum(w*w))
+    P = np.empty(M + 1)
+    for k in range(M + 1):
+        if k == 0 or k == M:
+            xr = z[0].real + z[0].imag if k == 0 else z[0].real - z[0].imag
+            P[k] = xr*xr*scale
+        else:
+            zk, zm = z[bitrev(k, logM)], z[bitrev(M - k, logM)]
+            er, ei = 0.5*(zk.real + zm.real), 0.5*(zk.imag - zm.imag)
+            orr, oi = 0.5*(zk.imag + zm.imag), -0.5*(zk.real - zm.real)
+            wv = tw[k]
+            xr = er + (orr*wv.real - oi*wv.imag)
+            xi = ei + (orr*wv.imag + oi*wv.real)
+            P[k] = (xr*xr + xi*xi)*scale*2.0
+    return P
+
+
+@pytest.mark.parametrize('N', [8, 16, 32, 64, 256, 1024])
+def test_fft_model(N):
+    rng = np.random.default_rng(N)
+    x = rng.standard_normal(N) + 0.3
+    f, t, S = spectrogram(x, fs=1000., window='hann', nperseg=N, noverlap=0,
+                          detrend='constant', scaling='density', mode='psd')
+    P = model_frame(x, 1000.)
+    assert np.allclose(P, S[:, 0], rtol=1e-9, atol=1e-22*np.max(S))

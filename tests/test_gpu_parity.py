@@ -1,0 +1,370 @@
+"""Parity of the sm_100a kernels (through the C ABI) with the CPU oracle.
+
+Tolerances (BASELINE.json north_star): min/max bit-exact; filtered/envelope
+traces max abs error <= 1e-6 of full scale; spectrogram power rtol 1e-5 (with
+an absolute floor of 1e-20 x the largest bin, below which two fp64 FFTs cannot
+agree to 1e-5 either).
+"""
+
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+from scipy.signal import butter, sosfilt
+
+from audian_b200 import _lib
+from audian_b200.synth import synth
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+FS_TOL = 1e-6          # of full scale
+SPEC_RTOL = 1e-5
+SPEC_ATOL_REL = 1e-20
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint64)
+
+
+def assert_trace_close(got, ref, what=''):
+    scale = max(1.0, float(np.max(np.abs(ref))) if ref.size else 1.0)
+    err = float(np.max(np.abs(got - ref))) if ref.size else 0.0
+    assert err <= FS_TOL*scale, f'{what}: max abs err {err:g} (scale {scale:g})'
+
+
+def assert_spec_close(got, ref, what=''):
+    atol = SPEC_ATOL_REL*float(np.max(ref)) if ref.size else 0.0
+    bad = np.abs(got - ref) > atol + SPEC_RTOL*np.abs(ref)
+    assert not bad.any(), f'{what}: {bad.sum()} bins off, worst rel ' \
+        f'{np.max(np.abs(got - ref)[bad]/np.maximum(np.abs(ref[bad]), 1e-300)):g}'
+
+
+# ---------------------------------------------------------------- min/max
+
+@pytest.mark.parametrize('n,C,step', [
+    (1, 1, 1), (7, 1, 1), (1000, 1, 7), (1000, 2, 1000), (1000, 2, 5000),
+    (4099, 3, 17), (50000, 3, 71), (100003, 4, 333), (65536, 8, 2048),
+    (300001, 8, 40000), (200000, 16, 100000), (30000, 64, 977), (5000, 5, 1250),
+    (1 << 20, 1, 1 << 18), (1 << 20, 2, 1 << 20), (777777, 6, 111111),
+])
+def test_minmax_bit_exact(n, C, step):
+    x = synth(5, n, C, 48000., seed=n + C)
+    ref = orc.minmax_rows(x, step)
+    got = _lib.minmax(x, step)
+    assert got.shape == ref.shape
+    assert np.array_equal(bits(got), bits(ref))
+
+
+def test_minmax_special_values():
+    rng = np.random.default_rng(3)
+    n, C = 60000, 4
+    x = rng.standard_normal((n, C))
+    x[rng.integers(0, n, 4000), rng.integers(0, C, 4000)] = 0.0
+    x[rng.integers(0, n, 4000), rng.integers(0, C, 4000)] = -0.0
+    x[rng.integers(0, n, 30), rng.integers(0, C, 30)] = np.inf
+    x[rng.integers(0, n, 30), rng.integers(0, C, 30)] = -np.inf
+    nan1 = np.array([0x7ff8000000000001], dtype=np.uint64).view(np.float64)[0]
+    nan2 = np.array([0xfff8000000000abc], dtype=np.uint64).view(np.float64)[0]
+    x[rng.integers(0, n, 6), rng.integers(0, C, 6)] = nan1
+    x[rng.integers(0, n, 6), rng.integers(0, C, 6)] = nan2
+    for step in (3, 500, 9000, 60000):
+        ref = orc.minmax_rows(x, step)
+        got = _lib.minmax(x, step)
+        assert np.array_equal(bits(got), bits(ref)), step
+    # signed zeros only: the later row decides the sign
+    z = np.where(rng.random((40000, 2)) < 0.5, 0.0, -0.0)
+    for step in (2, 64, 5000, 40000):
+        assert np.array_equal(bits(_lib.minmax(z, step)), bits(orc.minmax_rows(z, step)))
+
+
+def test_minmax_golden_fulltrace():
+    g = np.load(os.path.join(GOLDEN, 'fulltrace.npz'))
+    for name in ('short_3ch', 'short_1ch_step1', 'long_4ch'):
+        a = json.loads(str(g[name + '_args']))
+        x = synth(0, a['frames'], a['channels'], a['rate'], a['seed'])
+        step = max(1, a['frames']//a['max_pixel'])
+        got = _lib.minmax(x, step)
+        ref = g[name + '_datas']
+        assert np.array_equal(bits(got), bits(ref[:len(got)]))
+        assert not ref[len(got):].any()
+
+
+# ---------------------------------------------------------------- filter
+
+FILTERS = {
+    'lp2': lambda fs: butter(2, 0.2*fs, 'lowpass', fs=fs, output='sos'),
+    'hp2': lambda fs: butter(2, 0.02*fs, 'highpass', fs=fs, output='sos'),
+    'bp2': lambda fs: butter(2, (0.02*fs, 0.3*fs), 'bandpass', fs=fs, output='sos'),
+    'lp4': lambda fs: butter(4, 0.1*fs, 'lowpass', fs=fs, output='sos'),
+    'bp4': lambda fs: butter(4, (0.02*fs, 0.3*fs), 'bandpass', fs=fs, output='sos'),
+    'bp3': lambda fs: butter(3, (0.05*fs, 0.2*fs), 'bandpass', fs=fs, output='sos'),
+    'lp8': lambda fs: butter(8, 0.15*fs, 'lowpass', fs=fs, output='sos'),
+    'bp8': lambda fs: butter(8, (0.1*fs, 0.2*fs), 'bandpass', fs=fs, output='sos'),
+    'hp_low': lambda fs: butter(2, 0.0006*fs, 'highpass', fs=fs, output='sos'),
+}
+
+
+@pytest.mark.parametrize('C', [1, 2, 3, 4, 8, 16, 24, 64])
+@pytest.mark.parametrize('filt', ['lp2', 'bp2', 'bp4'])
+def test_sosfilt_channels(C, filt):
+    fs = 48000.
+    n = 70001
+    x = synth(0, n, C, fs, seed=C)
+    sos = FILTERS[filt](fs)
+    ref = np.empty((n, C))
+    orc.filter_process(sos, x, ref, 0)
+    got = np.empty((n, C))
+    _lib.sosfilt(sos, x, got, 0)
+    assert_trace_close(got, ref, f'{filt} C={C}')
+
+
+@pytest.mark.parametrize('filt', sorted(FILTERS))
+def test_sosfilt_filters(filt):
+    fs = 96000.
+    n, C = 123457, 4
+    x = synth(11, n, C, fs, seed=77)
+    sos = FILTERS[filt](fs)
+    ref = np.empty((n, C))
+    orc.filter_process(sos, x, ref, 0)
+    got = np.empty((n, C))
+    _lib.sosfilt(sos, x, got, 0)
+    assert_trace_close(got, ref, filt)
+
+
+@pytest.mark.parametrize('n', [1, 2, 31, 32, 33, 255, 1024, 8191, 8192, 8193, 20000])
+def test_sosfilt_lengths_and_nbefore(n):
+    fs = 20000.
+    sos = FILTERS['bp2'](fs)
+    for C in (1, 2, 8):
+        x = synth(3, n, C, fs, seed=n)
+        for nbefore in sorted({0, min(5, n - 1), n//2}):
+            ref = np.empty((n - nbefore, C))
+            orc.filter_process(sos, x, ref, nbefore)
+            got = np.full((n - nbefore, C), np.nan)
+            _lib.sosfilt(sos, x, got, nbefore)
+            assert_trace_close(got, ref, f'n={n} C={C} nbefore={nbefore}')
+
+
+def test_sosfilt_none_is_copy():
+    x = synth(0, 5000, 3, 1000.)
+    got = np.empty((4990, 3))
+    _lib.sosfilt(None, x, got, 10)
+    assert np.array_equal(got, x[10:])
+
+
+def test_sosfilt_streaming_zi():
+    fs = 48000.
+    C, n = 4, 300000
+    x = synth(0, n, C, fs, seed=5)
+    sos = FILTERS['bp4'](fs)
+    S = sos.shape[0]
+    ref = np.empty((n, C))
+    orc.filter_process(sos, x, ref, 0)
+    zi = np.zeros((C, S, 2))
+    got = np.empty((n, C))
+    pos = 0
+    for chunk in (1, 777, 8192, 100000, 50001, n):
+        stop = min(n, pos + chunk)
+        _lib.sosfilt(sos, x[pos:stop], got[pos:stop], 0, zi=zi)
+        pos = stop
+        if pos >= n:
+            break
+    assert pos == n
+    assert_trace_close(got, ref, 'streamed')
+    # final state equals scipy's zf
+    for c in range(C):
+        _, zf = sosfilt(sos, x[:, c], zi=np.zeros((S, 2)))
+        assert np.max(np.abs(zi[c] - zf)) <= 1e-9*max(1.0, np.max(np.abs(zf)))
+
+
+def test_sosfilt_impulse_response():
+    fs = 1000.
+    sos = FILTERS['lp4'](fs)
+    x = np.zeros((20000, 2))
+    x[0, 0] = 1.0
+    x[9000, 1] = -2.0
+    got = np.empty_like(x)
+    _lib.sosfilt(sos, x, got)
+    ref = np.empty_like(x)
+    orc.filter_process(sos, x, ref, 0)
+    assert np.max(np.abs(got - ref)) <= 1e-12
+
+
+# ---------------------------------------------------------------- envelope
+
+@pytest.mark.parametrize('C', [1, 2, 3, 8, 32, 64])
+def test_envelope_channels(C):
+    fs = 48000.
+    n = 50000
+    x = synth(0, n, C, fs, seed=C + 100)
+    sos = orc.envelope_design(fs, 500.)
+    ref = np.empty((n, C))
+    orc.envelope_process(sos, x, ref, 0, 0)
+    got = np.empty((n, C))
+    _lib.envelope(sos, x, got, 0, True)
+    assert_trace_close(got, ref, f'C={C}')
+    assert (got >= 0).all()
+
+
+@pytest.mark.parametrize('order,hp', [(2, 0), (4, 0), (2, 50.), (4, 20.)])
+def test_envelope_orders(order, hp):
+    fs = 20000.
+    n, C = 90000, 2
+    x = synth(7, n, C, fs, seed=9)
+    sos = orc.envelope_design(fs, 300., hp, order)
+    nbefore = 123
+    ref = np.empty((n - nbefore, C))
+    orc.envelope_process(sos, x, ref, nbefore, hp)
+    got = np.empty((n - nbefore, C))
+    _lib.envelope(sos, x, got, nbefore, hp == 0)
+    assert_trace_close(got, ref, f'order={order} hp={hp}')
+
+
+def test_envelope_short_input_raises():
+    sos = orc.envelope_design(1000., 100.)
+    edge = orc.sosfiltfilt_edge(sos)
+    x = synth(0, edge, 2, 1000.)
+    with pytest.raises(ValueError):
+        _lib.envelope(sos, x, np.empty_like(x))
+    x = synth(0, edge + 1, 2, 1000.)
+    ref = np.empty_like(x)
+    orc.envelope_process(sos, x, ref, 0, 0)
+    got = np.empty_like(x)
+    _lib.envelope(sos, x, got)
+    assert_trace_close(got, ref, 'edge+1')
+
+
+def test_envelope_none_is_zero():
+    x = synth(0, 100, 2, 1000.)
+    got = np.full_like(x, 7.0)
+    _lib.envelope(None, x, got)
+    assert not got.any()
+
+
+# ---------------------------------------------------------------- spectrogram
+
+@pytest.mark.parametrize('nfft', [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+def test_spectrogram_nfft(nfft):
+    fs = 48000.
+    C = 2
+    for hop in sorted({nfft, nfft//2, nfft//8}):
+        n_src = nfft*5 + hop*3 + 1
+        x = synth(0, n_src, C, fs, seed=nfft)
+        n_dst = (n_src + hop - 1)//hop
+        ref = np.empty((n_dst, C, nfft//2 + 1))
+        nref = orc.spectrogram_process(x, ref, fs, nfft, hop)
+        got = np.full_like(ref, np.nan)
+        ngot = _lib.spectrogram(x, fs, nfft, hop, got)
+        assert ngot == nref
+        assert_spec_close(got, ref, f'nfft={nfft} hop={hop}')
+        assert not got[ngot:].any()
+
+
+@pytest.mark.parametrize('C', [1, 2, 3, 5, 8, 16, 64])
+def test_spectrogram_channels(C):
+    fs = 250000.
+    nfft, hop = 256, 128
+    x = synth(100, 9000, C, fs, seed=C)
+    n_dst = 9000//hop
+    ref = np.empty((n_dst, C, nfft//2 + 1))
+    orc.spectrogram_process(x, ref, fs, nfft, hop)
+    got = np.empty_like(ref)
+    _lib.spectrogram(x, fs, nfft, hop, got)
+    assert_spec_close(got, ref, f'C={C}')
+
+
+def test_spectrogram_short_source_zero_fill():
+    x = synth(0, 100, 2, 1000.)
+    got = np.full((4, 2, 129), 5.0)
+    assert _lib.spectrogram(x, 1000., 256, 128, got) == 0
+    assert not got.any()
+
+
+def test_spectrogram_known_answers():
+    fs, N = 1000., 256
+    t = np.arange(N*8)
+    # sine exactly on bin k0: peak A^2 N/(3 fs), neighbours a quarter of it
+    k0, A = 20, 0.7
+    x = (A*np.sin(2*np.pi*k0*t/N))[:, None].copy()
+    got = np.empty((x.shape[0]//N, 1, N//2 + 1))
+    _lib.spectrogram(x, fs, N, N, got)
+    peak = A*A*N/(3*fs)
+    assert np.allclose(got[:, 0, k0], peak, rtol=1e-9)
+    assert np.allclose(got[:, 0, k0 - 1], peak/4, rtol=1e-9)
+    assert np.allclose(got[:, 0, k0 + 1], peak/4, rtol=1e-9)
+    # DC: the mean removal leaves nothing
+    x = np.full((N*4, 2), 0.37)
+    got = np.empty((4, 2, N//2 + 1))
+    _lib.spectrogram(x, fs, N, N, got)
+    assert np.max(got) <= 1e-30
+    db = np.empty_like(got)
+    _lib.spectrogram(x, fs, N, N, db, out_db=True)
+    assert np.all(np.isneginf(db))
+
+
+def test_spectrogram_db_and_decibel():
+    fs = 48000.
+    x = synth(0, 20000, 2, fs)
+    lin = np.empty((77, 2, 129))
+    _lib.spectrogram(x, fs, 256, 128, lin)
+    db = np.empty_like(lin)
+    _lib.spectrogram(x, fs, 256, 128, db, out_db=True)
+    ref = orc.decibel(lin)
+    assert np.allclose(db, ref, rtol=0, atol=1e-9)
+    assert np.allclose(_lib.decibel(lin), ref, rtol=0, atol=1e-9)
+    p = np.array([1e-20, 1e-21, 0.0, 2e-20, 1.0, 100.0])
+    assert np.array_equal(np.isneginf(_lib.decibel(p)), np.isneginf(orc.decibel(p)))
+
+
+def test_spectrogram_unsupported_nfft_fails_loudly():
+    x = synth(0, 5000, 1, 1000.)
+    with pytest.raises(_lib.AdnError):
+        _lib.spectrogram(x, 1000., 1000, 500, np.empty((8, 1, 501)))
+
+
+# ---------------------------------------------------------------- golden chains
+
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLDEN, 'chain_*.npz'))))
+def test_golden_chain(path):
+    g = np.load(path)
+    a = json.loads(str(g['args']))
+    x = synth(0, a['frames'], a['channels'], a['rate'], a['seed'])
+    boff = a['buf_offset']
+    blen = a['frames'] - boff if a['buf_frames'] is None else a['buf_frames']
+    raw = x[boff:boff + blen]
+    C = a['channels']
+    # filtered: the reference filters the part of the raw buffer that survives
+    # the align_buffer margins, from zero state
+    fbuf = g['filt_buffer']
+    foff = int(g['filt_offset'])
+    sos = g['filt_sos'] if len(g['filt_sos']) else None
+    src = raw[foff - boff:foff - boff + len(fbuf)]
+    got = np.empty_like(fbuf)
+    _lib.sosfilt(sos, src, got, 0)
+    assert_trace_close(got, fbuf, 'filtered')
+    # spectrogram of the reference's filtered buffer
+    sbuf = g['spec_buffer']
+    hop = int(g['spec_hop'])
+    so, sn, nb = orc.load_buffer_slice(int(g['spec_offset']), len(sbuf), float(g['spec_rate']),
+                                       a['rate'], foff, len(fbuf), 0, 10)
+    gots = np.empty_like(sbuf)
+    _lib.spectrogram(fbuf[so:so + sn], a['rate'], a['nfft'], hop, gots)
+    assert_spec_close(gots, sbuf, 'spectrogram')
+    # envelope of the reference's filtered buffer
+    ebuf = g['env_buffer']
+    eoff = int(g['env_offset'])
+    esos = g['env_sos'] if len(g['env_sos']) else None
+    so, sn, nb = orc.load_buffer_slice(eoff, len(ebuf), a['rate'], a['rate'], foff, len(fbuf), 1, 0)
+    gote = np.empty_like(ebuf)
+    _lib.envelope(esos, fbuf[so:so + sn], gote, nb, True)
+    assert_trace_close(gote, ebuf, 'envelope')
+
+
+def test_launch_counter_moves():
+    before = _lib.launch_count()
+    _lib.minmax(synth(0, 5000, 2, 1000.), 100)
+    assert _lib.launch_count() > before
