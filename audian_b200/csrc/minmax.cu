@@ -3,12 +3,14 @@
 // Replaces the np.minimum/maximum.reduceat idiom of the reference
 // (src/audian/compresseddata.py:49-52, :97-100 and src/audian/traceitem.py:58-61):
 //   dst[2j, c] = min(src[j*step:(j+1)*step, c]),  dst[2j+1, c] = max(...)
-// Bit-exact numpy semantics: the reduction is
-//   acc = (acc < v || isnan(acc)) ? acc : v      (max: >)
-// applied in time order, i.e. the first NaN sticks and among equal values
+// Bit-exact numpy semantics (probed on numpy 2.3.5 for the 2-D
+// axis-0 form the reference uses): applied in time order the reduction is
+//   acc = (isnan(v) || (!isnan(acc) && !(acc < v))) ? v : acc      (max: >)
+// i.e. NaN propagates (the LAST NaN's payload survives) and among equal values
 // (+0.0 / -0.0) the LATER row wins.  The parallel reduction keeps (value, row)
 // pairs, which makes that rule commutative, so any combination order gives
-// numpy's answer.
+// numpy's answer.  (For C == 1 numpy takes its 1-D SIMD path, which returns the
+// canonical quiet NaN; signed-zero ties are lane-order dependent there.)
 //
 // Pure read-bandwidth kernel: 8 B per input sample, roofline = HBM.
 #include "common.cuh"
@@ -33,8 +35,8 @@ __device__ __forceinline__ void merge(Best& a, const Best& b) {
     bool a_nan = a.v != a.v, b_nan = b.v != b.v;
     bool take_b;
     if (a_nan || b_nan) {
-        // the earliest NaN wins; a NaN beats any number
-        take_b = b_nan && (!a_nan || b.row < a.row);
+        // a NaN beats any number; among NaNs the latest row wins
+        take_b = b_nan && (!a_nan || b.row > a.row);
     } else if (a.v == b.v) {
         take_b = b.row > a.row;                     // ties: later row (signed zeros)
     } else {
@@ -46,8 +48,20 @@ __device__ __forceinline__ void merge(Best& a, const Best& b) {
 // rows are fed to one accumulator in increasing order: numpy's predicate directly
 __device__ __forceinline__ void feed(Best& mn, Best& mx, double v, int32_t row) {
     if (mn.row < 0) { mn.v = v; mn.row = row; mx.v = v; mx.row = row; return; }
-    if (!(mn.v < v || mn.v != mn.v)) { mn.v = v; mn.row = row; }
-    if (!(mx.v > v || mx.v != mx.v)) { mx.v = v; mx.row = row; }
+    const bool vnan = v != v;
+    if (vnan || (mn.v == mn.v && !(mn.v < v))) { mn.v = v; mn.row = row; }
+    if (vnan || (mx.v == mx.v && !(mx.v > v))) { mx.v = v; mx.row = row; }
+}
+
+// numpy's ordered update of a running min / max
+__device__ __forceinline__ void upd_min(double& acc, double v) {
+    if (v != v || (acc == acc && !(acc < v))) acc = v;
+}
+__device__ __forceinline__ void upd_max(double& acc, double v) {
+    if (v != v || (acc == acc && !(acc > v))) acc = v;
+}
+__device__ __forceinline__ double canon(double v, int32_t C) {
+    return (C == 1 && v != v) ? __longlong_as_double(0x7ff8000000000000ll) : v;
 }
 
 template <int VEC> struct VecT;
@@ -141,8 +155,8 @@ minmax_split_kernel(const double* __restrict__ src, int64_t n, int32_t C, int64_
     }
     for (int32_t c = tid; c < C; c += MM_THREADS) {
         if (nsplit == 1) {
-            dst[(2 * seg) * C + c] = s_mnv[c];
-            dst[(2 * seg + 1) * C + c] = s_mxv[c];
+            dst[(2 * seg) * C + c] = canon(s_mnv[c], C);
+            dst[(2 * seg + 1) * C + c] = canon(s_mxv[c], C);
         } else {
             int64_t o = ((seg * nsplit + p) * 2) * C + c;
             part[o] = s_mnv[c];
@@ -165,12 +179,11 @@ minmax_combine_kernel(const double* __restrict__ part, int64_t nseg, int32_t C, 
     const double* q = part + (seg * nsplit * 2) * C + c;
     double mn = q[0], mx = q[C];
     for (int64_t p = 1; p < used; ++p) {
-        double a = q[(p * 2) * C], b = q[(p * 2 + 1) * C];
-        if (!(mn < a || mn != mn)) mn = a;
-        if (!(mx > b || mx != mx)) mx = b;
+        upd_min(mn, q[(p * 2) * C]);
+        upd_max(mx, q[(p * 2 + 1) * C]);
     }
-    dst[(2 * seg) * C + c] = mn;
-    dst[(2 * seg + 1) * C + c] = mx;
+    dst[(2 * seg) * C + c] = canon(mn, C);
+    dst[(2 * seg + 1) * C + c] = canon(mx, C);
 }
 
 // short segments: one thread per (segment, channel), rows in order
@@ -189,22 +202,17 @@ minmax_small_kernel(const double* __restrict__ src, int64_t n, int32_t C, int64_
     int64_t r = 1;
     for (; r + 3 < len; r += 4) {
         double v0 = q[r * C], v1 = q[(r + 1) * C], v2 = q[(r + 2) * C], v3 = q[(r + 3) * C];
-        if (!(mn < v0 || mn != mn)) mn = v0;
-        if (!(mx > v0 || mx != mx)) mx = v0;
-        if (!(mn < v1 || mn != mn)) mn = v1;
-        if (!(mx > v1 || mx != mx)) mx = v1;
-        if (!(mn < v2 || mn != mn)) mn = v2;
-        if (!(mx > v2 || mx != mx)) mx = v2;
-        if (!(mn < v3 || mn != mn)) mn = v3;
-        if (!(mx > v3 || mx != mx)) mx = v3;
+        upd_min(mn, v0); upd_max(mx, v0);
+        upd_min(mn, v1); upd_max(mx, v1);
+        upd_min(mn, v2); upd_max(mx, v2);
+        upd_min(mn, v3); upd_max(mx, v3);
     }
     for (; r < len; ++r) {
         double v = q[r * C];
-        if (!(mn < v || mn != mn)) mn = v;
-        if (!(mx > v || mx != mx)) mx = v;
+        upd_min(mn, v); upd_max(mx, v);
     }
-    dst[(2 * seg) * C + c] = mn;
-    dst[(2 * seg + 1) * C + c] = mx;
+    dst[(2 * seg) * C + c] = canon(mn, C);
+    dst[(2 * seg + 1) * C + c] = canon(mx, C);
 }
 
 }  // namespace

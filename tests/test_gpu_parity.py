@@ -30,6 +30,16 @@ def bits(a):
     return np.ascontiguousarray(a).view(np.uint64)
 
 
+def assert_minmax_equal(got, ref, what=''):
+    """Bit-exact where the reference is a number (signed zeros included); NaN
+    wherever the reference is NaN.  NaN payloads depend on numpy's SIMD dispatch
+    on the host that runs the oracle, so they are compared separately."""
+    assert got.shape == ref.shape, what
+    rn = np.isnan(ref)
+    assert np.array_equal(np.isnan(got), rn), what
+    assert np.array_equal(bits(got)[~rn], bits(ref)[~rn]), what
+
+
 def assert_trace_close(got, ref, what=''):
     scale = max(1.0, float(np.max(np.abs(ref))) if ref.size else 1.0)
     err = float(np.max(np.abs(got - ref))) if ref.size else 0.0
@@ -74,7 +84,7 @@ def test_minmax_special_values():
     for step in (3, 500, 9000, 60000):
         ref = orc.minmax_rows(x, step)
         got = _lib.minmax(x, step)
-        assert np.array_equal(bits(got), bits(ref)), step
+        assert_minmax_equal(got, ref, step)
     # signed zeros only: the later row decides the sign
     z = np.where(rng.random((40000, 2)) < 0.5, 0.0, -0.0)
     for step in (2, 64, 5000, 40000):
@@ -368,3 +378,22 @@ def test_launch_counter_moves():
     before = _lib.launch_count()
     _lib.minmax(synth(0, 5000, 2, 1000.), 100)
     assert _lib.launch_count() > before
+
+
+def test_minmax_nan_payload_rule():
+    """The rule the kernel implements (numpy 2.3.5, 2-D axis-0 reduceat): the
+    last NaN of a segment survives; for C == 1 the canonical quiet NaN."""
+    nan1 = np.array([0x7ff8000000000001], dtype=np.uint64).view(np.float64)[0]
+    nan2 = np.array([0xfff8000000000abc], dtype=np.uint64).view(np.float64)[0]
+    for n in (20, 50000):
+        x = np.random.default_rng(0).standard_normal((n, 4))
+        x[5, :] = nan1
+        x[n - 3, :] = nan2
+        got = _lib.minmax(x, n)
+        assert (bits(got) == 0xfff8000000000abc).all()
+        x[5, :] = nan2
+        x[n - 3, :] = nan1
+        got = _lib.minmax(x, n)
+        assert (bits(got) == 0x7ff8000000000001).all()
+        got = _lib.minmax(np.ascontiguousarray(x[:, :1]), n)
+        assert (bits(got) == 0x7ff8000000000000).all()
