@@ -1,0 +1,145 @@
+"""Device-pointer operators: the *_dev entry points of the C ABI applied to
+torch CUDA tensors (torch is used for device memory and streams only).
+
+All functions enqueue work on torch's current stream and return without
+synchronising.  Traces are (frames, C) float64 contiguous CUDA tensors,
+spectrograms (frames, C, nfft//2+1).
+"""
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _stream():
+    torch = _torch()
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_trace(t, name):
+    torch = _torch()
+    if not t.is_cuda or t.dtype != torch.float64 or not t.is_contiguous():
+        raise TypeError(f'{name} must be a contiguous float64 CUDA tensor')
+    return t
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else None
+
+
+class CudaOps(object):
+    """The compute back end of audian_b200.sharded: sm_100a kernels."""
+
+    name = 'cuda'
+
+    def empty(self, shape, like=None):
+        torch = _torch()
+        return torch.empty(shape, dtype=torch.float64, device='cuda')
+
+    def zeros(self, shape, like=None):
+        torch = _torch()
+        return torch.zeros(shape, dtype=torch.float64, device='cuda')
+
+    def minmax(self, src, step):
+        return minmax(src, step)
+
+    def sosfilt(self, sos, src, nbefore=0, zi=None, want_zf=False, out=None,
+                state_only=False):
+        return sosfilt(sos, src, nbefore, zi, want_zf, out, state_only)
+
+    def spectrogram(self, src, rate, nfft, hop, n_dst, out_db=False):
+        return spectrogram(src, rate, nfft, hop, n_dst, out_db)
+
+    def envelope(self, sos, src, nbefore=0, clamp_negative=True):
+        return envelope(sos, src, nbefore, clamp_negative)
+
+
+def minmax(src, step, out=None):
+    _check_trace(src, 'src')
+    n, ch = src.shape
+    nseg = (n + step - 1)//step if n > 0 else 0
+    if out is None:
+        out = _torch().empty((2*nseg, ch), dtype=src.dtype, device=src.device)
+    _lib.check(_lib.lib().adn_minmax_f64_dev(_p(src), n, ch, int(step), _p(out), _stream()))
+    return out
+
+
+def sosfilt(sos, src, nbefore=0, zi=None, want_zf=False, out=None, state_only=False):
+    """Returns out, or (out, zf) if want_zf; state_only skips the output."""
+    torch = _torch()
+    _check_trace(src, 'src')
+    sos, S = _lib.sos_array(sos)
+    n, ch = src.shape
+    zf = None
+    if (want_zf or state_only) and S > 0:
+        zf = torch.empty((ch, S, 2), dtype=src.dtype, device=src.device)
+    if zi is not None:
+        _check_trace(zi, 'zi')
+    if state_only:
+        out = None
+        n_dst = 0
+    else:
+        if out is None:
+            out = torch.empty((n - nbefore, ch), dtype=src.dtype, device=src.device)
+        n_dst = out.shape[0]
+    _lib.check(_lib.lib().adn_sosfilt_f64_dev(
+        None if sos is None else sos.ctypes.data, S, _p(src), n, ch, int(nbefore),
+        _p(out), n_dst, _p(zi), _p(zf), _stream()))
+    if state_only:
+        return zf
+    return (out, zf) if want_zf else out
+
+
+def envelope(sos, src, nbefore=0, clamp_negative=True, out=None):
+    torch = _torch()
+    _check_trace(src, 'src')
+    sos, S = _lib.sos_array(sos)
+    n, ch = src.shape
+    if out is None:
+        out = torch.empty((n - nbefore, ch), dtype=src.dtype, device=src.device)
+    _lib.check(_lib.lib().adn_envelope_f64_dev(
+        None if sos is None else sos.ctypes.data, S, _p(src), n, ch, int(nbefore),
+        _p(out), out.shape[0], 1 if clamp_negative else 0, _stream()))
+    return out
+
+
+def spectrogram(src, rate, nfft, hop, n_dst, out_db=False, out=None):
+    """Returns (dst, n_computed)."""
+    torch = _torch()
+    _check_trace(src, 'src')
+    n, ch = src.shape
+    if out is None:
+        out = torch.empty((n_dst, ch, nfft//2 + 1), dtype=src.dtype, device=src.device)
+    ncomp = _lib._i64(0)
+    _lib.check(_lib.lib().adn_spectrogram_f64_dev(
+        _p(src), n, ch, float(rate), int(nfft), int(hop), _lib.ADN_WINDOW_HANN,
+        _lib.ADN_DETREND_CONSTANT, _p(out), out.shape[0], 1 if out_db else 0,
+        C.byref(ncomp), _stream()))
+    return out, ncomp.value
+
+
+def decibel(power, ref_power=1.0, min_power=1e-20, out=None):
+    torch = _torch()
+    if out is None:
+        out = torch.empty_like(power)
+    _lib.check(_lib.lib().adn_decibel_f64_dev(_p(power), power.numel(), float(ref_power),
+                                              float(min_power), _p(out), _stream()))
+    return out
+
+
+def synth(t0, nframes, channels, rate, seed=0xA0D1A9, out=None):
+    """Rows t0..t0+nframes of the synthetic recording, generated on the device
+    (bit-identical to audian_b200.synth.synth)."""
+    torch = _torch()
+    if out is None:
+        out = torch.empty((nframes, channels), dtype=torch.float64, device='cuda')
+    _lib.check(_lib.lib().adn_synth_f64_dev(_p(out), int(t0), int(nframes), int(channels),
+                                            float(rate), C.c_uint64(seed), _stream()))
+    return out

@@ -1,0 +1,178 @@
+"""Whole-recording passes, time-sharded over the GPUs of one box.
+
+New functionality relative to the reference (its only parallel code is the
+block-cyclic worker pool of the full-trace cache, compresseddata.py:104-122):
+one process per GPU (torch.distributed, NCCL over NVLink), the recording is
+split into contiguous time ranges, and only what the arithmetic needs crosses
+ranks:
+
+* min/max      -- shard boundaries are multiples of `step`; no exchange; the
+                  reduced rows are gathered to rank 0.
+* spectrogram  -- shard boundaries are multiples of `hop`; each rank receives the
+                  first nfft-hop rows of its right neighbour (halo); frames are
+                  indexed globally, results stay sharded.
+* filter       -- each rank computes the end state of its shard from zero state
+                  (state-only pass of the scan kernel), the (C, 2S) vectors are
+                  all-gathered, every rank folds its predecessors' states with the
+                  shard transition matrices A^len and filters its shard from that
+                  incoming state: equal to one sosfilt over the whole recording.
+
+The arithmetic is delegated to an `ops` object (default: the sm_100a kernels,
+audian_b200.device.CudaOps); the CPU tests of the exchange logic inject their
+own oracle-backed ops with the gloo backend.
+"""
+
+import numpy as np
+
+from . import _lib
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def shard_bounds(frames, world, align=1):
+    """Contiguous ranges [lo, hi) per rank, boundaries multiples of `align`
+    (except the end of the recording)."""
+    units = (frames + align - 1)//align
+    per, extra = divmod(units, world)
+    bounds = []
+    lo = 0
+    for r in range(world):
+        n = per + (1 if r < extra else 0)
+        hi = min(frames, lo + n*align)
+        bounds.append((lo, hi))
+        lo = hi
+    return bounds
+
+
+class ShardedRecording(object):
+    """One rank's time range [lo, hi) of a (frames, C) recording."""
+
+    def __init__(self, local, frames, rate, ops=None, rank=None, world=None,
+                 bounds=None):
+        dist = _dist()
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.frames = int(frames)
+        self.rate = float(rate)
+        self.local = local
+        self.channels = local.shape[1]
+        if ops is None:
+            from .device import CudaOps
+            ops = CudaOps()
+        self.ops = ops
+        self.bounds = bounds
+        if bounds is not None:
+            self.lo, self.hi = bounds[self.rank]
+            if self.hi - self.lo != local.shape[0]:
+                raise ValueError('local shard does not match its bounds')
+
+    # ------------------------------------------------------------ min/max
+    @staticmethod
+    def minmax_bounds(frames, world, step):
+        return shard_bounds(frames, world, step)
+
+    def minmax(self, step, dst_rank=0):
+        """Full-trace min/max rows (2*ceil(frames/step), C) on `dst_rank`
+        (None elsewhere).  Shards must come from minmax_bounds()."""
+        import torch
+        dist = _dist()
+        if self.lo % step != 0:
+            raise ValueError('shard boundary is not a multiple of step')
+        rows = self.ops.minmax(self.local, step)
+        nseg_total = (self.frames + step - 1)//step
+        counts = [2*((hi - lo + step - 1)//step) for lo, hi in self.bounds]
+        width = max(counts)
+        padded = rows
+        if rows.shape[0] < width:
+            padded = torch.zeros((width, self.channels), dtype=rows.dtype, device=rows.device)
+            padded[:rows.shape[0]] = rows
+        gathered = [torch.empty_like(padded) for _ in range(self.world)]
+        dist.all_gather(gathered, padded.contiguous())
+        if dst_rank is not None and self.rank != dst_rank:
+            return None
+        out = torch.cat([g[:c] for g, c in zip(gathered, counts)], dim=0)
+        assert out.shape[0] == 2*nseg_total
+        return out
+
+    # ------------------------------------------------------------ spectrogram
+    @staticmethod
+    def spectrogram_bounds(frames, world, hop):
+        return shard_bounds(frames, world, hop)
+
+    def spectrogram(self, nfft, hop, out_db=False):
+        """This rank's frames [lo/hop, ...) of the PSD spectrogram of the whole
+        recording, (n_local, C, nfft//2+1), plus the global index of its first
+        frame and the global frame count."""
+        import torch
+        dist = _dist()
+        if self.lo % hop != 0:
+            raise ValueError('shard boundary is not a multiple of hop')
+        halo = nfft - hop
+        nf_total = (self.frames - halo)//hop if self.frames >= nfft else 0
+        k0 = self.lo//hop
+        k1 = min(nf_total, self.hi//hop if self.rank + 1 < self.world else nf_total)
+        src = self.local
+        if self.world > 1 and halo > 0:
+            if any(hi - lo < halo for lo, hi in self.bounds):
+                raise ValueError('shards shorter than the STFT halo')
+            recv = torch.empty((halo, self.channels), dtype=src.dtype, device=src.device)
+            head = src[:halo].contiguous()
+            ops = []
+            if self.rank > 0:
+                ops.append(dist.P2POp(dist.isend, head, self.rank - 1))
+            if self.rank + 1 < self.world:
+                ops.append(dist.P2POp(dist.irecv, recv, self.rank + 1))
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+            if self.rank + 1 < self.world:
+                src = torch.cat([src, recv], dim=0)
+        n_local = max(0, k1 - k0)
+        out, ncomp = self.ops.spectrogram(src, self.rate, nfft, hop, n_local, out_db)
+        assert ncomp == n_local, (ncomp, n_local)
+        return out, k0, nf_total
+
+    # ------------------------------------------------------------ filter
+    def shard_matrices(self, sos):
+        """A^len for every shard: the homogeneous map of the cascade across it."""
+        return [_lib.sos_state_space(sos, hi - lo)[2] for lo, hi in self.bounds]
+
+    def sosfilt(self, sos, zi=None):
+        """This rank's part of sosfilt(sos, recording, axis=0) (zero initial
+        state, or `zi` (C, S, 2) applied at frame 0)."""
+        import torch
+        dist = _dist()
+        sos_a, S = _lib.sos_array(sos)
+        if S == 0:
+            return self.local.clone()
+        D = 2*S
+        C = self.channels
+        x = self.local
+        if self.world == 1:
+            return self.ops.sosfilt(sos_a, x, 0, zi)
+        # 1. end state of this shard from zero state (aggregate)
+        v = self.ops.sosfilt(sos_a, x, 0, None, state_only=True).reshape(C, D)
+        # 2. exchange
+        gathered = [torch.empty_like(v) for _ in range(self.world)]
+        dist.all_gather(gathered, v.contiguous())
+        # 3. fold the predecessors: s_{r+1} = A^len_r s_r + v_r
+        mats = self.shard_matrices(sos_a)
+        s = torch.zeros((C, D), dtype=v.dtype, device=v.device)
+        if zi is not None:
+            s = zi.reshape(C, D).clone()
+        for r in range(self.rank):
+            M = torch.as_tensor(mats[r], dtype=v.dtype, device=v.device)
+            s = s @ M.T + gathered[r]
+        # 4. filter the shard from its true incoming state
+        return self.ops.sosfilt(sos_a, x, 0, s.reshape(C, S, 2).contiguous())
+
+    def filter_chain(self, sos, nfft, hop):
+        """filtered -> spectrogram of the filtered trace, all sharded."""
+        y = self.sosfilt(sos)
+        f = ShardedRecording(y, self.frames, self.rate, self.ops, self.rank,
+                             self.world, self.bounds)
+        spec, k0, nf = f.spectrogram(nfft, hop)
+        return y, spec, k0, nf

@@ -1,0 +1,134 @@
+"""World-size-2 (and 3) CPU tests of the time-sharded whole-recording drivers
+(audian_b200/sharded.py) over the gloo backend.  The arithmetic is injected
+from the oracle (scipy on CPU tensors); what is under test is the shard
+geometry, the STFT halo exchange, the IIR boundary-state fold and the gather of
+the min/max rows -- shard-count invariance against one pass over the whole
+recording."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+from scipy.signal import butter, sosfilt
+
+from audian_b200 import sharded
+from audian_b200.synth import synth
+from oracle import oracle as orc
+
+
+class OracleOps(object):
+    """CPU stand-in for audian_b200.device.CudaOps (test infrastructure)."""
+
+    name = 'oracle'
+
+    def minmax(self, src, step):
+        return torch.from_numpy(orc.minmax_rows(src.numpy(), step))
+
+    def sosfilt(self, sos, src, nbefore=0, zi=None, want_zf=False, out=None,
+                state_only=False):
+        x = src.numpy()
+        S = sos.shape[0]
+        y = np.empty_like(x)
+        zf = np.empty((x.shape[1], S, 2))
+        for c in range(x.shape[1]):
+            z0 = np.zeros((S, 2)) if zi is None else zi.numpy()[c]
+            y[:, c], zf[c] = sosfilt(sos, x[:, c], zi=z0)
+        if state_only:
+            return torch.from_numpy(zf)
+        y = torch.from_numpy(y[nbefore:].copy())
+        return (y, torch.from_numpy(zf)) if want_zf else y
+
+    def spectrogram(self, src, rate, nfft, hop, n_dst, out_db=False):
+        dst = np.empty((n_dst, src.shape[1], nfft//2 + 1))
+        n = orc.spectrogram_process(src.numpy(), dst, rate, nfft, hop)
+        return torch.from_numpy(dst), n
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, frames, C, rate, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        ops = OracleOps()
+        out = {}
+        # ---- min/max
+        step = 777
+        b = sharded.shard_bounds(frames, world, step)
+        lo, hi = b[rank]
+        x = torch.from_numpy(synth(lo, hi - lo, C, rate, seed=99))
+        rec = sharded.ShardedRecording(x, frames, rate, ops, bounds=b)
+        rows = rec.minmax(step)
+        if rank == 0:
+            out['minmax'] = rows.numpy()
+        # ---- filter -> spectrogram chain, hop-aligned shards
+        nfft, hop = 256, 64
+        b = sharded.shard_bounds(frames, world, hop)
+        lo, hi = b[rank]
+        x = torch.from_numpy(synth(lo, hi - lo, C, rate, seed=99))
+        rec = sharded.ShardedRecording(x, frames, rate, ops, bounds=b)
+        sos = butter(4, (0.01*rate, 0.2*rate), 'bandpass', fs=rate, output='sos')
+        y, spec, k0, nf = rec.filter_chain(sos, nfft, hop)
+        parts = [None]*world
+        dist.all_gather_object(parts, (lo, y.numpy(), k0, spec.numpy(), nf))
+        if rank == 0:
+            out['chain'] = parts
+        if rank == 0:
+            q.put(out)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_sharded_matches_single_pass(world):
+    frames, C, rate = 20011, 3, 8000.
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, frames, C, rate, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    x = synth(0, frames, C, rate, seed=99)
+    # min/max: bit-exact regardless of the shard count
+    ref = orc.minmax_rows(x, 777)
+    assert np.array_equal(out['minmax'].view(np.uint64), ref.view(np.uint64))
+    # filter: equal to one sosfilt over the whole recording
+    sos = butter(4, (0.01*rate, 0.2*rate), 'bandpass', fs=rate, output='sos')
+    yref = np.empty_like(x)
+    orc.filter_process(sos, x, yref, 0)
+    y = np.concatenate([p[1] for p in sorted(out['chain'], key=lambda p: p[0])])
+    assert y.shape == yref.shape
+    assert np.max(np.abs(y - yref)) <= 1e-9
+    # spectrogram of the filtered recording: same frames as one pass
+    nfft, hop = 256, 64
+    nf = (frames - (nfft - hop))//hop
+    sref = np.empty((nf, C, nfft//2 + 1))
+    assert orc.spectrogram_process(yref, sref, rate, nfft, hop) == nf
+    spec = np.concatenate([p[3] for p in sorted(out['chain'], key=lambda p: p[2])])
+    assert out['chain'][0][4] == nf
+    assert spec.shape == sref.shape
+    assert np.allclose(spec, sref, rtol=1e-7, atol=1e-22*sref.max())
+
+
+def test_shard_bounds():
+    for frames, world, align in [(100, 4, 1), (1000, 3, 64), (5, 8, 2), (777777, 8, 1382)]:
+        b = sharded.shard_bounds(frames, world, align)
+        assert b[0][0] == 0 and b[-1][1] == frames
+        for (l0, h0), (l1, h1) in zip(b[:-1], b[1:]):
+            assert h0 == l1 and l1 % align == 0 or l1 == frames
