@@ -39,7 +39,9 @@ struct Ctx {
 
 Ctx& ctx();
 int32_t ensure_init();
-inline cudaStream_t pick(void* s) { return s ? static_cast<cudaStream_t>(s) : ctx().stream; }
+// *_dev entry points: the caller's stream as is (NULL = CUDA's default stream, which is
+// what torch.cuda.current_stream().cuda_stream is unless a side stream is active)
+inline cudaStream_t pick(void* s) { return static_cast<cudaStream_t>(s); }
 inline void count_launch(int n = 1) { ctx().launches += n; }
 
 // per-stream scratch that must outlive an asynchronous launch: handed out from a

@@ -66,8 +66,9 @@ int32_t synth_dev(double* dst, int64_t t0, int64_t n, int32_t C, double rate, ui
                   cudaStream_t st) {
     SynthInc incs;
     for (int c = 0; c < 64; ++c)
-        incs.inc[c] = (uint32_t)(uint64_t)llround(4294967296.0 * (0.05 + 0.005 * c));
-    long long period = llround(rate / 20.0), on = llround(rate / 40.0);
+        incs.inc[c] = (uint32_t)(uint64_t)llrint(4294967296.0 * (0.05 + 0.005 * c));
+    // round-half-even like Python's round() in audian_b200/synth.py
+    long long period = llrint(rate / 20.0), on = llrint(rate / 40.0);
     if (period < 2) period = 2;
     if (on < 1) on = 1;
     int64_t total = n * C;

@@ -338,6 +338,29 @@ def run_ours(args):
         for a in host_x + [h_filt, h_spec, h_env]:
             _lib.host_unregister(a)
 
+    parity = None
+    if rank == 0 and world == 1:
+        # outputs of the timed path against the oracle (not timed)
+        from oracle import oracle as orc
+        x0 = windows[0]
+        device.sosfilt(sos, x0, 0, out=filt)
+        device.spectrogram(filt, RATE, NFFT, HOP, nspec, out=spec)
+        device.envelope(esos, filt, 0, True, out=env)
+        torch.cuda.synchronize()
+        m = 400000
+        hx = np.ascontiguousarray(x0[:m].cpu().numpy())
+        hf = filt.cpu().numpy()
+        rf = np.empty((m, C))
+        orc.filter_process(sos, hx, rf, 0)
+        rs = np.empty((m//HOP, C, NFFT//2 + 1))
+        ns_ = orc.spectrogram_process(hf[:m], rs, RATE, NFFT, HOP)
+        gs = spec[:ns_].cpu().numpy()
+        re_ = np.empty((n, C))
+        orc.envelope_process(esos, hf, re_, 0, 0)
+        parity = {'filter_max_abs_err': float(np.max(np.abs(hf[:m] - rf))),
+                  'spectrogram_max_rel_err': float(np.max(np.abs(gs - rs[:ns_])/np.maximum(rs[:ns_], 1e-20*rs.max()))),
+                  'envelope_max_abs_err': float(np.max(np.abs(env.cpu().numpy() - re_))),
+                  'checked': f'filter/spectrogram on the first {m} frames, envelope on the whole window'}
     if rank == 0 and world == 1:
         # the oracle on the host's cores, bounded sample of the same workload
         sample_s = 10.0
@@ -369,7 +392,7 @@ def run_ours(args):
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
             'roofline': roofs[dominant], 'roofline_all': roofs, 'dominant': dominant,
             'op_ms': {'filter': t_f, 'spectrogram': t_s, 'envelope': t_e},
-            'cpu_baseline': cpu_baseline,
+            'cpu_baseline': cpu_baseline, 'parity': parity,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

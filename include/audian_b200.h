@@ -24,8 +24,9 @@
  * Host-pointer entry points copy to and from device memory that the library
  * owns, on the library's own stream, and block until the result is in `dst`.
  * The *_dev entry points take device pointers and a cudaStream_t (passed as
- * void*; NULL = the library's stream), only enqueue work and do not
- * synchronise.
+ * void*; NULL = CUDA's default stream), only enqueue work and do not
+ * synchronise.  Scratch memory of the library is shared by all *_dev calls:
+ * issue them from one stream at a time.
  */
 #ifndef AUDIAN_B200_H
 #define AUDIAN_B200_H
@@ -67,8 +68,8 @@ int32_t adn_host_unregister(void* ptr);
 
 /* dst (2*ceil(n/step), C): row 2j = min, row 2j+1 = max over source rows
  * [j*step, min((j+1)*step, n)).  numpy semantics bit for bit: NaN propagates
- * (the first NaN in time order), equal values resolve to the later row
- * (signed zeros). */
+ * (the last NaN in time order; the canonical quiet NaN when C == 1), equal
+ * values resolve to the later row (signed zeros). */
 int32_t adn_minmax_f64(const double* src, int64_t n, int32_t C, int64_t step,
                        double* dst);
 
