@@ -30,18 +30,23 @@ namespace adn {
 namespace {
 
 constexpr int SOS_L = 32;          // samples per thread
-constexpr int SOS_NT = 256;        // threads per block
+constexpr int SOS_NT = 128;        // threads per block
 constexpr int SOS_NW = SOS_NT / 32;
 constexpr int SOS_LOOK = 32;       // look-back window (tiles)
 
 enum { MODE_FWD = 0, MODE_ENVF = 1, MODE_REV = 2 };
 
-// table layout (D x D row-major matrices, DD = D*D doubles each)
-constexpr int TAB_SCAN = 0;        // 5:  A^(L 2^k), k = 0..4
-constexpr int TAB_FIX = 5;         // 32: A^(L j),   j = 0..31
-constexpr int TAB_WARP = 37;       // 1:  A^(L GW)
-constexpr int TAB_TILE = 38;       // 33: (A^T)^j,   j = 0..32
-constexpr int TAB_COUNT = 71;
+// table layout (D x D row-major matrices, DD = D*D doubles each), packed per channel-group
+// width CG (GW = 32/CG sub-chunks per warp):
+//   [0, nscan)                 A^(L 2^k),  k < log2(GW)     warp scan
+//   [off_fix, off_fix+GW)      A^(L j),    j < GW           fix-up inside the warp
+//   [off_wpow, off_wpow+NW+1)  A^(L GW k), k <= NW          warp prefixes
+//   -- the slots above are staged in shared memory (n_staged of them) --
+//   [off_tile, off_tile+33)    (A^T)^j,    j <= 32          look-back over tiles
+// tile records are self-validating: every double of an aggregate / inclusive state is
+// published with a plain 8-byte store and read back until it differs from this pattern
+// (a NaN payload no arithmetic produces), so no flag, fence or L1 invalidation is needed
+constexpr unsigned long long SOS_EMPTY = 0xFFFFFFFFFFFFFFFFull;
 
 template <int S>
 struct SosK {                      // lives in the kernel's constant bank
@@ -53,10 +58,9 @@ struct SosRun {
     const double* src;
     double* dst;                   // may be null: state only
     const double* tab;
-    uint32_t* flags;               // per tile: 0 none, 1 aggregate, 2 inclusive
-    double* agg;                   // [tile][CG][D]
+    double* agg;                   // [tile][CG][D], SOS_EMPTY until published
     double* incl;                  // [tile][CG][D]
-    uint32_t* ticket;
+    int32_t off_fix, off_wpow, off_tile, n_staged;
     const double* s0;              // [C][D] initial state or null
     double* zf;                    // [C][D] final state or null
     int64_t n;                     // logical length (rows the recurrence runs over)
@@ -71,13 +75,25 @@ struct SosRun {
     int32_t vec_in, vec_out;       // 16-byte granules allowed
 };
 
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ double ld_relaxed(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed(double* p, double v) {
+    if (__double_as_longlong(v) == (long long)SOS_EMPTY) v = __longlong_as_double(0x7ff8000000000000ll);
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+// all D words of a record, or false if any is still unpublished
+template <int D>
+__device__ __forceinline__ bool read_record(const double* p, double (&v)[D]) {
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        v[d] = ld_relaxed(p + d);
+        ok = ok && (__double_as_longlong(v[d]) != (long long)SOS_EMPTY);
+    }
+    return ok;
 }
 __device__ __forceinline__ void cp_async16(void* smem, const void* g, int src_bytes) {
     uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -99,23 +115,25 @@ __device__ __forceinline__ void matvec_acc(const double* __restrict__ M, const d
     for (int r = 0; r < D; ++r) {
         double a = v[r];
 #pragma unroll
-        for (int c = 0; c <= (r | 1); ++c) a = fma(__ldg(M + r * D + c), u[c], a);
+        for (int c = 0; c <= (r | 1); ++c) a = fma(M[r * D + c], u[c], a);
         v[r] = a;
     }
 }
+
+constexpr double HALF_PI = 1.5707963267948966;
 
 template <int S, int MODE>
 __global__ void __launch_bounds__(SOS_NT)
 sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRun R) {
     constexpr int D = 2 * S;
     constexpr int DD = D * D;
+    constexpr bool STAGE = S <= 4;           // small tables live in shared memory
     extern __shared__ __align__(16) double smem[];
-    __shared__ int s_tile;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = (int)atomicAdd(R.ticket, 1u);
-    __syncthreads();
-    const int64_t tile = s_tile;
+    // tiles only wait on lower-numbered tiles; like CUB's decoupled look-back this relies on
+    // the hardware dispatching the blocks of a 1-D grid in index order
+    const int64_t tile = blockIdx.x;
     const int64_t tt = tile / R.ngroups;
     const int grp = (int)(tile % R.ngroups);
     const int CG = R.CG, C = R.C;
@@ -131,13 +149,28 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
     const int GS = SOS_L * Cw + pad;
     const int G = SOS_NT / CG;
 
-    double* tile_s = smem;                                   // G * GS
+    double* tile_s = smem;                                   // G * (L*CG + pad)
     double* wagg = smem + (size_t)G * (SOS_L * CG + pad);    // [NW][CG][D]
-    double* wcar = wagg + SOS_NW * CG * D;                   // [NW][CG][D]
+    double* sin_s = wagg + SOS_NW * CG * D;                  // [CG][D]
+    double* tab_s = sin_s + CG * D;                          // n_staged * DD (if STAGE)
+    const double* tab = STAGE ? tab_s : R.tab;               // scan / fix / wpow tables
+    const double* tab_fix = tab + R.off_fix * DD;
+    const double* tab_wpow = tab + R.off_wpow * DD;
 
     // ---------------------------------------------------------------- load
+    if (STAGE) {
+        const int ngran = R.n_staged * DD / 2;
+        for (int q = tid; q < ngran; q += SOS_NT) cp_async16(tab_s + 2 * q, R.tab + 2 * q, 16);
+    }
+    // MODE_ENVF: tiles that do not touch the odd extension are loaded raw and
+    // rectified on the fly; the two edge tiles are built element by element
+    bool xform = false;
+    int64_t shift = 0;
     if (MODE == MODE_ENVF) {
-        // (pi/2)|x| with scipy's odd extension by `edge` rows at both ends
+        xform = t0 >= R.edge && t0 + T <= R.edge + R.nx;
+        shift = R.edge;
+    }
+    if (MODE == MODE_ENVF && !xform) {
         const int64_t nx = R.nx, edge = R.edge;
         const int total = T * Cw;
         for (int q = tid; q < total; q += SOS_NT) {
@@ -146,17 +179,16 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
             double val = 0.0;
             if (e < R.n) {
                 const double* xc = R.src + c0 + col;
-                const double hp = 1.5707963267948966;
                 if (e < edge) {
-                    double r0 = hp * fabs(__ldg(xc));
-                    double rk = hp * fabs(__ldg(xc + (edge - e) * C));
+                    double r0 = HALF_PI * fabs(__ldg(xc));
+                    double rk = HALF_PI * fabs(__ldg(xc + (edge - e) * C));
                     val = 2.0 * r0 - rk;
                 } else if (e < edge + nx) {
-                    val = hp * fabs(__ldcs(xc + (e - edge) * C));
+                    val = HALF_PI * fabs(__ldg(xc + (e - edge) * C));
                 } else {
                     int64_t k = e - edge - nx;
-                    double r1 = hp * fabs(__ldg(xc + (nx - 1) * C));
-                    double rk = hp * fabs(__ldg(xc + (nx - 2 - k) * C));
+                    double r1 = HALF_PI * fabs(__ldg(xc + (nx - 1) * C));
+                    double rk = HALF_PI * fabs(__ldg(xc + (nx - 2 - k) * C));
                     val = 2.0 * r1 - rk;
                 }
             }
@@ -168,10 +200,11 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
         const int total = T * gpr;
         int row = tid / gpr, col = tid - row * gpr;
         const int drow = SOS_NT / gpr, dcol = SOS_NT - drow * gpr;
+        const int64_t nlim = MODE == MODE_ENVF ? R.edge + R.nx : R.n;
         for (int q = tid; q < total; q += SOS_NT) {
             int64_t tau = t0 + row;
-            bool ok = tau < R.n;
-            int64_t phys = MODE == MODE_REV ? R.n - 1 - tau : tau;
+            bool ok = tau < nlim;
+            int64_t phys = MODE == MODE_REV ? R.n - 1 - tau : tau - shift;
             const double* gp = ok ? R.src + phys * C + c0 + col * gw : R.src;
             double* sp = tile_s + (row / SOS_L) * GS + (row % SOS_L) * Cw + col * gw;
             if (gw == 2) cp_async16(sp, gp, ok ? 16 : 0);
@@ -180,8 +213,8 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
             col += dcol;
             if (col >= gpr) { col -= gpr; ++row; }
         }
-        cp_async_wait_all();
     }
+    cp_async_wait_all();
     __syncthreads();
 
     // ---------------------------------------------------------------- pass A
@@ -193,6 +226,7 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
 #pragma unroll
         for (int i = 0; i < SOS_L; ++i) {
             double x = xp[i * Cw];
+            if (MODE == MODE_ENVF && xform) x = HALF_PI * fabs(x);
 #pragma unroll
             for (int d = 0; d < D; ++d) v[d] = fma(K.W[d][i], x, v[d]);
         }
@@ -205,7 +239,7 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
             double u[D];
 #pragma unroll
             for (int d = 0; d < D; ++d) u[d] = __shfl_up_sync(0xffffffffu, v[d], off);
-            if (lane >= off) matvec_acc<D>(R.tab + (TAB_SCAN + k) * DD, u, v);
+            if (lane >= off) matvec_acc<D>(tab + k * DD, u, v);
         }
     }
     double ex[D];                         // exclusive prefix inside the warp
@@ -220,127 +254,76 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
     }
     __syncthreads();
 
-    // ---------------------------------------------------------------- tile level (warp 0)
-    if (warp == 0) {
-        const double* Mw = R.tab + TAB_WARP * DD;
-        const double* Pt = R.tab + TAB_TILE * DD;
-        const bool ch = lane < CG;                  // one lane per channel of the group
-        const bool ch_real = ch && (c0 + lane < C);
+    // ---------------------------------------------------------------- tile level
+    // every thread: state entering its warp's chunk if the tile started from zero,
+    //   pre = sum_{j<warp} A^(L GW (warp-1-j)) wagg[j]
+    double pre[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) pre[d] = 0.0;
+    for (int j = 0; j < warp; ++j) {
+        double a[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) a[d] = wagg[(j * CG + cw) * D + d];
+        matvec_acc<D>(tab_wpow + (warp - 1 - j) * DD, a, pre);
+    }
+    // warp 0: aggregate of the tile, look-back for the incoming state (one lane per channel)
+    if (warp == 0 && lane < CG) {
+        const double* Pt = R.tab + (size_t)R.off_tile * DD;
+        const bool ch_real = c0 + lane < C;
         double acc[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) acc[d] = 0.0;
-        if (ch) {
-            for (int w = 0; w < SOS_NW; ++w) {
-                double nxt[D];
 #pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    wcar[(w * CG + lane) * D + d] = acc[d];          // prefix before warp w
-                    nxt[d] = wagg[(w * CG + lane) * D + d];
-                }
-                matvec_acc<D>(Mw, acc, nxt);
+        for (int j = 0; j < SOS_NW; ++j) {
+            double a[D];
 #pragma unroll
-                for (int d = 0; d < D; ++d) acc[d] = nxt[d];
-            }
+            for (int d = 0; d < D; ++d) a[d] = wagg[(j * CG + lane) * D + d];
+            matvec_acc<D>(tab_wpow + (SOS_NW - 1 - j) * DD, a, acc);
         }
         const bool publish = tt + 1 < R.ntt;
         const size_t rec = (size_t)tile * CG * D + (size_t)lane * D;
         if (publish) {
-            if (ch) {
 #pragma unroll
-                for (int d = 0; d < D; ++d) __stcg(R.agg + rec + d, acc[d]);
-                __threadfence();
-            }
-            __syncwarp();
-            if (lane == 0) st_release(R.flags + tile, 1u);
+            for (int d = 0; d < D; ++d) st_relaxed(R.agg + rec + d, acc[d]);
         }
-        // ---- incoming state of the tile
+        // ---- incoming state of the tile: sum_j (A^T)^(j-1) aggregate(tile-j), closed by the
+        // first inclusive state found, by the initial state, or where the weights have decayed
         double sin[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) sin[d] = 0.0;
-        if (tt == 0) {
-            if (ch_real && R.s0) {
+        for (int j = 1; j <= R.jdecay && j <= SOS_LOOK + 1; ++j) {
+            const int64_t b = tt - j;
+            double vec[D];
+            bool closed = false;
+            if (b < 0) {
 #pragma unroll
-                for (int d = 0; d < D; ++d) sin[d] = __ldg(R.s0 + (size_t)(c0 + lane) * D + d);
-            }
-        } else {
-            // lane j-1 watches predecessor j (same channel group, j time tiles back)
-            const int j = lane + 1;
-            const int64_t back = tt - j;                 // -1: the virtual tile holding s0
-            const bool decayed = j > R.jdecay;           // weight (A^T)^(j-1) ~ 0
-            const bool real = back >= 0 && !decayed;
-            const uint32_t* fp = R.flags + (real ? tile - (int64_t)j * R.ngroups : tile);
-            uint32_t status = real ? 0u : 2u;
-            int J;
-            unsigned ns = 8;
-            while (true) {
-                if (status != 2u && real) status = ld_acquire(fp);
-                unsigned m2 = __ballot_sync(0xffffffffu, status == 2u);
-                unsigned m0 = __ballot_sync(0xffffffffu, status == 0u);
-                if (m2) {
-                    J = __ffs(m2);                        // nearest inclusive, 1-based
-                    unsigned below = J >= 32 ? 0xffffffffu : ((1u << J) - 1u);
-                    if ((m0 & below) == 0) break;
-                }
-                __nanosleep(ns);
-                if (ns < 256) ns <<= 1;
-            }
-            __threadfence();
-            __syncwarp();
-            if (ch) {
-                for (int jj = 1; jj <= J; ++jj) {
-                    const int64_t b = tt - jj;
-                    double vec[D];
-                    bool zero = false;
-                    if (jj == J) {
-                        if (jj > R.jdecay) zero = true;
-                        else if (b < 0) {
-#pragma unroll
-                            for (int d = 0; d < D; ++d)
-                                vec[d] = (ch_real && R.s0) ? __ldg(R.s0 + (size_t)(c0 + lane) * D + d) : 0.0;
-                        } else {
-                            const double* p = R.incl + (size_t)(tile - (int64_t)jj * R.ngroups) * CG * D + (size_t)lane * D;
-#pragma unroll
-                            for (int d = 0; d < D; ++d) vec[d] = __ldcg(p + d);
-                        }
-                    } else {
-                        const double* p = R.agg + (size_t)(tile - (int64_t)jj * R.ngroups) * CG * D + (size_t)lane * D;
-#pragma unroll
-                        for (int d = 0; d < D; ++d) vec[d] = __ldcg(p + d);
-                    }
-                    if (!zero) matvec_acc<D>(Pt + (jj - 1) * DD, vec, sin);
+                for (int d = 0; d < D; ++d)
+                    vec[d] = (ch_real && R.s0) ? __ldg(R.s0 + (size_t)(c0 + lane) * D + d) : 0.0;
+                closed = true;
+            } else {
+                const size_t prec = (size_t)(tile - (int64_t)j * R.ngroups) * CG * D + (size_t)lane * D;
+                unsigned ns = 0;
+                while (true) {
+                    if (read_record<D>(R.incl + prec, vec)) { closed = true; break; }
+                    // the last slot of the window must be an inclusive state
+                    if (j <= SOS_LOOK && read_record<D>(R.agg + prec, vec)) break;
+                    if (ns) __nanosleep(ns);
+                    ns = ns ? (ns < 256 ? ns * 2 : ns) : 32;
                 }
             }
+            matvec_acc<D>(Pt + (size_t)(j - 1) * DD, vec, sin);
+            if (closed) break;
         }
+#pragma unroll
+        for (int d = 0; d < D; ++d) sin_s[lane * D + d] = sin[d];
         // ---- inclusive state of this tile, for the successors
         if (publish) {
-            if (ch) {
-                double inc[D];
+            double inc[D];
 #pragma unroll
-                for (int d = 0; d < D; ++d) inc[d] = acc[d];
-                matvec_acc<D>(Pt + DD, sin, inc);
+            for (int d = 0; d < D; ++d) inc[d] = acc[d];
+            matvec_acc<D>(Pt + DD, sin, inc);
 #pragma unroll
-                for (int d = 0; d < D; ++d) __stcg(R.incl + rec + d, inc[d]);
-                __threadfence();
-            }
-            __syncwarp();
-            if (lane == 0) st_release(R.flags + tile, 2u);
-        }
-        // ---- incoming state of every warp chunk
-        if (ch) {
-            double p[D];
-#pragma unroll
-            for (int d = 0; d < D; ++d) p[d] = sin[d];
-            for (int w = 0; w < SOS_NW; ++w) {
-                double q[D];
-#pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    wcar[(w * CG + lane) * D + d] += p[d];
-                    q[d] = 0.0;
-                }
-                matvec_acc<D>(Mw, p, q);
-#pragma unroll
-                for (int d = 0; d < D; ++d) p[d] = q[d];
-            }
+            for (int d = 0; d < D; ++d) st_relaxed(R.incl + rec + d, inc[d]);
         }
     }
     __syncthreads();
@@ -352,20 +335,25 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
     if (chan_ok && (R.dst != nullptr || want_state)) {
         double z[D];
         {
-            double wc[D];
+            // state entering the warp chunk: pre + A^(L GW warp) sin
+            double sv[D];
 #pragma unroll
-            for (int d = 0; d < D; ++d) { wc[d] = wcar[(warp * CG + cw) * D + d]; z[d] = ex[d]; }
+            for (int d = 0; d < D; ++d) sv[d] = sin_s[cw * D + d];
+            matvec_acc<D>(tab_wpow + warp * DD, sv, pre);
+#pragma unroll
+            for (int d = 0; d < D; ++d) z[d] = ex[d];
             if (gl == 0) {
 #pragma unroll
-                for (int d = 0; d < D; ++d) z[d] += wc[d];
+                for (int d = 0; d < D; ++d) z[d] += pre[d];
             } else {
-                matvec_acc<D>(R.tab + (TAB_FIX + gl) * DD, wc, z);
+                matvec_acc<D>(tab_fix + gl * DD, pre, z);
             }
         }
         const int ilast = want_state ? (int)(last - tau0) : -1;
 #pragma unroll
         for (int i = 0; i < SOS_L; ++i) {
             double x = xp[i * Cw];
+            if (MODE == MODE_ENVF && xform) x = HALF_PI * fabs(x);
 #pragma unroll
             for (int s = 0; s < S; ++s) {
                 double y = fma(K.coef[s][0], x, z[2 * s]);
@@ -493,6 +481,7 @@ struct Plan {
     std::vector<double> sos;      // key
     int S = 0, CG = 0;
     int jdecay = SOS_LOOK + 1;
+    int off_fix = 0, off_wpow = 0, off_tile = 0, n_staged = 0;
     std::vector<double> W;        // [D][L]
     double* dtab = nullptr;       // device tables
 };
@@ -531,27 +520,37 @@ int32_t get_plan(const double* sos, int S, int CG, cudaStream_t st, Plan** out) 
             v = nv;
         }
     }
-    std::vector<double> tab((size_t)TAB_COUNT * DD, 0.0);
+    const int GW = 32 / CG;
+    int nscan = 0;
+    while ((CG << nscan) < 32) ++nscan;
+    p.off_fix = nscan;
+    p.off_wpow = p.off_fix + GW;
+    p.n_staged = p.off_wpow + SOS_NW + 1;
+    p.off_tile = p.n_staged;
+    std::vector<double> tab((size_t)(p.off_tile + SOS_LOOK + 1) * DD, 0.0);
     auto put = [&](int slot, const Mat& m) {
         for (int i = 0; i < DD; ++i) tab[(size_t)slot * DD + i] = (double)m.a[i];
     };
     const Mat AL = mpow(A, SOS_L);
     {
         Mat m = AL;
-        for (int k = 0; k < 5; ++k) { put(TAB_SCAN + k, m); m = mul(m, m); }
+        for (int k = 0; k < nscan; ++k) { put(k, m); m = mul(m, m); }
     }
     {
         Mat m = Mat::eye(D);
-        for (int j = 0; j < 32; ++j) { put(TAB_FIX + j, m); m = mul(m, AL); }
+        for (int j = 0; j < GW; ++j) { put(p.off_fix + j, m); m = mul(m, AL); }
     }
-    const int GW = 32 / CG;
-    put(TAB_WARP, mpow(AL, GW));
+    {
+        const Mat AW = mpow(AL, GW);
+        Mat m = Mat::eye(D);
+        for (int k = 0; k <= SOS_NW; ++k) { put(p.off_wpow + k, m); m = mul(m, AW); }
+    }
     {
         const Mat AT = mpow(AL, SOS_NT / CG);         // one tile = NT/CG sub-chunks per channel
         Mat m = Mat::eye(D);
         p.jdecay = SOS_LOOK + 1;
-        for (int j = 0; j <= 32; ++j) {
-            put(TAB_TILE + j, m);
+        for (int j = 0; j <= SOS_LOOK; ++j) {
+            put(p.off_tile + j, m);
             ld mx = 0.0L;
             for (auto x : m.a) mx = fmaxl(mx, fabsl(x));
             if (j >= 1 && mx < 1e-30L && p.jdecay > SOS_LOOK) p.jdecay = j;
@@ -561,6 +560,7 @@ int32_t get_plan(const double* sos, int S, int CG, cudaStream_t st, Plan** out) 
     ADN_CK(cudaMalloc(&p.dtab, tab.size() * sizeof(double)));
     ADN_CK(cudaMemcpyAsync(p.dtab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     ADN_CK(cudaStreamSynchronize(st));           // `tab` is a stack-lifetime host buffer
+    if (g_plans.capacity() < 64) g_plans.reserve(64);
     g_plans.push_back(std::move(p));
     *out = &g_plans.back();
     return ADN_OK;
@@ -625,18 +625,18 @@ int32_t run_scan(int mode, const double* sos, int S, const double* src, int64_t 
     R.vec_out = even && dst && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
     const int64_t ntiles = R.ntt * R.ngroups;
     if (ntiles > 0x7fffffff) return fail(ADN_ERR_UNSUPPORTED, "sos scan: %lld tiles", (long long)ntiles);
-    // tile records: flags | ticket | agg | incl
-    const size_t nflag = ((size_t)ntiles + 1 + 3) & ~(size_t)3;          // keeps doubles 16B aligned
+    R.off_fix = plan->off_fix; R.off_wpow = plan->off_wpow; R.off_tile = plan->off_tile;
+    R.n_staged = plan->n_staged;
+    // tile records: agg | incl, every word SOS_EMPTY until published
     const size_t recs = (size_t)ntiles * CG * D;
     DevBuf& tb = scratch(tile_slot);
-    if ((rc = tb.reserve(nflag * 4 + recs * 16))) return rc;
-    R.flags = tb.as<uint32_t>();
-    R.ticket = R.flags + ntiles;
-    R.agg = reinterpret_cast<double*>(tb.as<char>() + nflag * 4);
+    if ((rc = tb.reserve(recs * 16))) return rc;
+    R.agg = tb.as<double>();
     R.incl = R.agg + recs;
-    ADN_CK(cudaMemsetAsync(R.flags, 0, nflag * 4, st));
+    ADN_CK(cudaMemsetAsync(R.agg, 0xFF, recs * 16, st));
     const int pad = CG < 16 ? CG : 0;
-    const size_t smem = ((size_t)(SOS_NT / CG) * (SOS_L * CG + pad) + 2 * (size_t)SOS_NW * CG * D) * 8;
+    const size_t smem = ((size_t)(SOS_NT / CG) * (SOS_L * CG + pad) + (size_t)(SOS_NW + 1) * CG * D +
+                         (S <= 4 ? (size_t)plan->n_staged * D * D : 0)) * 8;
     const unsigned grid = (unsigned)ntiles;
     switch (S) {
         case 1: return launch_S<1>(mode, *plan, R, smem, grid, st);

@@ -1,7 +1,7 @@
 """Host-side model of the sm_100a scan kernel (audian_b200/csrc/sosfilt.cu).
 
 Re-enacts, in numpy, exactly the decomposition the kernel uses -- pass A dot
-products, Kogge-Stone over sub-chunks with A^(L 2^k), serial scan over warps,
+products, Kogge-Stone over sub-chunks with A^(L 2^k), warp prefixes with A^(L GW k),
 look-back over tiles with (A^T)^j weights, fix-up with A^(L gl), pass B -- with
 the matrices the library's host code produces (adn_sos_state_space), and checks
 it against scipy.signal.sosfilt.  Runs on CPU: it pins the algebra the kernel
@@ -14,7 +14,7 @@ from scipy.signal import butter, sosfilt
 
 from audian_b200 import _lib
 
-L, NT, NW = 32, 256, 8
+L, NT, NW = 32, 128, 4
 
 
 def pick_cg(C):
@@ -55,7 +55,7 @@ def run_model(sos, x, CG, rng, zi=None):
         v = A @ v
     scan = [_lib.sos_state_space(sos, L*2**k)[2] for k in range(5)]
     fix = [_lib.sos_state_space(sos, L*j)[2] for j in range(32)]
-    Mw = _lib.sos_state_space(sos, L*GW)[2]
+    wpow = [_lib.sos_state_space(sos, L*GW*k)[2] for k in range(NW + 1)]
     Pt = [_lib.sos_state_space(sos, T*j)[2] for j in range(33)]
     ntt = (n + T - 1)//T
     xpad = np.zeros(ntt*T)
@@ -81,12 +81,14 @@ def run_model(sos, x, CG, rng, zi=None):
         ex = np.zeros_like(vv)
         ex[:, 1:] = vv[:, :-1]
         wagg = vv[:, GW - 1]                          # (NW, D)
-        # serial scan over warps
-        acc = np.zeros(D)
+        # every warp: its incoming state for a zero tile carry; warp 0: tile aggregate
         wpre = np.zeros((NW, D))
         for w in range(NW):
-            wpre[w] = acc
-            acc = Mw @ acc + wagg[w]
+            for j in range(w):
+                wpre[w] += wpow[w - 1 - j] @ wagg[j]
+        acc = np.zeros(D)
+        for j in range(NW):
+            acc += wpow[NW - 1 - j] @ wagg[j]
         agg[tt] = acc
         # look-back: nearest inclusive at a random distance J (1..min(tt+1, 32))
         if tt == 0:
@@ -102,11 +104,9 @@ def run_model(sos, x, CG, rng, zi=None):
                     vec = agg[b]
                 sin += Pt[jj - 1] @ vec
         incl[tt] = Pt[1] @ sin + acc
-        p = sin.copy()
         wcar = np.zeros((NW, D))
         for w in range(NW):
-            wcar[w] = wpre[w] + p
-            p = Mw @ p
+            wcar[w] = wpre[w] + wpow[w] @ sin
         for w in range(NW):
             for gl in range(GW):
                 z = ex[w, gl] + fix[gl] @ wcar[w]
