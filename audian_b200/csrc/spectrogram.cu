@@ -24,6 +24,7 @@ constexpr int SP_NT = 256;
 struct SpecPlan {
     int nfft = 0;
     double2* tw = nullptr;      // exp(-2 pi i j / nfft), j < nfft/2
+    double2* twA = nullptr;     // warp path: [16][T] W_M^(t k1), M = nfft/2, T = M/16
     double* win = nullptr;      // periodic Hann
     double sumw2 = 0.0;
 };
@@ -52,6 +53,18 @@ int32_t get_spec_plan(int nfft, cudaStream_t st, SpecPlan* out) {
         s2 += win[j] * win[j];
     }
     p.sumw2 = s2;
+    if (nfft >= 128 && nfft <= 1024) {
+        const int M = nfft / 2, T = M / 16;
+        std::vector<double2> twA((size_t)M);
+        for (int k1 = 0; k1 < 16; ++k1)
+            for (int t = 0; t < T; ++t) {
+                long double a = two_pi * (long double)((k1 * t) % M) / (long double)M;
+                twA[(size_t)k1 * T + t].x = (double)cosl(a);
+                twA[(size_t)k1 * T + t].y = (double)(-sinl(a));
+            }
+        ADN_CK(cudaMalloc(&p.twA, sizeof(double2) * twA.size()));
+        ADN_CK(cudaMemcpy(p.twA, twA.data(), sizeof(double2) * twA.size(), cudaMemcpyHostToDevice));
+    }
     ADN_CK(cudaMalloc(&p.tw, sizeof(double2) * tw.size()));
     ADN_CK(cudaMalloc(&p.win, sizeof(double) * win.size()));
     ADN_CK(cudaMemcpyAsync(p.tw, tw.data(), sizeof(double2) * tw.size(), cudaMemcpyHostToDevice, st));
@@ -60,6 +73,18 @@ int32_t get_spec_plan(int nfft, cudaStream_t st, SpecPlan* out) {
     g_splans.push_back(p);
     *out = p;
     return ADN_OK;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* g) {
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 w) {
@@ -197,6 +222,290 @@ spectrogram_kernel(const __grid_constant__ SpecArgs P) {
     }
 }
 
+
+// ======================================================================================
+// Register-resident path for nfft = 128 .. 1024 (the interactive sizes): one frame is
+// transformed by T = nfft/32 lanes of a warp (4 .. 32), 16 complex points per lane.
+//   M = nfft/2 = 16*T complex points z[j] = (x[2j], x[2j+1]);  lane t holds z[T p + t]
+//   pass 1   16-point DFT over p in registers, twiddle W_M^(t k1)
+//   exchange through a per-warp shared-memory buffer (conflict-free padded layout)
+//   pass 2   T-point DFTs over t in registers (T = 32: 16-point + one xor-shuffle stage)
+//   split    Z[k], Z[M-k] -> X[k], X[M-k] of the real transform, |X|^2 scaling, store
+// The input rows of FB consecutive frames x CB channels are staged once per block and
+// de-interleaved on the way in (8-byte cp.async), so every lane reads its 16-byte pairs
+// of consecutive samples without bank conflicts; only __syncwarp between the phases.
+
+constexpr int SW_NWARP = 4;
+constexpr int SW_NT = SW_NWARP * 32;
+
+struct SpecWArgs {
+    const double* src;
+    double* dst;
+    const double* win;          // nfft
+    const double2* twA;         // [16][T]: W_M^(t k1)
+    const double2* twS;         // W_N^k, k <= M/2
+    int64_t nframes;
+    int32_t C, hop, FB, CB, RP;
+    int32_t detrend, out_db;
+    double scale;               // 1 / (rate * sum(w^2))
+};
+
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+// a - i b  and  a + i b
+__device__ __forceinline__ double2 csub_i(double2 a, double2 b) { return make_double2(a.x + b.y, a.y - b.x); }
+__device__ __forceinline__ double2 cadd_i(double2 a, double2 b) { return make_double2(a.x - b.y, a.y + b.x); }
+
+__device__ __forceinline__ void dft4(double2 x0, double2 x1, double2 x2, double2 x3,
+                                     double2& y0, double2& y1, double2& y2, double2& y3) {
+    double2 s02 = cadd(x0, x2), d02 = csub(x0, x2), s13 = cadd(x1, x3), d13 = csub(x1, x3);
+    y0 = cadd(s02, s13);
+    y2 = csub(s02, s13);
+    y1 = csub_i(d02, d13);
+    y3 = cadd_i(d02, d13);
+}
+
+#define ADN_C1 0.92387953251128674     /* cos(pi/8) */
+#define ADN_S1 0.38268343236508977     /* sin(pi/8) */
+#define ADN_R2 0.70710678118654752     /* sqrt(1/2) */
+
+// natural-order 16-point forward DFT, 4 x 4 decomposition
+__device__ __forceinline__ void dft16(const double2 (&a)[16], double2 (&X)[16]) {
+    double2 u[4][4];
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2)
+        dft4(a[n2], a[n2 + 4], a[n2 + 8], a[n2 + 12], u[n2][0], u[n2][1], u[n2][2], u[n2][3]);
+    // u[n2][k1] *= W16^(n2 k1)
+    u[1][1] = cmul(u[1][1], make_double2(ADN_C1, -ADN_S1));
+    u[1][2] = cmul(u[1][2], make_double2(ADN_R2, -ADN_R2));
+    u[1][3] = cmul(u[1][3], make_double2(ADN_S1, -ADN_C1));
+    u[2][1] = cmul(u[2][1], make_double2(ADN_R2, -ADN_R2));
+    u[2][2] = make_double2(u[2][2].y, -u[2][2].x);                       // W16^4 = -i
+    u[2][3] = cmul(u[2][3], make_double2(-ADN_R2, -ADN_R2));
+    u[3][1] = cmul(u[3][1], make_double2(ADN_S1, -ADN_C1));
+    u[3][2] = cmul(u[3][2], make_double2(-ADN_R2, -ADN_R2));
+    u[3][3] = cmul(u[3][3], make_double2(-ADN_C1, ADN_S1));              // W16^9
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1)
+        dft4(u[0][k1], u[1][k1], u[2][k1], u[3][k1], X[k1], X[k1 + 4], X[k1 + 8], X[k1 + 12]);
+}
+
+// 8-point forward DFT of a[0..7] (2 x 4)
+__device__ __forceinline__ void dft8(const double2* a, double2* X) {
+    double2 u0[4], u1[4];
+    dft4(a[0], a[2], a[4], a[6], u0[0], u0[1], u0[2], u0[3]);
+    dft4(a[1], a[3], a[5], a[7], u1[0], u1[1], u1[2], u1[3]);
+    u1[1] = cmul(u1[1], make_double2(ADN_R2, -ADN_R2));
+    u1[2] = make_double2(u1[2].y, -u1[2].x);
+    u1[3] = cmul(u1[3], make_double2(-ADN_R2, -ADN_R2));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { X[k] = cadd(u0[k], u1[k]); X[k + 4] = csub(u0[k], u1[k]); }
+}
+
+// W32^k = exp(-2 pi i k / 32), k < 16
+__device__ __constant__ double c_w32[16][2] = {
+    {1.0, -0.0},
+    {0.98078528040323043, -0.19509032201612825}, {0.92387953251128674, -0.38268343236508977},
+    {0.83146961230254524, -0.55557023301960218}, {0.70710678118654752, -0.70710678118654752},
+    {0.55557023301960218, -0.83146961230254524}, {0.38268343236508977, -0.92387953251128674},
+    {0.19509032201612825, -0.98078528040323043}, {0.0, -1.0},
+    {-0.19509032201612825, -0.98078528040323043}, {-0.38268343236508977, -0.92387953251128674},
+    {-0.55557023301960218, -0.83146961230254524}, {-0.70710678118654752, -0.70710678118654752},
+    {-0.83146961230254524, -0.55557023301960218}, {-0.92387953251128674, -0.38268343236508977},
+    {-0.98078528040323043, -0.19509032201612825}};
+
+template <int LOGN> struct SWCfg {
+    static constexpr int N = 1 << LOGN, M = N / 2, T = M / 16, FPW = 32 / T;
+    // per-frame stride of the per-warp exchange buffer (complex elements), == 4 mod 8
+    static constexpr int FS = T == 32 ? 16 * 34 : (T * 17 + ((T * 17) % 8 == 4 ? 0 : 4));
+    static constexpr int WB = FS * FPW;
+};
+
+template <int LOGN>
+__global__ void __launch_bounds__(SW_NT)
+spectrogram_warp_kernel(const __grid_constant__ SpecWArgs P) {
+    using Cf = SWCfg<LOGN>;
+    constexpr int N = Cf::N, M = Cf::M, T = Cf::T, FPW = Cf::FPW, FS = Cf::FS;
+    constexpr int F = M + 1;
+    extern __shared__ __align__(16) double sbuf[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = P.C, hop = P.hop, RP = P.RP;
+    const int ngrp = (C + P.CB - 1) / P.CB;
+    const int grp = blockIdx.x % ngrp;
+    const int64_t f0 = (int64_t)(blockIdx.x / ngrp) * P.FB;
+    const int c0 = grp * P.CB;
+    const int FBa = (int)min((int64_t)P.FB, P.nframes - f0);
+    const int CBa = min(P.CB, C - c0);
+    const int items = FBa * CBa;
+
+    double* xs = sbuf;                                               // [CB][RP]
+    double2* twA_s = reinterpret_cast<double2*>(sbuf + (size_t)P.CB * RP);   // [16][T]
+    double2* wb = twA_s + M + (size_t)warp * Cf::WB;                 // per-warp exchange buffer
+
+    // ---- stage: rows [f0*hop, f0*hop + (FBa-1)*hop + N) x CBa channels, de-interleaved
+    {
+        const int rows = (FBa - 1) * hop + N;
+        const double* base = P.src + (f0 * hop) * (int64_t)C + c0;
+        const int total = rows * CBa;
+        for (int q = tid; q < total; q += SW_NT) {
+            int row = q / CBa, ci = q - row * CBa;
+            cp_async8(xs + (size_t)ci * RP + row, base + (int64_t)row * C + ci);
+        }
+        for (int q = tid; q < M; q += SW_NT) cp_async16(twA_s + q, P.twA + q);
+        cp_async_wait_all();
+    }
+    __syncthreads();
+
+    const int sub = lane / T, t = lane % T;
+    double2* wbf = wb + sub * FS;
+    const int niter = (items + SW_NWARP * FPW - 1) / (SW_NWARP * FPW);
+    for (int iter = 0; iter < niter; ++iter) {
+        const int it = (warp + SW_NWARP * iter) * FPW + sub;
+        const bool live = it < items;
+        const int ite = live ? it : 0;
+        const int fi = ite / CBa, ci = ite - fi * CBa;
+        const double* xr = xs + (size_t)ci * RP + fi * hop;
+
+        // ---- load, detrend, window
+        double2 a[16];
+#pragma unroll
+        for (int p = 0; p < 16; ++p) a[p] = *reinterpret_cast<const double2*>(xr + 2 * (T * p + t));
+        double mean = 0.0;
+        if (P.detrend) {
+            double s = 0.0;
+#pragma unroll
+            for (int p = 0; p < 16; ++p) s += a[p].x + a[p].y;
+#pragma unroll
+            for (int o = 1; o < T; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            mean = s * (1.0 / N);
+        }
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+            double2 w = __ldg(reinterpret_cast<const double2*>(P.win) + (T * p + t));
+            a[p].x = (a[p].x - mean) * w.x;
+            a[p].y = (a[p].y - mean) * w.y;
+        }
+        // ---- pass 1 + twiddle, into the exchange buffer at (k1, t)
+        double2 b[16];
+        dft16(a, b);
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) {
+            double2 v = k1 == 0 ? b[0] : cmul(b[k1], twA_s[k1 * T + t]);
+            const int f = k1 * T + t;
+            wbf[T == 32 ? k1 * 34 + t : f + (f >> 4)] = v;
+        }
+        __syncwarp();
+        // ---- pass 2: T-point DFTs over t
+        double2 zout[16];
+        int kout[16];
+        if (T == 32) {
+            const int k1 = lane >> 1, tp = lane & 1;
+#pragma unroll
+            for (int pp = 0; pp < 16; ++pp) a[pp] = wbf[k1 * 34 + 2 * pp + tp];
+            dft16(a, b);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                double2 e = b[k];
+                if (tp) e = cmul(e, make_double2(c_w32[k][0], c_w32[k][1]));
+                double2 o;
+                o.x = __shfl_xor_sync(0xffffffffu, e.x, 1);
+                o.y = __shfl_xor_sync(0xffffffffu, e.y, 1);
+                zout[k] = tp ? csub(o, e) : cadd(e, o);
+                kout[k] = k1 + 16 * k + 256 * tp;
+            }
+        } else {
+            constexpr int Q = 16 / (T == 32 ? 16 : T);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = wbf[t * 17 + i];
+            if (T == 16) {
+                dft16(a, b);
+            } else if (T == 8) {
+                dft8(&a[0], &b[0]);
+                dft8(&a[8], &b[8]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    dft4(a[4 * r], a[4 * r + 1], a[4 * r + 2], a[4 * r + 3],
+                         b[4 * r], b[4 * r + 1], b[4 * r + 2], b[4 * r + 3]);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int r = i / (16 / Q), k2 = i % (16 / Q);
+                zout[i] = b[i];
+                kout[i] = (t * Q + r) + 16 * k2;
+            }
+        }
+        __syncwarp();
+        // ---- Z in natural order
+#pragma unroll
+        for (int i = 0; i < 16; ++i) wbf[kout[i] + ((kout[i] >> 8) << 2)] = zout[i];
+        __syncwarp();
+        // ---- split step and power
+        if (live) {
+            double* out = P.dst + (((f0 + fi) * (int64_t)C + c0 + ci) * F);
+            const double sc = 0.5 * P.scale;
+            for (int k = 1 + t; k <= M / 2; k += T) {
+                const int km = M - k;
+                double2 zk = wbf[k + ((k >> 8) << 2)], zm = wbf[km + ((km >> 8) << 2)];
+                double2 w = __ldg(P.twS + k);
+                double e_r = zk.x + zm.x, e_i = zk.y - zm.y;          // Zk + conj(Zm)
+                double o_r = zk.y + zm.y, o_i = zm.x - zk.x;          // -i (Zk - conj(Zm))
+                double t_r = o_r * w.x - o_i * w.y, t_i = o_r * w.y + o_i * w.x;
+                double pr = e_r + t_r, pi = e_i + t_i, qr = e_r - t_r, qi = e_i - t_i;
+                double pk = (pr * pr + pi * pi) * sc, pm = (qr * qr + qi * qi) * sc;
+                if (P.out_db) {
+                    pk = pk > 1e-20 ? 10.0 * log10(pk) : (pk <= 1e-20 ? -INFINITY : pk);
+                    pm = pm > 1e-20 ? 10.0 * log10(pm) : (pm <= 1e-20 ? -INFINITY : pm);
+                }
+                out[k] = pk;
+                if (km != k) out[km] = pm;
+            }
+            if (t == 0) {
+                double2 z0 = wbf[0];
+                double p0 = (z0.x + z0.y) * (z0.x + z0.y) * P.scale;
+                double pM = (z0.x - z0.y) * (z0.x - z0.y) * P.scale;
+                if (P.out_db) {
+                    p0 = p0 > 1e-20 ? 10.0 * log10(p0) : (p0 <= 1e-20 ? -INFINITY : p0);
+                    pM = pM > 1e-20 ? 10.0 * log10(pM) : (pM <= 1e-20 ? -INFINITY : pM);
+                }
+                out[0] = p0;
+                out[M] = pM;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int LOGN>
+int32_t launch_warp_kernel(SpecWArgs& P, int64_t nf, cudaStream_t st) {
+    using Cf = SWCfg<LOGN>;
+    const int C = P.C;
+    // channels per block: 2 when they pair up (16-byte sectors shared by neighbour blocks in L2)
+    P.CB = C >= 2 ? 2 : 1;
+    int rows_budget = 2048 + Cf::N / 2;
+    int FB = (rows_budget - Cf::N) / P.hop + 1;
+    if (FB < 1) FB = 1;
+    if (FB > 64) FB = 64;
+    if ((int64_t)FB > nf) FB = (int)nf;
+    P.FB = FB;
+    int rows = (FB - 1) * P.hop + Cf::N;
+    P.RP = ((rows + 15) / 16) * 16 + 8;               // == 8 mod 16: channel arrays on disjoint banks
+    const size_t smem = (size_t)P.CB * P.RP * 8 + (size_t)Cf::M * 16 + (size_t)SW_NWARP * Cf::WB * 16;
+    auto kern = spectrogram_warp_kernel<LOGN>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        ADN_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done = true;
+    }
+    const int ngrp = (C + P.CB - 1) / P.CB;
+    int64_t grid = ((nf + FB - 1) / FB) * ngrp;
+    if (grid > 0x7fffffff) return fail(ADN_ERR_UNSUPPORTED, "spectrogram: grid %lld", (long long)grid);
+    kern<<<(unsigned)grid, SW_NT, smem, st>>>(P);
+    count_launch();
+    ADN_CK(cudaGetLastError());
+    return ADN_OK;
+}
+
 }  // namespace
 
 int32_t spectrogram_dev(const double* src, int64_t n_src, int32_t C, double rate, int32_t nfft,
@@ -218,6 +527,19 @@ int32_t spectrogram_dev(const double* src, int64_t n_src, int32_t C, double rate
     SpecPlan plan;
     int32_t rc = get_spec_plan(nfft, st, &plan);
     if (rc) return rc;
+    if (plan.twA && (hop % 2 == 0) && (reinterpret_cast<uintptr_t>(src) & 7) == 0) {
+        SpecWArgs W;
+        W.src = src; W.dst = dst; W.win = plan.win; W.twA = plan.twA; W.twS = plan.tw;
+        W.nframes = nf; W.C = C; W.hop = hop;
+        W.detrend = detrend_id == ADN_DETREND_CONSTANT; W.out_db = out_db;
+        W.scale = 1.0 / (rate * plan.sumw2);
+        switch (nfft) {
+            case 128: return launch_warp_kernel<7>(W, nf, st);
+            case 256: return launch_warp_kernel<8>(W, nf, st);
+            case 512: return launch_warp_kernel<9>(W, nf, st);
+            case 1024: return launch_warp_kernel<10>(W, nf, st);
+        }
+    }
     SpecArgs P;
     P.src = src; P.dst = dst; P.tw = plan.tw; P.win = plan.win;
     P.nframes = nf; P.C = C; P.nfft = nfft; P.hop = hop;
