@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 
 namespace adn {
@@ -73,6 +74,8 @@ struct SosRun {
     int32_t edge;                  // MODE_ENVF: odd-extension length
     int32_t clamp;                 // negative outputs -> 0
     int32_t vec_in, vec_out;       // 16-byte granules allowed
+    int32_t pf_tiles;              // L2 prefetch distance in time tiles (0 = off)
+    int32_t lc;                    // log2(CG), or -1: no fast path
 };
 
 __device__ __forceinline__ double ld_relaxed(const double* p) {
@@ -123,7 +126,7 @@ __device__ __forceinline__ void matvec_acc(const double* __restrict__ M, const d
 constexpr double HALF_PI = 1.5707963267948966;
 
 template <int S, int MODE>
-__global__ void __launch_bounds__(SOS_NT)
+__global__ void __launch_bounds__(SOS_NT, S <= 2 ? 5 : (S <= 4 ? 3 : 1))
 sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRun R) {
     constexpr int D = 2 * S;
     constexpr int DD = D * D;
@@ -158,6 +161,25 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
     const double* tab_wpow = tab + R.off_wpow * DD;
 
     // ---------------------------------------------------------------- load
+    // warm L2 for the tile a later block will load: one bulk prefetch (TMA unit) of the
+    // contiguous rows `R.pf_tiles` time tiles ahead
+    if (tid == 0 && grp == 0 && R.pf_tiles > 0) {
+        const int64_t pt0 = t0 + (int64_t)R.pf_tiles * T;
+        const int64_t lim = MODE == MODE_ENVF ? R.nx : R.n;
+        int64_t p0 = MODE == MODE_REV ? R.n - pt0 - T : (MODE == MODE_ENVF ? pt0 - R.edge : pt0);
+        int64_t p1 = p0 + T;
+        if (p0 < 0) p0 = 0;
+        if (p1 > lim) p1 = lim;
+        if (p1 > p0) {
+            const char* a = reinterpret_cast<const char*>(R.src + p0 * C);
+            int64_t bytes = (p1 - p0) * (int64_t)C * 8;
+            int64_t mis = reinterpret_cast<uintptr_t>(a) & 15;
+            a -= mis;
+            bytes = (bytes + mis + 15) & ~(int64_t)15;
+            if (a >= reinterpret_cast<const char*>(R.src))
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((uint32_t)bytes) : "memory");
+        }
+    }
     if (STAGE) {
         const int ngran = R.n_staged * DD / 2;
         for (int q = tid; q < ngran; q += SOS_NT) cp_async16(tab_s + 2 * q, R.tab + 2 * q, 16);
@@ -170,6 +192,31 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
         xform = t0 >= R.edge && t0 + T <= R.edge + R.nx;
         shift = R.edge;
     }
+    // fast path (block-uniform): a full channel group (CG = 2^k channels), every row of the
+    // tile inside the source: the addresses of the granules a thread copies are shifts and adds
+    const int lc = Cw == CG ? R.lc : -1;                   // log2(CG) when the group is full
+    const int64_t nlim = MODE == MODE_ENVF ? R.edge + R.nx : R.n;
+    const bool fast_in = lc >= 0 && t0 + T <= nlim && !(MODE == MODE_ENVF && !xform);
+    if (fast_in) {
+        const int64_t rowbase = MODE == MODE_REV ? R.n - 1 - t0 : t0 - shift;   // physical row of tile row 0
+        if (R.vec_in) {
+#pragma unroll
+            for (int k = 0; k < SOS_L / 2; ++k) {
+                const int f = 2 * (tid + SOS_NT * k);      // flat double index in the tile
+                const int r = f >> lc, c = c0 + (f & (CG - 1));
+                const int64_t grow = MODE == MODE_REV ? rowbase - r : rowbase + r;
+                cp_async16(tile_s + f + (r >> 5) * pad, R.src + grow * C + c, 16);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < SOS_L; ++k) {
+                const int f = tid + SOS_NT * k;
+                const int r = f >> lc, c = c0 + (f & (CG - 1));
+                const int64_t grow = MODE == MODE_REV ? rowbase - r : rowbase + r;
+                cp_async8(tile_s + f + (r >> 5) * pad, R.src + grow * C + c, 8);
+            }
+        }
+    } else
     if (MODE == MODE_ENVF && !xform) {
         const int64_t nx = R.nx, edge = R.edge;
         const int total = T * Cw;
@@ -200,7 +247,6 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
         const int total = T * gpr;
         int row = tid / gpr, col = tid - row * gpr;
         const int drow = SOS_NT / gpr, dcol = SOS_NT - drow * gpr;
-        const int64_t nlim = MODE == MODE_ENVF ? R.edge + R.nx : R.n;
         for (int q = tid; q < total; q += SOS_NT) {
             int64_t tau = t0 + row;
             bool ok = tau < nlim;
@@ -349,22 +395,41 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
                 matvec_acc<D>(tab_fix + gl * DD, pre, z);
             }
         }
-        const int ilast = want_state ? (int)(last - tau0) : -1;
+        const double* xr = xp;
+        if (!want_state) {
 #pragma unroll
-        for (int i = 0; i < SOS_L; ++i) {
-            double x = xp[i * Cw];
-            if (MODE == MODE_ENVF && xform) x = HALF_PI * fabs(x);
+            for (int i = 0; i < SOS_L; ++i) {
+                double x = *xr;
+                if (MODE == MODE_ENVF && xform) x = HALF_PI * fabs(x);
 #pragma unroll
-            for (int s = 0; s < S; ++s) {
-                double y = fma(K.coef[s][0], x, z[2 * s]);
-                z[2 * s] = fma(K.coef[s][1], x, z[2 * s + 1]) - K.coef[s][3] * y;
-                z[2 * s + 1] = K.coef[s][2] * x - K.coef[s][4] * y;
-                x = y;
+                for (int s = 0; s < S; ++s) {
+                    double y = fma(K.coef[s][0], x, z[2 * s]);
+                    z[2 * s] = fma(K.coef[s][1], x, z[2 * s + 1]) - K.coef[s][3] * y;
+                    z[2 * s + 1] = K.coef[s][2] * x - K.coef[s][4] * y;
+                    x = y;
+                }
+                *const_cast<double*>(xr) = x;
+                xr += Cw;
             }
-            xp[i * Cw] = x;
-            if (i == ilast) {
+        } else {
+            // the one sub-chunk per channel that contains the last sample: plain loop, state
+            // captured right after that sample
+            const int ilast = (int)(last - tau0);
+            for (int i = 0; i < SOS_L; ++i) {
+                double x = xp[i * Cw];
+                if (MODE == MODE_ENVF && xform) x = HALF_PI * fabs(x);
 #pragma unroll
-                for (int d = 0; d < D; ++d) R.zf[(size_t)(c0 + cw) * D + d] = z[d];
+                for (int s = 0; s < S; ++s) {
+                    double y = fma(K.coef[s][0], x, z[2 * s]);
+                    z[2 * s] = fma(K.coef[s][1], x, z[2 * s + 1]) - K.coef[s][3] * y;
+                    z[2 * s + 1] = K.coef[s][2] * x - K.coef[s][4] * y;
+                    x = y;
+                }
+                xp[i * Cw] = x;
+                if (i == ilast) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) R.zf[(size_t)(c0 + cw) * D + d] = z[d];
+                }
             }
         }
     }
@@ -372,6 +437,37 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
     __syncthreads();
 
     // ---------------------------------------------------------------- store
+    // fast path: contiguous tile, every row lands inside dst
+    bool fast_out = lc >= 0 && t0 + T <= R.n;
+    if (fast_out) {
+        const int64_t lo = MODE == MODE_REV ? R.n - t0 - T : t0, hi = lo + T;   // physical rows
+        fast_out = lo >= R.out_skip && hi <= R.out_skip + R.n_dst;
+    }
+    if (fast_out) {
+        const int64_t rowbase = (MODE == MODE_REV ? R.n - 1 - t0 : t0) - R.out_skip;
+        if (R.vec_out) {
+#pragma unroll
+            for (int k = 0; k < SOS_L / 2; ++k) {
+                const int f = 2 * (tid + SOS_NT * k);
+                const int r = f >> lc, c = c0 + (f & (CG - 1));
+                const int64_t orow = MODE == MODE_REV ? rowbase - r : rowbase + r;
+                double2 o = *reinterpret_cast<const double2*>(tile_s + f + (r >> 5) * pad);
+                if (R.clamp) { o.x = o.x < 0.0 ? 0.0 : o.x; o.y = o.y < 0.0 ? 0.0 : o.y; }
+                __stcs(reinterpret_cast<double2*>(R.dst + orow * C + c), o);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < SOS_L; ++k) {
+                const int f = tid + SOS_NT * k;
+                const int r = f >> lc, c = c0 + (f & (CG - 1));
+                const int64_t orow = MODE == MODE_REV ? rowbase - r : rowbase + r;
+                double o = tile_s[f + (r >> 5) * pad];
+                if (R.clamp) o = o < 0.0 ? 0.0 : o;
+                __stcs(R.dst + orow * C + c, o);
+            }
+        }
+        return;
+    }
     {
         const int gw = R.vec_out ? 2 : 1;
         const int gpr = Cw / gw;
@@ -623,6 +719,15 @@ int32_t run_scan(int mode, const double* sos, int S, const double* src, int64_t 
     const bool even = (C % 2 == 0) && (CG % 2 == 0);
     R.vec_in = even && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
     R.vec_out = even && dst && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    R.lc = 0;
+    while ((1 << R.lc) < CG) ++R.lc;
+    if (C % 2 && CG > 1) R.lc = -1;                   // odd C > 1: rows are not granule aligned
+    {
+        // measured on B200: no gain at any distance (the loads are not latency bound), so off
+        // unless asked for
+        const char* e = getenv("ADN_SOS_PREFETCH");
+        R.pf_tiles = e ? atoi(e) : 0;
+    }
     const int64_t ntiles = R.ntt * R.ngroups;
     if (ntiles > 0x7fffffff) return fail(ADN_ERR_UNSUPPORTED, "sos scan: %lld tiles", (long long)ntiles);
     R.off_fix = plan->off_fix; R.off_wpow = plan->off_wpow; R.off_tile = plan->off_tile;

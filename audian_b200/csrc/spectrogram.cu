@@ -342,14 +342,30 @@ spectrogram_warp_kernel(const __grid_constant__ SpecWArgs P) {
     double2* twA_s = reinterpret_cast<double2*>(sbuf + (size_t)P.CB * RP);   // [16][T]
     double2* wb = twA_s + M + (size_t)warp * Cf::WB;                 // per-warp exchange buffer
 
-    // ---- stage: rows [f0*hop, f0*hop + (FBa-1)*hop + N) x CBa channels, de-interleaved
+    // ---- stage: rows [f0*hop, f0*hop + (FBa-1)*hop + N) x CBa channels, de-interleaved;
+    // a thread keeps its channel, so addresses just advance by a constant
     {
         const int rows = (FBa - 1) * hop + N;
-        const double* base = P.src + (f0 * hop) * (int64_t)C + c0;
-        const int total = rows * CBa;
-        for (int q = tid; q < total; q += SW_NT) {
-            int row = q / CBa, ci = q - row * CBa;
-            cp_async8(xs + (size_t)ci * RP + row, base + (int64_t)row * C + ci);
+        const int CBs = P.CB;                          // 1 or 2
+        const int ci = tid % CBs, rstep = SW_NT / CBs;
+        if (ci < CBa) {
+            const double* gp = P.src + (f0 * hop) * (int64_t)C + c0 + ci + (int64_t)(tid / CBs) * C;
+            double* sp = xs + (size_t)ci * RP + tid / CBs;
+            const int64_t gstep = (int64_t)rstep * C;
+            int row = tid / CBs;
+            for (; row + 3 * rstep < rows; row += 4 * rstep) {
+                cp_async8(sp, gp);
+                cp_async8(sp + rstep, gp + gstep);
+                cp_async8(sp + 2 * rstep, gp + 2 * gstep);
+                cp_async8(sp + 3 * rstep, gp + 3 * gstep);
+                sp += 4 * rstep;
+                gp += 4 * gstep;
+            }
+            for (; row < rows; row += rstep) {
+                cp_async8(sp, gp);
+                sp += rstep;
+                gp += gstep;
+            }
         }
         for (int q = tid; q < M; q += SW_NT) cp_async16(twA_s + q, P.twA + q);
         cp_async_wait_all();
@@ -400,6 +416,7 @@ spectrogram_warp_kernel(const __grid_constant__ SpecWArgs P) {
         int kout[16];
         if (T == 32) {
             const int k1 = lane >> 1, tp = lane & 1;
+            const double sgn = tp ? -1.0 : 1.0;
 #pragma unroll
             for (int pp = 0; pp < 16; ++pp) a[pp] = wbf[k1 * 34 + 2 * pp + tp];
             dft16(a, b);
@@ -410,7 +427,7 @@ spectrogram_warp_kernel(const __grid_constant__ SpecWArgs P) {
                 double2 o;
                 o.x = __shfl_xor_sync(0xffffffffu, e.x, 1);
                 o.y = __shfl_xor_sync(0xffffffffu, e.y, 1);
-                zout[k] = tp ? csub(o, e) : cadd(e, o);
+                zout[k] = make_double2(fma(sgn, e.x, o.x), fma(sgn, e.y, o.y));   // e0 + e1 | e0 - e1
                 kout[k] = k1 + 16 * k + 256 * tp;
             }
         } else {
@@ -438,19 +455,26 @@ spectrogram_warp_kernel(const __grid_constant__ SpecWArgs P) {
         __syncwarp();
         // ---- Z in natural order
 #pragma unroll
-        for (int i = 0; i < 16; ++i) wbf[kout[i] + ((kout[i] >> 8) << 2)] = zout[i];
+        for (int i = 0; i < 16; ++i) wbf[kout[i] + (kout[i] > 256 ? 4 : 0)] = zout[i];
         __syncwarp();
         // ---- split step and power
         if (live) {
             double* out = P.dst + (((f0 + fi) * (int64_t)C + c0 + ci) * F);
             const double sc = 0.5 * P.scale;
-            for (int k = 1 + t; k <= M / 2; k += T) {
-                const int km = M - k;
-                double2 zk = wbf[k + ((k >> 8) << 2)], zm = wbf[km + ((km >> 8) << 2)];
-                double2 w = __ldg(P.twS + k);
-                double e_r = zk.x + zm.x, e_i = zk.y - zm.y;          // Zk + conj(Zm)
-                double o_r = zk.y + zm.y, o_i = zm.x - zk.x;          // -i (Zk - conj(Zm))
-                double t_r = o_r * w.x - o_i * w.y, t_i = o_r * w.y + o_i * w.x;
+            double2 zk[8], zm[8], tw[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {                  // k = 1 + t + T i  in [1, M/2]
+                const int k = 1 + t + T * i, km = M - k;
+                zk[i] = wbf[k];
+                zm[i] = wbf[km + (km > 256 ? 4 : 0)];
+                tw[i] = __ldg(P.twS + k);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = 1 + t + T * i, km = M - k;
+                double e_r = zk[i].x + zm[i].x, e_i = zk[i].y - zm[i].y;      // Zk + conj(Zm)
+                double o_r = zk[i].y + zm[i].y, o_i = zm[i].x - zk[i].x;      // -i (Zk - conj(Zm))
+                double t_r = o_r * tw[i].x - o_i * tw[i].y, t_i = o_r * tw[i].y + o_i * tw[i].x;
                 double pr = e_r + t_r, pi = e_i + t_i, qr = e_r - t_r, qi = e_i - t_i;
                 double pk = (pr * pr + pi * pi) * sc, pm = (qr * qr + qi * qi) * sc;
                 if (P.out_db) {
@@ -482,7 +506,7 @@ int32_t launch_warp_kernel(SpecWArgs& P, int64_t nf, cudaStream_t st) {
     const int C = P.C;
     // channels per block: 2 when they pair up (16-byte sectors shared by neighbour blocks in L2)
     P.CB = C >= 2 ? 2 : 1;
-    int rows_budget = 2048 + Cf::N / 2;
+    int rows_budget = 1024 + Cf::N / 2;
     int FB = (rows_budget - Cf::N) / P.hop + 1;
     if (FB < 1) FB = 1;
     if (FB > 64) FB = 64;
