@@ -322,7 +322,7 @@ template <int LOGN> struct SWCfg {
 };
 
 template <int LOGN>
-__global__ void __launch_bounds__(SW_NT)
+__global__ void __launch_bounds__(SW_NT, 3)
 spectrogram_warp_kernel(const __grid_constant__ SpecWArgs P) {
     using Cf = SWCfg<LOGN>;
     constexpr int N = Cf::N, M = Cf::M, T = Cf::T, FPW = Cf::FPW, FS = Cf::FS;
@@ -339,8 +339,7 @@ spectrogram_warp_kernel(const __grid_constant__ SpecWArgs P) {
     const int items = FBa * CBa;
 
     double* xs = sbuf;                                               // [CB][RP]
-    double2* twA_s = reinterpret_cast<double2*>(sbuf + (size_t)P.CB * RP);   // [16][T]
-    double2* wb = twA_s + M + (size_t)warp * Cf::WB;                 // per-warp exchange buffer
+    double2* wb = reinterpret_cast<double2*>(sbuf + (size_t)P.CB * RP) + (size_t)warp * Cf::WB;
 
     // ---- stage: rows [f0*hop, f0*hop + (FBa-1)*hop + N) x CBa channels, de-interleaved;
     // a thread keeps its channel, so addresses just advance by a constant
@@ -367,13 +366,15 @@ spectrogram_warp_kernel(const __grid_constant__ SpecWArgs P) {
                 gp += gstep;
             }
         }
-        for (int q = tid; q < M; q += SW_NT) cp_async16(twA_s + q, P.twA + q);
         cp_async_wait_all();
     }
     __syncthreads();
 
     const int sub = lane / T, t = lane % T;
     double2* wbf = wb + sub * FS;
+    // W_M^(t k1), k1 = 1, 2, 4, 8 from the table; the other powers are products of two of them
+    const double2 tw1 = __ldg(P.twA + 1 * T + t), tw2 = __ldg(P.twA + 2 * T + t);
+    const double2 tw4 = __ldg(P.twA + 4 * T + t), tw8 = __ldg(P.twA + 8 * T + t);
     const int niter = (items + SW_NWARP * FPW - 1) / (SW_NWARP * FPW);
     for (int iter = 0; iter < niter; ++iter) {
         const int it = (warp + SW_NWARP * iter) * FPW + sub;
@@ -404,11 +405,19 @@ spectrogram_warp_kernel(const __grid_constant__ SpecWArgs P) {
         // ---- pass 1 + twiddle, into the exchange buffer at (k1, t)
         double2 b[16];
         dft16(a, b);
+        {
+            double2 w[16];
+            w[1] = tw1; w[2] = tw2; w[4] = tw4; w[8] = tw8;
+            w[3] = cmul(tw2, tw1); w[5] = cmul(tw4, tw1); w[6] = cmul(tw4, tw2);
+            w[9] = cmul(tw8, tw1); w[10] = cmul(tw8, tw2); w[12] = cmul(tw8, tw4);
+            w[7] = cmul(w[6], tw1); w[11] = cmul(w[10], tw1); w[13] = cmul(w[12], tw1);
+            w[14] = cmul(w[12], tw2); w[15] = cmul(w[14], tw1);
 #pragma unroll
-        for (int k1 = 0; k1 < 16; ++k1) {
-            double2 v = k1 == 0 ? b[0] : cmul(b[k1], twA_s[k1 * T + t]);
-            const int f = k1 * T + t;
-            wbf[T == 32 ? k1 * 34 + t : f + (f >> 4)] = v;
+            for (int k1 = 0; k1 < 16; ++k1) {
+                double2 v = k1 == 0 ? b[0] : cmul(b[k1], w[k1]);
+                const int f = k1 * T + t;
+                wbf[T == 32 ? k1 * 34 + t : f + (f >> 4)] = v;
+            }
         }
         __syncwarp();
         // ---- pass 2: T-point DFTs over t
@@ -461,28 +470,31 @@ spectrogram_warp_kernel(const __grid_constant__ SpecWArgs P) {
         if (live) {
             double* out = P.dst + (((f0 + fi) * (int64_t)C + c0 + ci) * F);
             const double sc = 0.5 * P.scale;
-            double2 zk[8], zm[8], tw[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {                  // k = 1 + t + T i  in [1, M/2]
-                const int k = 1 + t + T * i, km = M - k;
-                zk[i] = wbf[k];
-                zm[i] = wbf[km + (km > 256 ? 4 : 0)];
-                tw[i] = __ldg(P.twS + k);
-            }
+            for (int h = 0; h < 2; ++h) {
+                double2 zk[4], zm[4], tw[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int k = 1 + t + T * i, km = M - k;
-                double e_r = zk[i].x + zm[i].x, e_i = zk[i].y - zm[i].y;      // Zk + conj(Zm)
-                double o_r = zk[i].y + zm[i].y, o_i = zm[i].x - zk[i].x;      // -i (Zk - conj(Zm))
-                double t_r = o_r * tw[i].x - o_i * tw[i].y, t_i = o_r * tw[i].y + o_i * tw[i].x;
-                double pr = e_r + t_r, pi = e_i + t_i, qr = e_r - t_r, qi = e_i - t_i;
-                double pk = (pr * pr + pi * pi) * sc, pm = (qr * qr + qi * qi) * sc;
-                if (P.out_db) {
-                    pk = pk > 1e-20 ? 10.0 * log10(pk) : (pk <= 1e-20 ? -INFINITY : pk);
-                    pm = pm > 1e-20 ? 10.0 * log10(pm) : (pm <= 1e-20 ? -INFINITY : pm);
+                for (int j = 0; j < 4; ++j) {              // k = 1 + t + T i  in [1, M/2]
+                    const int k = 1 + t + T * (4 * h + j), km = M - k;
+                    zk[j] = wbf[k];
+                    zm[j] = wbf[km + (km > 256 ? 4 : 0)];
+                    tw[j] = __ldg(P.twS + k);
                 }
-                out[k] = pk;
-                if (km != k) out[km] = pm;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = 1 + t + T * (4 * h + j), km = M - k;
+                    double e_r = zk[j].x + zm[j].x, e_i = zk[j].y - zm[j].y;      // Zk + conj(Zm)
+                    double o_r = zk[j].y + zm[j].y, o_i = zm[j].x - zk[j].x;      // -i (Zk - conj(Zm))
+                    double t_r = o_r * tw[j].x - o_i * tw[j].y, t_i = o_r * tw[j].y + o_i * tw[j].x;
+                    double pr = e_r + t_r, pi = e_i + t_i, qr = e_r - t_r, qi = e_i - t_i;
+                    double pk = (pr * pr + pi * pi) * sc, pm = (qr * qr + qi * qi) * sc;
+                    if (P.out_db) {
+                        pk = pk > 1e-20 ? 10.0 * log10(pk) : (pk <= 1e-20 ? -INFINITY : pk);
+                        pm = pm > 1e-20 ? 10.0 * log10(pm) : (pm <= 1e-20 ? -INFINITY : pm);
+                    }
+                    out[k] = pk;
+                    if (km != k) out[km] = pm;
+                }
             }
             if (t == 0) {
                 double2 z0 = wbf[0];
@@ -514,7 +526,7 @@ int32_t launch_warp_kernel(SpecWArgs& P, int64_t nf, cudaStream_t st) {
     P.FB = FB;
     int rows = (FB - 1) * P.hop + Cf::N;
     P.RP = ((rows + 15) / 16) * 16 + 8;               // == 8 mod 16: channel arrays on disjoint banks
-    const size_t smem = (size_t)P.CB * P.RP * 8 + (size_t)Cf::M * 16 + (size_t)SW_NWARP * Cf::WB * 16;
+    const size_t smem = (size_t)P.CB * P.RP * 8 + (size_t)SW_NWARP * Cf::WB * 16;
     auto kern = spectrogram_warp_kernel<LOGN>;
     static bool attr_done = false;
     if (!attr_done) {
