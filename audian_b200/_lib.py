@@ -57,6 +57,7 @@ SIGNATURES = {
     'adn_decibel_f64_dev': (_i32, [_dp, _i64, _f64, _f64, _dp, _dp]),
     'adn_synth_f64_dev': (_i32, [_dp, _i64, _i64, _i32, _f64, C.c_uint64, _dp]),
     'adn_sos_state_space': (_i32, [_dp, _i32, _dp, _dp, _i64, _dp]),
+    'adn_sos_decay_length': (_i64, [_dp, _i32, _f64]),
     'adn_sosfiltfilt_edge': (_i32, [_dp, _i32]),
 }
 
@@ -218,6 +219,13 @@ def sos_state_space(sos, power=1):
     check(lib().adn_sos_state_space(sos.ctypes.data, S, A.ctypes.data, B.ctypes.data,
                                     int(power), P.ctypes.data))
     return A, B, P
+
+
+def sos_decay_length(sos, tol=1e-30):
+    """Samples after which the cascade has forgotten its state to within tol
+    (a power of two), or -1."""
+    sos, S = sos_array(sos)
+    return int(lib().adn_sos_decay_length(sos.ctypes.data, S, float(tol)))
 
 
 def sosfiltfilt_edge(sos):

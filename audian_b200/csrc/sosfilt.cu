@@ -839,6 +839,22 @@ int32_t adn_sos_state_space(const double* sos, int32_t S, double* A, double* B, 
     return ADN_OK;
 }
 
+int64_t adn_sos_decay_length(const double* sos, int32_t S, double tol) {
+    if (!sos || S < 1 || S > ADN_MAX_SECTIONS || !(tol > 0)) return -1;
+    const int D = 2 * S;
+    Mat P(D);
+    std::vector<ld> Bv;
+    state_space(sos, S, P, Bv);
+    for (int j = 0; j <= 40; ++j) {
+        ld mx = 0.0L;
+        for (auto x : P.a) mx = fmaxl(mx, fabsl(x));
+        if (!(mx == mx)) return -1;
+        if (mx < (ld)tol) return (int64_t)1 << j;
+        P = mul(P, P);
+    }
+    return -1;
+}
+
 int32_t adn_sosfiltfilt_edge(const double* sos, int32_t S) {
     if (!sos || S < 1) return 0;
     int nb = 0, na = 0;

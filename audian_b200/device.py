@@ -54,8 +54,8 @@ class CudaOps(object):
                 state_only=False):
         return sosfilt(sos, src, nbefore, zi, want_zf, out, state_only)
 
-    def spectrogram(self, src, rate, nfft, hop, n_dst, out_db=False):
-        return spectrogram(src, rate, nfft, hop, n_dst, out_db)
+    def spectrogram(self, src, rate, nfft, hop, n_dst, out_db=False, out=None):
+        return spectrogram(src, rate, nfft, hop, n_dst, out_db, out)
 
     def envelope(self, sos, src, nbefore=0, clamp_negative=True):
         return envelope(sos, src, nbefore, clamp_negative)

@@ -50,9 +50,14 @@ def shard_bounds(frames, world, align=1):
 class ShardedRecording(object):
     """One rank's time range [lo, hi) of a (frames, C) recording."""
 
+    _matrix_cache = {}
+
     def __init__(self, local, frames, rate, ops=None, rank=None, world=None,
-                 bounds=None):
-        dist = _dist()
+                 bounds=None, dist=None):
+        # `dist`: torch.distributed (default) or an object with the same all_gather /
+        # P2POp / isend / irecv / batch_isend_irecv surface (single-device test clusters)
+        self.dist = _dist() if dist is None else dist
+        dist = self.dist
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
         self.frames = int(frames)
@@ -78,7 +83,7 @@ class ShardedRecording(object):
         """Full-trace min/max rows (2*ceil(frames/step), C) on `dst_rank`
         (None elsewhere).  Shards must come from minmax_bounds()."""
         import torch
-        dist = _dist()
+        dist = self.dist
         if self.lo % step != 0:
             raise ValueError('shard boundary is not a multiple of step')
         rows = self.ops.minmax(self.local, step)
@@ -107,7 +112,7 @@ class ShardedRecording(object):
         recording, (n_local, C, nfft//2+1), plus the global index of its first
         frame and the global frame count."""
         import torch
-        dist = _dist()
+        dist = self.dist
         if self.lo % hop != 0:
             raise ValueError('shard boundary is not a multiple of hop')
         halo = nfft - hop
@@ -115,6 +120,7 @@ class ShardedRecording(object):
         k0 = self.lo//hop
         k1 = min(nf_total, self.hi//hop if self.rank + 1 < self.world else nf_total)
         src = self.local
+        recv = None
         if self.world > 1 and halo > 0:
             if any(hi - lo < halo for lo, hi in self.bounds):
                 raise ValueError('shards shorter than the STFT halo')
@@ -128,11 +134,26 @@ class ShardedRecording(object):
             if ops:
                 for req in dist.batch_isend_irecv(ops):
                     req.wait()
-            if self.rank + 1 < self.world:
-                src = torch.cat([src, recv], dim=0)
+            if self.rank + 1 >= self.world:
+                recv = None
         n_local = max(0, k1 - k0)
-        out, ncomp = self.ops.spectrogram(src, self.rate, nfft, hop, n_local, out_db)
-        assert ncomp == n_local, (ncomp, n_local)
+        if recv is None:
+            out, ncomp = self.ops.spectrogram(src, self.rate, nfft, hop, n_local, out_db)
+            assert ncomp == n_local, (ncomp, n_local)
+            return out, k0, nf_total
+        # frames that lie inside the shard come straight from it; only the last few, which
+        # reach into the neighbour, are computed from a short tail + halo buffer
+        n_main = min(n_local, max(0, (src.shape[0] - nfft)//hop + 1))
+        out = self.ops.empty((n_local, self.channels, nfft//2 + 1))
+        if n_main > 0:
+            _, ncomp = self.ops.spectrogram(src, self.rate, nfft, hop, n_main, out_db,
+                                            out=out[:n_main])
+            assert ncomp == n_main, (ncomp, n_main)
+        if n_local > n_main:
+            tail = torch.cat([src[n_main*hop:], recv], dim=0)
+            _, ncomp = self.ops.spectrogram(tail, self.rate, nfft, hop, n_local - n_main,
+                                            out_db, out=out[n_main:])
+            assert ncomp == n_local - n_main, (ncomp, n_local - n_main)
         return out, k0, nf_total
 
     # ------------------------------------------------------------ filter
@@ -144,7 +165,7 @@ class ShardedRecording(object):
         """This rank's part of sosfilt(sos, recording, axis=0) (zero initial
         state, or `zi` (C, S, 2) applied at frame 0)."""
         import torch
-        dist = _dist()
+        dist = self.dist
         sos_a, S = _lib.sos_array(sos)
         if S == 0:
             return self.local.clone()
@@ -153,19 +174,28 @@ class ShardedRecording(object):
         x = self.local
         if self.world == 1:
             return self.ops.sosfilt(sos_a, x, 0, zi)
-        # 1. end state of this shard from zero state (aggregate)
-        v = self.ops.sosfilt(sos_a, x, 0, None, state_only=True).reshape(C, D)
+        # 1. end state of this shard from zero state (aggregate); a cascade that forgets its
+        # state within `keep` samples (|A^keep| < 1e-30) only needs the tail of the shard
+        keep = _lib.sos_decay_length(sos_a, 1e-30)
+        xs = x[-keep:] if 0 < keep < x.shape[0] else x
+        v = self.ops.sosfilt(sos_a, xs, 0, None, state_only=True).reshape(C, D)
         # 2. exchange
         gathered = [torch.empty_like(v) for _ in range(self.world)]
         dist.all_gather(gathered, v.contiguous())
         # 3. fold the predecessors: s_{r+1} = A^len_r s_r + v_r
-        mats = self.shard_matrices(sos_a)
+        key = (sos_a.tobytes(), tuple(self.bounds), str(v.device))
+        mats = ShardedRecording._matrix_cache.get(key)
+        if mats is None:
+            if len(ShardedRecording._matrix_cache) > 32:
+                ShardedRecording._matrix_cache.clear()
+            mats = [torch.as_tensor(m.T.copy(), dtype=v.dtype, device=v.device)
+                    for m in self.shard_matrices(sos_a)]
+            ShardedRecording._matrix_cache[key] = mats
         s = torch.zeros((C, D), dtype=v.dtype, device=v.device)
         if zi is not None:
             s = zi.reshape(C, D).clone()
         for r in range(self.rank):
-            M = torch.as_tensor(mats[r], dtype=v.dtype, device=v.device)
-            s = s @ M.T + gathered[r]
+            s = s @ mats[r] + gathered[r]
         # 4. filter the shard from its true incoming state
         return self.ops.sosfilt(sos_a, x, 0, s.reshape(C, S, 2).contiguous())
 
@@ -173,6 +203,6 @@ class ShardedRecording(object):
         """filtered -> spectrogram of the filtered trace, all sharded."""
         y = self.sosfilt(sos)
         f = ShardedRecording(y, self.frames, self.rate, self.ops, self.rank,
-                             self.world, self.bounds)
+                             self.world, self.bounds, self.dist)
         spec, k0, nf = f.spectrogram(nfft, hop)
         return y, spec, k0, nf

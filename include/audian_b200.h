@@ -138,6 +138,9 @@ int32_t adn_synth_f64_dev(double* dst, int64_t t0, int64_t n, int32_t C,
  * transition, D = 2*S), B (D), and A^power (D x D), all row-major doubles. */
 int32_t adn_sos_state_space(const double* sos, int32_t S, double* A, double* B,
                             int64_t power, double* A_pow);
+/* Smallest power of two n with max|A^n| < tol (the cascade forgets its state after n
+ * samples to within tol), or -1 if that needs more than 2^40 samples. */
+int64_t adn_sos_decay_length(const double* sos, int32_t S, double tol);
 /* pad length of scipy's sosfiltfilt for this cascade (3*ntaps) */
 int32_t adn_sosfiltfilt_edge(const double* sos, int32_t S);
 

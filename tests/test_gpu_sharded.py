@@ -1,0 +1,190 @@
+"""The time-sharded drivers on the real kernels.
+
+* fake cluster: N ranks as N host threads sharing one GPU, collectives done in
+  process (host barriers only -- no kernel waits on another rank), so the seam
+  logic runs on the sm_100a kernels even on a single-GPU box;
+* NCCL: world size 2 over two GPUs, when the box has them.
+
+Shard-count invariance: min/max bit-exact, filter and spectrogram equal to the
+single-pass oracle within the stated tolerances."""
+
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from audian_b200 import sharded
+from audian_b200.synth import synth
+from oracle import oracle as orc
+
+
+class FakeDist(object):
+    """In-process stand-in for torch.distributed for `world` threads."""
+
+    class P2POp(object):
+        def __init__(self, op, tensor, peer):
+            self.op, self.tensor, self.peer = op, tensor, peer
+
+    isend, irecv = 'isend', 'irecv'
+
+    def __init__(self, world):
+        self.world = world
+        self.barrier = threading.Barrier(world)
+        self.slots = {}
+        self.mail = {}
+        self.local = threading.local()
+
+    def bind(self, rank):
+        self.local.rank = rank
+
+    def get_rank(self):
+        return self.local.rank
+
+    def get_world_size(self):
+        return self.world
+
+    def all_gather(self, out_list, tensor):
+        import torch
+        torch.cuda.synchronize()
+        self.slots[self.local.rank] = tensor
+        self.barrier.wait()
+        for r in range(self.world):
+            out_list[r].copy_(self.slots[r])
+        torch.cuda.synchronize()
+        self.barrier.wait()
+
+    def batch_isend_irecv(self, ops):
+        import torch
+        torch.cuda.synchronize()
+        for op in ops:
+            if op.op == 'isend':
+                self.mail[(self.local.rank, op.peer)] = op.tensor
+        self.barrier.wait()
+        for op in ops:
+            if op.op == 'irecv':
+                op.tensor.copy_(self.mail[(op.peer, self.local.rank)])
+        torch.cuda.synchronize()
+        self.barrier.wait()
+
+        class Done(object):
+            def wait(self):
+                pass
+        return [Done() for _ in ops]
+
+
+@pytest.mark.parametrize('world', [2, 4, 8])
+def test_fake_cluster_matches_single_pass(world):
+    import torch
+    from audian_b200.device import CudaOps
+    frames, C, rate = 400003, 4, 96000.
+    x = synth(0, frames, C, rate, seed=31)
+    sos = orc.filter_design(rate, 1000., 15000., 4)
+    nfft, hop, step = 1024, 512, 1382
+    fd = FakeDist(world)
+    res = [None]*world
+    err = []
+
+    def run(rank):
+        try:
+            fd.bind(rank)
+            torch.cuda.set_device(0)
+            ops = CudaOps()
+            b = sharded.shard_bounds(frames, world, step)
+            lo, hi = b[rank]
+            rec = sharded.ShardedRecording(torch.from_numpy(x[lo:hi]).cuda(), frames, rate, ops,
+                                           rank, world, b, fd)
+            rows = rec.minmax(step)
+            b = sharded.shard_bounds(frames, world, hop)
+            lo, hi = b[rank]
+            rec = sharded.ShardedRecording(torch.from_numpy(x[lo:hi]).cuda(), frames, rate, ops,
+                                           rank, world, b, fd)
+            y, spec, k0, nf = rec.filter_chain(sos, nfft, hop)
+            torch.cuda.synchronize()
+            res[rank] = (rows.cpu().numpy() if rows is not None else None, lo, y.cpu().numpy(),
+                         k0, spec.cpu().numpy(), nf)
+        except Exception as e:          # pragma: no cover
+            err.append(e)
+            fd.barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not err, err
+    ref = orc.minmax_rows(x, step)
+    assert np.array_equal(res[0][0].view(np.uint64), ref.view(np.uint64))
+    yref = np.empty_like(x)
+    orc.filter_process(sos, x, yref, 0)
+    y = np.concatenate([r[2] for r in res])
+    assert np.max(np.abs(y - yref)) <= 1e-6
+    nf = (frames - (nfft - hop))//hop
+    sref = np.empty((nf, C, nfft//2 + 1))
+    orc.spectrogram_process(yref, sref, rate, nfft, hop)
+    spec = np.concatenate([r[4] for r in res])
+    assert spec.shape == sref.shape and res[0][5] == nf
+    assert np.allclose(spec, sref, rtol=1e-5, atol=1e-20*sref.max())
+
+
+def _nccl_worker(rank, world, port, frames, C, rate, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    from audian_b200 import _lib
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    _lib.init(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world,
+                            device_id=torch.device('cuda', rank))
+    try:
+        nfft, hop = 512, 256
+        b = sharded.shard_bounds(frames, world, hop)
+        lo, hi = b[rank]
+        x = torch.from_numpy(synth(lo, hi - lo, C, rate, seed=17)).cuda()
+        rec = sharded.ShardedRecording(x, frames, rate, bounds=b)
+        sos = orc.filter_design(rate, 500., 9000., 2)
+        y, spec, k0, nf = rec.filter_chain(sos, nfft, hop)
+        torch.cuda.synchronize()
+        parts = [None]*world
+        dist.all_gather_object(parts, (lo, y.cpu().numpy(), k0, spec.cpu().numpy(), nf))
+        if rank == 0:
+            q.put(parts)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nccl_two_gpus():
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    frames, C, rate = 300007, 8, 48000.
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, frames, C, rate, q))
+             for r in range(2)]
+    for p in procs:
+        p.start()
+    parts = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    x = synth(0, frames, C, rate, seed=17)
+    sos = orc.filter_design(rate, 500., 9000., 2)
+    yref = np.empty_like(x)
+    orc.filter_process(sos, x, yref, 0)
+    y = np.concatenate([p[1] for p in sorted(parts, key=lambda p: p[0])])
+    assert np.max(np.abs(y - yref)) <= 1e-6
+    nf = (frames - 256)//256
+    sref = np.empty((nf, C, 257))
+    orc.spectrogram_process(yref, sref, rate, 512, 256)
+    spec = np.concatenate([p[3] for p in sorted(parts, key=lambda p: p[2])])
+    assert np.allclose(spec, sref, rtol=1e-5, atol=1e-20*sref.max())

@@ -42,9 +42,15 @@ class OracleOps(object):
         y = torch.from_numpy(y[nbefore:].copy())
         return (y, torch.from_numpy(zf)) if want_zf else y
 
-    def spectrogram(self, src, rate, nfft, hop, n_dst, out_db=False):
+    def empty(self, shape):
+        return torch.empty(shape, dtype=torch.float64)
+
+    def spectrogram(self, src, rate, nfft, hop, n_dst, out_db=False, out=None):
         dst = np.empty((n_dst, src.shape[1], nfft//2 + 1))
         n = orc.spectrogram_process(src.numpy(), dst, rate, nfft, hop)
+        if out is not None:
+            out.copy_(torch.from_numpy(dst))
+            return out, n
         return torch.from_numpy(dst), n
 
 
