@@ -13,6 +13,7 @@
 // No cuFFT, no tensor cores.
 #include "common.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 
 namespace adn {
@@ -303,16 +304,19 @@ __device__ __forceinline__ void dft8(const double2* a, double2* X) {
 }
 
 // W32^k = exp(-2 pi i k / 32), k < 16
-__device__ __constant__ double c_w32[16][2] = {
-    {1.0, -0.0},
-    {0.98078528040323043, -0.19509032201612825}, {0.92387953251128674, -0.38268343236508977},
-    {0.83146961230254524, -0.55557023301960218}, {0.70710678118654752, -0.70710678118654752},
-    {0.55557023301960218, -0.83146961230254524}, {0.38268343236508977, -0.92387953251128674},
-    {0.19509032201612825, -0.98078528040323043}, {0.0, -1.0},
-    {-0.19509032201612825, -0.98078528040323043}, {-0.38268343236508977, -0.92387953251128674},
-    {-0.55557023301960218, -0.83146961230254524}, {-0.70710678118654752, -0.70710678118654752},
-    {-0.83146961230254524, -0.55557023301960218}, {-0.92387953251128674, -0.38268343236508977},
-    {-0.98078528040323043, -0.19509032201612825}};
+__host__ __device__ constexpr double w32c(int k, int im) {
+    constexpr double tab[16][2] = {
+        {1.0, -0.0},
+        {0.98078528040323043, -0.19509032201612825}, {0.92387953251128674, -0.38268343236508977},
+        {0.83146961230254524, -0.55557023301960218}, {0.70710678118654752, -0.70710678118654752},
+        {0.55557023301960218, -0.83146961230254524}, {0.38268343236508977, -0.92387953251128674},
+        {0.19509032201612825, -0.98078528040323043}, {0.0, -1.0},
+        {-0.19509032201612825, -0.98078528040323043}, {-0.38268343236508977, -0.92387953251128674},
+        {-0.55557023301960218, -0.83146961230254524}, {-0.70710678118654752, -0.70710678118654752},
+        {-0.83146961230254524, -0.55557023301960218}, {-0.92387953251128674, -0.38268343236508977},
+        {-0.98078528040323043, -0.19509032201612825}};
+    return tab[k][im];
+}
 
 template <int LOGN> struct SWCfg {
     static constexpr int N = 1 << LOGN, M = N / 2, T = M / 16, FPW = 32 / T;
@@ -432,7 +436,7 @@ spectrogram_warp_kernel(const __grid_constant__ SpecWArgs P) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 double2 e = b[k];
-                if (tp) e = cmul(e, make_double2(c_w32[k][0], c_w32[k][1]));
+                if (tp) e = cmul(e, make_double2(w32c(k, 0), w32c(k, 1)));
                 double2 o;
                 o.x = __shfl_xor_sync(0xffffffffu, e.x, 1);
                 o.y = __shfl_xor_sync(0xffffffffu, e.y, 1);
@@ -512,6 +516,433 @@ spectrogram_warp_kernel(const __grid_constant__ SpecWArgs P) {
     }
 }
 
+
+// ======================================================================================
+// Streaming variant of the register-resident path: a block owns a run of consecutive
+// frames of one channel group and walks along time.  The rows of the group are kept
+// de-interleaved in a shared-memory ring (one array per channel); every step the block
+//   - issues the 16-byte global loads of the rows the NEXT step adds (full row segments,
+//     coalesced; held in registers while the FFTs run),
+//   - transforms the FSTEP x W frames of this step,
+//   - scatters the loaded rows into the ring (two 8-byte stores per vector, conflict
+//     free because the channel arrays start RS = 4 mod 8 doubles apart), one barrier.
+// Every input row is read from global memory exactly once per run (plus nfft - hop rows
+// at the start of a run), nothing is staged through LDGSTS, and the loads overlap the
+// arithmetic instead of preceding it.  The ring is a power of two rows long (exactly one
+// frame when a step is one frame), so the chunk of the next step overwrites the oldest rows
+// between two barriers and positions wrap with a mask; three blocks of four warps fit an SM.
+// Differences in the arithmetic: the frame mean is removed after the transform (the
+// spectrum of the periodic Hann window is N/2 at bin 0 and -N/4 at bins +-1, so only the
+// output bins 0 and 1 change), which takes the reduction over the frame off the critical
+// path; for T = 32 the lane pair of a 32-point DFT reads all 32 points and does the first
+// radix-2 step itself (decimation in frequency) instead of exchanging results by shuffle.
+constexpr int SR_MAXNT = 128;
+constexpr int SR_PF = 8;            // 16-byte vectors in flight per thread and step
+
+struct SpecRArgs {
+    const double* src;
+    double* dst;
+    const double* win;          // nfft
+    const double2* twA;         // [16][T]: W_M^(t k1)
+    const double2* twS;         // W_N^k, k <= M/2
+    int64_t nframes;
+    int64_t nrows;              // source rows the frames read: (nframes-1)*hop + nfft
+    int32_t C, hop, CB, LW, ngrp;   // CB = 1 << LW channels per group
+    int32_t FSTEP, FRUN;        // frames per step / per block (FRUN % FSTEP == 0)
+    int32_t RC, RS;             // ring length in rows; per-channel stride in doubles
+    int32_t detrend;
+    double scale;               // 1 / (rate * sum(w^2))
+};
+
+template <int LOGN> struct SRCfg {
+    static constexpr int T = SWCfg<LOGN>::T;
+    // per-frame stride of the exchange buffer (complex): T = 32 rows of 33 (16 k1 rows read
+    // by 16 lane pairs: 16-byte offsets, two wavefronts per 128-bit load)
+    static constexpr int FS = T == 32 ? 16 * 33 : SWCfg<LOGN>::FS;
+    static constexpr int WB = FS * SWCfg<LOGN>::FPW;
+};
+
+__device__ __forceinline__ double to_db(double p) {
+    return p > 1e-20 ? 10.0 * log10(p) : (p <= 1e-20 ? -INFINITY : p);
+}
+
+template <int LOGN, bool DB>
+__global__ void __launch_bounds__(SR_MAXNT, 3)
+spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
+    using Cf = SWCfg<LOGN>;
+    constexpr int N = Cf::N, M = Cf::M, T = Cf::T, FPW = Cf::FPW;
+    constexpr int FS = SRCfg<LOGN>::FS;
+    constexpr int F = M + 1;
+    extern __shared__ __align__(16) double sbuf[];
+    int tid;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));    // read once: never rematerialised
+    const int lane = tid & 31, warp = tid >> 5;
+    const int NT = blockDim.x, NW = NT >> 5;
+    const int C = P.C, hop = P.hop, RM = P.RC - 1, RS = P.RS;
+    const int W = P.CB, LW = P.LW;                       // channels of a group = row width
+    const int grp = blockIdx.x % P.ngrp;
+    const int64_t f0 = (int64_t)(blockIdx.x / P.ngrp) * P.FRUN;
+    // the last group of a channel count that is no multiple of W overlaps its neighbour
+    const int c0 = min(grp * W, C - W);
+    const int FRa = (int)min((int64_t)P.FRUN, P.nframes - f0);
+    const int FSTEP = P.FSTEP, CH = FSTEP * hop;
+    const int nsteps = (FRa + FSTEP - 1) / FSTEP;
+    const int span0 = N + (FSTEP - 1) * hop;             // rows one step reads
+
+    double* xs = sbuf;                                               // [W][RS]
+    double* wins = sbuf + (size_t)W * RS;                            // [N]
+    constexpr int NTWS = T == 32 ? 0 : M / 2 + 2;                    // T == 32 builds them in registers
+    double2* tws = reinterpret_cast<double2*>(wins + N);             // [NTWS]
+    double2* wb = tws + NTWS + (size_t)warp * SRCfg<LOGN>::WB;
+
+    // the j-th 16-byte vector of this thread in a chunk: row r0 + j DR, channels col, col + 1
+    // (W == 1: rows r0 + j DR and the next one).  Rows past the end of the source are
+    // clamped to its last row(s): what they put into the ring is never read by a live frame.
+    const int r0 = (2 * tid) >> LW, col = (2 * tid) & (W - 1);
+    const int DR = (2 * NT) >> LW;
+    const double* gp0 = P.src + ((f0 * hop) * (int64_t)C + c0 + col);
+    const int rmax = (int)min((int64_t)0x3fffffff, P.nrows - f0 * hop - (W == 1 ? 2 : 1));
+    double* sp0 = xs + col * RS;
+
+    auto gaddr = [&](int row) {
+        return reinterpret_cast<const double2*>(gp0 + (int64_t)min(row, rmax) * C);
+    };
+    const int64_t gstep = (int64_t)DR * C, gchunk = (int64_t)CH * C;
+    const double* gnext = gp0 + (int64_t)(span0 + r0) * C;   // this thread's first vector of the next chunk
+    const int64_t rows_run = P.nrows - f0 * hop;             // source rows from the start of the run
+    auto put = [&](double2 v, int pos) {
+        pos &= RM;
+        if (W == 1) {
+            *reinterpret_cast<double2*>(sp0 + pos) = v;
+        } else {
+            sp0[pos] = v.x;
+            sp0[pos + RS] = v.y;
+        }
+    };
+    // rows [r_start + r, ...), r = r0 + j DR < nr, j >= jbegin -> ring at pos0 + r
+    auto stage_direct = [&](int r_start, int pos0, int nr, int jbegin) {
+        for (int r = r0 + jbegin * DR; r < nr; r += 4 * DR) {
+            double2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = __ldg(gaddr(r_start + r + u * DR));
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (r + u * DR < nr) put(v[u], pos0 + r + u * DR);
+        }
+    };
+
+    stage_direct(0, 0, span0, 0);
+    for (int i = tid; i < N; i += NT) wins[i] = __ldg(P.win + i);
+    if (NTWS > 0)
+        for (int i = tid; i <= M / 2; i += NT) tws[i] = __ldg(P.twS + i);
+    __syncthreads();
+
+    const int sub = lane / T, t = lane % T;
+    double2* wbf = wb + sub * FS;
+    // W_M^(t k1), k1 = 1, 2, 4, 8 from the table; the other powers are products of two of them
+    const double2 tw1 = __ldg(P.twA + 1 * T + t), tw2 = __ldg(P.twA + 2 * T + t);
+    const double2 tw4 = __ldg(P.twA + 4 * T + t), tw8 = __ldg(P.twA + 8 * T + t);
+    const double2 twl = __ldg(P.twS + lane);             // T == 32: W_N^lane of the split step
+    const int nitems = FSTEP * W;
+    const int niter = (nitems + NW * FPW - 1) / (NW * FPW);
+    const double corr = P.detrend ? 0.5 : 0.0;           // (sum x / N) * N/2
+
+    int ws = 0;                 // ring position of the first row of this step
+    int npos = span0;           // ring position / row of the chunk the next step adds
+    int nrow = span0;
+    for (int s = 0; s < nsteps; ++s) {
+        // pull the rows of the next step into L2 while this step computes
+        const bool more = s + 1 < nsteps;
+        const bool inside = nrow + CH <= rows_run;       // the whole next chunk exists
+        if (more && tid == 0) {
+            const int64_t nr = inside ? CH : rows_run - nrow;
+            if (nr > 0) {
+                const double* a0 = P.src + (f0 * hop + nrow) * (int64_t)C;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0),
+                             "r"((uint32_t)(nr * C * 8)) : "memory");
+            }
+        }
+
+        double2 pf[SR_PF];
+#pragma unroll
+        for (int j = 0; j < SR_PF; ++j) pf[j] = make_double2(0.0, 0.0);
+        bool loaded = false;
+        // the loads of the next chunk are issued late in the last item of the step, when the
+        // registers of the first pass are free again (they come from L2 by then)
+        auto issue_loads = [&]() {
+            if (inside) {
+                const double* gp = gnext;
+#pragma unroll
+                for (int j = 0; j < SR_PF; ++j) {
+                    if (r0 + j * DR < CH) pf[j] = __ldg(reinterpret_cast<const double2*>(gp));
+                    gp += gstep;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < SR_PF; ++j)
+                    if (r0 + j * DR < CH) pf[j] = __ldg(gaddr(nrow + r0 + j * DR));
+            }
+        };
+        for (int iter = 0; iter < niter; ++iter) {
+            const int it = (warp + NW * iter) * FPW + sub;
+            int fi = it >> LW, ci = it & (W - 1);
+            const bool live = it < nitems && s * FSTEP + fi < FRa;
+            if (!__any_sync(0xffffffffu, live)) continue;
+            const bool last_iter = more && iter == niter - 1;
+            if (!live) { fi = 0; ci = 0; }
+            const int start = ws + fi * hop + 2 * t;
+            const double* xr = xs + ci * RS;
+
+            // ---- load, window; the frame sum for the mean goes on in the background
+            double2 a[16];
+#pragma unroll
+            for (int p = 0; p < 16; ++p)
+                a[p] = *reinterpret_cast<const double2*>(xr + ((start + 2 * T * p) & RM));
+            double sm = 0.0;
+            {
+                double s0 = a[0].x + a[0].y, s1 = a[1].x + a[1].y, s2 = a[2].x + a[2].y, s3 = a[3].x + a[3].y;
+#pragma unroll
+                for (int p = 4; p < 16; p += 4) {
+                    s0 += a[p].x + a[p].y; s1 += a[p + 1].x + a[p + 1].y;
+                    s2 += a[p + 2].x + a[p + 2].y; s3 += a[p + 3].x + a[p + 3].y;
+                }
+                sm = (s0 + s1) + (s2 + s3);
+            }
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+                double2 w = *reinterpret_cast<const double2*>(wins + 2 * (T * p + t));
+                a[p].x *= w.x;
+                a[p].y *= w.y;
+            }
+            // ---- pass 1 + twiddle, into the exchange buffer at (k1, t)
+            double2 b[16];
+            dft16(a, b);
+            {
+                double2 w[16];
+                w[1] = tw1; w[2] = tw2; w[4] = tw4; w[8] = tw8;
+                w[3] = cmul(tw2, tw1); w[5] = cmul(tw4, tw1); w[6] = cmul(tw4, tw2);
+                w[9] = cmul(tw8, tw1); w[10] = cmul(tw8, tw2); w[12] = cmul(tw8, tw4);
+                w[7] = cmul(w[6], tw1); w[11] = cmul(w[10], tw1); w[13] = cmul(w[12], tw1);
+                w[14] = cmul(w[12], tw2); w[15] = cmul(w[14], tw1);
+#pragma unroll
+                for (int k1 = 0; k1 < 16; ++k1) {
+                    double2 v = k1 == 0 ? b[0] : cmul(b[k1], w[k1]);
+                    const int f = k1 * T + t;
+                    wbf[T == 32 ? k1 * 33 + t : f + (f >> 4)] = v;
+                }
+            }
+#pragma unroll
+            for (int o = 1; o < T; o <<= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+            __syncwarp();
+            // ---- pass 2: T-point DFTs over t, split step and power
+            double* out = P.dst + (((f0 + s * FSTEP + fi) * (int64_t)C + c0 + ci) * F);
+            const double sc = 0.5 * P.scale;
+            const double mN2 = sm * corr;                  // mean * N/2
+            if constexpr (T == 32) {
+                // lane (k1, tp): outputs k2 = 2 kk + tp of the 32-point DFT of row k1, i.e.
+                // Z[lane + 32 kk], kk < 16 (first radix-2 step done here, decimation in frequency)
+                const int k1 = lane & 15, tp = lane >> 4;
+                const double sgn = tp ? -1.0 : 1.0;
+                const double2* row = wbf + k1 * 33;
+#pragma unroll
+                for (int n = 0; n < 16; ++n) {
+                    double2 lo = row[n], hi = row[n + 16];
+                    a[n] = make_double2(fma(sgn, hi.x, lo.x), fma(sgn, hi.y, lo.y));
+                }
+                if (tp) {
+#pragma unroll
+                    for (int n = 1; n < 16; ++n) a[n] = cmul(a[n], make_double2(w32c(n, 0), w32c(n, 1)));
+                }
+                dft16(a, b);
+                if (last_iter) { issue_loads(); loaded = true; }
+                // split step in registers: Z[M - k] of k = lane + 32 kk sits in lane 32 - lane,
+                // register 15 - kk (lane 0: its own register 16 - kk), so a lane handles the
+                // pairs of its registers kk < 8 and fetches the partner by shuffle
+                const int partner = (32 - lane) & 31;
+                double* outk = out + lane;
+                double* outm = out + M - lane;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    double2 zk = b[kk], zm;
+                    zm.x = __shfl_sync(0xffffffffu, b[15 - kk].x, partner);
+                    zm.y = __shfl_sync(0xffffffffu, b[15 - kk].y, partner);
+                    if (kk > 0 && lane == 0) zm = b[16 - kk];
+                    double2 tw = kk == 0 ? twl : cmul(twl, make_double2(w32c(kk, 0), w32c(kk, 1)));
+                    double e_r = zk.x + zm.x, e_i = zk.y - zm.y;          // Zk + conj(Zm)
+                    double o_r = zk.y + zm.y, o_i = zm.x - zk.x;          // -i (Zk - conj(Zm))
+                    double t_r = o_r * tw.x - o_i * tw.y, t_i = o_r * tw.y + o_i * tw.x;
+                    double pr = e_r + t_r, pi = e_i + t_i, qr = e_r - t_r, qi = e_i - t_i;
+                    // p = 2 X[k]; the window's spectrum at bin 1 is -N/4
+                    if (kk == 0) pr += lane == 1 ? mN2 : 0.0;
+                    double pk = (pr * pr + pi * pi) * sc, pm = (qr * qr + qi * qi) * sc;
+                    if (kk == 0 && lane == 0) {                           // bins 0 and M from Z[0]
+                        double x0 = zk.x + zk.y - mN2, xM = zk.x - zk.y;
+                        pk = x0 * x0 * P.scale;
+                        pm = xM * xM * P.scale;
+                    }
+                    if (DB) { pk = to_db(pk); pm = to_db(pm); }
+                    if (live) {
+                        __stcs(outk + 32 * kk, pk);
+                        __stcs(outm - 32 * kk, pm);
+                    }
+                }
+                if (lane == 0 && live) {                                  // k = M/2 pairs with itself
+                    double2 zk = b[8];
+                    double2 tw = make_double2(w32c(8, 0), w32c(8, 1));    // W_N^(M/2) = -i
+                    double e_r = zk.x + zk.x, o_r = zk.y + zk.y;
+                    double t_r = o_r * tw.x, t_i = o_r * tw.y;
+                    double pr = e_r + t_r, pi = t_i;
+                    double pk = (pr * pr + pi * pi) * sc;
+                    if (DB) pk = to_db(pk);
+                    out[M / 2] = pk;
+                }
+            } else {
+                double2 zout[16];
+                int kout[16];
+                constexpr int Q = 16 / (T == 32 ? 16 : T);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) a[i] = wbf[t * 17 + i];
+                if (T == 16) {
+                    dft16(a, b);
+                } else if (T == 8) {
+                    dft8(&a[0], &b[0]);
+                    dft8(&a[8], &b[8]);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        dft4(a[4 * r], a[4 * r + 1], a[4 * r + 2], a[4 * r + 3],
+                             b[4 * r], b[4 * r + 1], b[4 * r + 2], b[4 * r + 3]);
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int r = i / (16 / Q), k2 = i % (16 / Q);
+                    zout[i] = b[i];
+                    kout[i] = (t * Q + r) + 16 * k2;
+                }
+                if (last_iter) { issue_loads(); loaded = true; }
+                __syncwarp();
+                // ---- Z in natural order
+#pragma unroll
+                for (int i = 0; i < 16; ++i) wbf[kout[i]] = zout[i];
+                __syncwarp();
+                if (live) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        double2 zk[4], zm[4], tw[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {              // k = 1 + t + T i  in [1, M/2]
+                            const int k = 1 + t + T * (4 * h + j), km = M - k;
+                            zk[j] = wbf[k];
+                            zm[j] = wbf[km];
+                            tw[j] = tws[k];
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int k = 1 + t + T * (4 * h + j), km = M - k;
+                            double e_r = zk[j].x + zm[j].x, e_i = zk[j].y - zm[j].y;
+                            double o_r = zk[j].y + zm[j].y, o_i = zm[j].x - zk[j].x;
+                            double t_r = o_r * tw[j].x - o_i * tw[j].y, t_i = o_r * tw[j].y + o_i * tw[j].x;
+                            double pr = e_r + t_r, pi = e_i + t_i, qr = e_r - t_r, qi = e_i - t_i;
+                            if (h == 0 && j == 0) pr += t == 0 ? mN2 : 0.0;
+                            double pk = (pr * pr + pi * pi) * sc, pm = (qr * qr + qi * qi) * sc;
+                            if (DB) { pk = to_db(pk); pm = to_db(pm); }
+                            __stcs(out + k, pk);
+                            if (km != k) __stcs(out + km, pm);
+                        }
+                    }
+                    if (t == 0) {
+                        double2 z0 = wbf[0];
+                        double x0 = z0.x + z0.y - mN2, xM = z0.x - z0.y;
+                        double p0 = x0 * x0 * P.scale, pM = xM * xM * P.scale;
+                        if (DB) { p0 = to_db(p0); pM = to_db(pM); }
+                        out[0] = p0;
+                        out[M] = pM;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+
+        if (more) {
+            if (!loaded) issue_loads();     // warps without an item in the last iteration
+            __syncthreads();            // every warp is done with the rows the chunk replaces
+#pragma unroll
+            for (int j = 0; j < SR_PF; ++j)
+                if (r0 + j * DR < CH) put(pf[j], npos + r0 + j * DR);
+            if (r0 + SR_PF * DR < CH) stage_direct(nrow, npos, CH, SR_PF);
+            __syncthreads();
+        }
+        ws = (ws + CH) & RM;
+        npos = (npos + CH) & RM;
+        nrow += CH;
+        gnext += gchunk;
+    }
+}
+
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
+
+// returns ADN_ERR_UNSUPPORTED (without an error message) when the shape does not fit
+template <int LOGN, bool DB>
+int32_t launch_ring_kernel(SpecRArgs& P, int64_t nf, cudaStream_t st) {
+    using Cf = SWCfg<LOGN>;
+    const int C = P.C, hop = P.hop;
+    int NW = env_int("ADN_SPEC_NW", 4);
+    if (NW < 1) NW = 1;
+    if (NW > SR_MAXNT / 32) NW = SR_MAXNT / 32;
+    int CBmax = env_int("ADN_SPEC_CB", 4);
+    P.LW = 0;
+    while ((2 << P.LW) <= C && (2 << P.LW) <= CBmax) ++P.LW;
+    P.CB = 1 << P.LW;
+    P.ngrp = (C + P.CB - 1) / P.CB;
+    P.nrows = (nf - 1) * hop + Cf::N;
+    const int items = NW * Cf::FPW;
+    P.FSTEP = items / P.CB > 1 ? items / P.CB : 1;
+    const size_t limit = 227 * 1024 - 1024;
+    size_t smem = 0;
+    for (;; P.FSTEP = (P.FSTEP + 1) / 2) {
+        const int64_t CH = (int64_t)P.FSTEP * hop, span0 = Cf::N + (int64_t)(P.FSTEP - 1) * hop;
+        (void)CH;
+        P.RC = Cf::N;
+        while (P.RC < span0) P.RC <<= 1;                   // power of two >= the rows of a step
+        P.RS = P.RC + 4;                                   // == 4 mod 8
+        smem = ((size_t)P.CB * P.RS + Cf::N) * 8 +
+               ((Cf::T == 32 ? 0 : (size_t)Cf::M / 2 + 2) + (size_t)NW * SRCfg<LOGN>::WB) * 16;
+        if (smem <= limit || P.FSTEP == 1) break;
+    }
+    if (smem > limit) return ADN_ERR_UNSUPPORTED;
+    auto kern = spectrogram_ring_kernel<LOGN, DB>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        ADN_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    int bps = 1;
+    ADN_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, NW * 32, smem));
+    if (bps < 1) return ADN_ERR_UNSUPPORTED;
+    // one resident wave of blocks, runs of at least 4 steps
+    int64_t nruns = (int64_t)ctx().sm_count * bps / P.ngrp;
+    if (nruns < 1) nruns = 1;
+    int64_t frun = (nf + nruns - 1) / nruns;
+    if (frun < 4 * P.FSTEP) frun = 4 * P.FSTEP;
+    frun = (frun + P.FSTEP - 1) / P.FSTEP * P.FSTEP;
+    if (frun * hop + Cf::N > 0x3fffffff) return ADN_ERR_UNSUPPORTED;
+    P.FRUN = (int32_t)frun;
+    const int64_t grid = ((nf + frun - 1) / frun) * P.ngrp;
+    if (grid > 0x7fffffff) return ADN_ERR_UNSUPPORTED;
+    kern<<<(unsigned)grid, NW * 32, smem, st>>>(P);
+    count_launch();
+    ADN_CK(cudaGetLastError());
+    return ADN_OK;
+}
+
+template <int LOGN>
+int32_t launch_ring(SpecRArgs& P, int64_t nf, int out_db, cudaStream_t st) {
+    return out_db ? launch_ring_kernel<LOGN, true>(P, nf, st) : launch_ring_kernel<LOGN, false>(P, nf, st);
+}
+
 template <int LOGN>
 int32_t launch_warp_kernel(SpecWArgs& P, int64_t nf, cudaStream_t st) {
     using Cf = SWCfg<LOGN>;
@@ -563,6 +994,23 @@ int32_t spectrogram_dev(const double* src, int64_t n_src, int32_t C, double rate
     SpecPlan plan;
     int32_t rc = get_spec_plan(nfft, st, &plan);
     if (rc) return rc;
+    const bool ring_ok = plan.twA && (hop % 2 == 0) && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+                         (C % 2 == 0 || C == 1) && env_int("ADN_SPEC_RING", 1) != 0;
+    if (ring_ok) {
+        SpecRArgs R;
+        R.src = src; R.dst = dst; R.win = plan.win; R.twA = plan.twA; R.twS = plan.tw;
+        R.nframes = nf; R.C = C; R.hop = hop;
+        R.detrend = detrend_id == ADN_DETREND_CONSTANT;
+        R.scale = 1.0 / (rate * plan.sumw2);
+        int32_t rr = ADN_ERR_UNSUPPORTED;
+        switch (nfft) {
+            case 128: rr = launch_ring<7>(R, nf, out_db, st); break;
+            case 256: rr = launch_ring<8>(R, nf, out_db, st); break;
+            case 512: rr = launch_ring<9>(R, nf, out_db, st); break;
+            case 1024: rr = launch_ring<10>(R, nf, out_db, st); break;
+        }
+        if (rr != ADN_ERR_UNSUPPORTED) return rr;
+    }
     if (plan.twA && (hop % 2 == 0) && (reinterpret_cast<uintptr_t>(src) & 7) == 0) {
         SpecWArgs W;
         W.src = src; W.dst = dst; W.win = plan.win; W.twA = plan.twA; W.twS = plan.tw;
