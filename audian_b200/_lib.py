@@ -22,6 +22,11 @@ ADN_ERR_SHORT = 4
 ADN_MAX_SECTIONS = 8
 ADN_MIN_NFFT = 8
 ADN_MAX_NFFT = 16384
+ADN_OPT_RESIDENT = 0
+ADN_OPT_VERIFY = 1
+ADN_OPT_CHUNK_BYTES = 2
+ADN_OPT_RESIDENT_MIN_BYTES = 3
+ADN_OPT_RESIDENT_CAP_BYTES = 4
 ADN_WINDOW_HANN = 0
 ADN_DETREND_NONE = 0
 ADN_DETREND_CONSTANT = 1
@@ -41,6 +46,11 @@ SIGNATURES = {
     'adn_synchronize': (_i32, []),
     'adn_host_register': (_i32, [_dp, _i64]),
     'adn_host_unregister': (_i32, [_dp]),
+    'adn_set_option': (_i32, [_i32, _i64]),
+    'adn_get_option': (_i64, [_i32]),
+    'adn_invalidate': (_i32, [_dp, _i64]),
+    'adn_resident_hits': (_i64, []),
+    'adn_transfer_bytes': (_i32, [C.POINTER(_i64), C.POINTER(_i64)]),
     'adn_minmax_f64': (_i32, [_dp, _i64, _i32, _i64, _dp]),
     'adn_sosfilt_f64': (_i32, [_dp, _i32, _dp, _i64, _i32, _i64, _dp, _i64, _dp]),
     'adn_envelope_f64': (_i32, [_dp, _i32, _dp, _i64, _i32, _i64, _dp, _i64, _i32]),
@@ -231,6 +241,39 @@ def sos_decay_length(sos, tol=1e-30):
 def sosfiltfilt_edge(sos):
     sos, S = sos_array(sos)
     return int(lib().adn_sosfiltfilt_edge(sos.ctypes.data, S))
+
+
+def set_option(option, value):
+    check(lib().adn_set_option(int(option), int(value)))
+
+
+def get_option(option):
+    return int(lib().adn_get_option(int(option)))
+
+
+def enable_resident(on=True):
+    """Results of the host-array calls stay on the device for the traces that
+    consume them (the trace classes invalidate them when audioio moves or
+    replaces a buffer).  Needs no GPU: only flips an option."""
+    lib().adn_set_option(ADN_OPT_RESIDENT, 1 if on else 0)
+
+
+def invalidate(a):
+    """Forget device copies of the host array `a` (it was changed by other
+    means than a call into the library)."""
+    if a is not None and a.size > 0:
+        lib().adn_invalidate(a.ctypes.data, a.nbytes)
+
+
+def resident_hits():
+    return int(lib().adn_resident_hits())
+
+
+def transfer_bytes():
+    """(host->device, device->host) bytes copied by the host-array calls so far."""
+    a, b = _i64(0), _i64(0)
+    lib().adn_transfer_bytes(C.byref(a), C.byref(b))
+    return a.value, b.value
 
 
 def host_register(a):

@@ -28,6 +28,7 @@ from math import ceil, floor
 
 import numpy as np
 
+from . import _lib
 from .bufferedarray import BufferedArray
 
 
@@ -82,6 +83,7 @@ class BufferedData(BufferedArray):
         self.follow = 0
 
     def open(self, source, step=1, more_shape=None):
+        _lib.enable_resident()
         self.source = source
         source.dests.append(self)
         self.ampl_min = source.ampl_min
@@ -97,6 +99,19 @@ class BufferedData(BufferedArray):
         self.update_step(step, more_shape)
 
     # ------------------------------------------------------------ buffers
+    # The library may keep the result of process() on the device, remembered by
+    # the host range of `dest` (ADN_OPT_RESIDENT), so that the traces further
+    # down the chain do not upload it again.  audioio moves the contents of
+    # `self.buffer` around (move_buffer recycles the overlap) and replaces the
+    # array (allocate_buffer): tell the library before that happens.
+    def move_buffer(self, offset, nframes):
+        _lib.invalidate(self.buffer)
+        super().move_buffer(offset, nframes)
+
+    def allocate_buffer(self, *args, **kwargs):
+        _lib.invalidate(self.buffer)
+        super().allocate_buffer(*args, **kwargs)
+
     def align_buffer(self):
         src = self.source
         first = src.offset
@@ -182,6 +197,7 @@ class BufferedData(BufferedArray):
         """Use `process()` directly on arrays without audian's data graph
         (bench / scripts): sets the attributes `open()` would take from a
         source, applies `params` and designs filters via `update()`."""
+        _lib.enable_resident()
         self.rate = float(rate)
         self.channels = int(channels)
         self.source = _Standalone(rate, channels)

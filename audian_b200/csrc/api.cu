@@ -91,19 +91,239 @@ int32_t ensure_init() {
     return rc;
 }
 
-// Stage `bytes` of host memory into the `in` staging buffer.
+// ---------------------------------------------------------------- host <-> device plumbing
+//
+// Host-pointer entry points move data on three streams -- uploads, kernels, downloads -- in
+// chunks, so that on pinned host memory the two PCIe directions and the kernels overlap.
+// Outputs of at least `resident_min` bytes can stay on the device, remembered by the host
+// range they were copied to (option ADN_OPT_RESIDENT, off by default): a later call whose
+// source lies inside such a range reads the device copy instead of uploading it again
+// (filtered -> spectrogram / envelope).  The caller owns the discipline: whoever changes such
+// a host buffer by other means calls adn_invalidate() -- the trace classes of audian_b200 do so
+// whenever audioio moves or reallocates a buffer.  As a safety net a hit is verified on a few
+// dozen sampled values before it is trusted (ADN_OPT_VERIFY, on by default).
+
+struct Resident {
+    const char* host = nullptr;
+    size_t bytes = 0;
+    DevBuf buf;
+    uint64_t stamp = 0;
+};
+
+static std::vector<Resident> g_res;
+static std::vector<DevBuf> g_pool;            // released device buffers, reused by size
+static DevBuf g_vbuf;                         // samples of a resident copy for verification
+static uint64_t g_stamp = 0;
+static int64_t g_opt[ADN_OPT_COUNT] = {0, 1, (int64_t)32 << 20, (int64_t)8 << 20, (int64_t)16 << 30};
+static cudaStream_t g_h2d = nullptr, g_d2h = nullptr;
+static std::vector<cudaEvent_t> g_events;
+static size_t g_event_next = 0;
+static int64_t g_res_hits = 0, g_res_misses = 0;
+static int64_t g_bytes_h2d = 0, g_bytes_d2h = 0;   // moved by the host-pointer entry points
+
+
+static cudaError_t h2d(void* dev, const void* host, size_t bytes, cudaStream_t st) {
+    g_bytes_h2d += (int64_t)bytes;
+    return cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, st);
+}
+static cudaError_t d2h(void* host, const void* dev, size_t bytes, cudaStream_t st) {
+    g_bytes_d2h += (int64_t)bytes;
+    return cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, st);
+}
+
+static int32_t ensure_streams() {
+    if (!g_h2d) ADN_CK(cudaStreamCreateWithFlags(&g_h2d, cudaStreamNonBlocking));
+    if (!g_d2h) ADN_CK(cudaStreamCreateWithFlags(&g_d2h, cudaStreamNonBlocking));
+    g_event_next = 0;
+    return ADN_OK;
+}
+
+static int32_t next_event(cudaEvent_t* e) {
+    if (g_event_next == g_events.size()) {
+        cudaEvent_t ev;
+        ADN_CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        g_events.push_back(ev);
+    }
+    *e = g_events[g_event_next++];
+    return ADN_OK;
+}
+
+// b waits for everything enqueued on a so far
+static int32_t chain(cudaStream_t a, cudaStream_t b) {
+    cudaEvent_t e;
+    int32_t rc = next_event(&e);
+    if (rc) return rc;
+    ADN_CK(cudaEventRecord(e, a));
+    ADN_CK(cudaStreamWaitEvent(b, e, 0));
+    return ADN_OK;
+}
+
+static void pool_put(DevBuf& b) {
+    if (!b.p) return;
+    if (g_pool.size() >= 8) {                  // bounded: free the smallest
+        size_t k = 0;
+        for (size_t i = 1; i < g_pool.size(); ++i) if (g_pool[i].cap < g_pool[k].cap) k = i;
+        g_pool[k].release();
+        g_pool.erase(g_pool.begin() + k);
+    }
+    g_pool.push_back(b);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+static int32_t pool_get(size_t bytes, DevBuf* out) {
+    size_t best = g_pool.size();
+    for (size_t i = 0; i < g_pool.size(); ++i)
+        if (g_pool[i].cap >= bytes && g_pool[i].cap <= 2 * bytes + 4096 &&
+            (best == g_pool.size() || g_pool[i].cap < g_pool[best].cap))
+            best = i;
+    if (best < g_pool.size()) {
+        *out = g_pool[best];
+        g_pool.erase(g_pool.begin() + best);
+        return ADN_OK;
+    }
+    DevBuf b;
+    int32_t rc = b.reserve(bytes);
+    if (rc) return rc;
+    *out = b;
+    return ADN_OK;
+}
+
+static void drop_overlapping(const void* host, size_t bytes) {
+    const char* lo = static_cast<const char*>(host);
+    const char* hi = lo + bytes;
+    for (size_t i = 0; i < g_res.size();) {
+        Resident& r = g_res[i];
+        if (r.host < hi && lo < r.host + r.bytes) {
+            pool_put(r.buf);
+            g_res.erase(g_res.begin() + i);
+        } else {
+            ++i;
+        }
+    }
+}
+
+static void release_residents() {
+    for (auto& r : g_res) r.buf.release();
+    g_res.clear();
+    for (auto& b : g_pool) b.release();
+    g_pool.clear();
+    g_vbuf.release();
+    for (auto e : g_events) cudaEventDestroy(e);
+    g_events.clear();
+    if (g_h2d) { cudaStreamDestroy(g_h2d); g_h2d = nullptr; }
+    if (g_d2h) { cudaStreamDestroy(g_d2h); g_d2h = nullptr; }
+}
+
+// Device buffer the result for host range [dst, dst + bytes) is computed into: a resident
+// one (registered under that range) or the shared staging buffer.
+static int32_t out_buffer(void* dst, size_t bytes, double** dev) {
+    Ctx& c = ctx();
+    drop_overlapping(dst, bytes);
+    if (g_opt[ADN_OPT_RESIDENT] && (int64_t)bytes >= g_opt[ADN_OPT_RESIDENT_MIN_BYTES]) {
+        size_t total = bytes;
+        for (auto& r : g_res) total += r.bytes;
+        while (!g_res.empty() && (int64_t)total > g_opt[ADN_OPT_RESIDENT_CAP_BYTES]) {
+            size_t k = 0;
+            for (size_t i = 1; i < g_res.size(); ++i) if (g_res[i].stamp < g_res[k].stamp) k = i;
+            total -= g_res[k].bytes;
+            pool_put(g_res[k].buf);
+            g_res.erase(g_res.begin() + k);
+        }
+        Resident r;
+        int32_t rc = pool_get(bytes, &r.buf);
+        if (rc == ADN_OK) {
+            r.host = static_cast<const char*>(dst);
+            r.bytes = bytes;
+            r.stamp = ++g_stamp;
+            *dev = r.buf.as<double>();
+            g_res.push_back(r);
+            return ADN_OK;
+        }
+        // out of device memory for a resident copy: fall through to the staging buffer
+    }
+    int32_t rc = c.out.reserve(bytes ? bytes : 16);
+    if (rc) return rc;
+    *dev = c.out.as<double>();
+    return ADN_OK;
+}
+
+__global__ void sample_kernel(const double* __restrict__ p, int64_t n, int32_t k, double* __restrict__ out) {
+    int i = threadIdx.x;
+    if (i < k) out[i] = p[(int64_t)((unsigned long long)i * 0x9E3779B97F4A7C15ull % (unsigned long long)n)];
+}
+
+// Device copy of the host range [src, src + bytes) if a verified resident one exists.
+static int32_t in_resident(const void* src, size_t bytes, const double** dev) {
+    *dev = nullptr;
+    if (!g_opt[ADN_OPT_RESIDENT] || (int64_t)bytes < g_opt[ADN_OPT_RESIDENT_MIN_BYTES]) return ADN_OK;
+    const char* lo = static_cast<const char*>(src);
+    for (size_t i = 0; i < g_res.size(); ++i) {
+        Resident& r = g_res[i];
+        if (lo < r.host || lo + bytes > r.host + r.bytes) continue;
+        const double* d = reinterpret_cast<const double*>(static_cast<const char*>(r.buf.p) + (lo - r.host));
+        if (g_opt[ADN_OPT_VERIFY]) {
+            Ctx& c = ctx();
+            const int K = 48;
+            const int64_t n = (int64_t)(bytes / 8);
+            int32_t rc = g_vbuf.reserve(4096);
+            if (rc) return rc;
+            sample_kernel<<<1, 64, 0, c.stream>>>(d, n, K, g_vbuf.as<double>());
+            count_launch();
+            double got[K];
+            ADN_CK(d2h(got, g_vbuf.p, sizeof got, c.stream));
+            ADN_CK(cudaStreamSynchronize(c.stream));
+            const double* h = static_cast<const double*>(src);
+            bool same = true;
+            for (int j = 0; j < K && same; ++j) {
+                int64_t idx = (int64_t)((unsigned long long)j * 0x9E3779B97F4A7C15ull % (unsigned long long)n);
+                same = memcmp(&got[j], &h[idx], 8) == 0;
+            }
+            if (!same) {                        // the host buffer changed behind our back
+                pool_put(r.buf);
+                g_res.erase(g_res.begin() + i);
+                ++g_res_misses;
+                return ADN_OK;
+            }
+        }
+        r.stamp = ++g_stamp;
+        ++g_res_hits;
+        *dev = d;
+        return ADN_OK;
+    }
+    ++g_res_misses;
+    return ADN_OK;
+}
+
+// Whole upload of `bytes` into the `in` staging buffer on the kernel stream.
 static int32_t stage_in(const void* host, size_t bytes) {
     Ctx& c = ctx();
     int32_t rc = c.in.reserve(bytes ? bytes : 16);
     if (rc) return rc;
-    if (bytes) ADN_CK(cudaMemcpyAsync(c.in.p, host, bytes, cudaMemcpyHostToDevice, c.stream));
+    if (bytes) ADN_CK(h2d(c.in.p, host, bytes, c.stream));
     return ADN_OK;
 }
 
-static int32_t stage_out(void* host, size_t bytes) {
+// Source of a host-pointer call: the resident copy, or a whole upload.
+static int32_t source_dev(const void* host, size_t bytes, const double** dev) {
+    int32_t rc = in_resident(host, bytes, dev);
+    if (rc || *dev) return rc;
+    if ((rc = stage_in(host, bytes))) return rc;
+    *dev = ctx().in.as<double>();
+    return ADN_OK;
+}
+
+static int32_t copy_out(void* host, const double* dev, size_t bytes) {
     Ctx& c = ctx();
-    if (bytes) ADN_CK(cudaMemcpyAsync(host, c.out.p, bytes, cudaMemcpyDeviceToHost, c.stream));
+    if (bytes) ADN_CK(d2h(host, dev, bytes, c.stream));
     ADN_CK(cudaStreamSynchronize(c.stream));
+    return ADN_OK;
+}
+
+static int32_t sync_pipeline() {
+    ADN_CK(cudaStreamSynchronize(g_h2d));
+    ADN_CK(cudaStreamSynchronize(ctx().stream));
+    ADN_CK(cudaStreamSynchronize(g_d2h));
     return ADN_OK;
 }
 
@@ -126,6 +346,7 @@ int32_t adn_shutdown(void) {
     g_ctx.in.release();
     g_ctx.out.release();
     g_ctx.aux.release();
+    release_residents();
     for (int i = 0; i < SCR_COUNT; ++i) g_scratch[i].release();
     cudaStreamDestroy(g_ctx.stream);
     g_ctx.stream = nullptr;
@@ -162,6 +383,38 @@ int32_t adn_host_unregister(void* ptr) {
 
 // ---------------------------------------------------------------- host entry points
 
+int32_t adn_set_option(int32_t option, int64_t value) {
+    if (option < 0 || option >= ADN_OPT_COUNT) return fail(ADN_ERR_INVALID, "adn_set_option: option %d", option);
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_opt[option] = value;
+    if (option == ADN_OPT_RESIDENT && value == 0 && g_ctx.ready) {
+        cudaSetDevice(g_ctx.device);
+        cudaStreamSynchronize(g_ctx.stream);
+        for (auto& r : g_res) pool_put(r.buf);
+        g_res.clear();
+    }
+    return ADN_OK;
+}
+
+int64_t adn_get_option(int32_t option) {
+    if (option < 0 || option >= ADN_OPT_COUNT) return -1;
+    return g_opt[option];
+}
+
+int32_t adn_invalidate(const void* host, int64_t bytes) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (host && bytes > 0 && !g_res.empty()) drop_overlapping(host, (size_t)bytes);
+    return ADN_OK;
+}
+
+int64_t adn_resident_hits(void) { return g_res_hits; }
+
+int32_t adn_transfer_bytes(int64_t* h2d_bytes, int64_t* d2h_bytes) {
+    if (h2d_bytes) *h2d_bytes = g_bytes_h2d;
+    if (d2h_bytes) *d2h_bytes = g_bytes_d2h;
+    return ADN_OK;
+}
+
 int32_t adn_minmax_f64(const double* src, int64_t n, int32_t C, int64_t step, double* dst) {
     if (n < 0 || C < 1 || step < 1) return fail(ADN_ERR_INVALID, "adn_minmax_f64: n=%lld C=%d step=%lld",
                                                (long long)n, C, (long long)step);
@@ -172,10 +425,29 @@ int32_t adn_minmax_f64(const double* src, int64_t n, int32_t C, int64_t step, do
     Ctx& c = ctx();
     int64_t nseg = (n + step - 1) / step;
     size_t in_b = (size_t)n * C * 8, out_b = (size_t)nseg * 2 * C * 8;
-    if ((rc = stage_in(src, in_b))) return rc;
+    const double* dsrc = nullptr;
+    if ((rc = in_resident(src, in_b, &dsrc))) return rc;
+    drop_overlapping(dst, out_b);
     if ((rc = c.out.reserve(out_b))) return rc;
-    if ((rc = minmax_dev(c.in.as<double>(), n, C, step, c.out.as<double>(), c.stream))) return rc;
-    return stage_out(dst, out_b);
+    if (dsrc) {
+        if ((rc = minmax_dev(dsrc, n, C, step, c.out.as<double>(), c.stream))) return rc;
+        return copy_out(dst, c.out.as<double>(), out_b);
+    }
+    // upload in chunks of whole segments; the kernel of a chunk runs while the next one arrives
+    if ((rc = ensure_streams())) return rc;
+    if ((rc = c.in.reserve(in_b))) return rc;
+    int64_t rows = g_opt[ADN_OPT_CHUNK_BYTES] / ((int64_t)C * 8);
+    int64_t segs = rows / step;
+    if (segs < 1) segs = 1;
+    for (int64_t s0 = 0; s0 < nseg; s0 += segs) {
+        const int64_t a = s0 * step, b = (s0 + segs) * step < n ? (s0 + segs) * step : n;
+        ADN_CK(h2d(c.in.as<double>() + a * C, src + a * C, (size_t)(b - a) * C * 8, g_h2d));
+        if ((rc = chain(g_h2d, c.stream))) return rc;
+        if ((rc = minmax_dev(c.in.as<double>() + a * C, b - a, C, step, c.out.as<double>() + 2 * s0 * C,
+                             c.stream)))
+            return rc;
+    }
+    return copy_out(dst, c.out.as<double>(), out_b);
 }
 
 int32_t adn_sosfilt_f64(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
@@ -189,25 +461,68 @@ int32_t adn_sosfilt_f64(const double* sos, int32_t S, const double* src, int64_t
     if ((S > 0 && !sos) || (n_src > 0 && !src) || (n_dst > 0 && !dst))
         return fail(ADN_ERR_INVALID, "adn_sosfilt_f64: NULL pointer");
     if (n_src == 0) return ADN_OK;
+    size_t in_b = (size_t)n_src * C * 8, out_b = (size_t)n_dst * C * 8;
+    if (S == 0) {                               // reference: sos is None -> dest = source[nbefore:]
+        { std::lock_guard<std::mutex> lk(g_mu); if (!g_res.empty()) drop_overlapping(dst, out_b); }
+        if (n_dst > 0) memmove(dst, src + nbefore * C, out_b);
+        return ADN_OK;
+    }
     int32_t rc = ensure_init();
     if (rc) return rc;
+    if ((rc = ensure_streams())) return rc;
     Ctx& c = ctx();
-    size_t in_b = (size_t)n_src * C * 8, out_b = (size_t)n_dst * C * 8;
-    size_t z_b = (size_t)C * (S > 0 ? S : 1) * 2 * 8;
-    if ((rc = stage_in(src, in_b))) return rc;
-    if ((rc = c.out.reserve(out_b ? out_b : 16))) return rc;
-    double* dzi = nullptr;
-    if (zi_inout && S > 0) {
-        if ((rc = c.aux.reserve(2 * z_b))) return rc;
-        dzi = c.aux.as<double>();
-        ADN_CK(cudaMemcpyAsync(dzi, zi_inout, z_b, cudaMemcpyHostToDevice, c.stream));
+    const size_t z_b = (size_t)C * S * 2 * 8;
+    // aux: [user zi][state A][state B]
+    if ((rc = c.aux.reserve(3 * z_b + 4096))) return rc;
+    double* d_zi = c.aux.as<double>();
+    double* d_state[2] = {d_zi + (size_t)C * S * 2, d_zi + (size_t)C * S * 4};
+    if (zi_inout) ADN_CK(h2d(d_zi, zi_inout, z_b, c.stream));
+    const double* dsrc = nullptr;
+    if ((rc = in_resident(src, in_b, &dsrc))) return rc;
+    double* dout = nullptr;
+    if ((rc = out_buffer(dst, out_b, &dout))) return rc;
+    if (dsrc) {
+        if ((rc = sosfilt_dev(sos, S, dsrc, n_src, C, nbefore, n_dst > 0 ? dout : nullptr, n_dst,
+                              zi_inout ? d_zi : nullptr, zi_inout ? d_state[0] : nullptr, c.stream)))
+            return rc;
+        if (zi_inout) ADN_CK(d2h(zi_inout, d_state[0], z_b, c.stream));
+        return copy_out(dst, dout, out_b);
     }
-    double* dzf = dzi ? dzi + (size_t)C * S * 2 : nullptr;
-    if ((rc = sosfilt_dev(sos, S, c.in.as<double>(), n_src, C, nbefore,
-                          n_dst > 0 ? c.out.as<double>() : nullptr, n_dst, dzi, dzf, c.stream)))
-        return rc;
-    if (dzf) ADN_CK(cudaMemcpyAsync(zi_inout, dzf, z_b, cudaMemcpyDeviceToHost, c.stream));
-    return stage_out(dst, out_b);
+    // chunks of rows: upload k+1, filter k (state carried from chunk to chunk: equal to one pass,
+    // the streamed == one-shot property of the scan), download k-1
+    if ((rc = c.in.reserve(in_b))) return rc;
+    double* din = c.in.as<double>();
+    int64_t R = g_opt[ADN_OPT_CHUNK_BYTES] / ((int64_t)C * 8);
+    if (R < 4096) R = 4096;
+    const int64_t nchunks = (n_src + R - 1) / R;
+    const double* zin = zi_inout ? d_zi : nullptr;
+    for (int64_t k = 0; k < nchunks; ++k) {
+        const int64_t a = k * R, b = a + R < n_src ? a + R : n_src;
+        ADN_CK(h2d(din + a * C, src + a * C, (size_t)(b - a) * C * 8, g_h2d));
+        if ((rc = chain(g_h2d, c.stream))) return rc;
+        int64_t nb = nbefore - a;
+        if (nb < 0) nb = 0;
+        if (nb > b - a) nb = b - a;
+        const int64_t o0 = a + nb - nbefore;                      // first output row of the chunk
+        int64_t no = b - a - nb;
+        if (no > n_dst - o0) no = n_dst - o0;
+        if (no < 0) no = 0;
+        const bool last = k + 1 == nchunks;
+        double* zout = (last && !zi_inout) ? nullptr : d_state[k & 1];
+        if (no > 0 || zout) {
+            if ((rc = sosfilt_dev(sos, S, din + a * C, b - a, C, nb, no > 0 ? dout + o0 * C : nullptr, no,
+                                  zin, zout, c.stream)))
+                return rc;
+        }
+        zin = zout;
+        if (no > 0) {
+            if ((rc = chain(c.stream, g_d2h))) return rc;
+            ADN_CK(d2h(dst + o0 * C, dout + o0 * C, (size_t)no * C * 8, g_d2h));
+        }
+        if (last && zi_inout)
+            ADN_CK(d2h(zi_inout, zout, z_b, c.stream));
+    }
+    return sync_pipeline();
 }
 
 int32_t adn_envelope_f64(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
@@ -220,8 +535,10 @@ int32_t adn_envelope_f64(const double* sos, int32_t S, const double* src, int64_
                     (long long)n_dst, (long long)(n_src - nbefore));
     if ((S > 0 && !sos) || (n_src > 0 && !src) || (n_dst > 0 && !dst))
         return fail(ADN_ERR_INVALID, "adn_envelope_f64: NULL pointer");
+    size_t in_b = (size_t)n_src * C * 8, out_b = (size_t)n_dst * C * 8;
     if (S == 0) {                               // reference: sos is None -> zeros
-        if (n_dst > 0) memset(dst, 0, (size_t)n_dst * C * 8);
+        { std::lock_guard<std::mutex> lk(g_mu); if (!g_res.empty()) drop_overlapping(dst, out_b); }
+        if (n_dst > 0) memset(dst, 0, out_b);
         return ADN_OK;
     }
     if (n_src <= adn_sosfiltfilt_edge(sos, S))
@@ -229,15 +546,14 @@ int32_t adn_envelope_f64(const double* sos, int32_t S, const double* src, int64_
                     "than the sosfiltfilt pad length %d", (long long)n_src, adn_sosfiltfilt_edge(sos, S));
     int32_t rc = ensure_init();
     if (rc) return rc;
-    Ctx& c = ctx();
-    size_t in_b = (size_t)n_src * C * 8, out_b = (size_t)n_dst * C * 8;
-    if ((rc = stage_in(src, in_b))) return rc;
-    if ((rc = c.out.reserve(out_b ? out_b : 16))) return rc;
+    const double* dsrc = nullptr;
+    if ((rc = source_dev(src, in_b, &dsrc))) return rc;
+    double* dout = nullptr;
+    if ((rc = out_buffer(dst, out_b, &dout))) return rc;
     if (n_dst > 0 &&
-        (rc = envelope_dev(sos, S, c.in.as<double>(), n_src, C, nbefore, c.out.as<double>(), n_dst,
-                           clamp_negative, c.stream)))
+        (rc = envelope_dev(sos, S, dsrc, n_src, C, nbefore, dout, n_dst, clamp_negative, ctx().stream)))
         return rc;
-    return stage_out(dst, out_b);
+    return copy_out(dst, dout, out_b);
 }
 
 int32_t adn_spectrogram_f64(const double* src, int64_t n_src, int32_t C, double rate, int32_t nfft,
@@ -253,21 +569,45 @@ int32_t adn_spectrogram_f64(const double* src, int64_t n_src, int32_t C, double 
     int64_t nf = spectrogram_frames(n_src, n_dst, nfft, hop);
     size_t F = (size_t)nfft / 2 + 1;
     if (nf == 0) {                              // reference: dest[:] = 0
+        { std::lock_guard<std::mutex> lk(g_mu); if (!g_res.empty()) drop_overlapping(dst, (size_t)n_dst * C * F * 8); }
         memset(dst, 0, (size_t)n_dst * C * F * 8);
         return ADN_OK;
     }
     int32_t rc = ensure_init();
     if (rc) return rc;
+    if ((rc = ensure_streams())) return rc;
     Ctx& c = ctx();
     int64_t nsource = (nf - 1) * (int64_t)hop + nfft;      // rows the frames actually read
     size_t in_b = (size_t)nsource * C * 8, out_b = (size_t)nf * C * F * 8;
-    if ((rc = stage_in(src, in_b))) return rc;
-    if ((rc = c.out.reserve(out_b))) return rc;
-    int64_t got = 0;
-    if ((rc = spectrogram_dev(c.in.as<double>(), nsource, C, rate, nfft, hop, window_id, detrend_id,
-                              c.out.as<double>(), nf, out_db, &got, c.stream)))
-        return rc;
-    if ((rc = stage_out(dst, out_b))) return rc;
+    const double* dsrc = nullptr;
+    if ((rc = in_resident(src, in_b, &dsrc))) return rc;
+    double* dout = nullptr;
+    if ((rc = out_buffer(dst, out_b, &dout))) return rc;
+    // chunks of frames: upload the rows chunk k adds, transform chunk k, download chunk k-1
+    const bool upload = dsrc == nullptr;
+    if (upload) {
+        if ((rc = c.in.reserve(in_b))) return rc;
+        dsrc = c.in.as<double>();
+    }
+    int64_t FR = g_opt[ADN_OPT_CHUNK_BYTES] / ((int64_t)C * (int64_t)F * 8);
+    if (FR < 16) FR = 16;
+    int64_t up = 0;                                        // rows uploaded so far
+    for (int64_t f0 = 0; f0 < nf; f0 += FR) {
+        const int64_t fc = f0 + FR < nf ? FR : nf - f0;
+        const int64_t r1 = (f0 + fc - 1) * hop + nfft;     // rows [0, r1) are needed
+        if (upload && r1 > up) {
+            ADN_CK(h2d(c.in.as<double>() + up * C, src + up * C, (size_t)(r1 - up) * C * 8, g_h2d));
+            up = r1;
+            if ((rc = chain(g_h2d, c.stream))) return rc;
+        }
+        int64_t got = 0;
+        if ((rc = spectrogram_dev(dsrc + f0 * hop * C, (fc - 1) * hop + nfft, C, rate, nfft, hop, window_id,
+                                  detrend_id, dout + (size_t)f0 * C * F, fc, out_db, &got, c.stream)))
+            return rc;
+        if ((rc = chain(c.stream, g_d2h))) return rc;
+        ADN_CK(d2h(dst + (size_t)f0 * C * F, dout + (size_t)f0 * C * F, (size_t)fc * C * F * 8, g_d2h));
+    }
+    if ((rc = sync_pipeline())) return rc;
     if (n_dst > nf) memset(dst + (size_t)nf * C * F, 0, (size_t)(n_dst - nf) * C * F * 8);
     if (n_computed) *n_computed = nf;
     return ADN_OK;
@@ -281,11 +621,13 @@ int32_t adn_decibel_f64(const double* power, int64_t n, double ref_power, double
     int32_t rc = ensure_init();
     if (rc) return rc;
     Ctx& c = ctx();
-    if ((rc = stage_in(power, (size_t)n * 8))) return rc;
+    const double* dsrc = nullptr;
+    if ((rc = source_dev(power, (size_t)n * 8, &dsrc))) return rc;
+    drop_overlapping(dst, (size_t)n * 8);
     if ((rc = c.out.reserve((size_t)n * 8))) return rc;
-    if ((rc = decibel_dev(c.in.as<double>(), n, ref_power, min_power, c.out.as<double>(), c.stream)))
+    if ((rc = decibel_dev(dsrc, n, ref_power, min_power, c.out.as<double>(), c.stream)))
         return rc;
-    return stage_out(dst, (size_t)n * 8);
+    return copy_out(dst, c.out.as<double>(), (size_t)n * 8);
 }
 
 // ---------------------------------------------------------------- device entry points

@@ -22,7 +22,8 @@
  * device every compute entry point fails with ADN_ERR_CUDA.
  *
  * Host-pointer entry points copy to and from device memory that the library
- * owns, on the library's own stream, and block until the result is in `dst`.
+ * owns, on the library's own streams (upload, kernels and download overlap
+ * chunk by chunk), and block until the result is in `dst`.
  * The *_dev entry points take device pointers and a cudaStream_t (passed as
  * void*; NULL = CUDA's default stream), only enqueue work and do not
  * synchronise.  Scratch memory of the library is shared by all *_dev calls:
@@ -48,6 +49,19 @@ extern "C" {
 #define ADN_MIN_NFFT         8
 #define ADN_MAX_NFFT         16384  /* single-kernel shared-memory FFT */
 
+/* adn_set_option() */
+#define ADN_OPT_RESIDENT            0  /* keep large results on the device, keyed by the host
+                                          range they were written to; later calls whose source
+                                          lies inside such a range skip the upload (default 0) */
+#define ADN_OPT_VERIFY              1  /* verify a resident copy on sampled values before it
+                                          is used (default 1) */
+#define ADN_OPT_CHUNK_BYTES         2  /* granularity of the upload/kernel/download pipeline
+                                          of the host-pointer entry points (default 32 MiB) */
+#define ADN_OPT_RESIDENT_MIN_BYTES  3  /* smaller results are never kept (default 8 MiB) */
+#define ADN_OPT_RESIDENT_CAP_BYTES  4  /* least recently used copies are dropped beyond this
+                                          total (default 16 GiB) */
+#define ADN_OPT_COUNT               5
+
 #define ADN_WINDOW_HANN      0   /* periodic Hann == scipy get_window('hann', nfft) */
 #define ADN_DETREND_NONE     0
 #define ADN_DETREND_CONSTANT 1   /* subtract the frame mean */
@@ -63,6 +77,14 @@ int32_t adn_synchronize(void);         /* waits for the library's stream */
  * PCIe rate (optional; plain pageable memory works too) */
 int32_t adn_host_register(void* ptr, int64_t bytes);
 int32_t adn_host_unregister(void* ptr);
+int32_t adn_set_option(int32_t option, int64_t value);
+int64_t adn_get_option(int32_t option);
+/* The host range changed by other means than a call of this library (a buffer
+ * was moved, reloaded, freed): forget device copies that overlap it. */
+int32_t adn_invalidate(const void* host, int64_t bytes);
+int64_t adn_resident_hits(void);       /* sources served from a resident copy so far */
+/* bytes the host-pointer entry points have copied to / from the device so far */
+int32_t adn_transfer_bytes(int64_t* h2d_bytes, int64_t* d2h_bytes);
 
 /* ---- host-pointer entry points (the plugin path) -------------------- */
 

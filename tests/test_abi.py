@@ -67,3 +67,22 @@ def test_product_does_not_import_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 text = open(os.path.join(dirpath, f)).read()
                 assert 'import oracle' not in text and 'from oracle' not in text, f
+
+
+def test_options_and_invalidate_need_no_gpu():
+    assert _lib.get_option(_lib.ADN_OPT_VERIFY) == 1
+    old = _lib.get_option(_lib.ADN_OPT_CHUNK_BYTES)
+    _lib.set_option(_lib.ADN_OPT_CHUNK_BYTES, 12345)
+    assert _lib.get_option(_lib.ADN_OPT_CHUNK_BYTES) == 12345
+    _lib.set_option(_lib.ADN_OPT_CHUNK_BYTES, old)
+    with pytest.raises(_lib.AdnError):
+        _lib.set_option(99, 1)
+    _lib.invalidate(np.zeros((10, 2)))           # nothing kept: a no-op
+    assert _lib.resident_hits() >= 0
+    # the copy / zero branches of the reference (sos is None) are host-side and need no device
+    x = np.arange(20.).reshape(10, 2)
+    y = np.empty((7, 2))
+    _lib.sosfilt(None, x, y, 3)
+    assert np.array_equal(y, x[3:])
+    _lib.envelope(None, x, y, 3)
+    assert not y.any()

@@ -1,0 +1,147 @@
+"""Host-pointer entry points: chunked upload/kernel/download pipeline and results
+kept resident on the device (ADN_OPT_RESIDENT) -- same answers as the oracle whatever
+the chunking, stale device copies are never used."""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from audian_b200 import _lib
+from audian_b200.synth import synth
+from oracle import oracle as orc
+
+
+@pytest.fixture
+def small_chunks():
+    old = _lib.get_option(_lib.ADN_OPT_CHUNK_BYTES)
+    _lib.set_option(_lib.ADN_OPT_CHUNK_BYTES, 1 << 16)       # 64 KiB: dozens of chunks
+    yield
+    _lib.set_option(_lib.ADN_OPT_CHUNK_BYTES, old)
+
+
+@pytest.fixture
+def resident():
+    oldr = _lib.get_option(_lib.ADN_OPT_RESIDENT)
+    oldm = _lib.get_option(_lib.ADN_OPT_RESIDENT_MIN_BYTES)
+    _lib.set_option(_lib.ADN_OPT_RESIDENT, 1)
+    _lib.set_option(_lib.ADN_OPT_RESIDENT_MIN_BYTES, 1 << 12)
+    yield
+    _lib.set_option(_lib.ADN_OPT_RESIDENT_MIN_BYTES, oldm)
+    _lib.set_option(_lib.ADN_OPT_RESIDENT, oldr)
+
+
+@pytest.mark.parametrize('C,nbefore', [(1, 0), (2, 777), (8, 5000), (3, 13)])
+def test_sosfilt_chunked_equals_one_shot(small_chunks, C, nbefore):
+    fs, n = 48000., 60000
+    x = synth(0, n, C, fs, seed=C)
+    sos = orc.filter_design(fs, 800., 12000., 4)
+    ref = np.empty((n - nbefore, C))
+    orc.filter_process(sos, x, ref, nbefore)
+    got = np.full_like(ref, np.nan)
+    _lib.sosfilt(sos, x, got, nbefore)
+    assert np.max(np.abs(got - ref)) <= 1e-9
+    # shorter destination and carried state
+    zi = np.zeros((C, sos.shape[0], 2))
+    h = n//3
+    a = np.empty((h, C))
+    b = np.empty((n - h, C))
+    _lib.sosfilt(sos, x[:h], a, 0, zi=zi)
+    _lib.sosfilt(sos, x[h:], b, 0, zi=zi)
+    full = np.empty((n, C))
+    orc.filter_process(sos, x, full, 0)
+    assert np.max(np.abs(np.concatenate([a, b]) - full)) <= 1e-9
+
+
+@pytest.mark.parametrize('nfft,hop', [(256, 128), (1024, 512), (1024, 128), (2048, 2048), (64, 16)])
+def test_spectrogram_chunked(small_chunks, nfft, hop):
+    fs, C, n = 48000., 4, 50000
+    x = synth(5, n, C, fs, seed=nfft)
+    n_dst = n//hop + 3
+    ref = np.empty((n_dst, C, nfft//2 + 1))
+    nref = orc.spectrogram_process(x, ref, fs, nfft, hop)
+    got = np.full_like(ref, np.nan)
+    assert _lib.spectrogram(x, fs, nfft, hop, got) == nref
+    assert np.allclose(got, ref, rtol=1e-5, atol=1e-20*ref.max())
+
+
+def test_minmax_chunked_bit_exact(small_chunks):
+    x = synth(0, 100000, 4, 48000., seed=3)
+    x[5000:5003] = np.nan
+    x[70000, 1] = -0.0
+    for step in (7, 1000, 33333, 100000):
+        got = _lib.minmax(x, step)
+        assert np.array_equal(got.view(np.uint64), orc.minmax_rows(x, step).view(np.uint64)), step
+
+
+def test_resident_chain_matches_oracle_and_skips_uploads(resident):
+    fs, C, n = 48000., 8, 120000
+    x = synth(0, n, C, fs, seed=11)
+    sos = orc.filter_design(fs, 1000., 15000., 2)
+    esos = orc.envelope_design(fs, 500.)
+    filt = np.empty((n, C))
+    hits0 = _lib.resident_hits()
+    _lib.sosfilt(sos, x, filt, 0)
+    rf = np.empty((n, C))
+    orc.filter_process(sos, x, rf, 0)
+    assert np.max(np.abs(filt - rf)) <= 1e-9
+    nfft, hop = 1024, 512
+    spec = np.empty((n//hop, C, nfft//2 + 1))
+    ns = _lib.spectrogram(filt, fs, nfft, hop, spec)
+    env = np.empty((n, C))
+    _lib.envelope(esos, filt, env, 0, True)
+    assert _lib.resident_hits() == hits0 + 2            # both consumers read the device copy
+    rs = np.empty_like(spec)
+    assert orc.spectrogram_process(filt, rs, fs, nfft, hop) == ns
+    assert np.allclose(spec, rs, rtol=1e-5, atol=1e-20*rs.max())
+    re = np.empty((n, C))
+    orc.envelope_process(esos, filt, re, 0, 0)
+    assert np.max(np.abs(env - re)) <= 1e-9
+    # a slice of the kept range hits too
+    part = np.empty((n - 40000, C))
+    _lib.envelope(esos, filt[40000:], part, 0, True)
+    assert _lib.resident_hits() == hits0 + 3
+    orc.envelope_process(esos, filt[40000:], re[:n - 40000], 0, 0)
+    assert np.max(np.abs(part - re[:n - 40000])) <= 1e-9
+
+
+def test_stale_resident_copy_is_not_used(resident):
+    fs, C, n = 48000., 2, 50000
+    x = synth(0, n, C, fs, seed=12)
+    sos = orc.filter_design(fs, 1000., 15000., 2)
+    filt = np.empty((n, C))
+    _lib.sosfilt(sos, x, filt, 0)
+    # the caller says so
+    filt *= 0.5
+    _lib.invalidate(filt)
+    hits = _lib.resident_hits()
+    got = _lib.minmax(filt, 100)
+    assert _lib.resident_hits() == hits
+    assert np.array_equal(got.view(np.uint64), orc.minmax_rows(filt, 100).view(np.uint64))
+    # the caller forgets to say so: the sampled verification notices
+    _lib.sosfilt(sos, x, filt, 0)
+    filt += 1.0
+    hits = _lib.resident_hits()
+    got = _lib.minmax(filt, 100)
+    assert _lib.resident_hits() == hits
+    assert np.array_equal(got.view(np.uint64), orc.minmax_rows(filt, 100).view(np.uint64))
+    # results written over a kept range replace it
+    _lib.sosfilt(sos, x, filt, 0)
+    _lib.sosfilt(sos, 2.0*x, filt, 0)
+    got = _lib.minmax(filt, 100)
+    assert np.array_equal(got.view(np.uint64), orc.minmax_rows(filt, 100).view(np.uint64))
+
+
+def test_traces_invalidate_on_buffer_moves(resident):
+    """The scroll / parameter-change scenario of the golden fixture with every
+    result kept resident: audioio recycles and replaces the buffers between the
+    calls, the traces must invalidate the device copies in time."""
+    from test_host_traces import replay, check_calls
+    hits = _lib.resident_hits()
+    g, log, states, filt, spect, env = replay(use_gpu=True)
+    check_calls(g, log, states)
+    assert _lib.resident_hits() > hits                   # the chain did use device copies
+    assert np.max(np.abs(filt.buffer - g['filt_buffer'])) <= 1e-6
+    assert np.max(np.abs(env.buffer - g['env_buffer'])) <= 1e-6
+    ref = g['spec_buffer']
+    assert np.allclose(spect.buffer, ref, rtol=1e-5, atol=1e-20*ref.max())

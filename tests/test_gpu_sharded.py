@@ -20,6 +20,30 @@ from audian_b200.synth import synth
 from oracle import oracle as orc
 
 
+class LockedOps(object):
+    """CudaOps for rank threads that share one process: the library is specified for one
+    host thread at a time (its scratch memory is shared), so every call runs under a lock
+    and is complete before the next thread enters."""
+
+    _lock = threading.Lock()
+
+    def __init__(self):
+        from audian_b200.device import CudaOps
+        self._ops = CudaOps()
+        self.name = self._ops.name
+
+    def __getattr__(self, name):
+        fn = getattr(self._ops, name)
+
+        def call(*args, **kwargs):
+            import torch
+            with LockedOps._lock:
+                out = fn(*args, **kwargs)
+                torch.cuda.synchronize()
+                return out
+        return call
+
+
 class FakeDist(object):
     """In-process stand-in for torch.distributed for `world` threads."""
 
@@ -90,7 +114,7 @@ def test_fake_cluster_matches_single_pass(world):
         try:
             fd.bind(rank)
             torch.cuda.set_device(0)
-            ops = CudaOps()
+            ops = LockedOps()
             b = sharded.shard_bounds(frames, world, step)
             lo, hi = b[rank]
             rec = sharded.ShardedRecording(torch.from_numpy(x[lo:hi]).cuda(), frames, rate, ops,
