@@ -62,6 +62,10 @@ SIGNATURES = {
                                    _dp, _dp, _dp]),
     'adn_envelope_f64_dev': (_i32, [_dp, _i32, _dp, _i64, _i32, _i64, _dp, _i64,
                                     _i32, _dp]),
+    'adn_envelope_forward_f64_dev': (_i32, [_dp, _i32, _dp, _i64, _i32, _i32, _i32, _dp, _dp,
+                                            _dp, _dp]),
+    'adn_sosfilt_reverse_f64_dev': (_i32, [_dp, _i32, _dp, _i64, _i32, _dp, _dp, _i64, _i64,
+                                           _i32, _dp, _dp]),
     'adn_spectrogram_f64_dev': (_i32, [_dp, _i64, _i32, _f64, _i32, _i32, _i32,
                                        _i32, _dp, _i64, _i32, C.POINTER(_i64), _dp]),
     'adn_decibel_f64_dev': (_i32, [_dp, _i64, _f64, _f64, _dp, _dp]),

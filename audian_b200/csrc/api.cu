@@ -675,6 +675,31 @@ int32_t adn_envelope_f64_dev(const double* sos, int32_t S, const double* src, in
     return envelope_dev(sos, S, src, n_src, C, nbefore, dst, n_dst, clamp_negative, pick(stream));
 }
 
+int32_t adn_envelope_forward_f64_dev(const double* sos, int32_t S, const double* src, int64_t n_src,
+                                     int32_t C, int32_t edge_left, int32_t edge_right,
+                                     const double* zi, double* dst, double* zf, void* stream) {
+    if (S < 1 || S > ADN_MAX_SECTIONS || C < 1 || n_src < 1 || edge_left < 0 || edge_right < 0 ||
+        edge_left >= n_src || edge_right >= n_src)
+        return fail(ADN_ERR_INVALID, "adn_envelope_forward_f64_dev: bad shape");
+    if (!sos || !src) return fail(ADN_ERR_INVALID, "adn_envelope_forward_f64_dev: NULL pointer");
+    int32_t rc = ensure_init();
+    if (rc) return rc;
+    return envelope_forward_dev(sos, S, src, n_src, C, edge_left, edge_right, zi, dst, zf, pick(stream));
+}
+
+int32_t adn_sosfilt_reverse_f64_dev(const double* sos, int32_t S, const double* src, int64_t n_src,
+                                    int32_t C, const double* zi, double* dst, int64_t first,
+                                    int64_t n_dst, int32_t clamp_negative, double* zf, void* stream) {
+    if (S < 1 || S > ADN_MAX_SECTIONS || C < 1 || n_src < 1 ||
+        (dst && (first < 0 || n_dst < 0 || first + n_dst > n_src)))
+        return fail(ADN_ERR_INVALID, "adn_sosfilt_reverse_f64_dev: bad shape");
+    if (!sos || !src) return fail(ADN_ERR_INVALID, "adn_sosfilt_reverse_f64_dev: NULL pointer");
+    int32_t rc = ensure_init();
+    if (rc) return rc;
+    return sosfilt_reverse_dev(sos, S, src, n_src, C, zi, dst, first, n_dst, clamp_negative, zf,
+                               pick(stream));
+}
+
 int32_t adn_spectrogram_f64_dev(const double* src, int64_t n_src, int32_t C, double rate,
                                 int32_t nfft, int32_t hop, int32_t window_id, int32_t detrend_id,
                                 double* dst, int64_t n_dst, int32_t out_db, int64_t* n_computed,

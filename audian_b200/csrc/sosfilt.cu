@@ -125,6 +125,13 @@ __device__ __forceinline__ void matvec_acc(const double* __restrict__ M, const d
 
 constexpr double HALF_PI = 1.5707963267948966;
 
+// results go out with a streaming store, except the forward sweep of the envelope: the reversed
+// sweep starts reading where that one stopped writing, so its tail is left to live in L2
+template <int MODE, class T>
+__device__ __forceinline__ void st_out(T* p, T v) {
+    if (MODE == MODE_ENVF) *p = v; else __stcs(p, v);
+}
+
 template <int S, int MODE>
 __global__ void __launch_bounds__(SOS_NT, S <= 2 ? 5 : (S <= 4 ? 3 : 1))
 sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRun R) {
@@ -453,7 +460,7 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
                 const int64_t orow = MODE == MODE_REV ? rowbase - r : rowbase + r;
                 double2 o = *reinterpret_cast<const double2*>(tile_s + f + (r >> 5) * pad);
                 if (R.clamp) { o.x = o.x < 0.0 ? 0.0 : o.x; o.y = o.y < 0.0 ? 0.0 : o.y; }
-                __stcs(reinterpret_cast<double2*>(R.dst + orow * C + c), o);
+                st_out<MODE>(reinterpret_cast<double2*>(R.dst + orow * C + c), o);
             }
         } else {
 #pragma unroll
@@ -463,7 +470,7 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
                 const int64_t orow = MODE == MODE_REV ? rowbase - r : rowbase + r;
                 double o = tile_s[f + (r >> 5) * pad];
                 if (R.clamp) o = o < 0.0 ? 0.0 : o;
-                __stcs(R.dst + orow * C + c, o);
+                st_out<MODE>(R.dst + orow * C + c, o);
             }
         }
         return;
@@ -484,11 +491,11 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
                 if (gw == 2) {
                     double2 o = *reinterpret_cast<const double2*>(sp);
                     if (R.clamp) { o.x = o.x < 0.0 ? 0.0 : o.x; o.y = o.y < 0.0 ? 0.0 : o.y; }
-                    __stcs(reinterpret_cast<double2*>(gp), o);
+                    st_out<MODE>(reinterpret_cast<double2*>(gp), o);
                 } else {
                     double o = *sp;
                     if (R.clamp) o = o < 0.0 ? 0.0 : o;
-                    __stcs(gp, o);
+                    st_out<MODE>(gp, o);
                 }
             }
             row += drow;
@@ -814,6 +821,27 @@ int32_t envelope_dev(const double* sos, int32_t S, const double* src, int64_t n_
     ADN_CK(cudaGetLastError());
     return run_scan(MODE_REV, sos, S, y1, next, next, 0, C, dst, edge + nbefore, n_dst,
                     clamp_negative ? 1 : 0, d_s0b, nullptr, SCR_SOS_MISC, st);
+}
+
+// The two sweeps of the envelope as separate steps (time-sharded recordings run them with the
+// boundary states exchanged in between): forward sosfilt of (pi/2)|src| with scipy's odd
+// extension of edge_left / edge_right rows at the respective end (0 = none), from state zi;
+// dst (if given) receives all edge_left + n_src + edge_right rows.
+int32_t envelope_forward_dev(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
+                             int32_t edge_left, int32_t edge_right, const double* zi, double* dst,
+                             double* zf, cudaStream_t st) {
+    const int64_t next = n_src + edge_left + edge_right;
+    return run_scan(MODE_ENVF, sos, S, src, next, n_src, edge_left, C, dst, 0, next, 0, zi, zf,
+                    SCR_SOS_TILES, st);
+}
+
+// Time-reversed sosfilt: rows are filtered from the last to the first starting from state zi;
+// dst[i] (if given) = result at row first + i, i < n_dst; zf = state after row 0.
+int32_t sosfilt_reverse_dev(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
+                            const double* zi, double* dst, int64_t first, int64_t n_dst,
+                            int32_t clamp_negative, double* zf, cudaStream_t st) {
+    return run_scan(MODE_REV, sos, S, src, n_src, n_src, 0, C, dst, first, dst ? n_dst : 0,
+                    clamp_negative ? 1 : 0, zi, zf, SCR_SOS_MISC, st);
 }
 
 }  // namespace adn

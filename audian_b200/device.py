@@ -60,6 +60,13 @@ class CudaOps(object):
     def envelope(self, sos, src, nbefore=0, clamp_negative=True):
         return envelope(sos, src, nbefore, clamp_negative)
 
+    def env_forward(self, sos, src, edge_left=0, edge_right=0, zi=None, state_only=False):
+        return env_forward(sos, src, edge_left, edge_right, zi, state_only)
+
+    def sosfilt_rev(self, sos, src, zi=None, first=0, n_dst=None, clamp_negative=False,
+                    state_only=False):
+        return sosfilt_rev(sos, src, zi, first, n_dst, clamp_negative, state_only)
+
 
 def minmax(src, step, out=None):
     _check_trace(src, 'src')
@@ -108,6 +115,47 @@ def envelope(sos, src, nbefore=0, clamp_negative=True, out=None):
         None if sos is None else sos.ctypes.data, S, _p(src), n, ch, int(nbefore),
         _p(out), out.shape[0], 1 if clamp_negative else 0, _stream()))
     return out
+
+
+def env_forward(sos, src, edge_left=0, edge_right=0, zi=None, state_only=False):
+    """Forward sweep of the envelope over one time shard: sosfilt of (pi/2)|src|
+    with scipy's odd extension at the ends that are ends of the recording.
+    Returns (y1, zf), y1 (edge_left + n + edge_right, C) or None if state_only."""
+    torch = _torch()
+    _check_trace(src, 'src')
+    sos, S = _lib.sos_array(sos)
+    n, ch = src.shape
+    zf = torch.empty((ch, S, 2), dtype=src.dtype, device=src.device)
+    out = None
+    if not state_only:
+        out = torch.empty((n + edge_left + edge_right, ch), dtype=src.dtype, device=src.device)
+    if zi is not None:
+        _check_trace(zi, 'zi')
+    _lib.check(_lib.lib().adn_envelope_forward_f64_dev(
+        sos.ctypes.data, S, _p(src), n, ch, int(edge_left), int(edge_right), _p(zi), _p(out),
+        _p(zf), _stream()))
+    return out, zf
+
+
+def sosfilt_rev(sos, src, zi=None, first=0, n_dst=None, clamp_negative=False, state_only=False):
+    """sosfilt over the rows of src in reversed order from state zi.
+    Returns (rows first..first+n_dst of the result or None, zf)."""
+    torch = _torch()
+    _check_trace(src, 'src')
+    sos, S = _lib.sos_array(sos)
+    n, ch = src.shape
+    zf = torch.empty((ch, S, 2), dtype=src.dtype, device=src.device)
+    out = None
+    if not state_only:
+        if n_dst is None:
+            n_dst = n - first
+        out = torch.empty((n_dst, ch), dtype=src.dtype, device=src.device)
+    if zi is not None:
+        _check_trace(zi, 'zi')
+    _lib.check(_lib.lib().adn_sosfilt_reverse_f64_dev(
+        sos.ctypes.data, S, _p(src), n, ch, _p(zi), _p(out), int(first),
+        0 if out is None else out.shape[0], 1 if clamp_negative else 0, _p(zf), _stream()))
+    return out, zf
 
 
 def spectrogram(src, rate, nfft, hop, n_dst, out_db=False, out=None):

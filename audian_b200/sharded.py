@@ -199,6 +199,88 @@ class ShardedRecording(object):
         # 4. filter the shard from its true incoming state
         return self.ops.sosfilt(sos_a, x, 0, s.reshape(C, S, 2).contiguous())
 
+    # ------------------------------------------------------------ envelope
+    def envelope(self, sos, clamp_negative=True):
+        """This rank's part of the envelope of the whole recording:
+        sosfiltfilt(sos, (pi/2)|recording|, axis=0) with scipy's odd padding at
+        the two ends of the recording (bufferedenvelope.py:34-41 over the whole
+        file), negatives clamped.  Two exchange steps: the forward boundary
+        states travel rank r -> r+1, the backward ones r+1 -> r."""
+        import torch
+        from scipy.signal import sosfilt_zi
+        dist = self.dist
+        sos_a, S = _lib.sos_array(sos)
+        x = self.local
+        C = self.channels
+        if S == 0:
+            return torch.zeros_like(x)
+        D = 2*S
+        edge = _lib.sosfiltfilt_edge(sos_a)
+        if self.frames <= edge:
+            raise ValueError('The length of the input vector x must be greater than '
+                             'padlen, which is %d.' % edge)
+        r, W = self.rank, self.world
+        first, last = r == 0, r == W - 1
+        if (self.bounds[0][1] - self.bounds[0][0] <= edge or
+                self.bounds[-1][1] - self.bounds[-1][0] <= edge):
+            raise ValueError('the first and last shard must be longer than the pad length')
+        el = edge if first else 0
+        er = edge if last else 0
+        lens = [hi - lo + (edge if i == 0 else 0) + (edge if i == W - 1 else 0)
+                for i, (lo, hi) in enumerate(self.bounds)]
+        zi = torch.as_tensor(sosfilt_zi(sos_a).reshape(1, D), dtype=x.dtype, device=x.device)
+        keep = _lib.sos_decay_length(sos_a, 1e-30)
+        key = (sos_a.tobytes(), tuple(lens), str(x.device))
+        mats = ShardedRecording._matrix_cache.get(key)
+        if mats is None:
+            if len(ShardedRecording._matrix_cache) > 32:
+                ShardedRecording._matrix_cache.clear()
+            mats = [torch.as_tensor(_lib.sos_state_space(sos_a, n)[2].T.copy(), dtype=x.dtype,
+                                    device=x.device) for n in lens]
+            ShardedRecording._matrix_cache[key] = mats
+        # ---- forward sweep
+        if W == 1:
+            v = None
+        elif 0 < keep < x.shape[0] - edge - 1:
+            _, v = self.ops.env_forward(sos_a, x[-keep:], 0, er, None, state_only=True)
+        else:
+            _, v = self.ops.env_forward(sos_a, x, el, er, None, state_only=True)
+        z0 = torch.zeros((C, D), dtype=x.dtype, device=x.device)
+        if first:
+            # scipy: zi * ext[0], ext[0] = 2 r[0] - r[edge], r = (pi/2)|x|
+            x0 = (np.pi/2)*(2.0*x[0].abs() - x[edge].abs())
+            z0 = x0.reshape(C, 1)*zi
+        if W > 1:
+            pack = torch.cat([v.reshape(C, D), z0], dim=1).contiguous()
+            got = [torch.empty_like(pack) for _ in range(W)]
+            dist.all_gather(got, pack)
+            s = got[0][:, D:].clone()
+            for i in range(r):
+                s = s @ mats[i] + got[i][:, :D]
+        else:
+            s = z0
+        y1, _ = self.ops.env_forward(sos_a, x, el, er, s.reshape(C, S, 2).contiguous())
+        # ---- backward sweep (time reversed: the last rank comes first)
+        q0 = torch.zeros((C, D), dtype=x.dtype, device=x.device)
+        if last:
+            q0 = y1[-1].reshape(C, 1)*zi
+        if W > 1:
+            if 0 < keep < y1.shape[0]:
+                _, w = self.ops.sosfilt_rev(sos_a, y1[:keep], None, state_only=True)
+            else:
+                _, w = self.ops.sosfilt_rev(sos_a, y1, None, state_only=True)
+            pack = torch.cat([w.reshape(C, D), q0], dim=1).contiguous()
+            got = [torch.empty_like(pack) for _ in range(W)]
+            dist.all_gather(got, pack)
+            q = got[W - 1][:, D:].clone()
+            for i in range(W - 1, r, -1):
+                q = q @ mats[i] + got[i][:, :D]
+        else:
+            q = q0
+        out, _ = self.ops.sosfilt_rev(sos_a, y1, q.reshape(C, S, 2).contiguous(), el,
+                                      x.shape[0], clamp_negative)
+        return out
+
     def filter_chain(self, sos, nfft, hop):
         """filtered -> spectrogram of the filtered trace, all sharded."""
         y = self.sosfilt(sos)

@@ -143,6 +143,24 @@ int32_t adn_envelope_f64_dev(const double* sos, int32_t S,
                              const double* src, int64_t n_src, int32_t C,
                              int64_t nbefore, double* dst, int64_t n_dst,
                              int32_t clamp_negative, void* stream);
+/* The two sweeps of the envelope as separate steps, for time-sharded recordings
+ * (audian_b200/sharded.py exchanges the boundary states in between):
+ * forward sosfilt of (pi/2)*|src| extended by scipy's odd padding of edge_left /
+ * edge_right rows (0 = that end is not an end of the recording) from state zi
+ * (device (C, S, 2) or NULL = zero); dst (or NULL) receives all
+ * edge_left + n_src + edge_right rows, zf (or NULL) the final state. */
+int32_t adn_envelope_forward_f64_dev(const double* sos, int32_t S,
+                                     const double* src, int64_t n_src, int32_t C,
+                                     int32_t edge_left, int32_t edge_right,
+                                     const double* zi, double* dst, double* zf,
+                                     void* stream);
+/* sosfilt over the rows in reversed order from state zi; dst[i] (or NULL) =
+ * result at row first + i, i < n_dst; zf = state after row 0. */
+int32_t adn_sosfilt_reverse_f64_dev(const double* sos, int32_t S,
+                                    const double* src, int64_t n_src, int32_t C,
+                                    const double* zi, double* dst, int64_t first,
+                                    int64_t n_dst, int32_t clamp_negative,
+                                    double* zf, void* stream);
 int32_t adn_spectrogram_f64_dev(const double* src, int64_t n_src, int32_t C,
                                 double rate, int32_t nfft, int32_t hop,
                                 int32_t window_id, int32_t detrend_id,

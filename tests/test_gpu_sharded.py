@@ -15,7 +15,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-from audian_b200 import sharded
+from audian_b200 import _lib, sharded
 from audian_b200.synth import synth
 from oracle import oracle as orc
 
@@ -106,6 +106,8 @@ def test_fake_cluster_matches_single_pass(world):
     x = synth(0, frames, C, rate, seed=31)
     sos = orc.filter_design(rate, 1000., 15000., 4)
     nfft, hop, step = 1024, 512, 1382
+    esos = orc.envelope_design(rate, 500.)
+    esos_slow = orc.envelope_design(rate, 2.0)            # remembers ~1e5 samples: crosses shards
     fd = FakeDist(world)
     res = [None]*world
     err = []
@@ -125,9 +127,12 @@ def test_fake_cluster_matches_single_pass(world):
             rec = sharded.ShardedRecording(torch.from_numpy(x[lo:hi]).cuda(), frames, rate, ops,
                                            rank, world, b, fd)
             y, spec, k0, nf = rec.filter_chain(sos, nfft, hop)
+            frec = sharded.ShardedRecording(y, frames, rate, ops, rank, world, b, fd)
+            env = frec.envelope(esos, True)
+            slow = frec.envelope(esos_slow, True)
             torch.cuda.synchronize()
             res[rank] = (rows.cpu().numpy() if rows is not None else None, lo, y.cpu().numpy(),
-                         k0, spec.cpu().numpy(), nf)
+                         k0, spec.cpu().numpy(), nf, env.cpu().numpy(), slow.cpu().numpy())
         except Exception as e:          # pragma: no cover
             err.append(e)
             fd.barrier.abort()
@@ -150,6 +155,47 @@ def test_fake_cluster_matches_single_pass(world):
     spec = np.concatenate([r[4] for r in res])
     assert spec.shape == sref.shape and res[0][5] == nf
     assert np.allclose(spec, sref, rtol=1e-5, atol=1e-20*sref.max())
+    # envelope of the filtered recording == one sosfiltfilt over all of it
+    for k, es in ((6, esos), (7, esos_slow)):
+        eref = np.empty_like(x)
+        orc.envelope_process(es, yref, eref, 0, 0)
+        env = np.concatenate([r[k] for r in res])
+        assert env.shape == eref.shape
+        assert np.max(np.abs(env - eref)) <= 1e-6
+
+
+def test_envelope_sweeps_match_scipy_pieces():
+    """The two sweeps exposed for the sharded driver, against scipy on the same pieces."""
+    import torch
+    from scipy.signal import sosfilt
+    from audian_b200 import device
+    fs, C, n = 48000., 3, 30011
+    hx = synth(0, n, C, fs, seed=41)
+    x = torch.from_numpy(hx).cuda()
+    sos = orc.envelope_design(fs, 300.)
+    S = sos.shape[0]
+    edge = _lib.sosfiltfilt_edge(sos)
+    r = (np.pi/2)*np.abs(hx)
+    zi = np.random.default_rng(1).standard_normal((C, S, 2))
+    for el, er in ((0, 0), (edge, 0), (0, edge), (edge, edge)):
+        seq = np.concatenate(([2*r[0] - r[el:0:-1]] if el else []) + [r] +
+                             ([2*r[-1] - r[-2:-er - 2:-1]] if er else []))
+        ref = np.empty_like(seq)
+        zref = np.empty((C, S, 2))
+        for c in range(C):
+            ref[:, c], zref[c] = sosfilt(sos, seq[:, c], zi=zi[c])
+        y1, zf = device.env_forward(sos, x, el, er, torch.from_numpy(zi).cuda())
+        assert np.max(np.abs(y1.cpu().numpy() - ref)) <= 1e-9
+        assert np.max(np.abs(zf.cpu().numpy() - zref)) <= 1e-9
+        _, z2 = device.env_forward(sos, x, el, er, torch.from_numpy(zi).cuda(), state_only=True)
+        assert torch.equal(z2, zf)
+    rev = np.empty_like(hx)
+    zref = np.empty((C, S, 2))
+    for c in range(C):
+        rev[:, c], zref[c] = sosfilt(sos, hx[::-1, c], zi=zi[c])
+    out, zf = device.sosfilt_rev(sos, x, torch.from_numpy(zi).cuda(), 100, n - 300, False)
+    assert np.max(np.abs(out.cpu().numpy() - rev[::-1][100:n - 200])) <= 1e-9
+    assert np.max(np.abs(zf.cpu().numpy() - zref)) <= 1e-9
 
 
 def _nccl_worker(rank, world, port, frames, C, rate, q):
@@ -171,9 +217,12 @@ def _nccl_worker(rank, world, port, frames, C, rate, q):
         rec = sharded.ShardedRecording(x, frames, rate, bounds=b)
         sos = orc.filter_design(rate, 500., 9000., 2)
         y, spec, k0, nf = rec.filter_chain(sos, nfft, hop)
+        frec = sharded.ShardedRecording(y, frames, rate, bounds=b)
+        env = frec.envelope(orc.envelope_design(rate, 20.), True)
         torch.cuda.synchronize()
         parts = [None]*world
-        dist.all_gather_object(parts, (lo, y.cpu().numpy(), k0, spec.cpu().numpy(), nf))
+        dist.all_gather_object(parts, (lo, y.cpu().numpy(), k0, spec.cpu().numpy(), nf,
+                                       env.cpu().numpy()))
         if rank == 0:
             q.put(parts)
     finally:
@@ -212,3 +261,7 @@ def test_nccl_two_gpus():
     orc.spectrogram_process(yref, sref, rate, 512, 256)
     spec = np.concatenate([p[3] for p in sorted(parts, key=lambda p: p[2])])
     assert np.allclose(spec, sref, rtol=1e-5, atol=1e-20*sref.max())
+    eref = np.empty_like(x)
+    orc.envelope_process(orc.envelope_design(rate, 20.), yref, eref, 0, 0)
+    env = np.concatenate([p[5] for p in sorted(parts, key=lambda p: p[0])])
+    assert np.max(np.abs(env - eref)) <= 1e-6

@@ -45,6 +45,39 @@ class OracleOps(object):
     def empty(self, shape):
         return torch.empty(shape, dtype=torch.float64)
 
+    def _filt(self, sos, seq, zi):
+        S = sos.shape[0]
+        y = np.empty_like(seq)
+        zf = np.empty((seq.shape[1], S, 2))
+        for c in range(seq.shape[1]):
+            z0 = np.zeros((S, 2)) if zi is None else zi.numpy()[c]
+            y[:, c], zf[c] = sosfilt(sos, seq[:, c], zi=z0)
+        return y, zf
+
+    def env_forward(self, sos, src, edge_left=0, edge_right=0, zi=None, state_only=False):
+        r = (np.pi/2)*np.abs(src.numpy())
+        parts = []
+        if edge_left:
+            parts.append(2*r[0] - r[edge_left:0:-1])
+        parts.append(r)
+        if edge_right:
+            parts.append(2*r[-1] - r[-2:-edge_right - 2:-1])
+        y, zf = self._filt(sos, np.concatenate(parts), zi)
+        return (None if state_only else torch.from_numpy(y)), torch.from_numpy(zf)
+
+    def sosfilt_rev(self, sos, src, zi=None, first=0, n_dst=None, clamp_negative=False,
+                    state_only=False):
+        y, zf = self._filt(sos, src.numpy()[::-1].copy(), zi)
+        if state_only:
+            return None, torch.from_numpy(zf)
+        y = y[::-1]
+        if n_dst is None:
+            n_dst = len(y) - first
+        y = y[first:first + n_dst].copy()
+        if clamp_negative:
+            y[y < 0] = 0
+        return torch.from_numpy(y), torch.from_numpy(zf)
+
     def spectrogram(self, src, rate, nfft, hop, n_dst, out_db=False, out=None):
         dst = np.empty((n_dst, src.shape[1], nfft//2 + 1))
         n = orc.spectrogram_process(src.numpy(), dst, rate, nfft, hop)
@@ -90,6 +123,14 @@ def _worker(rank, world, port, frames, C, rate, q):
         dist.all_gather_object(parts, (lo, y.numpy(), k0, spec.numpy(), nf))
         if rank == 0:
             out['chain'] = parts
+        # ---- envelope of the whole recording, slow (long memory) and fast cut-off
+        for name, fc in (('env_slow', 0.0005*rate), ('env_fast', 0.05*rate)):
+            esos = butter(2, fc, 'lowpass', fs=rate, output='sos')
+            e = rec.envelope(esos, True)
+            parts = [None]*world
+            dist.all_gather_object(parts, (lo, e.numpy()))
+            if rank == 0:
+                out[name] = parts
         if rank == 0:
             q.put(out)
     finally:
@@ -130,6 +171,16 @@ def test_sharded_matches_single_pass(world):
     assert out['chain'][0][4] == nf
     assert spec.shape == sref.shape
     assert np.allclose(spec, sref, rtol=1e-7, atol=1e-22*sref.max())
+
+
+    # envelope: equal to one sosfiltfilt over the whole recording
+    for name, fc in (('env_slow', 0.0005*rate), ('env_fast', 0.05*rate)):
+        esos = butter(2, fc, 'lowpass', fs=rate, output='sos')
+        eref = np.empty_like(x)
+        orc.envelope_process(esos, x, eref, 0, 0)
+        e = np.concatenate([p[1] for p in sorted(out[name], key=lambda p: p[0])])
+        assert e.shape == eref.shape
+        assert np.max(np.abs(e - eref)) <= 1e-9, name
 
 
 def test_shard_bounds():
