@@ -64,6 +64,8 @@ SIGNATURES = {
                                     _i32, _dp]),
     'adn_envelope_forward_f64_dev': (_i32, [_dp, _i32, _dp, _i64, _i32, _i32, _i32, _dp, _dp,
                                             _dp, _dp]),
+    'adn_envelope_state0_f64_dev': (_i32, [_dp, _i32, _dp, _i32, _i32, _i32, _dp, _dp]),
+    'adn_fold_states_f64_dev': (_i32, [_dp, _dp, _i32, _i32, _i32, _i32, _i32, _dp, _dp]),
     'adn_sosfilt_reverse_f64_dev': (_i32, [_dp, _i32, _dp, _i64, _i32, _dp, _dp, _i64, _i64,
                                            _i32, _dp, _dp]),
     'adn_spectrogram_f64_dev': (_i32, [_dp, _i64, _i32, _f64, _i32, _i32, _i32,

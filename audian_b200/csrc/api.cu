@@ -687,6 +687,25 @@ int32_t adn_envelope_forward_f64_dev(const double* sos, int32_t S, const double*
     return envelope_forward_dev(sos, S, src, n_src, C, edge_left, edge_right, zi, dst, zf, pick(stream));
 }
 
+int32_t adn_envelope_state0_f64_dev(const double* sos, int32_t S, const double* src, int32_t C,
+                                    int32_t edge, int32_t which, double* out, void* stream) {
+    if (S < 1 || S > ADN_MAX_SECTIONS || C < 1 || edge < 0 || which < 0 || which > 1 || !sos || !src || !out)
+        return fail(ADN_ERR_INVALID, "adn_envelope_state0_f64_dev: bad arguments");
+    int32_t rc = ensure_init();
+    if (rc) return rc;
+    return envelope_state0_dev(sos, S, src, C, edge, which, out, pick(stream));
+}
+
+int32_t adn_fold_states_f64_dev(const double* packs, const double* mats, int32_t world, int32_t C,
+                                int32_t D, int32_t rank, int32_t backward, double* out, void* stream) {
+    if (world < 1 || C < 1 || D < 2 || D > 2 * ADN_MAX_SECTIONS || rank < 0 || rank >= world ||
+        !packs || !mats || !out)
+        return fail(ADN_ERR_INVALID, "adn_fold_states_f64_dev: bad arguments");
+    int32_t rc = ensure_init();
+    if (rc) return rc;
+    return fold_states_dev(packs, mats, world, C, D, rank, backward, out, pick(stream));
+}
+
 int32_t adn_sosfilt_reverse_f64_dev(const double* sos, int32_t S, const double* src, int64_t n_src,
                                     int32_t C, const double* zi, double* dst, int64_t first,
                                     int64_t n_dst, int32_t clamp_negative, double* zf, void* stream) {

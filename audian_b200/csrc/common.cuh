@@ -62,6 +62,10 @@ int32_t envelope_dev(const double* sos, int32_t S, const double* src, int64_t n_
 int32_t envelope_forward_dev(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
                              int32_t edge_left, int32_t edge_right, const double* zi, double* dst,
                              double* zf, cudaStream_t st);
+int32_t envelope_state0_dev(const double* sos, int32_t S, const double* src, int32_t C, int32_t edge,
+                            int32_t which, double* out, cudaStream_t st);
+int32_t fold_states_dev(const double* packs, const double* mats, int32_t W, int32_t C, int32_t D,
+                        int32_t rank, int32_t backward, double* out, cudaStream_t st);
 int32_t sosfilt_reverse_dev(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
                             const double* zi, double* dst, int64_t first, int64_t n_dst,
                             int32_t clamp_negative, double* zf, cudaStream_t st);

@@ -507,11 +507,14 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
 
 // initial states of the two sosfiltfilt sweeps: s0[c][d] = zi[d] * x0[c]
 // which = 0: x0 = ext[0] = 2 r(0) - r(edge) of the raw input;  which = 1: x0 = row[c]
+struct ZiK { double z[2 * ADN_MAX_SECTIONS]; };      // sosfilt_zi(sos), passed by value
+
 __global__ void env_s0_kernel(int which, const double* __restrict__ src, int32_t C, int32_t D,
-                              int64_t edge, const double* __restrict__ zi, double* __restrict__ s0) {
+                              int64_t edge, const __grid_constant__ ZiK zik, double* __restrict__ s0) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= C * D) return;
     int c = i / D, d = i - c * D;
+    const double* zi = zik.z;
     double x0;
     if (which == 0) {
         const double hp = 1.5707963267948966;
@@ -779,44 +782,91 @@ int32_t sosfilt_dev(const double* sos, int32_t S, const double* src, int64_t n_s
                     SCR_SOS_TILES, st);
 }
 
+// zi = sosfilt_zi(sos): per section scale * lfilter_zi(b, a), scale *= sum(b)/sum(a)
+static void sosfilt_zi_host(const double* sos, int S, double* zi) {
+    double scale = 1.0;
+    for (int s = 0; s < S; ++s) {
+        const double* q = sos + 6 * s;
+        double b0 = q[0], b1 = q[1], b2 = q[2], a0 = q[3], a1 = q[4], a2 = q[5];
+        double B0 = b1 - a1 * b0, B1 = b2 - a2 * b0;
+        double det = 1.0 + a1 + a2;
+        zi[2 * s] = scale * ((B0 + B1) / det);
+        zi[2 * s + 1] = scale * (((1.0 + a1) * B1 - a2 * B0) / det);
+        scale *= (b0 + b1 + b2) / (a0 + a1 + a2);
+    }
+}
+
+// out (C, S, 2) = sosfilt_zi(sos) * x0 per channel: which = 0: x0 = ext[0] = 2 r(0) - r(edge) of
+// the raw rows at src (the start of the recording), which = 1: x0 = the row at src
+int32_t envelope_state0_dev(const double* sos, int32_t S, const double* src, int32_t C, int32_t edge,
+                            int32_t which, double* out, cudaStream_t st) {
+    ZiK zik;
+    sosfilt_zi_host(sos, S, zik.z);
+    const int D = 2 * S;
+    env_s0_kernel<<<(C * D + 127) / 128, 128, 0, st>>>(which, src, C, D, edge, zik, out);
+    count_launch();
+    ADN_CK(cudaGetLastError());
+    return ADN_OK;
+}
+
+// incoming state of rank `rank` from the gathered boundary records, packs (W, 2, C, D):
+// [i][0] = end state of shard i from zero state, [i][1] = state entering the recording (used
+// from shard 0 forward, from shard W-1 backward); mats (W, D, D) = A^len(shard i), row major
+__global__ void fold_states_kernel(const double* __restrict__ packs, const double* __restrict__ mats,
+                                   int32_t W, int32_t C, int32_t D, int32_t rank, int32_t backward,
+                                   double* __restrict__ out) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s[2 * ADN_MAX_SECTIONS], t[2 * ADN_MAX_SECTIONS];
+    const int first = backward ? W - 1 : 0;
+    const double* init = packs + ((size_t)(first * 2 + 1) * C + c) * D;
+    for (int d = 0; d < D; ++d) s[d] = init[d];
+    for (int k = 0; k < (backward ? W - 1 - rank : rank); ++k) {
+        const int i = backward ? W - 1 - k : k;
+        const double* M = mats + (size_t)i * D * D;
+        const double* v = packs + ((size_t)(i * 2) * C + c) * D;
+        for (int r = 0; r < D; ++r) {
+            double a = v[r];
+            for (int q = 0; q < D; ++q) a = fma(M[r * D + q], s[q], a);
+            t[r] = a;
+        }
+        for (int d = 0; d < D; ++d) s[d] = t[d];
+    }
+    for (int d = 0; d < D; ++d) out[(size_t)c * D + d] = s[d];
+}
+
+int32_t fold_states_dev(const double* packs, const double* mats, int32_t W, int32_t C, int32_t D,
+                        int32_t rank, int32_t backward, double* out, cudaStream_t st) {
+    fold_states_kernel<<<(C + 63) / 64, 64, 0, st>>>(packs, mats, W, C, D, rank, backward, out);
+    count_launch();
+    ADN_CK(cudaGetLastError());
+    return ADN_OK;
+}
+
 int32_t envelope_dev(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
                      int64_t nbefore, double* dst, int64_t n_dst, int32_t clamp_negative,
                      cudaStream_t st) {
     const int D = 2 * S;
     const int edge = adn_sosfiltfilt_edge(sos, S);
     const int64_t next = n_src + 2 * (int64_t)edge;
-    // zi = sosfilt_zi(sos): per section scale * lfilter_zi(b, a), scale *= sum(b)/sum(a)
-    double zi[2 * ADN_MAX_SECTIONS];
-    {
-        double scale = 1.0;
-        for (int s = 0; s < S; ++s) {
-            const double* q = sos + 6 * s;
-            double b0 = q[0], b1 = q[1], b2 = q[2], a0 = q[3], a1 = q[4], a2 = q[5];
-            double B0 = b1 - a1 * b0, B1 = b2 - a2 * b0;
-            double det = 1.0 + a1 + a2;
-            zi[2 * s] = scale * ((B0 + B1) / det);
-            zi[2 * s + 1] = scale * (((1.0 + a1) * B1 - a2 * B0) / det);
-            scale *= (b0 + b1 + b2) / (a0 + a1 + a2);
-        }
-    }
+    ZiK zik;
+    sosfilt_zi_host(sos, S, zik.z);
     DevBuf& fwd = scratch(SCR_ENV_FWD);
     DevBuf& misc = scratch(SCR_ENV_MISC);
     int32_t rc;
     if ((rc = fwd.reserve((size_t)next * C * 8))) return rc;
-    if ((rc = misc.reserve((size_t)(D + 2 * C * D) * 8))) return rc;
-    double* d_zi = misc.as<double>();
-    double* d_s0f = d_zi + D;
+    if ((rc = misc.reserve((size_t)(2 * C * D) * 8))) return rc;
+    double* d_s0f = misc.as<double>();
     double* d_s0b = d_s0f + (size_t)C * D;
-    ADN_CK(cudaMemcpyAsync(d_zi, zi, D * 8, cudaMemcpyHostToDevice, st));
     const int nb = (C * D + 127) / 128;
-    env_s0_kernel<<<nb, 128, 0, st>>>(0, src, C, D, edge, d_zi, d_s0f);
+    env_s0_kernel<<<nb, 128, 0, st>>>(0, src, C, D, edge, zik, d_s0f);
     count_launch();
     ADN_CK(cudaGetLastError());
     double* y1 = fwd.as<double>();
     if ((rc = run_scan(MODE_ENVF, sos, S, src, next, n_src, edge, C, y1, 0, next, 0, d_s0f, nullptr,
                        SCR_SOS_TILES, st)))
         return rc;
-    env_s0_kernel<<<nb, 128, 0, st>>>(1, y1 + (next - 1) * C, C, D, 0, d_zi, d_s0b);
+    env_s0_kernel<<<nb, 128, 0, st>>>(1, y1 + (next - 1) * C, C, D, 0, zik, d_s0b);
     count_launch();
     ADN_CK(cudaGetLastError());
     return run_scan(MODE_REV, sos, S, y1, next, next, 0, C, dst, edge + nbefore, n_dst,

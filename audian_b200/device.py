@@ -51,8 +51,8 @@ class CudaOps(object):
         return minmax(src, step)
 
     def sosfilt(self, sos, src, nbefore=0, zi=None, want_zf=False, out=None,
-                state_only=False):
-        return sosfilt(sos, src, nbefore, zi, want_zf, out, state_only)
+                state_only=False, zf_out=None):
+        return sosfilt(sos, src, nbefore, zi, want_zf, out, state_only, zf_out)
 
     def spectrogram(self, src, rate, nfft, hop, n_dst, out_db=False, out=None):
         return spectrogram(src, rate, nfft, hop, n_dst, out_db, out)
@@ -60,12 +60,19 @@ class CudaOps(object):
     def envelope(self, sos, src, nbefore=0, clamp_negative=True):
         return envelope(sos, src, nbefore, clamp_negative)
 
-    def env_forward(self, sos, src, edge_left=0, edge_right=0, zi=None, state_only=False):
-        return env_forward(sos, src, edge_left, edge_right, zi, state_only)
+    def env_forward(self, sos, src, edge_left=0, edge_right=0, zi=None, state_only=False,
+                    zf_out=None):
+        return env_forward(sos, src, edge_left, edge_right, zi, state_only, zf_out)
 
     def sosfilt_rev(self, sos, src, zi=None, first=0, n_dst=None, clamp_negative=False,
-                    state_only=False):
-        return sosfilt_rev(sos, src, zi, first, n_dst, clamp_negative, state_only)
+                    state_only=False, zf_out=None):
+        return sosfilt_rev(sos, src, zi, first, n_dst, clamp_negative, state_only, zf_out)
+
+    def env_state0(self, sos, src, edge, which, out):
+        return env_state0(sos, src, edge, which, out)
+
+    def fold_states(self, packs, mats, rank, backward=False):
+        return fold_states(packs, mats, rank, backward)
 
 
 def minmax(src, step, out=None):
@@ -78,14 +85,16 @@ def minmax(src, step, out=None):
     return out
 
 
-def sosfilt(sos, src, nbefore=0, zi=None, want_zf=False, out=None, state_only=False):
-    """Returns out, or (out, zf) if want_zf; state_only skips the output."""
+def sosfilt(sos, src, nbefore=0, zi=None, want_zf=False, out=None, state_only=False,
+            zf_out=None):
+    """Returns out, or (out, zf) if want_zf; state_only skips the output.
+    zf_out: (C, S, 2)-sized contiguous tensor that receives the final state."""
     torch = _torch()
     _check_trace(src, 'src')
     sos, S = _lib.sos_array(sos)
     n, ch = src.shape
-    zf = None
-    if (want_zf or state_only) and S > 0:
+    zf = zf_out
+    if zf is None and (want_zf or state_only) and S > 0:
         zf = torch.empty((ch, S, 2), dtype=src.dtype, device=src.device)
     if zi is not None:
         _check_trace(zi, 'zi')
@@ -117,7 +126,7 @@ def envelope(sos, src, nbefore=0, clamp_negative=True, out=None):
     return out
 
 
-def env_forward(sos, src, edge_left=0, edge_right=0, zi=None, state_only=False):
+def env_forward(sos, src, edge_left=0, edge_right=0, zi=None, state_only=False, zf_out=None):
     """Forward sweep of the envelope over one time shard: sosfilt of (pi/2)|src|
     with scipy's odd extension at the ends that are ends of the recording.
     Returns (y1, zf), y1 (edge_left + n + edge_right, C) or None if state_only."""
@@ -125,7 +134,7 @@ def env_forward(sos, src, edge_left=0, edge_right=0, zi=None, state_only=False):
     _check_trace(src, 'src')
     sos, S = _lib.sos_array(sos)
     n, ch = src.shape
-    zf = torch.empty((ch, S, 2), dtype=src.dtype, device=src.device)
+    zf = zf_out if zf_out is not None else torch.empty((ch, S, 2), dtype=src.dtype, device=src.device)
     out = None
     if not state_only:
         out = torch.empty((n + edge_left + edge_right, ch), dtype=src.dtype, device=src.device)
@@ -137,14 +146,15 @@ def env_forward(sos, src, edge_left=0, edge_right=0, zi=None, state_only=False):
     return out, zf
 
 
-def sosfilt_rev(sos, src, zi=None, first=0, n_dst=None, clamp_negative=False, state_only=False):
+def sosfilt_rev(sos, src, zi=None, first=0, n_dst=None, clamp_negative=False, state_only=False,
+                zf_out=None):
     """sosfilt over the rows of src in reversed order from state zi.
     Returns (rows first..first+n_dst of the result or None, zf)."""
     torch = _torch()
     _check_trace(src, 'src')
     sos, S = _lib.sos_array(sos)
     n, ch = src.shape
-    zf = torch.empty((ch, S, 2), dtype=src.dtype, device=src.device)
+    zf = zf_out if zf_out is not None else torch.empty((ch, S, 2), dtype=src.dtype, device=src.device)
     out = None
     if not state_only:
         if n_dst is None:
@@ -156,6 +166,25 @@ def sosfilt_rev(sos, src, zi=None, first=0, n_dst=None, clamp_negative=False, st
         sos.ctypes.data, S, _p(src), n, ch, _p(zi), _p(out), int(first),
         0 if out is None else out.shape[0], 1 if clamp_negative else 0, _p(zf), _stream()))
     return out, zf
+
+
+def env_state0(sos, src, edge, which, out):
+    """out (C, S, 2)-sized = sosfilt_zi(sos) * x0: which 0: x0 = 2 r[0] - r[edge] of
+    the rows at src, r = (pi/2)|src|; which 1: x0 = src[0]."""
+    sos, S = _lib.sos_array(sos)
+    _lib.check(_lib.lib().adn_envelope_state0_f64_dev(
+        sos.ctypes.data, S, _p(src), src.shape[-1], int(edge), int(which), _p(out), _stream()))
+    return out
+
+
+def fold_states(packs, mats, rank, backward=False):
+    """State entering shard `rank`: packs (W, 2, C, D), mats (W, D, D) -> (C, D)."""
+    torch = _torch()
+    W, _, ch, D = packs.shape
+    out = torch.empty((ch, D), dtype=packs.dtype, device=packs.device)
+    _lib.check(_lib.lib().adn_fold_states_f64_dev(_p(packs), _p(mats), W, ch, D, int(rank),
+                                                  1 if backward else 0, _p(out), _stream()))
+    return out
 
 
 def spectrogram(src, rate, nfft, hop, n_dst, out_db=False, out=None):

@@ -48,12 +48,16 @@ def shard_bounds(frames, world, align=1):
 
 
 class ShardedRecording(object):
-    """One rank's time range [lo, hi) of a (frames, C) recording."""
+    """One rank's time range [lo, hi) of a (frames, C) recording.
+
+    `buffer`: optionally the tensor `local` is the head of -- (hi-lo + room, C)
+    with spare rows behind the shard; the STFT halo is then received in place
+    and the whole shard is transformed by one kernel launch."""
 
     _matrix_cache = {}
 
     def __init__(self, local, frames, rate, ops=None, rank=None, world=None,
-                 bounds=None, dist=None):
+                 bounds=None, dist=None, buffer=None):
         # `dist`: torch.distributed (default) or an object with the same all_gather /
         # P2POp / isend / irecv / batch_isend_irecv surface (single-device test clusters)
         self.dist = _dist() if dist is None else dist
@@ -63,6 +67,7 @@ class ShardedRecording(object):
         self.frames = int(frames)
         self.rate = float(rate)
         self.local = local
+        self.buffer = buffer
         self.channels = local.shape[1]
         if ops is None:
             from .device import CudaOps
@@ -74,6 +79,36 @@ class ShardedRecording(object):
             if self.hi - self.lo != local.shape[0]:
                 raise ValueError('local shard does not match its bounds')
 
+    # ------------------------------------------------------------ plumbing
+    def _gather(self, pack):
+        """(W,) + pack.shape tensor of every rank's `pack` (one collective, no copies)."""
+        import torch
+        dist = self.dist
+        out = torch.empty((self.world,) + tuple(pack.shape), dtype=pack.dtype, device=pack.device)
+        fn = getattr(dist, 'all_gather_into_tensor', None)
+        if fn is not None:
+            try:
+                fn(out, pack)
+                return out
+            except (RuntimeError, NotImplementedError):
+                pass
+        parts = [out[i] for i in range(self.world)]
+        dist.all_gather(parts, pack)
+        return out
+
+    def _matrices(self, sos_a, lens, like):
+        """(W, D, D) tensor of A^len_i: the homogeneous map of the cascade across shard i."""
+        import torch
+        key = (sos_a.tobytes(), tuple(lens), str(like.device))
+        mats = ShardedRecording._matrix_cache.get(key)
+        if mats is None:
+            if len(ShardedRecording._matrix_cache) > 32:
+                ShardedRecording._matrix_cache.clear()
+            m = np.stack([_lib.sos_state_space(sos_a, n)[2] for n in lens])
+            mats = torch.as_tensor(m, dtype=like.dtype, device=like.device).contiguous()
+            ShardedRecording._matrix_cache[key] = mats
+        return mats
+
     # ------------------------------------------------------------ min/max
     @staticmethod
     def minmax_bounds(frames, world, step):
@@ -83,7 +118,6 @@ class ShardedRecording(object):
         """Full-trace min/max rows (2*ceil(frames/step), C) on `dst_rank`
         (None elsewhere).  Shards must come from minmax_bounds()."""
         import torch
-        dist = self.dist
         if self.lo % step != 0:
             raise ValueError('shard boundary is not a multiple of step')
         rows = self.ops.minmax(self.local, step)
@@ -94,11 +128,10 @@ class ShardedRecording(object):
         if rows.shape[0] < width:
             padded = torch.zeros((width, self.channels), dtype=rows.dtype, device=rows.device)
             padded[:rows.shape[0]] = rows
-        gathered = [torch.empty_like(padded) for _ in range(self.world)]
-        dist.all_gather(gathered, padded.contiguous())
+        gathered = self._gather(padded.contiguous())
         if dst_rank is not None and self.rank != dst_rank:
             return None
-        out = torch.cat([g[:c] for g, c in zip(gathered, counts)], dim=0)
+        out = torch.cat([gathered[i, :c] for i, c in enumerate(counts)], dim=0)
         assert out.shape[0] == 2*nseg_total
         return out
 
@@ -120,15 +153,20 @@ class ShardedRecording(object):
         k0 = self.lo//hop
         k1 = min(nf_total, self.hi//hop if self.rank + 1 < self.world else nf_total)
         src = self.local
+        n = src.shape[0]
         recv = None
+        inplace = False
         if self.world > 1 and halo > 0:
             if any(hi - lo < halo for lo, hi in self.bounds):
                 raise ValueError('shards shorter than the STFT halo')
-            recv = torch.empty((halo, self.channels), dtype=src.dtype, device=src.device)
-            head = src[:halo].contiguous()
+            buf = self.buffer
+            inplace = (buf is not None and buf.shape[0] >= n + halo and
+                       buf.data_ptr() == src.data_ptr() and buf.is_contiguous())
+            recv = buf[n:n + halo] if inplace else \
+                torch.empty((halo, self.channels), dtype=src.dtype, device=src.device)
             ops = []
             if self.rank > 0:
-                ops.append(dist.P2POp(dist.isend, head, self.rank - 1))
+                ops.append(dist.P2POp(dist.isend, src[:halo], self.rank - 1))
             if self.rank + 1 < self.world:
                 ops.append(dist.P2POp(dist.irecv, recv, self.rank + 1))
             if ops:
@@ -141,9 +179,14 @@ class ShardedRecording(object):
             out, ncomp = self.ops.spectrogram(src, self.rate, nfft, hop, n_local, out_db)
             assert ncomp == n_local, (ncomp, n_local)
             return out, k0, nf_total
+        if inplace:
+            out, ncomp = self.ops.spectrogram(self.buffer[:n + halo], self.rate, nfft, hop,
+                                              n_local, out_db)
+            assert ncomp == n_local, (ncomp, n_local)
+            return out, k0, nf_total
         # frames that lie inside the shard come straight from it; only the last few, which
         # reach into the neighbour, are computed from a short tail + halo buffer
-        n_main = min(n_local, max(0, (src.shape[0] - nfft)//hop + 1))
+        n_main = min(n_local, max(0, (n - nfft)//hop + 1))
         out = self.ops.empty((n_local, self.channels, nfft//2 + 1))
         if n_main > 0:
             _, ncomp = self.ops.spectrogram(src, self.rate, nfft, hop, n_main, out_db,
@@ -161,43 +204,41 @@ class ShardedRecording(object):
         """A^len for every shard: the homogeneous map of the cascade across it."""
         return [_lib.sos_state_space(sos, hi - lo)[2] for lo, hi in self.bounds]
 
-    def sosfilt(self, sos, zi=None):
+    def sosfilt(self, sos, zi=None, room=0):
         """This rank's part of sosfilt(sos, recording, axis=0) (zero initial
-        state, or `zi` (C, S, 2) applied at frame 0)."""
+        state, or `zi` (C, S, 2) applied at frame 0).  room: spare rows to
+        allocate behind the result (the returned tensor is the head of
+        `self.last_buffer`), for a following in-place halo exchange."""
         import torch
-        dist = self.dist
         sos_a, S = _lib.sos_array(sos)
-        if S == 0:
-            return self.local.clone()
-        D = 2*S
-        C = self.channels
         x = self.local
+        n, C = x.shape
+        self.last_buffer = None
+        if S == 0:
+            return x.clone()
+        D = 2*S
+        ybuf = self.ops.empty((n + room, C))
+        y = ybuf[:n]
+        self.last_buffer = ybuf
         if self.world == 1:
-            return self.ops.sosfilt(sos_a, x, 0, zi)
+            self.ops.sosfilt(sos_a, x, 0, zi, out=y)
+            return y
         # 1. end state of this shard from zero state (aggregate); a cascade that forgets its
         # state within `keep` samples (|A^keep| < 1e-30) only needs the tail of the shard
         keep = _lib.sos_decay_length(sos_a, 1e-30)
-        xs = x[-keep:] if 0 < keep < x.shape[0] else x
-        v = self.ops.sosfilt(sos_a, xs, 0, None, state_only=True).reshape(C, D)
-        # 2. exchange
-        gathered = [torch.empty_like(v) for _ in range(self.world)]
-        dist.all_gather(gathered, v.contiguous())
-        # 3. fold the predecessors: s_{r+1} = A^len_r s_r + v_r
-        key = (sos_a.tobytes(), tuple(self.bounds), str(v.device))
-        mats = ShardedRecording._matrix_cache.get(key)
-        if mats is None:
-            if len(ShardedRecording._matrix_cache) > 32:
-                ShardedRecording._matrix_cache.clear()
-            mats = [torch.as_tensor(m.T.copy(), dtype=v.dtype, device=v.device)
-                    for m in self.shard_matrices(sos_a)]
-            ShardedRecording._matrix_cache[key] = mats
-        s = torch.zeros((C, D), dtype=v.dtype, device=v.device)
-        if zi is not None:
-            s = zi.reshape(C, D).clone()
-        for r in range(self.rank):
-            s = s @ mats[r] + gathered[r]
+        xs = x[-keep:] if 0 < keep < n else x
+        pack = self.ops.zeros((2, C, D)) if zi is None or self.rank > 0 else None
+        if pack is None:
+            pack = self.ops.empty((2, C, D))
+            pack[1].copy_(zi.reshape(C, D))
+        self.ops.sosfilt(sos_a, xs, 0, None, state_only=True, zf_out=pack[0])
+        # 2. exchange, 3. fold the predecessors: s_{r+1} = A^len_r s_r + v_r
+        packs = self._gather(pack)
+        mats = self._matrices(sos_a, [hi - lo for lo, hi in self.bounds], x)
+        s = self.ops.fold_states(packs, mats, self.rank, False)
         # 4. filter the shard from its true incoming state
-        return self.ops.sosfilt(sos_a, x, 0, s.reshape(C, S, 2).contiguous())
+        self.ops.sosfilt(sos_a, x, 0, s.reshape(C, S, 2), out=y)
+        return y
 
     # ------------------------------------------------------------ envelope
     def envelope(self, sos, clamp_negative=True):
@@ -207,11 +248,9 @@ class ShardedRecording(object):
         file), negatives clamped.  Two exchange steps: the forward boundary
         states travel rank r -> r+1, the backward ones r+1 -> r."""
         import torch
-        from scipy.signal import sosfilt_zi
-        dist = self.dist
         sos_a, S = _lib.sos_array(sos)
         x = self.local
-        C = self.channels
+        n, C = x.shape
         if S == 0:
             return torch.zeros_like(x)
         D = 2*S
@@ -228,63 +267,37 @@ class ShardedRecording(object):
         er = edge if last else 0
         lens = [hi - lo + (edge if i == 0 else 0) + (edge if i == W - 1 else 0)
                 for i, (lo, hi) in enumerate(self.bounds)]
-        zi = torch.as_tensor(sosfilt_zi(sos_a).reshape(1, D), dtype=x.dtype, device=x.device)
         keep = _lib.sos_decay_length(sos_a, 1e-30)
-        key = (sos_a.tobytes(), tuple(lens), str(x.device))
-        mats = ShardedRecording._matrix_cache.get(key)
-        if mats is None:
-            if len(ShardedRecording._matrix_cache) > 32:
-                ShardedRecording._matrix_cache.clear()
-            mats = [torch.as_tensor(_lib.sos_state_space(sos_a, n)[2].T.copy(), dtype=x.dtype,
-                                    device=x.device) for n in lens]
-            ShardedRecording._matrix_cache[key] = mats
-        # ---- forward sweep
-        if W == 1:
-            v = None
-        elif 0 < keep < x.shape[0] - edge - 1:
-            _, v = self.ops.env_forward(sos_a, x[-keep:], 0, er, None, state_only=True)
-        else:
-            _, v = self.ops.env_forward(sos_a, x, el, er, None, state_only=True)
-        z0 = torch.zeros((C, D), dtype=x.dtype, device=x.device)
-        if first:
-            # scipy: zi * ext[0], ext[0] = 2 r[0] - r[edge], r = (pi/2)|x|
-            x0 = (np.pi/2)*(2.0*x[0].abs() - x[edge].abs())
-            z0 = x0.reshape(C, 1)*zi
+        mats = self._matrices(sos_a, lens, x)
+        # ---- forward sweep: pack[0] = end state from zero state, pack[1] = scipy's initial
+        # state zi * ext[0] (rank 0 only)
+        pack = self.ops.zeros((2, C, D))
         if W > 1:
-            pack = torch.cat([v.reshape(C, D), z0], dim=1).contiguous()
-            got = [torch.empty_like(pack) for _ in range(W)]
-            dist.all_gather(got, pack)
-            s = got[0][:, D:].clone()
-            for i in range(r):
-                s = s @ mats[i] + got[i][:, :D]
-        else:
-            s = z0
-        y1, _ = self.ops.env_forward(sos_a, x, el, er, s.reshape(C, S, 2).contiguous())
-        # ---- backward sweep (time reversed: the last rank comes first)
-        q0 = torch.zeros((C, D), dtype=x.dtype, device=x.device)
-        if last:
-            q0 = y1[-1].reshape(C, 1)*zi
-        if W > 1:
-            if 0 < keep < y1.shape[0]:
-                _, w = self.ops.sosfilt_rev(sos_a, y1[:keep], None, state_only=True)
+            if 0 < keep < n - edge - 1:
+                self.ops.env_forward(sos_a, x[-keep:], 0, er, None, state_only=True, zf_out=pack[0])
             else:
-                _, w = self.ops.sosfilt_rev(sos_a, y1, None, state_only=True)
-            pack = torch.cat([w.reshape(C, D), q0], dim=1).contiguous()
-            got = [torch.empty_like(pack) for _ in range(W)]
-            dist.all_gather(got, pack)
-            q = got[W - 1][:, D:].clone()
-            for i in range(W - 1, r, -1):
-                q = q @ mats[i] + got[i][:, :D]
-        else:
-            q = q0
-        out, _ = self.ops.sosfilt_rev(sos_a, y1, q.reshape(C, S, 2).contiguous(), el,
-                                      x.shape[0], clamp_negative)
+                self.ops.env_forward(sos_a, x, el, er, None, state_only=True, zf_out=pack[0])
+        if first:
+            self.ops.env_state0(sos_a, x, edge, 0, pack[1])
+        packs = self._gather(pack) if W > 1 else pack.reshape(1, 2, C, D)
+        s = self.ops.fold_states(packs, mats, r, False)
+        y1, _ = self.ops.env_forward(sos_a, x, el, er, s.reshape(C, S, 2))
+        # ---- backward sweep (time reversed: the last rank comes first)
+        pack = self.ops.zeros((2, C, D))
+        if W > 1:
+            ys = y1[:keep] if 0 < keep < y1.shape[0] else y1
+            self.ops.sosfilt_rev(sos_a, ys, None, state_only=True, zf_out=pack[0])
+        if last:
+            self.ops.env_state0(sos_a, y1[-1:], 0, 1, pack[1])
+        packs = self._gather(pack) if W > 1 else pack.reshape(1, 2, C, D)
+        q = self.ops.fold_states(packs, mats, r, True)
+        out, _ = self.ops.sosfilt_rev(sos_a, y1, q.reshape(C, S, 2), el, n, clamp_negative)
         return out
 
     def filter_chain(self, sos, nfft, hop):
         """filtered -> spectrogram of the filtered trace, all sharded."""
-        y = self.sosfilt(sos)
+        y = self.sosfilt(sos, room=max(0, nfft - hop))
         f = ShardedRecording(y, self.frames, self.rate, self.ops, self.rank,
-                             self.world, self.bounds, self.dist)
+                             self.world, self.bounds, self.dist, buffer=self.last_buffer)
         spec, k0, nf = f.spectrogram(nfft, hop)
         return y, spec, k0, nf

@@ -218,13 +218,14 @@ def run_ours(args):
             y = filt
         else:
             rec = sharded.ShardedRecording(x, n*world, RATE, ops, rank, world, bounds)
-            y = rec.sosfilt(sos)
+            y = rec.sosfilt(sos, room=NFFT - HOP)
+            frec = sharded.ShardedRecording(y, n*world, RATE, ops, rank, world, bounds,
+                                            buffer=rec.last_buffer)
         if record:
             e[1].record()
         if world == 1:
             device.spectrogram(y, RATE, NFFT, HOP, nspec, out=spec)
         else:
-            frec = sharded.ShardedRecording(y, n*world, RATE, ops, rank, world, bounds)
             frec.spectrogram(NFFT, HOP)
         if record:
             e[2].record()
@@ -245,6 +246,32 @@ def run_ours(args):
     for i in range(args.warmup):
         step(i)
     sync_all()
+    # N > 1: one CUDA graph per input window (kernels, NCCL collectives and the small torch ops
+    # of the exchange in one launch); falls back to eager launches if capture is refused
+    graphs = None
+    graph_launches = 0
+    if world > 1 and args.graphs:
+        try:
+            graphs = []
+            l0 = _lib.launch_count()
+            for w in range(N_WINDOWS):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    step(w)
+                graphs.append(g)
+            graph_launches = (_lib.launch_count() - l0)//N_WINDOWS
+            for g in graphs:
+                g.replay()
+            sync_all()
+        except Exception as exc:                      # pragma: no cover
+            sys.stderr.write('CUDA graph capture failed (%s): eager launches\n' % (exc,))
+            graphs = None
+    ok = torch.tensor([1 if graphs is not None else 0], device='cuda')
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            graphs = None
+    # per-op times (and, without graphs, the timed region itself) from eager steps
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -252,12 +279,23 @@ def run_ours(args):
     launches0 = _lib.launch_count()
     sync_all()
     t_start, t_stop = ev(), ev()
-    t_start.record()
-    for i in range(args.steps):
-        step(args.warmup + i, record=True)
-    t_stop.record()
-    sync_all()
-    launches = _lib.launch_count() - launches0
+    if graphs is None:
+        t_start.record()
+        for i in range(args.steps):
+            step(args.warmup + i, record=True)
+        t_stop.record()
+        sync_all()
+        launches = _lib.launch_count() - launches0
+    else:
+        for i in range(min(args.steps, 5)):
+            step(i, record=True)
+        sync_all()
+        t_start.record()
+        for i in range(args.steps):
+            graphs[(args.warmup + i) % N_WINDOWS].replay()
+        t_stop.record()
+        sync_all()
+        launches = graph_launches*args.steps
     ms_total = t_start.elapsed_time(t_stop)
     tt = torch.tensor([ms_total], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -396,7 +434,8 @@ def run_ours(args):
                        'envelope_cutoff_hz': ENV_CUTOFF,
                        'l2': 'inputs larger than L2: each step reads a different 246 MB window',
                        'parallelism': 'single GPU' if world == 1 else
-                                      f'time-sharded x{world} (IIR state all-gather + STFT halo over NCCL)'},
+                                      f'time-sharded x{world} (IIR state all-gather + STFT halo over NCCL)',
+                       'launch': 'eager' if graphs is None else 'one CUDA graph per step; op_ms from eager steps'},
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
             'roofline': roofs[dominant], 'roofline_all': roofs, 'dominant': dominant,
             'op_ms': {'filter': t_f, 'spectrogram': t_s, 'envelope': t_e},
@@ -404,7 +443,15 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        torch.cuda.synchronize()
         dist.barrier()
+        torch.cuda.synchronize()
+        if graphs is not None:
+            # tearing down CUDA graphs that hold captured NCCL work together with their
+            # communicator can deadlock: everything is done and flushed, leave directly
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
@@ -414,6 +461,8 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-graphs', dest='graphs', action='store_false',
+                    help='N > 1: launch every step eagerly instead of replaying CUDA graphs')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -154,6 +154,21 @@ int32_t adn_envelope_forward_f64_dev(const double* sos, int32_t S,
                                      int32_t edge_left, int32_t edge_right,
                                      const double* zi, double* dst, double* zf,
                                      void* stream);
+/* out (C, S, 2) = sosfilt_zi(sos) * x0 per channel, the initial state scipy's
+ * sosfiltfilt gives a sweep: which = 0: x0 = 2 r[0] - r[edge], r = (pi/2)|src|
+ * (src = first rows of the recording); which = 1: x0 = the row at src. */
+int32_t adn_envelope_state0_f64_dev(const double* sos, int32_t S,
+                                    const double* src, int32_t C, int32_t edge,
+                                    int32_t which, double* out, void* stream);
+/* State entering shard `rank` of a time-sharded linear recurrence from the
+ * all-gathered boundary records: packs (world, 2, C, D), [i][0] = end state of
+ * shard i from zero state, [i][1] = state entering the recording (read from
+ * shard 0, or from shard world-1 if backward); mats (world, D, D) = A^len_i:
+ * s <- mats[i] s + packs[i][0] over the shards before (after) `rank`. */
+int32_t adn_fold_states_f64_dev(const double* packs, const double* mats,
+                                int32_t world, int32_t C, int32_t D,
+                                int32_t rank, int32_t backward, double* out,
+                                void* stream);
 /* sosfilt over the rows in reversed order from state zi; dst[i] (or NULL) =
  * result at row first + i, i < n_dst; zf = state after row 0. */
 int32_t adn_sosfilt_reverse_f64_dev(const double* sos, int32_t S,

@@ -79,6 +79,16 @@ class FakeDist(object):
         torch.cuda.synchronize()
         self.barrier.wait()
 
+    def all_gather_into_tensor(self, out, tensor):
+        import torch
+        torch.cuda.synchronize()
+        self.slots[self.local.rank] = tensor
+        self.barrier.wait()
+        for r in range(self.world):
+            out[r].copy_(self.slots[r])
+        torch.cuda.synchronize()
+        self.barrier.wait()
+
     def batch_isend_irecv(self, ops):
         import torch
         torch.cuda.synchronize()

@@ -29,32 +29,60 @@ class OracleOps(object):
         return torch.from_numpy(orc.minmax_rows(src.numpy(), step))
 
     def sosfilt(self, sos, src, nbefore=0, zi=None, want_zf=False, out=None,
-                state_only=False):
+                state_only=False, zf_out=None):
         x = src.numpy()
         S = sos.shape[0]
         y = np.empty_like(x)
         zf = np.empty((x.shape[1], S, 2))
         for c in range(x.shape[1]):
-            z0 = np.zeros((S, 2)) if zi is None else zi.numpy()[c]
+            z0 = np.zeros((S, 2)) if zi is None else zi.numpy().reshape(-1, S, 2)[c]
             y[:, c], zf[c] = sosfilt(sos, x[:, c], zi=z0)
+        if zf_out is not None:
+            zf_out.copy_(torch.from_numpy(zf).reshape(zf_out.shape))
         if state_only:
             return torch.from_numpy(zf)
         y = torch.from_numpy(y[nbefore:].copy())
+        if out is not None:
+            out.copy_(y)
+            y = out
         return (y, torch.from_numpy(zf)) if want_zf else y
 
     def empty(self, shape):
         return torch.empty(shape, dtype=torch.float64)
 
-    def _filt(self, sos, seq, zi):
+    def zeros(self, shape):
+        return torch.zeros(shape, dtype=torch.float64)
+
+    def env_state0(self, sos, src, edge, which, out):
+        from scipy.signal import sosfilt_zi
+        zi = sosfilt_zi(sos).reshape(1, -1)
+        x = src.numpy()
+        x0 = (np.pi/2)*(2*np.abs(x[0]) - np.abs(x[edge])) if which == 0 else x[0]
+        out.copy_(torch.from_numpy(x0.reshape(-1, 1)*zi).reshape(out.shape))
+        return out
+
+    def fold_states(self, packs, mats, rank, backward=False):
+        P, M = packs.numpy(), mats.numpy()
+        W = P.shape[0]
+        s = P[W - 1 if backward else 0, 1].copy()
+        order = range(W - 1, rank, -1) if backward else range(rank)
+        for i in order:
+            s = s @ M[i].T + P[i, 0]
+        return torch.from_numpy(s)
+
+    def _filt(self, sos, seq, zi, zf_out=None):
         S = sos.shape[0]
         y = np.empty_like(seq)
         zf = np.empty((seq.shape[1], S, 2))
         for c in range(seq.shape[1]):
-            z0 = np.zeros((S, 2)) if zi is None else zi.numpy()[c]
+            z0 = np.zeros((S, 2)) if zi is None else zi.numpy().reshape(-1, S, 2)[c]
             y[:, c], zf[c] = sosfilt(sos, seq[:, c], zi=z0)
+        if zf_out is not None:
+            zf_out.copy_(torch.from_numpy(zf).reshape(zf_out.shape))
         return y, zf
 
-    def env_forward(self, sos, src, edge_left=0, edge_right=0, zi=None, state_only=False):
+    def env_forward(self, sos, src, edge_left=0, edge_right=0, zi=None, state_only=False,
+                    zf_out=None):
         r = (np.pi/2)*np.abs(src.numpy())
         parts = []
         if edge_left:
@@ -62,12 +90,12 @@ class OracleOps(object):
         parts.append(r)
         if edge_right:
             parts.append(2*r[-1] - r[-2:-edge_right - 2:-1])
-        y, zf = self._filt(sos, np.concatenate(parts), zi)
+        y, zf = self._filt(sos, np.concatenate(parts), zi, zf_out)
         return (None if state_only else torch.from_numpy(y)), torch.from_numpy(zf)
 
     def sosfilt_rev(self, sos, src, zi=None, first=0, n_dst=None, clamp_negative=False,
-                    state_only=False):
-        y, zf = self._filt(sos, src.numpy()[::-1].copy(), zi)
+                    state_only=False, zf_out=None):
+        y, zf = self._filt(sos, src.numpy()[::-1].copy(), zi, zf_out)
         if state_only:
             return None, torch.from_numpy(zf)
         y = y[::-1]
