@@ -21,7 +21,7 @@ ADN_ERR_UNSUPPORTED = 3
 ADN_ERR_SHORT = 4
 ADN_MAX_SECTIONS = 8
 ADN_MIN_NFFT = 8
-ADN_MAX_NFFT = 16384
+ADN_MAX_NFFT = 1 << 20
 ADN_OPT_RESIDENT = 0
 ADN_OPT_VERIFY = 1
 ADN_OPT_CHUNK_BYTES = 2

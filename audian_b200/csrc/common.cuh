@@ -48,7 +48,7 @@ inline void count_launch(int n = 1) { ctx().launches += n; }
 // small pool keyed by purpose; grown (never shrunk) under the caller's stream order.
 DevBuf& scratch(int slot);
 enum { SCR_SOS_TILES = 0, SCR_SOS_TABLES, SCR_SOS_MISC, SCR_ENV_FWD, SCR_ENV_MISC,
-       SCR_MINMAX_PART, SCR_SPEC_TABLES, SCR_COUNT };
+       SCR_MINMAX_PART, SCR_SPEC_TABLES, SCR_SPEC_WORK, SCR_COUNT };
 
 // ---- kernels' host launchers (device pointers, asynchronous) ----
 int32_t minmax_dev(const double* src, int64_t n, int32_t C, int64_t step, double* dst,

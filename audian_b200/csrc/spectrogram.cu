@@ -28,10 +28,17 @@ struct SpecPlan {
     double2* twA = nullptr;     // warp path: [16][T] W_M^(t k1), M = nfft/2, T = M/16
     double* win = nullptr;      // periodic Hann
     double sumw2 = 0.0;
+    // nfft not a power of two (Bluestein): transforms of length L = 2^logL
+    int logL = 0;
+    double2* twL = nullptr;     // exp(-2 pi i j / L), j < L/2
+    double2* chirp = nullptr;   // exp(+i pi n^2 / nfft), n < nfft
+    double2* Bbr = nullptr;     // transform of the wrapped chirp, bit-reversed order
 };
 
 std::vector<SpecPlan> g_splans;
 std::mutex g_splan_mu;
+
+int32_t big_fft_dif(double2* work, int64_t items, int logL, const double2* tw, int twlog, cudaStream_t st);
 
 int32_t get_spec_plan(int nfft, cudaStream_t st, SpecPlan* out) {
     std::lock_guard<std::mutex> lk(g_splan_mu);
@@ -66,11 +73,39 @@ int32_t get_spec_plan(int nfft, cudaStream_t st, SpecPlan* out) {
         ADN_CK(cudaMalloc(&p.twA, sizeof(double2) * twA.size()));
         ADN_CK(cudaMemcpy(p.twA, twA.data(), sizeof(double2) * twA.size(), cudaMemcpyHostToDevice));
     }
-    ADN_CK(cudaMalloc(&p.tw, sizeof(double2) * tw.size()));
+    ADN_CK(cudaMalloc(&p.tw, sizeof(double2) * (tw.size() + 1)));
     ADN_CK(cudaMalloc(&p.win, sizeof(double) * win.size()));
     ADN_CK(cudaMemcpyAsync(p.tw, tw.data(), sizeof(double2) * tw.size(), cudaMemcpyHostToDevice, st));
     ADN_CK(cudaMemcpyAsync(p.win, win.data(), sizeof(double) * win.size(), cudaMemcpyHostToDevice, st));
     ADN_CK(cudaStreamSynchronize(st));
+    if (nfft & (nfft - 1)) {
+        // circular length: the lags k - n, k <= nfft/2, n < nfft must not alias
+        int logL = 1;
+        while (((int64_t)1 << logL) < (int64_t)nfft + nfft / 2 + 1) ++logL;
+        const int64_t L = (int64_t)1 << logL;
+        p.logL = logL;
+        std::vector<double2> twL((size_t)(L / 2)), ch((size_t)nfft), b((size_t)L, make_double2(0.0, 0.0));
+        for (int64_t j = 0; j < L / 2; ++j) {
+            long double a = two_pi * (long double)j / (long double)L;
+            twL[(size_t)j] = make_double2((double)cosl(a), (double)(-sinl(a)));
+        }
+        for (int64_t n = 0; n < nfft; ++n) {
+            const int64_t q = (n * n) % (2 * (int64_t)nfft);          // exact: n < 2^20
+            long double a = (two_pi / 2) * (long double)q / (long double)nfft;
+            ch[(size_t)n] = make_double2((double)cosl(a), (double)sinl(a));
+        }
+        for (int64_t j = 0; j <= nfft / 2; ++j) b[(size_t)j] = ch[(size_t)j];
+        for (int64_t m = 1; m < nfft; ++m) b[(size_t)(L - m)] = ch[(size_t)m];
+        ADN_CK(cudaMalloc(&p.twL, sizeof(double2) * twL.size()));
+        ADN_CK(cudaMalloc(&p.chirp, sizeof(double2) * ch.size()));
+        ADN_CK(cudaMalloc(&p.Bbr, sizeof(double2) * b.size()));
+        ADN_CK(cudaMemcpyAsync(p.twL, twL.data(), sizeof(double2) * twL.size(), cudaMemcpyHostToDevice, st));
+        ADN_CK(cudaMemcpyAsync(p.chirp, ch.data(), sizeof(double2) * ch.size(), cudaMemcpyHostToDevice, st));
+        ADN_CK(cudaMemcpyAsync(p.Bbr, b.data(), sizeof(double2) * b.size(), cudaMemcpyHostToDevice, st));
+        int32_t rc = big_fft_dif(p.Bbr, 1, logL, p.twL, logL, st);
+        if (rc) return rc;
+        ADN_CK(cudaStreamSynchronize(st));
+    }
     g_splans.push_back(p);
     *out = p;
     return ADN_OK;
@@ -973,6 +1008,340 @@ int32_t launch_warp_kernel(SpecWArgs& P, int64_t nf, cudaStream_t st) {
     return ADN_OK;
 }
 
+
+// ======================================================================================
+// Frames longer than one block's shared memory (nfft 2^15 .. 2^20; the GUI offers up to 2^19,
+// databrowser.py:516): the complex transforms live in a work buffer in global memory.
+//   pack    frame -> minus mean, x window -> M = nfft/2 complex points (even, odd samples)
+//   stages  radix-2^2 decimation-in-frequency passes over the whole buffer while the
+//           sub-transforms are longer than what a block holds in shared memory
+//   tail    the remaining stages of each 4096-point sub-block in shared memory
+//   split   Z (bit-reversed order) -> |X|^2 scaling of the real transform -> dst
+constexpr int BIG_LOGSL = 12;                 // sub-block of the tail kernel: 4096 complex, 64 KB
+constexpr int BIG_NT = 256;
+
+// two DIF stages (n = 2^lg and n/2) on four points z[0], z[q4], z[2 q4], z[3 q4]
+__device__ __forceinline__ void dif4(double2* z, int q4, double2 w1, double2 w2) {
+    double2 a0 = z[0], a1 = z[q4], a2 = z[2 * q4], a3 = z[3 * q4];
+    double2 b0 = make_double2(a0.x + a2.x, a0.y + a2.y);
+    double2 b2 = cmul(make_double2(a0.x - a2.x, a0.y - a2.y), w1);
+    double2 b1 = make_double2(a1.x + a3.x, a1.y + a3.y);
+    double2 d13 = make_double2(a1.x - a3.x, a1.y - a3.y);
+    double2 b3 = cmul(make_double2(d13.y, -d13.x), w1);        // W_n^(k+n/4) = -i W_n^k
+    z[0] = make_double2(b0.x + b1.x, b0.y + b1.y);
+    z[q4] = cmul(make_double2(b0.x - b1.x, b0.y - b1.y), w2);
+    z[2 * q4] = make_double2(b2.x + b3.x, b2.y + b3.y);
+    z[3 * q4] = cmul(make_double2(b2.x - b3.x, b2.y - b3.y), w2);
+}
+
+// tw: exp(-2 pi i j / 2^twlog), j < 2^(twlog-1);  W_n^k = tw[k << (twlog - lg)]
+__global__ void __launch_bounds__(BIG_NT)
+big_stage2_kernel(double2* __restrict__ work, const double2* __restrict__ tw, int64_t items,
+                  int32_t logL, int32_t twlog, int32_t lg) {
+    const int64_t total = items << (logL - 2);
+    const int q4 = 1 << (lg - 2), sh = twlog - lg;
+    for (int64_t idx = (int64_t)blockIdx.x * BIG_NT + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * BIG_NT) {
+        const int64_t it = idx >> (logL - 2);
+        const int r = (int)(idx & (((int64_t)1 << (logL - 2)) - 1));
+        const int blk = r >> (lg - 2), k = r & (q4 - 1);
+        double2* z = work + (it << logL) + ((int64_t)blk << lg) + k;
+        dif4(z, q4, __ldg(tw + ((int64_t)k << sh)), __ldg(tw + ((int64_t)(2 * k) << sh)));
+    }
+}
+
+__global__ void __launch_bounds__(BIG_NT)
+big_stage1_kernel(double2* __restrict__ work, const double2* __restrict__ tw, int64_t items,
+                  int32_t logL, int32_t twlog, int32_t lg) {
+    const int64_t total = items << (logL - 1);
+    const int h = 1 << (lg - 1), sh = twlog - lg;
+    for (int64_t idx = (int64_t)blockIdx.x * BIG_NT + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * BIG_NT) {
+        const int64_t it = idx >> (logL - 1);
+        const int r = (int)(idx & (((int64_t)1 << (logL - 1)) - 1));
+        const int blk = r >> (lg - 1), k = r & (h - 1);
+        double2* z = work + (it << logL) + ((int64_t)blk << lg) + k;
+        double2 a = z[0], b = z[h];
+        z[0] = make_double2(a.x + b.x, a.y + b.y);
+        z[h] = cmul(make_double2(a.x - b.x, a.y - b.y), __ldg(tw + ((int64_t)k << sh)));
+    }
+}
+
+// the last lgs stages of one 2^lgs-point sub-block per block, in shared memory
+__global__ void __launch_bounds__(BIG_NT)
+big_tail_kernel(double2* __restrict__ work, const double2* __restrict__ tw, int32_t twlog, int32_t lgs) {
+    extern __shared__ __align__(16) double sbuf[];
+    double2* zs = reinterpret_cast<double2*>(sbuf);
+    const int SL = 1 << lgs;
+    double2* g = work + ((int64_t)blockIdx.x << lgs);
+    for (int j = threadIdx.x; j < SL; j += BIG_NT) zs[j] = g[j];
+    __syncthreads();
+    int lg = lgs;
+    for (; lg >= 2; lg -= 2) {
+        const int q4 = 1 << (lg - 2), sh = twlog - lg;
+        for (int r = threadIdx.x; r < (SL >> 2); r += BIG_NT) {
+            const int blk = r >> (lg - 2), k = r & (q4 - 1);
+            dif4(zs + (blk << lg) + k, q4, __ldg(tw + ((int64_t)k << sh)), __ldg(tw + ((int64_t)(2 * k) << sh)));
+        }
+        __syncthreads();
+    }
+    if (lg == 1) {
+        for (int r = threadIdx.x; r < (SL >> 1); r += BIG_NT) {
+            double2 u = zs[2 * r], v = zs[2 * r + 1];
+            zs[2 * r] = make_double2(u.x + v.x, u.y + v.y);
+            zs[2 * r + 1] = make_double2(u.x - v.x, u.y - v.y);
+        }
+        __syncthreads();
+    }
+    for (int j = threadIdx.x; j < SL; j += BIG_NT) g[j] = zs[j];
+}
+
+// forward transform of `items` arrays of 2^logL complex points, in place, bit-reversed result
+int32_t big_fft_dif(double2* work, int64_t items, int logL, const double2* tw, int twlog, cudaStream_t st) {
+    const int lgs = logL < BIG_LOGSL ? logL : BIG_LOGSL;
+    const int64_t cap = (int64_t)ctx().sm_count * 32;
+    int lg = logL;
+    while (lg > lgs) {
+        if (lg - lgs >= 2) {
+            int64_t nb = ((items << (logL - 2)) + BIG_NT - 1) / BIG_NT;
+            big_stage2_kernel<<<(unsigned)(nb < cap ? nb : cap), BIG_NT, 0, st>>>(work, tw, items, logL, twlog, lg);
+            lg -= 2;
+        } else {
+            int64_t nb = ((items << (logL - 1)) + BIG_NT - 1) / BIG_NT;
+            big_stage1_kernel<<<(unsigned)(nb < cap ? nb : cap), BIG_NT, 0, st>>>(work, tw, items, logL, twlog, lg);
+            lg -= 1;
+        }
+        count_launch();
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        ADN_CK(cudaFuncSetAttribute(big_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+        attr_done = true;
+    }
+    const int64_t nblk = items << (logL - lgs);
+    if (nblk > 0x7fffffff) return fail(ADN_ERR_UNSUPPORTED, "spectrogram: %lld tail blocks", (long long)nblk);
+    big_tail_kernel<<<(unsigned)nblk, BIG_NT, (size_t)16 << lgs, st>>>(work, tw, twlog, lgs);
+    count_launch();
+    ADN_CK(cudaGetLastError());
+    return ADN_OK;
+}
+
+// frame (f0 + item / C, channel item % C) -> work[item][0 .. M)
+__global__ void __launch_bounds__(BIG_NT)
+big_pack_kernel(const double* __restrict__ src, int32_t C, int64_t hop, int32_t N, int64_t f0,
+                const double* __restrict__ win, int32_t detrend, double2* __restrict__ work) {
+    __shared__ double red[BIG_NT / 32];
+    __shared__ double s_mean;
+    const int64_t item = blockIdx.x;
+    const int64_t fi = item / C;
+    const int c = (int)(item - fi * C);
+    const double* x = src + ((f0 + fi) * hop) * C + c;
+    const int M = N >> 1;
+    double mean = 0.0;
+    if (detrend) {
+        double s = 0.0;
+        for (int j = threadIdx.x; j < N; j += BIG_NT) s += __ldg(x + (int64_t)j * C);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int i = 0; i < BIG_NT / 32; ++i) t += red[i];
+            s_mean = t / (double)N;
+        }
+        __syncthreads();
+        mean = s_mean;
+    }
+    double2* z = work + item * M;
+    for (int j = threadIdx.x; j < M; j += BIG_NT) {
+        double a = __ldg(x + (int64_t)(2 * j) * C), b = __ldg(x + (int64_t)(2 * j + 1) * C);
+        z[j] = make_double2((a - mean) * __ldg(win + 2 * j), (b - mean) * __ldg(win + 2 * j + 1));
+    }
+}
+
+__global__ void __launch_bounds__(BIG_NT)
+big_split_kernel(const double2* __restrict__ work, const double2* __restrict__ tw, int64_t items,
+                 int32_t logM, double scale, int32_t out_db, double* __restrict__ dst) {
+    const int M = 1 << logM, F = M + 1, sh = 32 - logM;
+    const int64_t total = items * F;
+    for (int64_t idx = (int64_t)blockIdx.x * BIG_NT + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * BIG_NT) {
+        const int64_t it = idx / F;
+        const int k = (int)(idx - it * F);
+        const double2* z = work + (it << logM);
+        double xr, xi, fac;
+        if (k == 0 || k == M) {
+            double2 z0 = z[0];
+            xr = k == 0 ? z0.x + z0.y : z0.x - z0.y;
+            xi = 0.0;
+            fac = 1.0;
+        } else {
+            double2 zk = z[__brev((unsigned)k) >> sh];
+            double2 zm = z[__brev((unsigned)(M - k)) >> sh];
+            double er = 0.5 * (zk.x + zm.x), ei = 0.5 * (zk.y - zm.y);
+            double orr = 0.5 * (zk.y + zm.y), oi = -0.5 * (zk.x - zm.x);
+            double2 w = __ldg(tw + k);
+            xr = er + (orr * w.x - oi * w.y);
+            xi = ei + (orr * w.y + oi * w.x);
+            fac = 2.0;
+        }
+        double pw = (xr * xr + xi * xi) * (scale * fac);
+        if (out_db) pw = to_db(pw);
+        dst[idx] = pw;
+    }
+}
+
+int32_t spectrogram_big(const SpecPlan& plan, const double* src, int32_t C, double rate, int32_t nfft,
+                        int32_t hop, int32_t detrend, double* dst, int64_t nf, int32_t out_db,
+                        cudaStream_t st) {
+    int logN = 0;
+    while ((1 << logN) < nfft) ++logN;
+    const int logM = logN - 1;
+    const int64_t M = (int64_t)1 << logM, F = M + 1;
+    // frames per pass: the work buffer stays below 1 GiB (at least one frame of all channels)
+    int64_t fr = ((int64_t)1 << 30) / (M * 16 * C);
+    if (fr < 1) fr = 1;
+    if (fr > nf) fr = nf;
+    DevBuf& wb = scratch(SCR_SPEC_WORK);
+    int32_t rc = wb.reserve((size_t)(fr * C * M * 16));
+    if (rc) return rc;
+    double2* work = wb.as<double2>();
+    const double scale = 1.0 / (rate * plan.sumw2);
+    const int64_t cap = (int64_t)ctx().sm_count * 32;
+    for (int64_t f0 = 0; f0 < nf; f0 += fr) {
+        const int64_t fc = f0 + fr < nf ? fr : nf - f0;
+        const int64_t items = fc * C;
+        if (items > 0x7fffffff) return fail(ADN_ERR_UNSUPPORTED, "spectrogram: %lld items", (long long)items);
+        big_pack_kernel<<<(unsigned)items, BIG_NT, 0, st>>>(src, C, hop, nfft, f0, plan.win, detrend, work);
+        count_launch();
+        if ((rc = big_fft_dif(work, items, logM, plan.tw, logN, st))) return rc;
+        int64_t nb = (items * F + BIG_NT - 1) / BIG_NT;
+        big_split_kernel<<<(unsigned)(nb < cap ? nb : cap), BIG_NT, 0, st>>>(work, plan.tw, items, logM, scale,
+                                                                           out_db, dst + f0 * C * F);
+        count_launch();
+        ADN_CK(cudaGetLastError());
+    }
+    return ADN_OK;
+}
+
+
+// ======================================================================================
+// nfft that is no power of two (reachable through update(): nfft is clamped to
+// len(source)//2, bufferedspectrogram.py:88): Bluestein's chirp-z form of the DFT,
+//   Y[k] = conj(c[k]) sum_n (y[n] conj(c[n])) c[k - n],   c[n] = exp(i pi n^2 / N),
+// as a circular convolution of length L = 2^logL >= 1.5 N by two power-of-two transforms in
+// the work buffer.  Only |Y[k]|^2 is wanted, so the final chirp multiplication drops out.
+__global__ void __launch_bounds__(BIG_NT)
+blue_pack_kernel(const double* __restrict__ src, int32_t C, int64_t hop, int32_t N, int32_t logL, int64_t f0,
+                 const double* __restrict__ win, const double2* __restrict__ chirp, int32_t detrend,
+                 double2* __restrict__ work) {
+    __shared__ double red[BIG_NT / 32];
+    __shared__ double s_mean;
+    const int64_t item = blockIdx.x;
+    const int64_t fi = item / C;
+    const int c = (int)(item - fi * C);
+    const double* x = src + ((f0 + fi) * hop) * C + c;
+    double mean = 0.0;
+    if (detrend) {
+        double s = 0.0;
+        for (int j = threadIdx.x; j < N; j += BIG_NT) s += __ldg(x + (int64_t)j * C);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int i = 0; i < BIG_NT / 32; ++i) t += red[i];
+            s_mean = t / (double)N;
+        }
+        __syncthreads();
+        mean = s_mean;
+    }
+    double2* z = work + (item << logL);
+    const int L = 1 << logL;
+    for (int j = threadIdx.x; j < L; j += BIG_NT) {
+        double2 v = make_double2(0.0, 0.0);
+        if (j < N) {
+            double y = (__ldg(x + (int64_t)j * C) - mean) * __ldg(win + j);
+            double2 ch = __ldg(chirp + j);
+            v = make_double2(y * ch.x, -y * ch.y);
+        }
+        z[j] = v;
+    }
+}
+
+// b[brev(i)] = conj(a[i] * B[i]): product of the two spectra, back in natural order for the
+// second forward transform (ifft(x) = conj(fft(conj(x))) / L)
+__global__ void __launch_bounds__(BIG_NT)
+blue_mul_kernel(const double2* __restrict__ a, const double2* __restrict__ B, int64_t items, int32_t logL,
+                double2* __restrict__ b) {
+    const int64_t total = items << logL;
+    const int sh = 32 - logL;
+    for (int64_t idx = (int64_t)blockIdx.x * BIG_NT + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * BIG_NT) {
+        const int64_t it = idx >> logL;
+        const unsigned i = (unsigned)(idx & (((int64_t)1 << logL) - 1));
+        double2 v = cmul(a[idx], __ldg(B + i));
+        b[(it << logL) + (__brev(i) >> sh)] = make_double2(v.x, -v.y);
+    }
+}
+
+__global__ void __launch_bounds__(BIG_NT)
+blue_power_kernel(const double2* __restrict__ r, int64_t items, int32_t N, int32_t logL, double scale,
+                  int32_t out_db, double* __restrict__ dst) {
+    const int F = N / 2 + 1, sh = 32 - logL;
+    const int64_t total = items * F;
+    const double inv = 1.0 / (double)((int64_t)1 << logL);
+    for (int64_t idx = (int64_t)blockIdx.x * BIG_NT + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * BIG_NT) {
+        const int64_t it = idx / F;
+        const int k = (int)(idx - it * F);
+        double2 v = r[(it << logL) + (__brev((unsigned)k) >> sh)];
+        const double xr = v.x * inv, xi = v.y * inv;
+        const bool edge = k == 0 || (N % 2 == 0 && k == N / 2);
+        double pw = (xr * xr + xi * xi) * (scale * (edge ? 1.0 : 2.0));
+        if (out_db) pw = to_db(pw);
+        dst[idx] = pw;
+    }
+}
+
+int32_t spectrogram_bluestein(const SpecPlan& plan, const double* src, int32_t C, double rate, int32_t nfft,
+                              int32_t hop, int32_t detrend, double* dst, int64_t nf, int32_t out_db,
+                              cudaStream_t st) {
+    const int logL = plan.logL;
+    const int64_t L = (int64_t)1 << logL, F = nfft / 2 + 1;
+    int64_t fr = ((int64_t)1 << 29) / (L * 16 * C);             // two buffers of at most 512 MiB
+    if (fr < 1) fr = 1;
+    if (fr > nf) fr = nf;
+    DevBuf& wb = scratch(SCR_SPEC_WORK);
+    int32_t rc = wb.reserve((size_t)(2 * fr * C * L * 16));
+    if (rc) return rc;
+    double2* wa = wb.as<double2>();
+    double2* wc = wa + fr * C * L;
+    const double scale = 1.0 / (rate * plan.sumw2);
+    const int64_t cap = (int64_t)ctx().sm_count * 32;
+    for (int64_t f0 = 0; f0 < nf; f0 += fr) {
+        const int64_t fc = f0 + fr < nf ? fr : nf - f0;
+        const int64_t items = fc * C;
+        if (items > 0x7fffffff) return fail(ADN_ERR_UNSUPPORTED, "spectrogram: %lld items", (long long)items);
+        blue_pack_kernel<<<(unsigned)items, BIG_NT, 0, st>>>(src, C, hop, nfft, logL, f0, plan.win, plan.chirp,
+                                                           detrend, wa);
+        count_launch();
+        if ((rc = big_fft_dif(wa, items, logL, plan.twL, logL, st))) return rc;
+        int64_t nb = ((items << logL) + BIG_NT - 1) / BIG_NT;
+        blue_mul_kernel<<<(unsigned)(nb < cap ? nb : cap), BIG_NT, 0, st>>>(wa, plan.Bbr, items, logL, wc);
+        count_launch();
+        if ((rc = big_fft_dif(wc, items, logL, plan.twL, logL, st))) return rc;
+        nb = (items * F + BIG_NT - 1) / BIG_NT;
+        blue_power_kernel<<<(unsigned)(nb < cap ? nb : cap), BIG_NT, 0, st>>>(wc, items, nfft, logL, scale, out_db,
+                                                                            dst + f0 * C * F);
+        count_launch();
+        ADN_CK(cudaGetLastError());
+    }
+    return ADN_OK;
+}
+
 }  // namespace
 
 int32_t spectrogram_dev(const double* src, int64_t n_src, int32_t C, double rate, int32_t nfft,
@@ -982,8 +1351,8 @@ int32_t spectrogram_dev(const double* src, int64_t n_src, int32_t C, double rate
         return fail(ADN_ERR_UNSUPPORTED, "spectrogram: window_id %d (only ADN_WINDOW_HANN)", window_id);
     if (detrend_id != ADN_DETREND_NONE && detrend_id != ADN_DETREND_CONSTANT)
         return fail(ADN_ERR_INVALID, "spectrogram: detrend_id %d", detrend_id);
-    if (nfft < ADN_MIN_NFFT || nfft > ADN_MAX_NFFT || (nfft & (nfft - 1)))
-        return fail(ADN_ERR_UNSUPPORTED, "spectrogram: nfft=%d (power of two in [%d, %d] required)",
+    if (nfft < ADN_MIN_NFFT || nfft > ADN_MAX_NFFT)
+        return fail(ADN_ERR_UNSUPPORTED, "spectrogram: nfft=%d (supported: %d .. %d)",
                     nfft, ADN_MIN_NFFT, ADN_MAX_NFFT);
     const int64_t nf = spectrogram_frames(n_src, n_dst, nfft, hop);
     const size_t F = (size_t)nfft / 2 + 1;
@@ -994,6 +1363,9 @@ int32_t spectrogram_dev(const double* src, int64_t n_src, int32_t C, double rate
     SpecPlan plan;
     int32_t rc = get_spec_plan(nfft, st, &plan);
     if (rc) return rc;
+    if (nfft & (nfft - 1))
+        return spectrogram_bluestein(plan, src, C, rate, nfft, hop, detrend_id == ADN_DETREND_CONSTANT, dst,
+                                     nf, out_db, st);
     const bool ring_ok = plan.twA && (hop % 2 == 0) && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
                          (C % 2 == 0 || C == 1) && env_int("ADN_SPEC_RING", 1) != 0;
     if (ring_ok) {
@@ -1024,6 +1396,9 @@ int32_t spectrogram_dev(const double* src, int64_t n_src, int32_t C, double rate
             case 1024: return launch_warp_kernel<10>(W, nf, st);
         }
     }
+    if (nfft > 16384)
+        return spectrogram_big(plan, src, C, rate, nfft, hop, detrend_id == ADN_DETREND_CONSTANT, dst, nf,
+                               out_db, st);
     SpecArgs P;
     P.src = src; P.dst = dst; P.tw = plan.tw; P.win = plan.win;
     P.nframes = nf; P.C = C; P.nfft = nfft; P.hop = hop;

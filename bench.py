@@ -279,6 +279,7 @@ def run_ours(args):
     launches0 = _lib.launch_count()
     sync_all()
     t_start, t_stop = ev(), ev()
+    torch.cuda.nvtx.range_push('timed')          # ncu --nvtx --nvtx-include "timed/"
     if graphs is None:
         t_start.record()
         for i in range(args.steps):
@@ -296,6 +297,7 @@ def run_ours(args):
         t_stop.record()
         sync_all()
         launches = graph_launches*args.steps
+    torch.cuda.nvtx.range_pop()
     ms_total = t_start.elapsed_time(t_stop)
     tt = torch.tensor([ms_total], dtype=torch.float64, device='cuda')
     if world > 1:

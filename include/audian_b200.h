@@ -47,7 +47,8 @@ extern "C" {
 
 #define ADN_MAX_SECTIONS     8   /* biquad sections per cascade */
 #define ADN_MIN_NFFT         8
-#define ADN_MAX_NFFT         16384  /* single-kernel shared-memory FFT */
+#define ADN_MAX_NFFT         1048576 /* 2^20; up to 16384 one kernel, beyond that the
+                                       transforms run in a global-memory work buffer */
 
 /* adn_set_option() */
 #define ADN_OPT_RESIDENT            0  /* keep large results on the device, keyed by the host
@@ -117,7 +118,7 @@ int32_t adn_envelope_f64(const double* sos, int32_t S,
 /* One-sided power spectral density frames (V**2/Hz), scipy 'density' scaling:
  * nsource = min((n_dst-1)*hop + nfft, n_src); n = (nsource - (nfft-hop))/hop
  * frames are computed, dst[n:] is zero-filled (all of dst if nsource < nfft).
- * dst is (n_dst, C, nfft/2+1).  nfft: power of two in [8, 16384];
+ * dst is (n_dst, C, nfft/2+1).  nfft: power of two in [8, 2^20];
  * 1 <= hop <= nfft.  out_db != 0 stores decibel(P) instead of P.
  * n_computed (may be NULL) receives n. */
 int32_t adn_spectrogram_f64(const double* src, int64_t n_src, int32_t C,

@@ -257,7 +257,8 @@ def test_envelope_none_is_zero():
 
 # ---------------------------------------------------------------- spectrogram
 
-@pytest.mark.parametrize('nfft', [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+@pytest.mark.parametrize('nfft', [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384,
+                                  32768, 131072])
 def test_spectrogram_nfft(nfft):
     fs = 48000.
     C = 2
@@ -285,6 +286,22 @@ def test_spectrogram_channels(C):
     got = np.empty_like(ref)
     _lib.spectrogram(x, fs, nfft, hop, got)
     assert_spec_close(got, ref, f'C={C}')
+
+
+def test_spectrogram_largest_gui_nfft():
+    # 2^19 is the largest size the GUI offers (databrowser.py:516)
+    fs, nfft = 500000., 1 << 19
+    hop = nfft//2
+    x = synth(0, nfft*2 + hop + 17, 1, fs, seed=19)
+    n_dst = 4
+    ref = np.empty((n_dst, 1, nfft//2 + 1))
+    nref = orc.spectrogram_process(x, ref, fs, nfft, hop)
+    got = np.full_like(ref, np.nan)
+    assert _lib.spectrogram(x, fs, nfft, hop, got) == nref == 4
+    assert_spec_close(got, ref, 'nfft=2^19')
+    db = np.empty_like(ref)
+    _lib.spectrogram(x, fs, nfft, hop, db, out_db=True)
+    assert np.allclose(db, orc.decibel(ref), rtol=0, atol=1e-6)
 
 
 def test_spectrogram_short_source_zero_fill():
@@ -330,10 +347,29 @@ def test_spectrogram_db_and_decibel():
     assert np.array_equal(np.isneginf(_lib.decibel(p)), np.isneginf(orc.decibel(p)))
 
 
+@pytest.mark.parametrize('nfft,hop,C', [(1000, 500, 2), (12, 5, 3), (999, 333, 1), (3072, 3072, 2),
+                                        (25000, 12500, 2), (100, 67, 4), (40001, 20000, 1)])
+def test_spectrogram_nfft_not_a_power_of_two(nfft, hop, C):
+    # update() clamps nfft to len(source)//2 (bufferedspectrogram.py:88), open() truncates
+    # hop = int(nfft*(1 - overlap)): any integer pair can arrive
+    fs = 44100.
+    n_src = nfft*3 + hop*2 + 5
+    x = synth(0, n_src, C, fs, seed=nfft) + 0.25          # a DC offset the mean removal must take out
+    n_dst = (n_src + hop - 1)//hop
+    ref = np.empty((n_dst, C, nfft//2 + 1))
+    nref = orc.spectrogram_process(x, ref, fs, nfft, hop)
+    got = np.full_like(ref, np.nan)
+    assert _lib.spectrogram(x, fs, nfft, hop, got) == nref
+    assert_spec_close(got, ref, f'nfft={nfft} hop={hop}')
+    assert not got[nref:].any()
+
+
 def test_spectrogram_unsupported_nfft_fails_loudly():
-    x = synth(0, 5000, 1, 1000.)
+    x = synth(0, (1 << 20) + 5000, 1, 1000.)
     with pytest.raises(_lib.AdnError):
-        _lib.spectrogram(x, 1000., 1000, 500, np.empty((8, 1, 501)))
+        _lib.spectrogram(x, 1000., (1 << 20) + 2, 500, np.empty((2, 1, (1 << 19) + 2)))
+    with pytest.raises(_lib.AdnError):
+        _lib.spectrogram(x[:5000], 1000., 4, 2, np.empty((8, 1, 3)))
 
 
 # ---------------------------------------------------------------- golden chains
