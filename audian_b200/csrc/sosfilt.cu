@@ -402,8 +402,8 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
                 matvec_acc<D>(tab_fix + gl * DD, pre, z);
             }
         }
-        const double* xr = xp;
-        if (!want_state) {
+        if (!want_state && S > 4) {
+            const double* xr = xp;
 #pragma unroll
             for (int i = 0; i < SOS_L; ++i) {
                 double x = *xr;
@@ -417,6 +417,30 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
                 }
                 *const_cast<double*>(xr) = x;
                 xr += Cw;
+            }
+        } else if (!want_state) {
+            // the sections run skewed by one sample each (section s works on sample j - s in
+            // step j): the S recurrences of a step are independent of each other, which hides
+            // the latency of the dependent fp64 operations; the arithmetic per sample is unchanged
+            double xin[S + 1];
+#pragma unroll
+            for (int j = 0; j < SOS_L + S - 1; ++j) {
+#pragma unroll
+                for (int s = S - 1; s >= 0; --s) {
+                    const int i = j - s;
+                    if (i < 0 || i >= SOS_L) continue;
+                    double x;
+                    if (s == 0) {
+                        x = xp[i * Cw];
+                        if (MODE == MODE_ENVF && xform) x = HALF_PI * fabs(x);
+                    } else {
+                        x = xin[s];
+                    }
+                    double y = fma(K.coef[s][0], x, z[2 * s]);
+                    z[2 * s] = fma(K.coef[s][1], x, z[2 * s + 1]) - K.coef[s][3] * y;
+                    z[2 * s + 1] = K.coef[s][2] * x - K.coef[s][4] * y;
+                    if (s == S - 1) xp[i * Cw] = y; else xin[s + 1] = y;
+                }
             }
         } else {
             // the one sub-chunk per channel that contains the last sample: plain loop, state
@@ -673,8 +697,15 @@ int32_t get_plan(const double* sos, int S, int CG, cudaStream_t st, Plan** out) 
 }
 
 int pick_cg(int C) {
+    static int cap = -1;
+    if (cap < 0) {
+        const char* e = getenv("ADN_SOS_CG");
+        cap = e ? atoi(e) : 8;       // measured on B200: groups of 8 channels (64-byte row segments)
+        if (cap < 1) cap = 1;
+        if (cap > 32) cap = 32;
+    }
     int cg = 1;
-    while (cg < C && cg < 32) cg <<= 1;
+    while (cg < C && cg < cap) cg <<= 1;
     return cg;
 }
 

@@ -69,3 +69,30 @@ def test_side_stream_ordering():
         z = y*2.0                      # torch op on the same stream sees the kernel's output
     st.synchronize()
     assert torch.equal(z, ref*2.0)
+
+
+def test_wholefile_streaming_on_device():
+    """Chunked whole-file passes (audian_b200.wholefile) with the recording generated on the
+    device chunk by chunk: independent of the chunking, equal to one pass."""
+    import torch
+    from audian_b200 import device
+    from audian_b200.wholefile import WholeFile
+    frames, C, rate, seed = 300017, 4, 96000., 21
+    hx = synth(0, frames, C, rate, seed)
+
+    def source(t0, n):
+        return device.synth(t0, n, C, rate, seed)
+    wf = WholeFile(source, frames, C, rate, chunk_frames=37000)
+    step = 50
+    sos = orc.filter_design(rate, 1000., 15000., 4)
+    parts = []
+    rows = wf.fulltrace_and_filter(sos, step, lambda t0, y: parts.append(y.cpu().numpy()))
+    assert np.array_equal(rows.cpu().numpy().view(np.uint64), orc.minmax_rows(hx, step).view(np.uint64))
+    yref = np.empty_like(hx)
+    orc.filter_process(sos, hx, yref, 0)
+    assert np.max(np.abs(np.concatenate(parts) - yref)) <= 1e-6
+    frames_out = []
+    nf = wf.spectrogram(1024, 512, lambda k, P: frames_out.append(P.cpu().numpy()))
+    sref = np.empty((nf, C, 513))
+    assert orc.spectrogram_process(hx, sref, rate, 1024, 512) == nf
+    assert np.allclose(np.concatenate(frames_out), sref, rtol=1e-5, atol=1e-20*sref.max())

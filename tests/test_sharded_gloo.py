@@ -217,3 +217,74 @@ def test_shard_bounds():
         assert b[0][0] == 0 and b[-1][1] == frames
         for (l0, h0), (l1, h1) in zip(b[:-1], b[1:]):
             assert h0 == l1 and l1 % align == 0 or l1 == frames
+
+
+# ---------------------------------------------------------------- streamed whole-file passes
+
+def _wf_worker(rank, world, port, frames, C, rate, q):
+    from audian_b200.wholefile import WholeFile
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        def source(t0, n):
+            return torch.from_numpy(synth(t0, n, C, rate, seed=7))
+        wf = WholeFile(source, frames, C, rate, OracleOps(), rank, world, dist, chunk_frames=3000)
+        out = {}
+        rows = wf.minmax(250)
+        got = {}
+        for name, sos in (('fast', butter(2, 0.2*rate, 'lowpass', fs=rate, output='sos')),
+                          ('slow', butter(2, 1e-5*rate, 'highpass', fs=rate, output='sos'))):
+            parts = []
+            wf.sosfilt(sos, lambda t0, y: parts.append((t0, y.numpy().copy())))
+            got[name] = parts
+        both = []
+        rows2 = wf.fulltrace_and_filter(butter(4, 0.1*rate, 'lowpass', fs=rate, output='sos'), 250,
+                                        lambda t0, y: both.append((t0, y.numpy().copy())))
+        frames_out = []
+        nf = wf.spectrogram(128, 32, lambda k, P: frames_out.append((k, P.numpy().copy())))
+        allp = [None]*world
+        dist.all_gather_object(allp, (got, both, frames_out, nf))
+        if rank == 0:
+            q.put((rows.numpy(), rows2.numpy(), allp))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [1, 2])
+def test_wholefile_streaming_matches_single_pass(world):
+    frames, C, rate = 20011, 2, 8000.
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_wf_worker, args=(r, world, port, frames, C, rate, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    rows, rows2, allp = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    x = synth(0, frames, C, rate, seed=7)
+    ref = orc.minmax_rows(x, 250)
+    assert np.array_equal(rows.view(np.uint64), ref.view(np.uint64))
+    assert np.array_equal(rows2.view(np.uint64), ref.view(np.uint64))
+
+    def join(parts):
+        parts = sorted((p for rk in parts for p in rk), key=lambda p: p[0])
+        return np.concatenate([p[1] for p in parts])
+    for name, sos in (('fast', butter(2, 0.2*rate, 'lowpass', fs=rate, output='sos')),
+                      ('slow', butter(2, 1e-5*rate, 'highpass', fs=rate, output='sos'))):
+        yref = np.empty_like(x)
+        orc.filter_process(sos, x, yref, 0)
+        y = join([a[0][name] for a in allp])
+        assert y.shape == yref.shape and np.max(np.abs(y - yref)) <= 1e-9, name
+    yref = np.empty_like(x)
+    orc.filter_process(butter(4, 0.1*rate, 'lowpass', fs=rate, output='sos'), x, yref, 0)
+    assert np.max(np.abs(join([a[1] for a in allp]) - yref)) <= 1e-9
+    nf = (frames - 96)//32
+    sref = np.empty((nf, C, 65))
+    orc.spectrogram_process(x, sref, rate, 128, 32)
+    spec = join([a[2] for a in allp])
+    assert allp[0][3] == nf and spec.shape == sref.shape
+    assert np.allclose(spec, sref, rtol=1e-7, atol=1e-22*sref.max())
