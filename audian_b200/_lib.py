@@ -57,6 +57,12 @@ SIGNATURES = {
     'adn_spectrogram_f64': (_i32, [_dp, _i64, _i32, _f64, _i32, _i32, _i32, _i32,
                                    _dp, _i64, _i32, C.POINTER(_i64)]),
     'adn_decibel_f64': (_i32, [_dp, _i64, _f64, _f64, _dp]),
+    'adn_spec_image_db_f64': (_i32, [_dp, _i64, _i32, _i32, _i32, _dp]),
+    'adn_mean_power_db_f64': (_i32, [_dp, _i64, _i32, _i32, _i32, _i64, _i64, _f64, _dp]),
+    'adn_pcm_to_f64': (_i32, [_dp, _i64, _i32, _f64, _dp]),
+    'adn_spec_image_db_f64_dev': (_i32, [_dp, _i64, _i32, _i32, _i32, _dp, _dp]),
+    'adn_mean_power_db_f64_dev': (_i32, [_dp, _i32, _i32, _i32, _i64, _i64, _f64, _dp, _dp]),
+    'adn_pcm_to_f64_dev': (_i32, [_dp, _i64, _i32, _f64, _dp, _dp]),
     'adn_minmax_f64_dev': (_i32, [_dp, _i64, _i32, _i64, _dp, _dp]),
     'adn_sosfilt_f64_dev': (_i32, [_dp, _i32, _dp, _i64, _i32, _i64, _dp, _i64,
                                    _dp, _dp, _dp]),
@@ -223,6 +229,41 @@ def decibel(power, ref_power=1.0, min_power=1e-20):
     check(lib().adn_decibel_f64(ptr(power), power.size, float(ref_power),
                                 float(min_power), ptr(out)))
     return out
+
+
+def spec_image_db(spec, channel):
+    """decibel(spec[:, channel, :].T) as a new (F, n) array (specitem.py:33-39)."""
+    spec = _f64_array(spec, 'spec')
+    if spec.ndim != 3:
+        raise ValueError('spec must be (frames, channels, bins)')
+    n, ch, F = spec.shape
+    out = np.empty((F, n))
+    check(lib().adn_spec_image_db_f64(ptr(spec), n, ch, F, int(channel), ptr(out)))
+    return out
+
+
+def mean_power_db(spec, channel, i0, i1, floor_db=-200.0):
+    """max(decibel(mean(spec[i0:i1, channel, :], axis=0)), floor_db) (spectrogramplot.py:158-160)."""
+    spec = _f64_array(spec, 'spec')
+    n, ch, F = spec.shape
+    out = np.empty(F)
+    check(lib().adn_mean_power_db_f64(ptr(spec), n, ch, F, int(channel), int(i0), int(i1),
+                                      float(floor_db), ptr(out)))
+    return out
+
+
+def pcm_to_f64(pcm, bits, channels, gain=1.0, dst=None):
+    """(frames, channels) float64 = PCM / 2**(bits-1) * gain from a bytes-like /
+    integer array of interleaved little-endian samples (int16, packed int24, int32)."""
+    raw = np.ascontiguousarray(pcm).view(np.uint8).reshape(-1)
+    n = raw.size//(bits//8)
+    if dst is None:
+        dst = np.empty((n//channels, channels))
+    dst = _f64_array(dst, 'dst')
+    if dst.size != n:
+        raise ValueError('dst does not match the number of samples')
+    check(lib().adn_pcm_to_f64(raw.ctypes.data if n else None, n, int(bits), float(gain), ptr(dst)))
+    return dst
 
 
 def sos_state_space(sos, power=1):

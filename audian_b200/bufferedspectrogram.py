@@ -90,9 +90,10 @@ class BufferedSpectrogram(BufferedData):
         if not self.init or len(self.buffer) == 0 or len(self.buffer.shape) < 3:
             return None, None
         nf = max(1, self.buffer.shape[2]//16)
-        db = _lib.decibel(self.buffer[:, channel, :])
+        # (bins, frames) decibel image of the channel, from the device copy of the buffer
+        db = _lib.spec_image_db(self.buffer, channel)
         with np.errstate(all='ignore'):
-            zmin = np.percentile(db[:, -nf:], 95)
+            zmin = np.percentile(db[-nf:, :], 95)
         zmax = np.max(db)
         if not np.isfinite(zmin) or not np.isfinite(zmax):
             return None, None

@@ -630,7 +630,114 @@ int32_t adn_decibel_f64(const double* power, int64_t n, double ref_power, double
     return copy_out(dst, c.out.as<double>(), (size_t)n * 8);
 }
 
+// one channel of a (n, C, F) spectrogram buffer on the device: the resident copy of the whole
+// buffer if there is one (then *Cd = C, *chd = channel), else only that channel's rows are
+// uploaded with a strided copy (*Cd = 1, *chd = 0)
+static int32_t spec_channel_dev(const double* spec, int64_t n, int32_t C, int32_t F, int32_t channel,
+                                const double** dev, int32_t* Cd, int32_t* chd) {
+    int32_t rc = in_resident(spec, (size_t)n * C * F * 8, dev);
+    if (rc) return rc;
+    if (*dev) { *Cd = C; *chd = channel; return ADN_OK; }
+    Ctx& c = ctx();
+    if ((rc = c.in.reserve((size_t)n * F * 8))) return rc;
+    g_bytes_h2d += (int64_t)n * F * 8;
+    ADN_CK(cudaMemcpy2DAsync(c.in.p, (size_t)F * 8, spec + (size_t)channel * F, (size_t)C * F * 8,
+                             (size_t)F * 8, (size_t)n, cudaMemcpyHostToDevice, c.stream));
+    *dev = c.in.as<double>();
+    *Cd = 1;
+    *chd = 0;
+    return ADN_OK;
+}
+
+int32_t adn_spec_image_db_f64(const double* spec, int64_t n, int32_t C, int32_t F, int32_t channel,
+                              double* dst) {
+    if (n < 0 || C < 1 || F < 1 || channel < 0 || channel >= C)
+        return fail(ADN_ERR_INVALID, "adn_spec_image_db_f64: n=%lld C=%d F=%d channel=%d", (long long)n, C, F, channel);
+    if (n == 0) return ADN_OK;
+    if (!spec || !dst) return fail(ADN_ERR_INVALID, "adn_spec_image_db_f64: NULL pointer");
+    int32_t rc = ensure_init();
+    if (rc) return rc;
+    Ctx& c = ctx();
+    const double* d = nullptr;
+    int32_t Cd = C, chd = channel;
+    if ((rc = spec_channel_dev(spec, n, C, F, channel, &d, &Cd, &chd))) return rc;
+    drop_overlapping(dst, (size_t)n * F * 8);
+    if ((rc = c.out.reserve((size_t)n * F * 8))) return rc;
+    if ((rc = spec_image_dev(d, n, Cd, F, chd, c.out.as<double>(), c.stream))) return rc;
+    return copy_out(dst, c.out.as<double>(), (size_t)n * F * 8);
+}
+
+int32_t adn_mean_power_db_f64(const double* spec, int64_t n, int32_t C, int32_t F, int32_t channel,
+                              int64_t i0, int64_t i1, double floor_db, double* dst) {
+    if (n < 1 || C < 1 || F < 1 || channel < 0 || channel >= C || i0 < 0 || i1 <= i0 || i1 > n)
+        return fail(ADN_ERR_INVALID, "adn_mean_power_db_f64: n=%lld C=%d F=%d channel=%d i0=%lld i1=%lld",
+                    (long long)n, C, F, channel, (long long)i0, (long long)i1);
+    if (!spec || !dst) return fail(ADN_ERR_INVALID, "adn_mean_power_db_f64: NULL pointer");
+    int32_t rc = ensure_init();
+    if (rc) return rc;
+    Ctx& c = ctx();
+    const double* d = nullptr;
+    int32_t Cd = C, chd = channel;
+    // without a resident copy only the rows i0..i1 of the channel go up
+    rc = in_resident(spec, (size_t)n * C * F * 8, &d);
+    if (rc) return rc;
+    int64_t a0 = i0, a1 = i1;
+    if (!d) {
+        if ((rc = spec_channel_dev(spec + (size_t)i0 * C * F, i1 - i0, C, F, channel, &d, &Cd, &chd))) return rc;
+        a0 = 0;
+        a1 = i1 - i0;
+    }
+    if ((rc = c.out.reserve((size_t)F * 8))) return rc;
+    if ((rc = mean_power_dev(d, Cd, F, chd, a0, a1, floor_db, c.out.as<double>(), c.stream))) return rc;
+    return copy_out(dst, c.out.as<double>(), (size_t)F * 8);
+}
+
+int32_t adn_pcm_to_f64(const void* pcm, int64_t n, int32_t bits, double gain, double* dst) {
+    if (n < 0 || (bits != 16 && bits != 24 && bits != 32))
+        return fail(ADN_ERR_INVALID, "adn_pcm_to_f64: n=%lld bits=%d (16, 24 or 32)", (long long)n, bits);
+    if (n == 0) return ADN_OK;
+    if (!pcm || !dst) return fail(ADN_ERR_INVALID, "adn_pcm_to_f64: NULL pointer");
+    int32_t rc = ensure_init();
+    if (rc) return rc;
+    Ctx& c = ctx();
+    const size_t in_b = (size_t)n * (bits / 8), out_b = (size_t)n * 8;
+    if ((rc = stage_in(pcm, in_b))) return rc;
+    double* dout = nullptr;
+    if ((rc = out_buffer(dst, out_b, &dout))) return rc;       // the decoded trace can stay resident
+    if ((rc = pcm_dev(c.in.p, n, bits, gain, dout, c.stream))) return rc;
+    return copy_out(dst, dout, out_b);
+}
+
 // ---------------------------------------------------------------- device entry points
+
+int32_t adn_spec_image_db_f64_dev(const double* spec, int64_t n, int32_t C, int32_t F, int32_t channel,
+                                  double* dst, void* stream) {
+    if (n < 0 || C < 1 || F < 1 || channel < 0 || channel >= C || (n > 0 && (!spec || !dst)))
+        return fail(ADN_ERR_INVALID, "adn_spec_image_db_f64_dev: bad arguments");
+    if (n == 0) return ADN_OK;
+    int32_t rc = ensure_init();
+    if (rc) return rc;
+    return spec_image_dev(spec, n, C, F, channel, dst, pick(stream));
+}
+
+int32_t adn_mean_power_db_f64_dev(const double* spec, int32_t C, int32_t F, int32_t channel, int64_t i0,
+                                  int64_t i1, double floor_db, double* dst, void* stream) {
+    if (C < 1 || F < 1 || channel < 0 || channel >= C || i0 < 0 || i1 <= i0 || !spec || !dst)
+        return fail(ADN_ERR_INVALID, "adn_mean_power_db_f64_dev: bad arguments");
+    int32_t rc = ensure_init();
+    if (rc) return rc;
+    return mean_power_dev(spec, C, F, channel, i0, i1, floor_db, dst, pick(stream));
+}
+
+int32_t adn_pcm_to_f64_dev(const void* pcm, int64_t n, int32_t bits, double gain, double* dst, void* stream) {
+    if (n < 0 || (bits != 16 && bits != 24 && bits != 32) || (n > 0 && (!pcm || !dst)))
+        return fail(ADN_ERR_INVALID, "adn_pcm_to_f64_dev: bad arguments");
+    if (n == 0) return ADN_OK;
+    int32_t rc = ensure_init();
+    if (rc) return rc;
+    return pcm_dev(pcm, n, bits, gain, dst, pick(stream));
+}
+
 
 int32_t adn_minmax_f64_dev(const double* src, int64_t n, int32_t C, int64_t step, double* dst,
                            void* stream) {

@@ -74,6 +74,11 @@ int32_t spectrogram_dev(const double* src, int64_t n_src, int32_t C, double rate
                         int64_t n_dst, int32_t out_db, int64_t* n_computed, cudaStream_t st);
 int32_t decibel_dev(const double* p, int64_t n, double ref_power, double min_power, double* dst,
                     cudaStream_t st);
+int32_t spec_image_dev(const double* spec, int64_t n, int32_t C, int32_t F, int32_t channel, double* dst,
+                       cudaStream_t st);
+int32_t mean_power_dev(const double* spec, int32_t C, int32_t F, int32_t channel, int64_t i0, int64_t i1,
+                       double floor_db, double* dst, cudaStream_t st);
+int32_t pcm_dev(const void* pcm, int64_t n, int32_t bits, double gain, double* dst, cudaStream_t st);
 int32_t synth_dev(double* dst, int64_t t0, int64_t n, int32_t C, double rate, uint64_t seed,
                   cudaStream_t st);
 

@@ -32,6 +32,109 @@ int32_t decibel_dev(const double* p, int64_t n, double ref_power, double min_pow
     return ADN_OK;
 }
 
+// decibel image of one channel of a spectrogram buffer (specitem.py:33-39):
+// dst (F, n) = decibel(spec[:, channel, :].T); spec is (n, C, F) or, with C == 1, the
+// (n, F) slice of one channel
+__global__ void __launch_bounds__(256)
+spec_image_kernel(const double* __restrict__ spec, int64_t n, int32_t C, int32_t F, int32_t channel,
+                  double* __restrict__ dst) {
+    __shared__ double tile[32][33];
+    const int64_t t0 = (int64_t)blockIdx.x * 32;
+    const int f0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t t = t0 + r;
+        const int f = f0 + tx;
+        double v = 0.0;
+        if (t < n && f < F) v = spec[(t * C + channel) * F + f];
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int f = f0 + r;
+        const int64_t t = t0 + tx;
+        if (t < n && f < F) {
+            double v = tile[tx][r];
+            double o = v;
+            if (v > 1e-20) o = 10.0 * log10(v);
+            else if (v <= 1e-20) o = -INFINITY;
+            dst[(int64_t)f * n + t] = o;
+        }
+    }
+}
+
+int32_t spec_image_dev(const double* spec, int64_t n, int32_t C, int32_t F, int32_t channel, double* dst,
+                       cudaStream_t st) {
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((F + 31) / 32));
+    spec_image_kernel<<<grid, 256, 0, st>>>(spec, n, C, F, channel, dst);
+    count_launch();
+    ADN_CK(cudaGetLastError());
+    return ADN_OK;
+}
+
+// power spectrum of the visible frames (spectrogramplot.py:158-160):
+// dst[f] = max(decibel(mean(spec[i0:i1, channel, f])), floor_db)
+__global__ void __launch_bounds__(256)
+mean_power_kernel(const double* __restrict__ spec, int32_t C, int32_t F, int32_t channel, int64_t i0,
+                  int64_t i1, double floor_db, double* __restrict__ dst) {
+    __shared__ double part[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int f = blockIdx.x * 32 + tx;
+    double s = 0.0;
+    if (f < F)
+        for (int64_t t = i0 + ty; t < i1; t += 8) s += spec[(t * C + channel) * F + f];
+    part[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && f < F) {
+        // numpy's mean adds pairwise; the order here differs: ~1e-16 relative
+        double a = 0.0;
+        for (int k = 0; k < 8; ++k) a += part[k][tx];
+        a /= (double)(i1 - i0);
+        double o = a;
+        if (a > 1e-20) o = 10.0 * log10(a);
+        else if (a <= 1e-20) o = -INFINITY;
+        if (o < floor_db) o = floor_db;
+        dst[f] = o;
+    }
+}
+
+int32_t mean_power_dev(const double* spec, int32_t C, int32_t F, int32_t channel, int64_t i0, int64_t i1,
+                       double floor_db, double* dst, cudaStream_t st) {
+    mean_power_kernel<<<(unsigned)((F + 31) / 32), 256, 0, st>>>(spec, C, F, channel, i0, i1, floor_db, dst);
+    count_launch();
+    ADN_CK(cudaGetLastError());
+    return ADN_OK;
+}
+
+// PCM samples -> float64 in [-1, 1) times gain, the scaling audio readers apply
+// (int16: / 2^15, packed little-endian int24: / 2^23, int32: / 2^31)
+__global__ void __launch_bounds__(256)
+pcm_kernel(const unsigned char* __restrict__ pcm, int64_t n, int32_t bytes, double scale,
+           double* __restrict__ dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const unsigned char* q = pcm + i * bytes;
+        int32_t v;
+        if (bytes == 2) v = (int16_t)((uint32_t)q[0] | ((uint32_t)q[1] << 8));
+        else if (bytes == 3) v = ((int32_t)(((uint32_t)q[0] << 8) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 24))) >> 8;
+        else v = (int32_t)((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24));
+        dst[i] = (double)v * scale;
+    }
+}
+
+int32_t pcm_dev(const void* pcm, int64_t n, int32_t bits, double gain, double* dst, cudaStream_t st) {
+    const int bytes = bits / 8;
+    const double scale = gain / (double)((int64_t)1 << (bits - 1));
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)ctx().sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    pcm_kernel<<<(unsigned)blocks, 256, 0, st>>>(static_cast<const unsigned char*>(pcm), n, bytes, scale, dst);
+    count_launch();
+    ADN_CK(cudaGetLastError());
+    return ADN_OK;
+}
+
 __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
     z += 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;

@@ -131,7 +131,35 @@ int32_t adn_spectrogram_f64(const double* src, int64_t n_src, int32_t C,
 int32_t adn_decibel_f64(const double* power, int64_t n, double ref_power,
                         double min_power, double* dst);
 
+/* ---- display side and ingest (SURVEY.md 8f "next" rows) -------------- */
+
+/* Decibel image of one channel, what SpecItem.update_plot hands to setImage()
+ * (src/audian/specitem.py:33-39): dst (F, n) = decibel(spec[:, channel, :].T),
+ * spec (n, C, F).  If the buffer is resident on the device (it was written by
+ * adn_spectrogram_f64 with ADN_OPT_RESIDENT) nothing is uploaded; otherwise only
+ * the rows of that channel are (strided copy). */
+int32_t adn_spec_image_db_f64(const double* spec, int64_t n, int32_t C, int32_t F,
+                              int32_t channel, double* dst);
+/* Power spectrum of the visible frames (src/audian/spectrogramplot.py:158-160):
+ * dst[f] = max(decibel(mean(spec[i0:i1, channel, f])), floor_db), F values. */
+int32_t adn_mean_power_db_f64(const double* spec, int64_t n, int32_t C, int32_t F,
+                              int32_t channel, int64_t i0, int64_t i1,
+                              double floor_db, double* dst);
+/* Raw-data ingest: n little-endian PCM samples of 16, 24 (packed) or 32 bits ->
+ * float64 value / 2^(bits-1) * gain, the scaling the audio readers behind
+ * thunderlab's DataLoader apply (src/audian/data.py:172-180 loads float64).  The
+ * host path moves bits/8 bytes per sample over PCIe instead of 8. */
+int32_t adn_pcm_to_f64(const void* pcm, int64_t n, int32_t bits, double gain,
+                       double* dst);
+
 /* ---- device-pointer entry points (bench / multi-GPU path) ----------- */
+int32_t adn_spec_image_db_f64_dev(const double* spec, int64_t n, int32_t C, int32_t F,
+                                  int32_t channel, double* dst, void* stream);
+int32_t adn_mean_power_db_f64_dev(const double* spec, int32_t C, int32_t F,
+                                  int32_t channel, int64_t i0, int64_t i1,
+                                  double floor_db, double* dst, void* stream);
+int32_t adn_pcm_to_f64_dev(const void* pcm, int64_t n, int32_t bits, double gain,
+                           double* dst, void* stream);
 int32_t adn_minmax_f64_dev(const double* src, int64_t n, int32_t C,
                            int64_t step, double* dst, void* stream);
 /* sos is a HOST pointer; zi / zf are device pointers to (C, S, 2) or NULL.

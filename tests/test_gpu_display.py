@@ -1,0 +1,117 @@
+"""Display-side reductions and raw-data ingest against numpy /
+the oracle's restatement of the reference's plot-item code."""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from audian_b200 import _lib, display
+from audian_b200.synth import synth
+from oracle import oracle as orc
+
+
+class Trace(object):
+    def __init__(self, buffer, offset, frames, rate, fres=1.0):
+        self.buffer, self.offset, self.frames, self.rate = buffer, offset, frames, rate
+        self.fresolution = fres
+
+    def __len__(self):
+        return self.frames
+
+
+def make_spec(n=700, C=3, nfft=256, hop=128, fs=48000.):
+    x = synth(0, n*hop + nfft, C, fs, seed=5)
+    spec = np.empty((n, C, nfft//2 + 1))
+    _lib.spectrogram(x, fs, nfft, hop, spec)
+    return spec
+
+
+@pytest.mark.parametrize('resident', [0, 1])
+def test_spec_image_and_power_spectrum(resident):
+    old = _lib.get_option(_lib.ADN_OPT_RESIDENT), _lib.get_option(_lib.ADN_OPT_RESIDENT_MIN_BYTES)
+    _lib.set_option(_lib.ADN_OPT_RESIDENT, resident)
+    _lib.set_option(_lib.ADN_OPT_RESIDENT_MIN_BYTES, 4096)
+    try:
+        spec = make_spec()
+        spec[17, 1, 5] = 0.0                       # decibel floor: -inf
+        if resident:
+            _lib.invalidate(spec)                  # changed behind the library's back
+            spec2 = spec.copy()
+            x = synth(0, 700*128 + 256, 3, 48000., seed=5)
+            _lib.spectrogram(x, 48000., 256, 128, spec2)      # resident again, untouched
+            hits = _lib.resident_hits()
+            img = _lib.spec_image_db(spec2, 2)
+            assert _lib.resident_hits() == hits + 1
+            assert np.allclose(img, orc.decibel(spec2[:, 2, :].T), rtol=0, atol=1e-9)
+        for ch in range(3):
+            img = _lib.spec_image_db(spec, ch)
+            ref = orc.decibel(spec[:, ch, :].T)
+            assert img.shape == ref.shape
+            assert np.array_equal(np.isneginf(img), np.isneginf(ref))
+            fin = np.isfinite(ref)
+            assert np.allclose(img[fin], ref[fin], rtol=0, atol=1e-9)
+        tr = Trace(spec, 100, 5000, 48000./128, 48000./256)
+        for t0, t1 in ((0.3, 1.0), (0.27, 0.28), (1.5, 2.1)):
+            p, f = display.power_spectrum(tr, 1, t0, t1)
+            i0 = int(t0*tr.rate)
+            i1 = max(int(t1*tr.rate) - 1, i0 + 1)
+            ref = orc.decibel(np.mean(spec[i0 - 100:i1 - 100, 1, :], axis=0))
+            ref[ref < -200] = -200
+            assert np.allclose(p, ref, rtol=0, atol=1e-9)
+            assert np.array_equal(f, np.arange(len(p))*tr.fresolution)
+    finally:
+        _lib.set_option(_lib.ADN_OPT_RESIDENT, old[0])
+        _lib.set_option(_lib.ADN_OPT_RESIDENT_MIN_BYTES, old[1])
+
+
+def test_noise_levels_match_reference_formula():
+    from audian_b200.bufferedspectrogram import BufferedSpectrogram
+    spec = make_spec(n=300, C=2)
+    s = BufferedSpectrogram()
+    s.buffer = spec
+    s.init = True
+    zmin, zmax = s.estimate_noiselevels(1)
+    db = orc.decibel(spec[:, 1, :])
+    nf = spec.shape[2]//16
+    rmin = np.percentile(db[:, -nf:], 95)
+    rmax = np.max(db)
+    rmax = rmin + 0.95*(rmax - rmin)
+    if rmax - rmin < 20:
+        rmax = rmin + 20
+    if rmax - rmin > 80:
+        rmin = rmax - 80
+    assert abs(zmin - rmin) < 1e-8 and abs(zmax - rmax) < 1e-8
+
+
+def test_trace_decimate_matches_traceitem():
+    fs, C = 48000., 4
+    x = synth(0, 900000, C, fs, seed=8)
+    off = 50000
+    tr = Trace(x, off, 5_000_000, fs)
+    for t0, t1, px in ((2.0, 15.0, 1920), (1.0, 19.9, 800), (1.1, 1.12, 1920), (0.0, 30.0, 1000)):
+        for ch in (0, 3):
+            step, start, ref = orc.traceitem_decimate(len(tr), off, x, fs, ch, t0, t1, px)
+            gstep, gt, gd = display.trace_decimate(tr, ch, t0, t1, px)
+            assert gstep == step
+            assert np.array_equal(gd.view(np.uint64), np.asarray(ref).view(np.uint64))
+            if step > 1:
+                assert np.array_equal(gt, np.arange(start, start + len(ref)*step/2, step/2)/fs)
+
+
+@pytest.mark.parametrize('bits', [16, 24, 32])
+def test_pcm_ingest(bits):
+    rng = np.random.default_rng(bits)
+    n, C = 50001, 3
+    lim = 1 << (bits - 1)
+    v = rng.integers(-lim, lim, size=n*C, dtype=np.int64)
+    v[:4] = [-lim, lim - 1, 0, -1]
+    if bits == 16:
+        raw = v.astype('<i2').view(np.uint8)
+    elif bits == 32:
+        raw = v.astype('<i4').view(np.uint8)
+    else:
+        raw = (v.astype('<i4').view(np.uint8).reshape(-1, 4)[:, :3]).copy().reshape(-1)
+    got = _lib.pcm_to_f64(raw, bits, C, gain=2.5)
+    ref = (v.astype(np.float64)/lim*2.5).reshape(n, C)
+    assert got.shape == (n, C) and np.array_equal(got, ref)
