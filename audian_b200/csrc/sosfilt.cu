@@ -161,7 +161,8 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
 
     double* tile_s = smem;                                   // G * (L*CG + pad)
     double* wagg = smem + (size_t)G * (SOS_L * CG + pad);    // [NW][CG][D]
-    double* sin_s = wagg + SOS_NW * CG * D;                  // [CG][D]
+    double* wtile = wagg + SOS_NW * CG * D;                  // [NW][CG][D]
+    double* sin_s = wtile + SOS_NW * CG * D;                 // [CG][D]
     double* tab_s = sin_s + CG * D;                          // n_staged * DD (if STAGE)
     const double* tab = STAGE ? tab_s : R.tab;               // scan / fix / wpow tables
     const double* tab_fix = tab + R.off_fix * DD;
@@ -304,6 +305,14 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
     if (gl == GW - 1) {
 #pragma unroll
         for (int d = 0; d < D; ++d) wagg[(warp * CG + cw) * D + d] = v[d];
+        // this warp's share of the tile aggregate, A^(L GW (NW-1-warp)) v: computed here, in
+        // parallel over the warps, so that the look-back lanes only have to add four vectors
+        double wv[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) wv[d] = 0.0;
+        matvec_acc<D>(tab_wpow + (SOS_NW - 1 - warp) * DD, v, wv);
+#pragma unroll
+        for (int d = 0; d < D; ++d) wtile[(warp * CG + cw) * D + d] = wv[d];
     }
     __syncthreads();
 
@@ -328,10 +337,8 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
         for (int d = 0; d < D; ++d) acc[d] = 0.0;
 #pragma unroll
         for (int j = 0; j < SOS_NW; ++j) {
-            double a[D];
 #pragma unroll
-            for (int d = 0; d < D; ++d) a[d] = wagg[(j * CG + lane) * D + d];
-            matvec_acc<D>(tab_wpow + (SOS_NW - 1 - j) * DD, a, acc);
+            for (int d = 0; d < D; ++d) acc[d] += wtile[(j * CG + lane) * D + d];
         }
         const bool publish = tt + 1 < R.ntt;
         const size_t rec = (size_t)tile * CG * D + (size_t)lane * D;
@@ -357,9 +364,18 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
                 const size_t prec = (size_t)(tile - (int64_t)j * R.ngroups) * CG * D + (size_t)lane * D;
                 unsigned ns = 0;
                 while (true) {
-                    if (read_record<D>(R.incl + prec, vec)) { closed = true; break; }
-                    // the last slot of the window must be an inclusive state
-                    if (j <= SOS_LOOK && read_record<D>(R.agg + prec, vec)) break;
+                    // both records in one round trip to L2: the inclusive state closes the
+                    // look-back, else the aggregate is taken (the last slot of the window
+                    // must be an inclusive state)
+                    double va[D];
+                    const bool ok_i = read_record<D>(R.incl + prec, vec);
+                    const bool ok_a = read_record<D>(R.agg + prec, va);
+                    if (ok_i) { closed = true; break; }
+                    if (j <= SOS_LOOK && ok_a) {
+#pragma unroll
+                        for (int d = 0; d < D; ++d) vec[d] = va[d];
+                        break;
+                    }
                     if (ns) __nanosleep(ns);
                     ns = ns ? (ns < 256 ? ns * 2 : ns) : 32;
                 }
@@ -781,7 +797,7 @@ int32_t run_scan(int mode, const double* sos, int S, const double* src, int64_t 
     R.incl = R.agg + recs;
     ADN_CK(cudaMemsetAsync(R.agg, 0xFF, recs * 16, st));
     const int pad = CG < 16 ? CG : 0;
-    const size_t smem = ((size_t)(SOS_NT / CG) * (SOS_L * CG + pad) + (size_t)(SOS_NW + 1) * CG * D +
+    const size_t smem = ((size_t)(SOS_NT / CG) * (SOS_L * CG + pad) + (size_t)(2 * SOS_NW + 1) * CG * D +
                          (S <= 4 ? (size_t)plan->n_staged * D * D : 0)) * 8;
     const unsigned grid = (unsigned)ntiles;
     switch (S) {
