@@ -1010,6 +1010,255 @@ int32_t launch_warp_kernel(SpecWArgs& P, int64_t nf, cudaStream_t st) {
 
 
 // ======================================================================================
+// nfft 2048 .. 16384: one block per frame and channel pair, R complex points per thread in
+// registers, Stockham autosort passes (radix R, then the remaining factor) with the exchanges
+// through one padded shared-memory buffer.  Pass with accumulated length Ns, radix r,
+// butterfly b < M/r:   y[(b / Ns) Ns r + b % Ns + m Ns] = sum_k W_(Ns r)^((b % Ns) k) x[b + k M/r] W_r^(k m)
+// Natural order in, natural order out, so the split step reads Z[k] and Z[M - k] directly.
+// The raw rows of both channels of a pair come in as 16-byte loads and stay in registers
+// while the channels are transformed one after the other; the frame mean is removed after
+// the transform (bins 0 and 1, see the ring kernel).
+struct SpecMArgs {
+    const double* src;
+    double* dst;
+    const double* win;          // nfft
+    const double2* tw;          // exp(-2 pi i j / nfft), j < nfft/2
+    int64_t nframes;
+    int32_t C, hop, npair;      // channel pairs (the last one may be a single channel)
+    int32_t detrend;
+    double scale;
+};
+
+template <int LOGN>
+__device__ __forceinline__ double2 tw_full(const double2* __restrict__ tw, int n) {
+    // exp(-2 pi i n / N) for any n from the half table
+    constexpr int N = 1 << LOGN;
+    n &= N - 1;
+    double2 v = __ldg(tw + (n & (N / 2 - 1)));
+    return n >= N / 2 ? make_double2(-v.x, -v.y) : v;
+}
+
+__device__ __forceinline__ int mp_pad(int i) { return i + (i >> 3); }
+
+template <int r>
+__device__ __forceinline__ void mp_dft(const double2* x, double2* y) {
+    if (r == 2) {
+        y[0] = cadd(x[0], x[1]);
+        y[1] = csub(x[0], x[1]);
+    } else if (r == 4) {
+        dft4(x[0], x[1], x[2], x[3], y[0], y[1], y[2], y[3]);
+    } else if (r == 8) {
+        dft8(x, y);
+    } else {
+        double2 a[16], b[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = x[i];
+        dft16(a, b);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] = b[i];
+    }
+}
+
+// one pass over the R points of this thread: R/r butterflies of radix r
+// wb: exp(-2 pi i (t mod Ns) / (Ns r)) of this thread (Ns <= T), or for the last pass with
+// Ns > T exp(-2 pi i t / (Ns r)): the twiddle of butterfly b = t + q T is then wb W_(Ns r / T)^q
+template <int LOGN, int R, int r, bool FROM_REGS, bool FIRST>
+__device__ __forceinline__ void mp_pass(double2 (&z)[R], double2* S, double2 wb, int t, int logNs) {
+    constexpr int M = 1 << (LOGN - 1), T = M / R, NB = M / r, Q = R / r;
+    constexpr int LOGR = r == 2 ? 1 : (r == 4 ? 2 : (r == 8 ? 3 : 4));
+    if (!FROM_REGS) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+#pragma unroll
+            for (int k = 0; k < r; ++k) z[q * r + k] = S[mp_pad(t + q * T + k * NB)];
+        __syncthreads();
+    }
+    const int Ns = 1 << logNs;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const int b = t + q * T;
+        const int bl = b & (Ns - 1);
+        double2 x[r], y[r];
+#pragma unroll
+        for (int k = 0; k < r; ++k) x[k] = z[q * r + k];
+        if (!FIRST) {
+            // W_(Ns r)^(bl k), k < r: powers of the thread's base twiddle
+            double2 w[r];
+            w[1] = wb;
+            if (Q > 1 && q > 0) {
+                // bl = t + q T: times exp(-2 pi i q T / (Ns r)), a power of W_(2 Q) or finer
+                constexpr int LT = LOGN - 1 - (R == 8 ? 3 : 4);       // log2 T
+                const int sh = logNs + LOGR - LT;                      // Ns r / T = 2^sh
+                // angle = -2 pi q / 2^sh, sh <= 5: from the 32nd roots of unity
+                const int idx = (q << (5 - sh)) & 31;
+                double2 c = idx < 16 ? make_double2(w32c(idx & 15, 0), w32c(idx & 15, 1))
+                                     : make_double2(-w32c(idx & 15, 0), -w32c(idx & 15, 1));
+                w[1] = cmul(wb, c);
+            }
+            if (r > 2) w[2] = cmul(w[1], w[1]);
+            if (r > 4) w[4] = cmul(w[2], w[2]);
+            if (r > 8) w[8] = cmul(w[4], w[4]);
+            if (r > 2) w[3] = cmul(w[2], w[1]);
+            if (r > 4) { w[5] = cmul(w[4], w[1]); w[6] = cmul(w[4], w[2]); w[7] = cmul(w[6], w[1]); }
+            if (r > 8) {
+                w[9] = cmul(w[8], w[1]); w[10] = cmul(w[8], w[2]); w[12] = cmul(w[8], w[4]);
+                w[11] = cmul(w[10], w[1]); w[13] = cmul(w[12], w[1]); w[14] = cmul(w[12], w[2]);
+                w[15] = cmul(w[14], w[1]);
+            }
+#pragma unroll
+            for (int k = 1; k < r; ++k) x[k] = cmul(x[k], w[k]);
+        }
+        mp_dft<r>(x, y);
+        const int base = ((b - bl) << LOGR) + bl;
+#pragma unroll
+        for (int m = 0; m < r; ++m) S[mp_pad(base + (m << logNs))] = y[m];
+    }
+    __syncthreads();
+}
+
+template <int LOGN, int R>
+__device__ __forceinline__ void mp_fft(double2 (&z)[R], double2* S, const double2 (&wb)[5], int t) {
+    constexpr int LOGM = LOGN - 1;
+    constexpr int LOGR = R == 8 ? 3 : 4;
+    constexpr int NFULL = LOGM / LOGR;                 // passes of radix R
+    constexpr int REM = LOGM - NFULL * LOGR;           // log2 of the last, smaller radix
+    mp_pass<LOGN, R, R, true, true>(z, S, make_double2(1.0, 0.0), t, 0);
+#pragma unroll
+    for (int p = 1; p < NFULL; ++p) mp_pass<LOGN, R, R, false, false>(z, S, wb[p], t, p * LOGR);
+    if (REM == 1) mp_pass<LOGN, R, 2, false, false>(z, S, wb[NFULL], t, NFULL * LOGR);
+    if (REM == 2) mp_pass<LOGN, R, 4, false, false>(z, S, wb[NFULL], t, NFULL * LOGR);
+    if (REM == 3) mp_pass<LOGN, R, 8, false, false>(z, S, wb[NFULL], t, NFULL * LOGR);
+}
+
+// base twiddles of thread t for the passes 1 .. (wb[0] unused): exp(-2 pi i (t mod Ns) / (Ns r))
+template <int LOGN, int R>
+__device__ __forceinline__ void mp_twiddles(double2 (&wb)[5], const double2* __restrict__ tw, int t) {
+    constexpr int LOGM = LOGN - 1;
+    constexpr int LOGR = R == 8 ? 3 : 4;
+    constexpr int NFULL = LOGM / LOGR;
+    constexpr int REM = LOGM - NFULL * LOGR;
+    constexpr int T = (1 << LOGM) / R;
+    wb[0] = make_double2(1.0, 0.0);
+#pragma unroll
+    for (int p = 1; p < 5; ++p) {
+        wb[p] = make_double2(1.0, 0.0);
+        if (p < NFULL || (p == NFULL && REM > 0)) {
+            const int logNs = p * LOGR;
+            const int logr = p < NFULL ? LOGR : REM;
+            const int Ns = 1 << logNs;
+            const int bl = Ns <= T ? (t & (Ns - 1)) : t;
+            wb[p] = tw_full<LOGN>(tw, bl << (LOGN - logNs - logr));
+        }
+    }
+}
+
+template <int LOGN, int R, int CP, bool DB>
+__global__ void __launch_bounds__((1 << (LOGN - 1)) / R)
+spectrogram_mp_kernel(const __grid_constant__ SpecMArgs P) {
+    constexpr int N = 1 << LOGN, M = N / 2, T = M / R, F = M + 1;
+    extern __shared__ __align__(16) double sbuf[];
+    double2* S = reinterpret_cast<double2*>(sbuf);               // M + M/8 complex
+    __shared__ double red[2][32];
+    const int t = threadIdx.x;
+    const int64_t frame = blockIdx.x / P.npair;
+    const int pair = blockIdx.x % P.npair;
+    const int C = P.C;
+    const int c0 = pair * CP;
+    const int nch = min(CP, C - c0);
+    const double* x0 = P.src + (frame * P.hop) * (int64_t)C + c0;
+
+    double2 za[R], zb[CP == 2 ? R : 1];
+    double sa = 0.0, sb = 0.0;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        const int64_t row = 2 * (t + k * T);
+        if (CP == 2 && nch == 2) {
+            double2 v0 = __ldg(reinterpret_cast<const double2*>(x0 + row * C));
+            double2 v1 = __ldg(reinterpret_cast<const double2*>(x0 + (row + 1) * C));
+            za[k] = make_double2(v0.x, v1.x);
+            zb[CP == 2 ? k : 0] = make_double2(v0.y, v1.y);
+            sb += v0.y + v1.y;
+        } else {
+            za[k] = make_double2(__ldg(x0 + row * C), __ldg(x0 + (row + 1) * C));
+        }
+        sa += za[k].x + za[k].y;
+    }
+    // frame sums (for the mean): warp shuffle, then one value per warp through shared memory
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+        sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    }
+    if ((t & 31) == 0) { red[0][t >> 5] = sa; red[1][t >> 5] = sb; }
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        double2 w = __ldg(reinterpret_cast<const double2*>(P.win) + (t + k * T));
+        za[k].x *= w.x; za[k].y *= w.y;
+        if (CP == 2) { zb[CP == 2 ? k : 0].x *= w.x; zb[CP == 2 ? k : 0].y *= w.y; }
+    }
+    const double sc = 0.5 * P.scale;
+    double2 wb[5];
+    mp_twiddles<LOGN, R>(wb, P.tw, t);
+    for (int ch = 0; ch < nch; ++ch) {
+        if (CP == 2 && ch == 1) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) za[k] = zb[CP == 2 ? k : 0];
+        }
+        mp_fft<LOGN, R>(za, S, wb, t);                // ends with a barrier: red[] is visible too
+        double fsum = 0.0;
+        for (int i = 0; i < T / 32; ++i) fsum += red[ch][i];
+        const double mN2 = P.detrend ? fsum * 0.5 : 0.0;          // mean * N/2
+        double* out = P.dst + ((frame * C + c0 + ch) * (int64_t)F);
+#pragma unroll
+        for (int q = 0; q < R / 2; ++q) {
+            const int k = 1 + t + q * T, km = M - k;              // k in [1, M/2]
+            double2 zk = S[mp_pad(k)], zm = S[mp_pad(km)];
+            double2 w = __ldg(P.tw + k);
+            double e_r = zk.x + zm.x, e_i = zk.y - zm.y;          // Zk + conj(Zm)
+            double o_r = zk.y + zm.y, o_i = zm.x - zk.x;          // -i (Zk - conj(Zm))
+            double t_r = o_r * w.x - o_i * w.y, t_i = o_r * w.y + o_i * w.x;
+            double pr = e_r + t_r, pi = e_i + t_i, qr = e_r - t_r, qi = e_i - t_i;
+            if (k == 1) pr += mN2;                                // the window's spectrum at bin 1 is -N/4
+            double pk = (pr * pr + pi * pi) * sc, pm = (qr * qr + qi * qi) * sc;
+            if (DB) { pk = to_db(pk); pm = to_db(pm); }
+            __stcs(out + k, pk);
+            if (km != k) __stcs(out + km, pm);
+        }
+        if (t == 0) {
+            double2 z0 = S[0];
+            double x0v = z0.x + z0.y - mN2, xM = z0.x - z0.y;
+            double p0 = x0v * x0v * P.scale, pM = xM * xM * P.scale;
+            if (DB) { p0 = to_db(p0); pM = to_db(pM); }
+            out[0] = p0;
+            out[M] = pM;
+        }
+        __syncthreads();                              // S is reused by the second channel
+    }
+}
+
+template <int LOGN, int R, int CP>
+int32_t launch_mp(SpecMArgs& P, int64_t nf, int out_db, cudaStream_t st) {
+    constexpr int M = 1 << (LOGN - 1), T = M / R;
+    P.npair = (P.C + CP - 1) / CP;
+    const size_t smem = (size_t)(M + M / 8 + 8) * 16;
+    const int64_t grid = nf * P.npair;
+    if (grid > 0x7fffffff) return fail(ADN_ERR_UNSUPPORTED, "spectrogram: grid %lld", (long long)grid);
+    auto k0 = spectrogram_mp_kernel<LOGN, R, CP, false>;
+    auto k1 = spectrogram_mp_kernel<LOGN, R, CP, true>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        ADN_CK(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ADN_CK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done = true;
+    }
+    if (out_db) k1<<<(unsigned)grid, T, smem, st>>>(P);
+    else k0<<<(unsigned)grid, T, smem, st>>>(P);
+    count_launch();
+    ADN_CK(cudaGetLastError());
+    return ADN_OK;
+}
+
+// ======================================================================================
 // Frames longer than one block's shared memory (nfft 2^15 .. 2^20; the GUI offers up to 2^19,
 // databrowser.py:516): the complex transforms live in a work buffer in global memory.
 //   pack    frame -> minus mean, x window -> M = nfft/2 complex points (even, odd samples)
@@ -1399,6 +1648,21 @@ int32_t spectrogram_dev(const double* src, int64_t n_src, int32_t C, double rate
     if (nfft > 16384)
         return spectrogram_big(plan, src, C, rate, nfft, hop, detrend_id == ADN_DETREND_CONSTANT, dst, nf,
                                out_db, st);
+    if (nfft >= 2048 && env_int("ADN_SPEC_MP", 1) != 0) {
+        SpecMArgs Q;
+        Q.src = src; Q.dst = dst; Q.win = plan.win; Q.tw = plan.tw;
+        Q.nframes = nf; Q.C = C; Q.hop = hop;
+        Q.detrend = detrend_id == ADN_DETREND_CONSTANT;
+        Q.scale = 1.0 / (rate * plan.sumw2);
+        // channel pairs need 16-byte aligned rows: even C and an aligned base
+        const bool pairs = C % 2 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+        switch (nfft) {
+            case 2048: return pairs ? launch_mp<11, 8, 2>(Q, nf, out_db, st) : launch_mp<11, 8, 1>(Q, nf, out_db, st);
+            case 4096: return pairs ? launch_mp<12, 8, 2>(Q, nf, out_db, st) : launch_mp<12, 8, 1>(Q, nf, out_db, st);
+            case 8192: return launch_mp<13, 16, 1>(Q, nf, out_db, st);
+            case 16384: return launch_mp<14, 16, 1>(Q, nf, out_db, st);
+        }
+    }
     SpecArgs P;
     P.src = src; P.dst = dst; P.tw = plan.tw; P.win = plan.win;
     P.nframes = nf; P.C = C; P.nfft = nfft; P.hop = hop;

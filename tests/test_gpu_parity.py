@@ -288,6 +288,23 @@ def test_spectrogram_channels(C):
     assert_spec_close(got, ref, f'C={C}')
 
 
+@pytest.mark.parametrize('nfft,C', [(2048, 1), (2048, 3), (4096, 8), (8192, 5), (16384, 2), (4096, 64)])
+def test_spectrogram_midsize_channels(nfft, C):
+    fs = 250000.
+    hop = nfft//4
+    n_src = nfft*2 + hop*5 + 3
+    x = synth(7, n_src, C, fs, seed=nfft + C) - 0.125
+    n_dst = n_src//hop
+    ref = np.empty((n_dst, C, nfft//2 + 1))
+    nref = orc.spectrogram_process(x, ref, fs, nfft, hop)
+    got = np.full_like(ref, np.nan)
+    assert _lib.spectrogram(x, fs, nfft, hop, got) == nref
+    assert_spec_close(got, ref, f'nfft={nfft} C={C}')
+    db = np.empty_like(ref)
+    _lib.spectrogram(x, fs, nfft, hop, db, out_db=True)
+    assert np.allclose(db[:nref], orc.decibel(ref[:nref]), rtol=0, atol=1e-6)
+
+
 def test_spectrogram_largest_gui_nfft():
     # 2^19 is the largest size the GUI offers (databrowser.py:516)
     fs, nfft = 500000., 1 << 19
