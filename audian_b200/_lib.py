@@ -27,6 +27,7 @@ ADN_OPT_VERIFY = 1
 ADN_OPT_CHUNK_BYTES = 2
 ADN_OPT_RESIDENT_MIN_BYTES = 3
 ADN_OPT_RESIDENT_CAP_BYTES = 4
+ADN_OPT_ENVELOPE_CHUNK_BYTES = 5
 ADN_WINDOW_HANN = 0
 ADN_DETREND_NONE = 0
 ADN_DETREND_CONSTANT = 1

@@ -114,7 +114,9 @@ static std::vector<Resident> g_res;
 static std::vector<DevBuf> g_pool;            // released device buffers, reused by size
 static DevBuf g_vbuf;                         // samples of a resident copy for verification
 static uint64_t g_stamp = 0;
-static int64_t g_opt[ADN_OPT_COUNT] = {0, 1, (int64_t)32 << 20, (int64_t)8 << 20, (int64_t)16 << 30};
+static int64_t g_opt[ADN_OPT_COUNT] = {0, 1, (int64_t)32 << 20, (int64_t)8 << 20, (int64_t)16 << 30,
+                                       0};
+int64_t option(int32_t which) { return g_opt[which]; }
 static cudaStream_t g_h2d = nullptr, g_d2h = nullptr;
 static std::vector<cudaEvent_t> g_events;
 static size_t g_event_next = 0;

@@ -901,6 +901,70 @@ int32_t envelope_dev(const double* sos, int32_t S, const double* src, int64_t n_
     DevBuf& fwd = scratch(SCR_ENV_FWD);
     DevBuf& misc = scratch(SCR_ENV_MISC);
     int32_t rc;
+    // Optional schedule (ADN_OPT_ENVELOPE_CHUNK_BYTES > 0, off by default: see the header):
+    // cascades that forget their state within `keep` rows (|A^keep| < 1e-30) are swept in
+    // chunks that live in L2: forward over chunk j+1, then backward over chunk j, whose
+    // incoming state comes from a zero-state reverse pass over the first `keep` rows of chunk
+    // j+1 (exact to 1e-30).  The forward result only ever exists in a three-slot ring that
+    // stays cache resident, so HBM sees the input once and the result once (16 B/sample)
+    // instead of the 32 B/sample of two full sweeps.
+    {
+        const int64_t chunk_bytes = option(ADN_OPT_ENVELOPE_CHUNK_BYTES);
+        const int64_t keep = chunk_bytes > 0 ? adn_sos_decay_length(sos, S, 1e-30) : -1;
+        int64_t rpc = chunk_bytes / ((int64_t)C * 8);             // rows per chunk
+        if (keep > 0 && rpc >= 8 * keep && rpc > 4 * edge && n_src >= 3 * rpc) {
+            const int64_t nch = n_src / rpc;
+            rpc = (n_src + nch - 1) / nch;
+            const int64_t slot_rows = rpc + 2 * edge;
+            if ((rc = fwd.reserve((size_t)(3 * slot_rows) * C * 8))) return rc;
+            if ((rc = misc.reserve((size_t)(4 * C * D) * 8))) return rc;
+            double* st_f[2] = {misc.as<double>(), misc.as<double>() + (size_t)C * D};
+            double* st_b = st_f[1] + (size_t)C * D;
+            double* st_k = st_b + (size_t)C * D;
+            const int nb = (C * D + 127) / 128;
+            auto slot = [&](int64_t j) { return fwd.as<double>() + (size_t)(j % 3) * slot_rows * C; };
+            auto a_of = [&](int64_t j) { return j * rpc < n_src ? j * rpc : n_src; };
+            auto len_of = [&](int64_t j) {                        // rows of chunk j of the forward result
+                return a_of(j + 1) - a_of(j) + (j == 0 ? edge : 0) + (j == nch - 1 ? edge : 0);
+            };
+            auto forward = [&](int64_t j) -> int32_t {
+                const int64_t a = a_of(j), b = a_of(j + 1);
+                const double* zi = st_f[(j + 1) & 1];
+                if (j == 0) {
+                    env_s0_kernel<<<nb, 128, 0, st>>>(0, src, C, D, edge, zik, st_f[1]);
+                    count_launch();
+                }
+                return envelope_forward_dev(sos, S, src + a * C, b - a, C, j == 0 ? edge : 0,
+                                            j == nch - 1 ? edge : 0, zi, slot(j), st_f[j & 1], st);
+            };
+            if ((rc = forward(0))) return rc;
+            for (int64_t j = 0; j < nch; ++j) {
+                if (j + 1 < nch) {
+                    if ((rc = forward(j + 1))) return rc;
+                    // state entering chunk j from behind: the next chunk's first rows, reversed
+                    if ((rc = sosfilt_reverse_dev(sos, S, slot(j + 1), keep, C, nullptr, nullptr, 0, 0, 0,
+                                                  st_k, st)))
+                        return rc;
+                } else {
+                    env_s0_kernel<<<nb, 128, 0, st>>>(1, slot(j) + (len_of(j) - 1) * C, C, D, 0, zik, st_k);
+                    count_launch();
+                }
+                const int64_t L = len_of(j);
+                const int64_t G = j == 0 ? 0 : edge + a_of(j);    // position in the extended sequence
+                int64_t r_lo = edge + nbefore - G, r_hi = edge + nbefore + n_dst - G;
+                if (r_lo < 0) r_lo = 0;
+                if (r_hi > L) r_hi = L;
+                if (r_hi > r_lo) {
+                    if ((rc = sosfilt_reverse_dev(sos, S, slot(j), L, C, st_k,
+                                                  dst + (G + r_lo - edge - nbefore) * C, r_lo, r_hi - r_lo,
+                                                  clamp_negative, nullptr, st)))
+                        return rc;
+                }
+            }
+            ADN_CK(cudaGetLastError());
+            return ADN_OK;
+        }
+    }
     if ((rc = fwd.reserve((size_t)next * C * 8))) return rc;
     if ((rc = misc.reserve((size_t)(2 * C * D) * 8))) return rc;
     double* d_s0f = misc.as<double>();

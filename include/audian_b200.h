@@ -61,7 +61,14 @@ extern "C" {
 #define ADN_OPT_RESIDENT_MIN_BYTES  3  /* smaller results are never kept (default 8 MiB) */
 #define ADN_OPT_RESIDENT_CAP_BYTES  4  /* least recently used copies are dropped beyond this
                                           total (default 16 GiB) */
-#define ADN_OPT_COUNT               5
+#define ADN_OPT_ENVELOPE_CHUNK_BYTES 5 /* > 0: the two envelope sweeps run chunk by chunk (forward
+                                          over chunk j+1, backward over chunk j) when the cascade
+                                          forgets its state well within a chunk, so that the
+                                          forward result stays in L2.  Default 0 = two full
+                                          sweeps: measured on B200 the scan kernel is not HBM
+                                          bound enough for the saved traffic to pay for the
+                                          extra launches (16 MiB chunks: 0.74 ms vs 0.25 ms) */
+#define ADN_OPT_COUNT               6
 
 #define ADN_WINDOW_HANN      0   /* periodic Hann == scipy get_window('hann', nfft) */
 #define ADN_DETREND_NONE     0

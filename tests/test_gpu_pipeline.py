@@ -145,3 +145,30 @@ def test_traces_invalidate_on_buffer_moves(resident):
     assert np.max(np.abs(env.buffer - g['env_buffer'])) <= 1e-6
     ref = g['spec_buffer']
     assert np.allclose(spect.buffer, ref, rtol=1e-5, atol=1e-20*ref.max())
+
+
+@pytest.mark.parametrize('C,nbefore,cut', [(2, 0, 500.), (8, 4321, 300.), (3, 17, 2000.), (1, 0, 800.)])
+def test_envelope_chunked_schedule_equals_two_full_sweeps(C, nbefore, cut):
+    """The L2-resident chunked schedule of the envelope (forward over chunk j+1, backward over
+    chunk j from a decay-length warm-up) against scipy and against the two-full-sweeps path."""
+    fs, n = 48000., 400000
+    x = synth(3, n, C, fs, seed=50 + C)
+    esos = orc.envelope_design(fs, cut)
+    ref = np.empty((n - nbefore, C))
+    orc.envelope_process(esos, x, ref, nbefore, 0)
+    old = _lib.get_option(_lib.ADN_OPT_ENVELOPE_CHUNK_BYTES)
+    try:
+        _lib.set_option(_lib.ADN_OPT_ENVELOPE_CHUNK_BYTES, 0)
+        full = np.empty_like(ref)
+        _lib.envelope(esos, x, full, nbefore, True)
+        _lib.set_option(_lib.ADN_OPT_ENVELOPE_CHUNK_BYTES, 40000*C*8)      # 10 chunks
+        got = np.full_like(ref, np.nan)
+        _lib.envelope(esos, x, got, nbefore, True)
+        short = np.full((1000, C), np.nan)
+        _lib.envelope(esos, x, short, nbefore, True)                      # n_dst < n_src - nbefore
+    finally:
+        _lib.set_option(_lib.ADN_OPT_ENVELOPE_CHUNK_BYTES, old)
+    assert np.max(np.abs(full - ref)) <= 1e-9
+    assert np.max(np.abs(got - ref)) <= 1e-9
+    assert np.max(np.abs(got - full)) <= 1e-12
+    assert np.array_equal(short, got[:1000])
