@@ -133,7 +133,7 @@ __device__ __forceinline__ void st_out(T* p, T v) {
 }
 
 template <int S, int MODE>
-__global__ void __launch_bounds__(SOS_NT, S <= 2 ? 5 : (S <= 4 ? 3 : 1))
+__global__ void __launch_bounds__(SOS_NT, S <= 2 ? 6 : (S <= 4 ? 4 : 1))
 sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRun R) {
     constexpr int D = 2 * S;
     constexpr int DD = D * D;
