@@ -682,6 +682,11 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
     const int niter = (nitems + NW * FPW - 1) / (NW * FPW);
     const double corr = P.detrend ? 0.5 : 0.0;           // (sum x / N) * N/2
 
+    // all SR_PF vectors of all threads lie inside a chunk (then no load or store is predicated)
+    const bool allv = (SR_PF - 1) * DR + ((2 * (NT - 1)) >> LW) < CH;
+    // frames start at multiples of 64 rows in a ring of exactly one frame: the 16 loads of a
+    // lane are a rotation of 16 fixed 64-row slices (immediate offsets, picked by a switch)
+    const bool rot_ok = T == 32 && RM == N - 1 && (hop & 63) == 0;
     int ws = 0;                 // ring position of the first row of this step
     int npos = span0;           // ring position / row of the chunk the next step adds
     int nrow = span0;
@@ -689,7 +694,7 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
         // pull the rows of the next step into L2 while this step computes
         const bool more = s + 1 < nsteps;
         const bool inside = nrow + CH <= rows_run;       // the whole next chunk exists
-        if (more && tid == 0) {
+        if (more && tid == 0) {                  // whole rows (every group's block: measured faster)
             const int64_t nr = inside ? CH : rows_run - nrow;
             if (nr > 0) {
                 const double* a0 = P.src + (f0 * hop + nrow) * (int64_t)C;
@@ -699,23 +704,23 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
         }
 
         double2 pf[SR_PF];
-#pragma unroll
-        for (int j = 0; j < SR_PF; ++j) pf[j] = make_double2(0.0, 0.0);
         bool loaded = false;
         // the loads of the next chunk are issued late in the last item of the step, when the
         // registers of the first pass are free again (they come from L2 by then)
         auto issue_loads = [&]() {
-            if (inside) {
+            if (inside && allv) {                   // every vector of every thread exists
                 const double* gp = gnext;
 #pragma unroll
                 for (int j = 0; j < SR_PF; ++j) {
-                    if (r0 + j * DR < CH) pf[j] = __ldg(reinterpret_cast<const double2*>(gp));
+                    pf[j] = __ldg(reinterpret_cast<const double2*>(gp));
                     gp += gstep;
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < SR_PF; ++j)
+                for (int j = 0; j < SR_PF; ++j) {
+                    pf[j] = make_double2(0.0, 0.0);
                     if (r0 + j * DR < CH) pf[j] = __ldg(gaddr(nrow + r0 + j * DR));
+                }
             }
         };
         for (int iter = 0; iter < niter; ++iter) {
@@ -730,9 +735,20 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
 
             // ---- load, window; the frame sum for the mean goes on in the background
             double2 a[16];
+            if (T == 32 && rot_ok) {
+                const double* xb = xr + 2 * t;
+                switch (((ws + fi * hop) >> 6) & 15) {
+#define ADN_ROT(Q) case Q: _Pragma("unroll") for (int p = 0; p < 16; ++p) \
+                        a[p] = *reinterpret_cast<const double2*>(xb + (((p + Q) & 15) << 6)); break;
+                    ADN_ROT(0) ADN_ROT(1) ADN_ROT(2) ADN_ROT(3) ADN_ROT(4) ADN_ROT(5) ADN_ROT(6) ADN_ROT(7)
+                    ADN_ROT(8) ADN_ROT(9) ADN_ROT(10) ADN_ROT(11) ADN_ROT(12) ADN_ROT(13) ADN_ROT(14) ADN_ROT(15)
+#undef ADN_ROT
+                }
+            } else {
 #pragma unroll
-            for (int p = 0; p < 16; ++p)
-                a[p] = *reinterpret_cast<const double2*>(xr + ((start + 2 * T * p) & RM));
+                for (int p = 0; p < 16; ++p)
+                    a[p] = *reinterpret_cast<const double2*>(xr + ((start + 2 * T * p) & RM));
+            }
             double sm = 0.0;
             {
                 double s0 = a[0].x + a[0].y, s1 = a[1].x + a[1].y, s2 = a[2].x + a[2].y, s3 = a[3].x + a[3].y;
@@ -903,7 +919,7 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
             __syncthreads();            // every warp is done with the rows the chunk replaces
 #pragma unroll
             for (int j = 0; j < SR_PF; ++j)
-                if (r0 + j * DR < CH) put(pf[j], npos + r0 + j * DR);
+                if (allv || r0 + j * DR < CH) put(pf[j], npos + r0 + j * DR);
             if (r0 + SR_PF * DR < CH) stage_direct(nrow, npos, CH, SR_PF);
             __syncthreads();
         }
