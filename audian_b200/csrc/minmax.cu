@@ -53,6 +53,36 @@ __device__ __forceinline__ void feed(Best& mn, Best& mx, double v, int32_t row) 
     if (vnan || (mx.v == mx.v && !(mx.v > v))) { mx.v = v; mx.row = row; }
 }
 
+struct Fast {
+    double mn, mx;         // over the non-NaN elements
+    double special;        // value of the latest zero (row zrow) ...
+    double nanv;           // ... and of the latest NaN (row nrow)
+    int32_t zrow, nrow, any;
+    __device__ __forceinline__ void reset() {
+        mn = __longlong_as_double(0x7ff0000000000000ll);      // +inf
+        mx = __longlong_as_double(0xfff0000000000000ll);      // -inf
+        special = 0.0; nanv = 0.0; zrow = -1; nrow = -1; any = -1;
+    }
+    __device__ __forceinline__ void feed(double v, int32_t row) {
+        mn = fmin(mn, v);
+        mx = fmax(mx, v);
+        any = row;
+        if (!(fabs(v) > 0.0)) {                                // zero or NaN: rare
+            if (v != v) { nanv = v; nrow = row; }
+            else { special = v; zrow = row; }
+        }
+    }
+    // numpy's result for the rows this thread saw, with the row that decides ties in the merge
+    __device__ __forceinline__ void resolve(Best& bmn, Best& bmx) const {
+        if (any < 0) { bmn.v = 0; bmn.row = -1; bmx.v = 0; bmx.row = -1; return; }
+        if (nrow >= 0) { bmn.v = nanv; bmn.row = nrow; bmx.v = nanv; bmx.row = nrow; return; }
+        bmn.v = mn; bmn.row = any;
+        bmx.v = mx; bmx.row = any;
+        if (mn == 0.0) { bmn.v = special; bmn.row = zrow; }
+        if (mx == 0.0) { bmx.v = special; bmx.row = zrow; }
+    }
+};
+
 // numpy's ordered update of a running min / max
 __device__ __forceinline__ void upd_min(double& acc, double v) {
     if (v != v || (acc == acc && !(acc < v))) acc = v;
@@ -93,9 +123,14 @@ minmax_split_kernel(const double* __restrict__ src, int64_t n, int32_t C, int64_
     if (row1 > seg1) row1 = seg1;
     const int tid = threadIdx.x;
 
-    Best mn[VEC], mx[VEC];
+    // Fast accumulation: plain fmin / fmax (they skip NaNs) plus, on the rare elements that are
+    // a zero or a NaN, the row and value of the latest one.  numpy's ordered rule follows from
+    // that: any NaN -> the latest NaN; a zero extremum -> the sign of the latest zero; every
+    // other tie is between identical bit patterns.
+    Fast acc[VEC];
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) { mn[e].row = -1; mx[e].row = -1; mn[e].v = 0; mx[e].v = 0; }
+    for (int e = 0; e < VEC; ++e) acc[e].reset();
+    Best mn[VEC], mx[VEC];
 
     if (row0 < row1 && tid < active) {
         const int64_t nflat = (row1 - row0) * C;              // multiple of VEC by construction
@@ -116,7 +151,7 @@ minmax_split_kernel(const double* __restrict__ src, int64_t n, int32_t C, int64_
                 double el[VEC];
                 unpack(v[k], el);
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) feed(mn[e], mx[e], el[e], r[e] + k * rpi);
+                for (int e = 0; e < VEC; ++e) acc[e].feed(el[e], r[e] + k * rpi);
             }
 #pragma unroll
             for (int e = 0; e < VEC; ++e) r[e] += MM_UNROLL * rpi;
@@ -125,9 +160,11 @@ minmax_split_kernel(const double* __restrict__ src, int64_t n, int32_t C, int64_
             double el[VEC];
             unpack(__ldcs(base + u), el);
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) { feed(mn[e], mx[e], el[e], r[e]); r[e] += rpi; }
+            for (int e = 0; e < VEC; ++e) { acc[e].feed(el[e], r[e]); r[e] += rpi; }
         }
     }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[e].resolve(mn[e], mx[e]);
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
         s_mnv[tid * VEC + e] = mn[e].v; s_mni[tid * VEC + e] = mn[e].row;
