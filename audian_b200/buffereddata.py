@@ -122,9 +122,10 @@ class BufferedData(BufferedArray):
             count -= margin
         if src.offset + len(src.buffer) < src.frames:
             count -= floor(self.source_tafter*src.rate)
-        ratio = self.rate/src.rate
-        offset = ceil(first*ratio)
-        nframes = floor((first + count)*ratio) - offset
+        # the reference's expression order, kept for its floating-point rounding:
+        # (frames*rate)/source_rate, not frames*(rate/source_rate)
+        offset = ceil(first*self.rate/src.rate)
+        nframes = floor((first + count)*self.rate/src.rate) - offset
         self.move_buffer(offset, nframes)
         self.bufferframes = len(self.buffer)
 
@@ -132,9 +133,8 @@ class BufferedData(BufferedArray):
         """(start, count, nbefore) of the slice of the source buffer that
         load_buffer() hands to process() for derived frames offset..+nframes."""
         src = self.source
-        ratio = src.rate/self.rate
-        start = floor(offset*ratio)
-        count = ceil((offset + nframes)*ratio) - start
+        start = floor(offset*src.rate/self.rate)               # same expression order as the
+        count = ceil((offset + nframes)*src.rate/self.rate) - start     # reference (rounding)
         nbefore = floor(self.source_tbefore/src.rate)      # sic (8-Q1)
         nafter = ceil(self.source_tafter/src.rate)         # sic
         start -= nbefore

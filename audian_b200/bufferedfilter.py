@@ -36,9 +36,9 @@ class BufferedFilter(BufferedData):
 
     def design(self):
         """Mode thresholds of bufferedfilter.py:40-52."""
-        nyquist = self.rate/2
-        no_highpass = self.highpass_cutoff < 0.001*nyquist
-        no_lowpass = self.lowpass_cutoff >= nyquist - 1e-8
+        # the reference's expressions, term for term (floating-point rounding at the thresholds)
+        no_highpass = self.highpass_cutoff < 0.001*self.rate/2
+        no_lowpass = self.lowpass_cutoff >= self.rate/2 - 1e-8
         if no_highpass and no_lowpass:
             return None
         if no_highpass:
