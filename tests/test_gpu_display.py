@@ -115,3 +115,27 @@ def test_pcm_ingest(bits):
     got = _lib.pcm_to_f64(raw, bits, C, gain=2.5)
     ref = (v.astype(np.float64)/lim*2.5).reshape(n, C)
     assert got.shape == (n, C) and np.array_equal(got, ref)
+
+
+def test_compresseddata_class_matches_reference_fixture():
+    """audian_b200.CompressedData.start() (short and long path) against what the reference's
+    CompressedData.start / down_sample_worker produced (tests/golden/fulltrace.npz)."""
+    import json
+    import os
+    from audian_b200.compresseddata import CompressedData
+    from oracle.ref_harness import ArrayLoader
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'fulltrace.npz'))
+    for name in ('short_3ch', 'short_1ch_step1', 'long_4ch'):
+        a = json.loads(str(g[name + '_args']))
+        x = synth(0, a['frames'], a['channels'], a['rate'], a['seed'])
+        if name.startswith('short'):
+            data = ArrayLoader(x, a['rate'])                     # whole recording in the buffer
+        else:
+            data = ArrayLoader(x, a['rate'], 0, 50000)           # buffer shorter than the file
+        cd = CompressedData(data)
+        cd.start(a['max_pixel'], {})
+        assert cd.short_data == name.startswith('short')
+        assert np.array_equal(cd.times, g[name + '_times'])
+        ref = g[name + '_datas']
+        assert cd.datas.shape == ref.shape
+        assert np.array_equal(cd.datas.view(np.uint64), ref.view(np.uint64)), name
