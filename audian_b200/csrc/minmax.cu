@@ -162,9 +162,66 @@ minmax_split_kernel(const double* __restrict__ src, int64_t n, int32_t C, int64_
 #pragma unroll
             for (int e = 0; e < VEC; ++e) { acc[e].feed(el[e], r[e]); r[e] += rpi; }
         }
+        // single channel read as pairs of rows: an odd row count leaves one element over
+        if (VEC == 2 && (nflat & 1) && tid == (int)(nunits % active))
+            acc[0].feed(src[row0 * C + nflat - 1], (int32_t)(nflat - 1));
     }
 #pragma unroll
     for (int e = 0; e < VEC; ++e) acc[e].resolve(mn[e], mx[e]);
+    // Channel counts that tile a warp (slot period C/VEC lanes divides 32; C == 1 as pairs of
+    // rows): butterfly over the lanes that hold the same channels, one row of shared memory per
+    // warp, one barrier.  Other channel counts: tree over shared memory below.
+    {
+        const bool single = VEC == 2 && C == 1;
+        const int lq = single ? 1 : C / VEC;
+        if ((single || (C % VEC == 0 && lq >= 1 && lq <= 32 && (32 % lq) == 0)) && active == MM_THREADS) {
+            if (single) { merge<true>(mn[0], mn[VEC - 1]); merge<false>(mx[0], mx[VEC - 1]); }
+            const int nslot = single ? 1 : VEC;
+            for (int o = lq; o < 32; o <<= 1) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    if (e < nslot) {
+                        Best a, b;
+                        a.v = __shfl_xor_sync(0xffffffffu, mn[e].v, o);
+                        a.row = __shfl_xor_sync(0xffffffffu, mn[e].row, o);
+                        b.v = __shfl_xor_sync(0xffffffffu, mx[e].v, o);
+                        b.row = __shfl_xor_sync(0xffffffffu, mx[e].row, o);
+                        merge<true>(mn[e], a);
+                        merge<false>(mx[e], b);
+                    }
+                }
+            }
+            const int lane = tid & 31, warp = tid >> 5;
+            if (lane < lq) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    if (e < nslot) {
+                        const int ch = single ? 0 : lane * VEC + e;
+                        s_mnv[warp * C + ch] = mn[e].v; s_mni[warp * C + ch] = mn[e].row;
+                        s_mxv[warp * C + ch] = mx[e].v; s_mxi[warp * C + ch] = mx[e].row;
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid < C) {
+                Best a{s_mnv[tid], s_mni[tid]}, b{s_mxv[tid], s_mxi[tid]};
+                for (int w = 1; w < MM_THREADS / 32; ++w) {
+                    Best c{s_mnv[w * C + tid], s_mni[w * C + tid]}, d{s_mxv[w * C + tid], s_mxi[w * C + tid]};
+                    merge<true>(a, c);
+                    merge<false>(b, d);
+                }
+                if (nsplit == 1) {
+                    dst[(2 * seg) * C + tid] = canon(a.v, C);
+                    dst[(2 * seg + 1) * C + tid] = canon(b.v, C);
+                } else {
+                    int64_t o = ((seg * nsplit + p) * 2) * C + tid;
+                    part[o] = a.v;
+                    part[o + C] = b.v;
+                }
+            }
+            return;
+        }
+    }
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
         s_mnv[tid * VEC + e] = mn[e].v; s_mni[tid * VEC + e] = mn[e].row;
@@ -202,25 +259,121 @@ minmax_split_kernel(const double* __restrict__ src, int64_t n, int32_t C, int64_
     }
 }
 
-// splits of one segment are consecutive row ranges: numpy's predicate in order
+// Short segments (up to 48 KB; longer ones are faster block-wise): one warp per segment, eight independent warps per
+// block, no block barrier at all -- 16-byte loads of consecutive lanes are contiguous, four
+// in flight per lane, and the lanes that hold the same channels are folded by shuffles.
+// Needs a channel count that tiles a warp (32*VEC % C == 0), or C == 1 read as pairs of rows.
+template <int VEC>
+__global__ void __launch_bounds__(MM_THREADS)
+minmax_warp_kernel(const double* __restrict__ src, int64_t n, int32_t C, int64_t step, int64_t nseg,
+                   double* __restrict__ dst) {
+    using V = typename VecT<VEC>::type;
+    const int lane = threadIdx.x & 31;
+    const int64_t seg = (int64_t)blockIdx.x * (MM_THREADS / 32) + (threadIdx.x >> 5);
+    if (seg >= nseg) return;
+    const int64_t seg0 = seg * step;
+    int64_t seg1 = seg0 + step;
+    if (seg1 > n) seg1 = n;
+    const int64_t nflat = (seg1 - seg0) * C;
+    const int64_t nunits = nflat / VEC;
+    const V* base = reinterpret_cast<const V*>(src + seg0 * C);
+    const bool single = VEC == 2 && C == 1;
+    const int32_t rpi = (32 * VEC) / C;                    // rows advanced per 32 units
+    Fast acc[VEC];
+    int32_t r[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) { acc[e].reset(); r[e] = (lane * VEC + e) / C; }
+    int64_t u = lane;
+    for (; u + (MM_UNROLL - 1) * 32 < nunits; u += MM_UNROLL * 32) {
+        V v[MM_UNROLL];
+#pragma unroll
+        for (int k = 0; k < MM_UNROLL; ++k) v[k] = __ldcs(base + u + k * 32);
+#pragma unroll
+        for (int k = 0; k < MM_UNROLL; ++k) {
+            double el[VEC];
+            unpack(v[k], el);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[e].feed(el[e], r[e] + k * rpi);
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) r[e] += MM_UNROLL * rpi;
+    }
+    for (; u < nunits; u += 32) {
+        double el[VEC];
+        unpack(__ldcs(base + u), el);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) { acc[e].feed(el[e], r[e]); r[e] += rpi; }
+    }
+    if (VEC == 2 && (nflat & 1) && lane == (int)(nunits & 31))
+        acc[0].feed(src[seg0 * C + nflat - 1], (int32_t)(nflat - 1));
+    Best mn[VEC], mx[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[e].resolve(mn[e], mx[e]);
+    if (single) { merge<true>(mn[0], mn[VEC - 1]); merge<false>(mx[0], mx[VEC - 1]); }
+    const int lq = single ? 1 : C / VEC;
+    const int nslot = single ? 1 : VEC;
+    for (int o = lq; o < 32; o <<= 1) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            if (e < nslot) {
+                Best a, b;
+                a.v = __shfl_xor_sync(0xffffffffu, mn[e].v, o);
+                a.row = __shfl_xor_sync(0xffffffffu, mn[e].row, o);
+                b.v = __shfl_xor_sync(0xffffffffu, mx[e].v, o);
+                b.row = __shfl_xor_sync(0xffffffffu, mx[e].row, o);
+                merge<true>(mn[e], a);
+                merge<false>(mx[e], b);
+            }
+        }
+    }
+    if (lane < lq) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            if (e < nslot) {
+                const int ch = single ? 0 : lane * VEC + e;
+                dst[(2 * seg) * C + ch] = canon(mn[e].v, C);
+                dst[(2 * seg + 1) * C + ch] = canon(mx[e].v, C);
+            }
+        }
+    }
+}
+
+// One warp per (segment, channel) folds the partial results of the splits.  Splits are
+// consecutive row ranges, so numpy's ordered rule is "the later split wins ties"; with the
+// split index as the row of a (value, row) pair the merge is commutative and can run as a
+// strided loop per lane followed by a shuffle reduction.
 __global__ void __launch_bounds__(256)
 minmax_combine_kernel(const double* __restrict__ part, int64_t nseg, int32_t C, int32_t nsplit,
                       int64_t n, int64_t step, int64_t rows_per_split, double* __restrict__ dst) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= nseg * C) return;
-    int64_t seg = i / C;
-    int32_t c = (int32_t)(i % C);
+    const int64_t seg = i / C;
+    const int32_t c = (int32_t)(i % C);
     int64_t seg0 = seg * step, seg1 = seg0 + step;
     if (seg1 > n) seg1 = n;
-    int64_t used = (seg1 - seg0 + rows_per_split - 1) / rows_per_split;   // non-empty splits
+    const int32_t used = (int32_t)((seg1 - seg0 + rows_per_split - 1) / rows_per_split);   // non-empty splits
     const double* q = part + (seg * nsplit * 2) * C + c;
-    double mn = q[0], mx = q[C];
-    for (int64_t p = 1; p < used; ++p) {
-        upd_min(mn, q[(p * 2) * C]);
-        upd_max(mx, q[(p * 2 + 1) * C]);
+    Best mn{0.0, -1}, mx{0.0, -1};
+    for (int32_t p = lane; p < used; p += 32) {
+        Best a{q[((int64_t)p * 2) * C], p}, b{q[((int64_t)p * 2 + 1) * C], p};
+        merge<true>(mn, a);
+        merge<false>(mx, b);
     }
-    dst[(2 * seg) * C + c] = canon(mn, C);
-    dst[(2 * seg + 1) * C + c] = canon(mx, C);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Best a, b;
+        a.v = __shfl_xor_sync(0xffffffffu, mn.v, o);
+        a.row = __shfl_xor_sync(0xffffffffu, mn.row, o);
+        b.v = __shfl_xor_sync(0xffffffffu, mx.v, o);
+        b.row = __shfl_xor_sync(0xffffffffu, mx.row, o);
+        merge<true>(mn, a);
+        merge<false>(mx, b);
+    }
+    if (lane == 0) {
+        dst[(2 * seg) * C + c] = canon(mn.v, C);
+        dst[(2 * seg + 1) * C + c] = canon(mx.v, C);
+    }
 }
 
 // short segments: one thread per (segment, channel), rows in order
@@ -258,7 +411,10 @@ int32_t minmax_dev(const double* src, int64_t n, int32_t C, int64_t step, double
                    cudaStream_t st) {
     const int64_t nseg = (n + step - 1) / step;
     const int64_t seg_elems = (step < n ? step : n) * (int64_t)C;
-    const bool vec2 = (C % 2 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    // 16-byte loads: rows of an even channel count, or a single channel read as pairs of rows
+    // (every block then starts at an even row: even step, even rows per split)
+    const bool vec2 = ((C % 2 == 0) || (C == 1 && step % 2 == 0)) &&
+                      ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
     const int VEC = vec2 ? 2 : 1;
     if (seg_elems < 2048 || C > MM_THREADS * VEC) {
         int64_t total = nseg * C;
@@ -266,6 +422,23 @@ int32_t minmax_dev(const double* src, int64_t n, int32_t C, int64_t step, double
         count_launch();
         ADN_CK(cudaGetLastError());
         return ADN_OK;
+    }
+    {
+        // short segments and enough of them: a warp per segment
+        const bool single = vec2 && C == 1;
+        const bool tiles = single || (C % VEC == 0 && (32 * VEC) % C == 0);
+        const int64_t seg_bytes = seg_elems * 8;
+        if (tiles && seg_bytes <= ((int64_t)48 << 10) && nseg >= (int64_t)ctx().sm_count * 8 &&
+            seg_elems / C < ((int64_t)1 << 30)) {
+            const int64_t blocks = (nseg + MM_THREADS / 32 - 1) / (MM_THREADS / 32);
+            if (vec2)
+                minmax_warp_kernel<2><<<(unsigned)blocks, MM_THREADS, 0, st>>>(src, n, C, step, nseg, dst);
+            else
+                minmax_warp_kernel<1><<<(unsigned)blocks, MM_THREADS, 0, st>>>(src, n, C, step, nseg, dst);
+            count_launch();
+            ADN_CK(cudaGetLastError());
+            return ADN_OK;
+        }
     }
     // threads whose per-iteration flat stride is a multiple of C
     int32_t q = C / (C % VEC == 0 ? VEC : 1);
@@ -276,6 +449,7 @@ int32_t minmax_dev(const double* src, int64_t n, int32_t C, int64_t step, double
     int64_t want_blocks = (int64_t)ctx().sm_count * 8;
     int64_t seg_rows = step < n ? step : n;
     while (rows > 4096 / C + 1 && nseg * ((seg_rows + rows - 1) / rows) < want_blocks) rows /= 2;
+    if (C == 1 && vec2 && rows > 1) rows &= ~(int64_t)1;
     if (rows > seg_rows) rows = seg_rows;
     if (rows >= (int64_t)1 << 30) rows = ((int64_t)1 << 30) - 1;          // row index is int32
     int64_t nsplit64 = (seg_rows + rows - 1) / rows;
@@ -299,8 +473,8 @@ int32_t minmax_dev(const double* src, int64_t n, int32_t C, int64_t step, double
     ADN_CK(cudaGetLastError());
     if (nsplit > 1) {
         int64_t total = nseg * C;
-        minmax_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(part, nseg, C, nsplit, n,
-                                                                           step, rows, dst);
+        minmax_combine_kernel<<<(unsigned)((total + 7) / 8), 256, 0, st>>>(part, nseg, C, nsplit, n,
+                                                                       step, rows, dst);
         count_launch();
         ADN_CK(cudaGetLastError());
     }
