@@ -127,9 +127,12 @@ constexpr double HALF_PI = 1.5707963267948966;
 
 // results go out with a streaming store, except the forward sweep of the envelope: the reversed
 // sweep starts reading where that one stopped writing, so its tail is left to live in L2
+#ifndef ENVF_PLAIN_STORE
+#define ENVF_PLAIN_STORE 0
+#endif
 template <int MODE, class T>
 __device__ __forceinline__ void st_out(T* p, T v) {
-    if (MODE == MODE_ENVF) *p = v; else __stcs(p, v);
+    if (MODE == MODE_ENVF && ENVF_PLAIN_STORE) *p = v; else __stcs(p, v);
 }
 
 template <int S, int MODE>
