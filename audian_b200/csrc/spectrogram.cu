@@ -593,7 +593,7 @@ template <int LOGN> struct SRCfg {
     static constexpr int T = SWCfg<LOGN>::T;
     // per-frame stride of the exchange buffer (complex): T = 32 rows of 33 (16 k1 rows read
     // by 16 lane pairs: 16-byte offsets, two wavefronts per 128-bit load)
-    static constexpr int FS = T == 32 ? 16 * 33 : SWCfg<LOGN>::FS;
+    static constexpr int FS = T == 32 ? 16 * 33 / 2 + 4 : SWCfg<LOGN>::FS;   // T == 32: 16 x 33 doubles
     static constexpr int WB = FS * SWCfg<LOGN>::FPW;
 };
 
@@ -778,8 +778,16 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
 #pragma unroll
                 for (int k1 = 0; k1 < 16; ++k1) {
                     double2 v = k1 == 0 ? b[0] : cmul(b[k1], w[k1]);
-                    const int f = k1 * T + t;
-                    wbf[T == 32 ? k1 * 33 + t : f + (f >> 4)] = v;
+                    if (T == 32) {
+                        // real parts now, imaginary parts in a second round through the same
+                        // buffer of doubles (half the shared memory; the 64-bit reads of the 16
+                        // lane pairs are one 128-byte wavefront each)
+                        b[k1] = v;
+                        reinterpret_cast<double*>(wbf)[k1 * 33 + t] = v.x;
+                    } else {
+                        const int f = k1 * T + t;
+                        wbf[f + (f >> 4)] = v;
+                    }
                 }
             }
 #pragma unroll
@@ -794,12 +802,16 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
                 // Z[lane + 32 kk], kk < 16 (first radix-2 step done here, decimation in frequency)
                 const int k1 = lane & 15, tp = lane >> 4;
                 const double sgn = tp ? -1.0 : 1.0;
-                const double2* row = wbf + k1 * 33;
+                double* wre = reinterpret_cast<double*>(wbf);
+                const double* row = wre + k1 * 33;
 #pragma unroll
-                for (int n = 0; n < 16; ++n) {
-                    double2 lo = row[n], hi = row[n + 16];
-                    a[n] = make_double2(fma(sgn, hi.x, lo.x), fma(sgn, hi.y, lo.y));
-                }
+                for (int n = 0; n < 16; ++n) a[n].x = fma(sgn, row[n + 16], row[n]);
+                __syncwarp();
+#pragma unroll
+                for (int kq = 0; kq < 16; ++kq) wre[kq * 33 + t] = b[kq].y;
+                __syncwarp();
+#pragma unroll
+                for (int n = 0; n < 16; ++n) a[n].y = fma(sgn, row[n + 16], row[n]);
                 if (tp) {
 #pragma unroll
                     for (int n = 1; n < 16; ++n) a[n] = cmul(a[n], make_double2(w32c(n, 0), w32c(n, 1)));
