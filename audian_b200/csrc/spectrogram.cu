@@ -572,6 +572,14 @@ spectrogram_warp_kernel(const __grid_constant__ SpecWArgs P) {
 // path; for T = 32 the lane pair of a 32-point DFT reads all 32 points and does the first
 // radix-2 step itself (decimation in frequency) instead of exchanging results by shuffle.
 constexpr int SR_MAXNT = 128;
+// measured on B200 (nfft 1024, hop 512, 8 ch): 3 resident blocks, window in shared memory 172 us;
+// window through L1 instead 183 us; 4 resident blocks at 128 registers (spills) 232 us
+#ifndef SR_BLOCKS
+#define SR_BLOCKS 3
+#endif
+#ifndef SR_WIN_SMEM
+#define SR_WIN_SMEM 1
+#endif
 constexpr int SR_PF = 8;            // 16-byte vectors in flight per thread and step
 
 struct SpecRArgs {
@@ -602,7 +610,7 @@ __device__ __forceinline__ double to_db(double p) {
 }
 
 template <int LOGN, bool DB>
-__global__ void __launch_bounds__(SR_MAXNT, 3)
+__global__ void __launch_bounds__(SR_MAXNT, SR_BLOCKS)
 spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
     using Cf = SWCfg<LOGN>;
     constexpr int N = Cf::N, M = Cf::M, T = Cf::T, FPW = Cf::FPW;
@@ -625,9 +633,10 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
     const int span0 = N + (FSTEP - 1) * hop;             // rows one step reads
 
     double* xs = sbuf;                                               // [W][RS]
-    double* wins = sbuf + (size_t)W * RS;                            // [N]
+    double* wins = sbuf + (size_t)W * RS;                            // [N] (if SR_WIN_SMEM)
+    constexpr int NWIN = SR_WIN_SMEM ? N : 0;
     constexpr int NTWS = T == 32 ? 0 : M / 2 + 2;                    // T == 32 builds them in registers
-    double2* tws = reinterpret_cast<double2*>(wins + N);             // [NTWS]
+    double2* tws = reinterpret_cast<double2*>(wins + NWIN);          // [NTWS]
     double2* wb = tws + NTWS + (size_t)warp * SRCfg<LOGN>::WB;
 
     // the j-th 16-byte vector of this thread in a chunk: row r0 + j DR, channels col, col + 1
@@ -667,7 +676,8 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
     };
 
     stage_direct(0, 0, span0, 0);
-    for (int i = tid; i < N; i += NT) wins[i] = __ldg(P.win + i);
+    if (SR_WIN_SMEM)
+        for (int i = tid; i < N; i += NT) wins[i] = __ldg(P.win + i);
     if (NTWS > 0)
         for (int i = tid; i <= M / 2; i += NT) tws[i] = __ldg(P.twS + i);
     __syncthreads();
@@ -761,7 +771,8 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
             }
 #pragma unroll
             for (int p = 0; p < 16; ++p) {
-                double2 w = *reinterpret_cast<const double2*>(wins + 2 * (T * p + t));
+                double2 w = SR_WIN_SMEM ? *reinterpret_cast<const double2*>(wins + 2 * (T * p + t))
+                                        : __ldg(reinterpret_cast<const double2*>(P.win) + (T * p + t));
                 a[p].x *= w.x;
                 a[p].y *= w.y;
             }
@@ -971,7 +982,7 @@ int32_t launch_ring_kernel(SpecRArgs& P, int64_t nf, cudaStream_t st) {
         P.RC = Cf::N;
         while (P.RC < span0) P.RC <<= 1;                   // power of two >= the rows of a step
         P.RS = P.RC + 4;                                   // == 4 mod 8
-        smem = ((size_t)P.CB * P.RS + Cf::N) * 8 +
+        smem = ((size_t)P.CB * P.RS + (SR_WIN_SMEM ? Cf::N : 0)) * 8 +
                ((Cf::T == 32 ? 0 : (size_t)Cf::M / 2 + 2) + (size_t)NW * SRCfg<LOGN>::WB) * 16;
         if (smem <= limit || P.FSTEP == 1) break;
     }
