@@ -58,6 +58,8 @@ SIGNATURES = {
     'adn_spectrogram_f64': (_i32, [_dp, _i64, _i32, _f64, _i32, _i32, _i32, _i32,
                                    _dp, _i64, _i32, C.POINTER(_i64)]),
     'adn_decibel_f64': (_i32, [_dp, _i64, _f64, _f64, _dp]),
+    'adn_sosfiltfilt_f64': (_i32, [_dp, _i32, _dp, _i64, _i32, _dp, _i64]),
+    'adn_sosfiltfilt_f64_dev': (_i32, [_dp, _i32, _dp, _i64, _i32, _dp, _i64, _dp]),
     'adn_spec_image_db_f64': (_i32, [_dp, _i64, _i32, _i32, _i32, _dp]),
     'adn_mean_power_db_f64': (_i32, [_dp, _i64, _i32, _i32, _i32, _i64, _i64, _f64, _dp]),
     'adn_pcm_to_f64': (_i32, [_dp, _i64, _i32, _f64, _dp]),
@@ -204,6 +206,18 @@ def envelope(sos, src, dst, nbefore=0, clamp_negative=True):
     check(lib().adn_envelope_f64(None if sos is None else sos.ctypes.data, S,
                                  ptr(src), src.shape[0], src.shape[1], int(nbefore),
                                  ptr(dst), dst.shape[0], 1 if clamp_negative else 0))
+    return dst
+
+
+def sosfiltfilt(sos, src, dst=None):
+    """scipy.signal.sosfiltfilt(sos, src, axis=0) (databrowser.py:1725, play-back path)."""
+    src = _f64_array(src, 'src')
+    sos, S = sos_array(sos)
+    if dst is None:
+        dst = np.empty_like(src)
+    dst = _f64_array(dst, 'dst')
+    check(lib().adn_sosfiltfilt_f64(sos.ctypes.data, S, ptr(src), src.shape[0], src.shape[1],
+                                    ptr(dst), dst.shape[0]))
     return dst
 
 

@@ -558,6 +558,28 @@ int32_t adn_envelope_f64(const double* sos, int32_t S, const double* src, int64_
     return copy_out(dst, dout, out_b);
 }
 
+int32_t adn_sosfiltfilt_f64(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
+                            double* dst, int64_t n_dst) {
+    if (S < 1 || S > ADN_MAX_SECTIONS || C < 1 || n_src < 0 || n_dst < 0 || n_dst > n_src)
+        return fail(ADN_ERR_INVALID, "adn_sosfiltfilt_f64: S=%d C=%d n_src=%lld n_dst=%lld", S, C,
+                    (long long)n_src, (long long)n_dst);
+    if (!sos || (n_src > 0 && !src) || (n_dst > 0 && !dst))
+        return fail(ADN_ERR_INVALID, "adn_sosfiltfilt_f64: NULL pointer");
+    if (n_src <= adn_sosfiltfilt_edge(sos, S))
+        return fail(ADN_ERR_SHORT, "adn_sosfiltfilt_f64: the length of the input (%lld) must be greater "
+                    "than the pad length %d", (long long)n_src, adn_sosfiltfilt_edge(sos, S));
+    if (n_dst == 0) return ADN_OK;
+    int32_t rc = ensure_init();
+    if (rc) return rc;
+    size_t in_b = (size_t)n_src * C * 8, out_b = (size_t)n_dst * C * 8;
+    const double* dsrc = nullptr;
+    if ((rc = source_dev(src, in_b, &dsrc))) return rc;
+    double* dout = nullptr;
+    if ((rc = out_buffer(dst, out_b, &dout))) return rc;
+    if ((rc = sosfiltfilt_dev(sos, S, dsrc, n_src, C, 0, dout, n_dst, ctx().stream))) return rc;
+    return copy_out(dst, dout, out_b);
+}
+
 int32_t adn_spectrogram_f64(const double* src, int64_t n_src, int32_t C, double rate, int32_t nfft,
                             int32_t hop, int32_t window_id, int32_t detrend_id, double* dst,
                             int64_t n_dst, int32_t out_db, int64_t* n_computed) {
@@ -782,6 +804,19 @@ int32_t adn_envelope_f64_dev(const double* sos, int32_t S, const double* src, in
     if (n_src <= adn_sosfiltfilt_edge(sos, S))
         return fail(ADN_ERR_SHORT, "adn_envelope_f64_dev: input not longer than the sosfiltfilt pad");
     return envelope_dev(sos, S, src, n_src, C, nbefore, dst, n_dst, clamp_negative, pick(stream));
+}
+
+int32_t adn_sosfiltfilt_f64_dev(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
+                                double* dst, int64_t n_dst, void* stream) {
+    if (S < 1 || S > ADN_MAX_SECTIONS || C < 1 || n_src < 1 || n_dst < 0 || n_dst > n_src || !sos || !src ||
+        (n_dst > 0 && !dst))
+        return fail(ADN_ERR_INVALID, "adn_sosfiltfilt_f64_dev: bad arguments");
+    if (n_src <= adn_sosfiltfilt_edge(sos, S))
+        return fail(ADN_ERR_SHORT, "adn_sosfiltfilt_f64_dev: input not longer than the pad");
+    if (n_dst == 0) return ADN_OK;
+    int32_t rc = ensure_init();
+    if (rc) return rc;
+    return sosfiltfilt_dev(sos, S, src, n_src, C, 0, dst, n_dst, pick(stream));
 }
 
 int32_t adn_envelope_forward_f64_dev(const double* sos, int32_t S, const double* src, int64_t n_src,

@@ -70,6 +70,8 @@ int32_t fold_states_dev(const double* packs, const double* mats, int32_t W, int3
 int32_t sosfilt_reverse_dev(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
                             const double* zi, double* dst, int64_t first, int64_t n_dst,
                             int32_t clamp_negative, double* zf, cudaStream_t st);
+int32_t sosfiltfilt_dev(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
+                        int64_t nbefore, double* dst, int64_t n_dst, cudaStream_t st);
 int32_t spectrogram_dev(const double* src, int64_t n_src, int32_t C, double rate, int32_t nfft,
                         int32_t hop, int32_t window_id, int32_t detrend_id, double* dst,
                         int64_t n_dst, int32_t out_db, int64_t* n_computed, cudaStream_t st);

@@ -35,7 +35,10 @@ constexpr int SOS_NT = 128;        // threads per block
 constexpr int SOS_NW = SOS_NT / 32;
 constexpr int SOS_LOOK = 32;       // look-back window (tiles)
 
-enum { MODE_FWD = 0, MODE_ENVF = 1, MODE_REV = 2 };
+// MODE_ENVF: forward sweep of the envelope (rectified input, odd extension); MODE_ZPF: the same
+// without the rectification = forward sweep of a plain sosfiltfilt
+enum { MODE_FWD = 0, MODE_ENVF = 1, MODE_REV = 2, MODE_ZPF = 3 };
+#define ADN_EXT(MODE) ((MODE) == MODE_ENVF || (MODE) == MODE_ZPF)
 
 // table layout (D x D row-major matrices, DD = D*D doubles each), packed per channel-group
 // width CG (GW = 32/CG sub-chunks per warp):
@@ -124,6 +127,10 @@ __device__ __forceinline__ void matvec_acc(const double* __restrict__ M, const d
 }
 
 constexpr double HALF_PI = 1.5707963267948966;
+// input transform of the forward sweeps: (pi/2)|x| for the envelope, identity otherwise
+template <int MODE> __device__ __forceinline__ double pre_x(double x) {
+    return MODE == MODE_ENVF ? HALF_PI * fabs(x) : x;
+}
 
 // results go out with a streaming store, except the forward sweep of the envelope: the reversed
 // sweep starts reading where that one stopped writing, so its tail is left to live in L2
@@ -176,8 +183,8 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
     // contiguous rows `R.pf_tiles` time tiles ahead
     if (tid == 0 && grp == 0 && R.pf_tiles > 0) {
         const int64_t pt0 = t0 + (int64_t)R.pf_tiles * T;
-        const int64_t lim = MODE == MODE_ENVF ? R.nx : R.n;
-        int64_t p0 = MODE == MODE_REV ? R.n - pt0 - T : (MODE == MODE_ENVF ? pt0 - R.edge : pt0);
+        const int64_t lim = ADN_EXT(MODE) ? R.nx : R.n;
+        int64_t p0 = MODE == MODE_REV ? R.n - pt0 - T : (ADN_EXT(MODE) ? pt0 - R.edge : pt0);
         int64_t p1 = p0 + T;
         if (p0 < 0) p0 = 0;
         if (p1 > lim) p1 = lim;
@@ -199,15 +206,15 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
     // rectified on the fly; the two edge tiles are built element by element
     bool xform = false;
     int64_t shift = 0;
-    if (MODE == MODE_ENVF) {
+    if (ADN_EXT(MODE)) {
         xform = t0 >= R.edge && t0 + T <= R.edge + R.nx;
         shift = R.edge;
     }
     // fast path (block-uniform): a full channel group (CG = 2^k channels), every row of the
     // tile inside the source: the addresses of the granules a thread copies are shifts and adds
     const int lc = Cw == CG ? R.lc : -1;                   // log2(CG) when the group is full
-    const int64_t nlim = MODE == MODE_ENVF ? R.edge + R.nx : R.n;
-    const bool fast_in = lc >= 0 && t0 + T <= nlim && !(MODE == MODE_ENVF && !xform);
+    const int64_t nlim = ADN_EXT(MODE) ? R.edge + R.nx : R.n;
+    const bool fast_in = lc >= 0 && t0 + T <= nlim && !(ADN_EXT(MODE) && !xform);
     if (fast_in) {
         const int64_t rowbase = MODE == MODE_REV ? R.n - 1 - t0 : t0 - shift;   // physical row of tile row 0
         if (R.vec_in) {
@@ -228,7 +235,7 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
             }
         }
     } else
-    if (MODE == MODE_ENVF && !xform) {
+    if (ADN_EXT(MODE) && !xform) {
         const int64_t nx = R.nx, edge = R.edge;
         const int total = T * Cw;
         for (int q = tid; q < total; q += SOS_NT) {
@@ -238,15 +245,15 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
             if (e < R.n) {
                 const double* xc = R.src + c0 + col;
                 if (e < edge) {
-                    double r0 = HALF_PI * fabs(__ldg(xc));
-                    double rk = HALF_PI * fabs(__ldg(xc + (edge - e) * C));
+                    double r0 = pre_x<MODE>(__ldg(xc));
+                    double rk = pre_x<MODE>(__ldg(xc + (edge - e) * C));
                     val = 2.0 * r0 - rk;
                 } else if (e < edge + nx) {
-                    val = HALF_PI * fabs(__ldg(xc + (e - edge) * C));
+                    val = pre_x<MODE>(__ldg(xc + (e - edge) * C));
                 } else {
                     int64_t k = e - edge - nx;
-                    double r1 = HALF_PI * fabs(__ldg(xc + (nx - 1) * C));
-                    double rk = HALF_PI * fabs(__ldg(xc + (nx - 2 - k) * C));
+                    double r1 = pre_x<MODE>(__ldg(xc + (nx - 1) * C));
+                    double rk = pre_x<MODE>(__ldg(xc + (nx - 2 - k) * C));
                     val = 2.0 * r1 - rk;
                 }
             }
@@ -283,7 +290,7 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
 #pragma unroll
         for (int i = 0; i < SOS_L; ++i) {
             double x = xp[i * Cw];
-            if (MODE == MODE_ENVF && xform) x = HALF_PI * fabs(x);
+            if (MODE == MODE_ENVF && xform) x = pre_x<MODE>(x);
 #pragma unroll
             for (int d = 0; d < D; ++d) v[d] = fma(K.W[d][i], x, v[d]);
         }
@@ -426,7 +433,7 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
 #pragma unroll
             for (int i = 0; i < SOS_L; ++i) {
                 double x = *xr;
-                if (MODE == MODE_ENVF && xform) x = HALF_PI * fabs(x);
+                if (MODE == MODE_ENVF && xform) x = pre_x<MODE>(x);
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     double y = fma(K.coef[s][0], x, z[2 * s]);
@@ -451,7 +458,7 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
                     double x;
                     if (s == 0) {
                         x = xp[i * Cw];
-                        if (MODE == MODE_ENVF && xform) x = HALF_PI * fabs(x);
+                        if (MODE == MODE_ENVF && xform) x = pre_x<MODE>(x);
                     } else {
                         x = xin[s];
                     }
@@ -467,7 +474,7 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
             const int ilast = (int)(last - tau0);
             for (int i = 0; i < SOS_L; ++i) {
                 double x = xp[i * Cw];
-                if (MODE == MODE_ENVF && xform) x = HALF_PI * fabs(x);
+                if (MODE == MODE_ENVF && xform) x = pre_x<MODE>(x);
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     double y = fma(K.coef[s][0], x, z[2 * s]);
@@ -562,6 +569,8 @@ __global__ void env_s0_kernel(int which, const double* __restrict__ src, int32_t
     if (which == 0) {
         const double hp = 1.5707963267948966;
         x0 = 2.0 * (hp * fabs(src[c])) - hp * fabs(src[edge * C + c]);
+    } else if (which == 2) {
+        x0 = 2.0 * src[c] - src[edge * C + c];       // ext[0] of the plain odd extension
     } else {
         x0 = src[c];
     }
@@ -754,6 +763,7 @@ int32_t launch_S(int mode, const Plan& plan, SosRun& R, size_t smem, unsigned gr
     switch (mode) {
         case MODE_FWD: return launch_mode<S, MODE_FWD>(plan, R, smem, grid, st);
         case MODE_ENVF: return launch_mode<S, MODE_ENVF>(plan, R, smem, grid, st);
+        case MODE_ZPF: return launch_mode<S, MODE_ZPF>(plan, R, smem, grid, st);
         default: return launch_mode<S, MODE_REV>(plan, R, smem, grid, st);
     }
 }
@@ -893,9 +903,26 @@ int32_t fold_states_dev(const double* packs, const double* mats, int32_t W, int3
     return ADN_OK;
 }
 
+static int32_t zero_phase_dev(bool rect, const double* sos, int32_t S, const double* src, int64_t n_src,
+                              int32_t C, int64_t nbefore, double* dst, int64_t n_dst,
+                              int32_t clamp_negative, cudaStream_t st);
+
 int32_t envelope_dev(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
                      int64_t nbefore, double* dst, int64_t n_dst, int32_t clamp_negative,
                      cudaStream_t st) {
+    return zero_phase_dev(true, sos, S, src, n_src, C, nbefore, dst, n_dst, clamp_negative, st);
+}
+
+// scipy.signal.sosfiltfilt(sos, src, axis=0)[nbefore:][:n_dst] (default odd padding)
+int32_t sosfiltfilt_dev(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
+                        int64_t nbefore, double* dst, int64_t n_dst, cudaStream_t st) {
+    return zero_phase_dev(false, sos, S, src, n_src, C, nbefore, dst, n_dst, 0, st);
+}
+
+// rect: the envelope ((pi/2)|x| in front of the filter); else the plain zero-phase filter
+static int32_t zero_phase_dev(bool rect, const double* sos, int32_t S, const double* src, int64_t n_src,
+                              int32_t C, int64_t nbefore, double* dst, int64_t n_dst,
+                              int32_t clamp_negative, cudaStream_t st) {
     const int D = 2 * S;
     const int edge = adn_sosfiltfilt_edge(sos, S);
     const int64_t next = n_src + 2 * (int64_t)edge;
@@ -915,7 +942,7 @@ int32_t envelope_dev(const double* sos, int32_t S, const double* src, int64_t n_
         const int64_t chunk_bytes = option(ADN_OPT_ENVELOPE_CHUNK_BYTES);
         const int64_t keep = chunk_bytes > 0 ? adn_sos_decay_length(sos, S, 1e-30) : -1;
         int64_t rpc = chunk_bytes / ((int64_t)C * 8);             // rows per chunk
-        if (keep > 0 && rpc >= 8 * keep && rpc > 4 * edge && n_src >= 3 * rpc) {
+        if (rect && keep > 0 && rpc >= 8 * keep && rpc > 4 * edge && n_src >= 3 * rpc) {
             const int64_t nch = n_src / rpc;
             rpc = (n_src + nch - 1) / nch;
             const int64_t slot_rows = rpc + 2 * edge;
@@ -973,11 +1000,11 @@ int32_t envelope_dev(const double* sos, int32_t S, const double* src, int64_t n_
     double* d_s0f = misc.as<double>();
     double* d_s0b = d_s0f + (size_t)C * D;
     const int nb = (C * D + 127) / 128;
-    env_s0_kernel<<<nb, 128, 0, st>>>(0, src, C, D, edge, zik, d_s0f);
+    env_s0_kernel<<<nb, 128, 0, st>>>(rect ? 0 : 2, src, C, D, edge, zik, d_s0f);
     count_launch();
     ADN_CK(cudaGetLastError());
     double* y1 = fwd.as<double>();
-    if ((rc = run_scan(MODE_ENVF, sos, S, src, next, n_src, edge, C, y1, 0, next, 0, d_s0f, nullptr,
+    if ((rc = run_scan(rect ? MODE_ENVF : MODE_ZPF, sos, S, src, next, n_src, edge, C, y1, 0, next, 0, d_s0f, nullptr,
                        SCR_SOS_TILES, st)))
         return rc;
     env_s0_kernel<<<nb, 128, 0, st>>>(1, y1 + (next - 1) * C, C, D, 0, zik, d_s0b);

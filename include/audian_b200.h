@@ -159,7 +159,18 @@ int32_t adn_mean_power_db_f64(const double* spec, int64_t n, int32_t C, int32_t 
 int32_t adn_pcm_to_f64(const void* pcm, int64_t n, int32_t bits, double gain,
                        double* dst);
 
+/* dst = scipy.signal.sosfiltfilt(sos, src, axis=0)[:n_dst] (default odd padding):
+ * the zero-phase low-pass of the play-back path (src/audian/databrowser.py:1725;
+ * the caller heterodynes before and decimates after).  Same kernels as the envelope,
+ * without the rectification. */
+int32_t adn_sosfiltfilt_f64(const double* sos, int32_t S,
+                            const double* src, int64_t n_src, int32_t C,
+                            double* dst, int64_t n_dst);
+
 /* ---- device-pointer entry points (bench / multi-GPU path) ----------- */
+int32_t adn_sosfiltfilt_f64_dev(const double* sos, int32_t S,
+                                const double* src, int64_t n_src, int32_t C,
+                                double* dst, int64_t n_dst, void* stream);
 int32_t adn_spec_image_db_f64_dev(const double* spec, int64_t n, int32_t C, int32_t F,
                                   int32_t channel, double* dst, void* stream);
 int32_t adn_mean_power_db_f64_dev(const double* spec, int32_t C, int32_t F,

@@ -139,3 +139,22 @@ def test_compresseddata_class_matches_reference_fixture():
         ref = g[name + '_datas']
         assert cd.datas.shape == ref.shape
         assert np.array_equal(cd.datas.view(np.uint64), ref.view(np.uint64)), name
+
+
+@pytest.mark.parametrize('C,order,fc', [(2, 2, 20000.), (1, 4, 3000.), (8, 2, 500.)])
+def test_sosfiltfilt_playback_filter(C, order, fc):
+    """The zero-phase low-pass of play_region (databrowser.py:1702-1731): heterodyne, sosfiltfilt,
+    decimate -- the filter on the device, against scipy."""
+    from scipy.signal import butter, sosfiltfilt
+    rate, n = 250000., 120001
+    x = synth(0, n, C, rate, seed=60 + C)
+    het = np.sin(2*np.pi*40000.*np.arange(n)/rate)
+    play = np.ascontiguousarray((x.T*het).T)
+    sos = butter(order, fc, 'low', output='sos', fs=rate)
+    ref = sosfiltfilt(sos, play, 0)
+    got = _lib.sosfiltfilt(sos, play)
+    assert np.max(np.abs(got - ref)) <= 1e-9
+    nstep = max(1, int(np.round(rate/(2*fc))))
+    assert np.max(np.abs(got[::nstep] - ref[::nstep])) <= 1e-9
+    with pytest.raises(ValueError):
+        _lib.sosfiltfilt(sos, play[:5])
