@@ -1191,6 +1191,43 @@ __device__ __forceinline__ void mp_twiddles(double2 (&wb)[5], const double2* __r
     }
 }
 
+// transform of one channel-frame held in za (windowed), split step, power, store of its F bins;
+// red: per-warp partial sums of the raw frame (visible after the first barrier of the transform)
+template <int LOGN, int R, bool DB>
+__device__ __forceinline__ void mp_channel(double2 (&za)[R], double2* S, const double2 (&wb)[5], int t,
+                                           const double* red, int detrend, double scale,
+                                           const double2* __restrict__ tw, double* __restrict__ out) {
+    constexpr int N = 1 << LOGN, M = N / 2, T = M / R;
+    const double sc = 0.5 * scale;
+    mp_fft<LOGN, R>(za, S, wb, t);                // ends with a barrier: red[] is visible too
+    double fsum = 0.0;
+    for (int i = 0; i < T / 32; ++i) fsum += red[i];
+    const double mN2 = detrend ? fsum * 0.5 : 0.0;          // mean * N/2
+#pragma unroll
+    for (int q = 0; q < R / 2; ++q) {
+        const int k = 1 + t + q * T, km = M - k;              // k in [1, M/2]
+        double2 zk = S[mp_pad(k)], zm = S[mp_pad(km)];
+        double2 w = __ldg(tw + k);
+        double e_r = zk.x + zm.x, e_i = zk.y - zm.y;          // Zk + conj(Zm)
+        double o_r = zk.y + zm.y, o_i = zm.x - zk.x;          // -i (Zk - conj(Zm))
+        double t_r = o_r * w.x - o_i * w.y, t_i = o_r * w.y + o_i * w.x;
+        double pr = e_r + t_r, pi = e_i + t_i, qr = e_r - t_r, qi = e_i - t_i;
+        if (k == 1) pr += mN2;                                // the window's spectrum at bin 1 is -N/4
+        double pk = (pr * pr + pi * pi) * sc, pm = (qr * qr + qi * qi) * sc;
+        if (DB) { pk = to_db(pk); pm = to_db(pm); }
+        __stcs(out + k, pk);
+        if (km != k) __stcs(out + km, pm);
+    }
+    if (t == 0) {
+        double2 z0 = S[0];
+        double x0v = z0.x + z0.y - mN2, xM = z0.x - z0.y;
+        double p0 = x0v * x0v * scale, pM = xM * xM * scale;
+        if (DB) { p0 = to_db(p0); pM = to_db(pM); }
+        out[0] = p0;
+        out[M] = pM;
+    }
+}
+
 template <int LOGN, int R, int CP, bool DB>
 __global__ void __launch_bounds__((1 << (LOGN - 1)) / R)
 spectrogram_mp_kernel(const __grid_constant__ SpecMArgs P) {
@@ -1235,7 +1272,6 @@ spectrogram_mp_kernel(const __grid_constant__ SpecMArgs P) {
         za[k].x *= w.x; za[k].y *= w.y;
         if (CP == 2) { zb[CP == 2 ? k : 0].x *= w.x; zb[CP == 2 ? k : 0].y *= w.y; }
     }
-    const double sc = 0.5 * P.scale;
     double2 wb[5];
     mp_twiddles<LOGN, R>(wb, P.tw, t);
     for (int ch = 0; ch < nch; ++ch) {
@@ -1243,36 +1279,113 @@ spectrogram_mp_kernel(const __grid_constant__ SpecMArgs P) {
 #pragma unroll
             for (int k = 0; k < R; ++k) za[k] = zb[CP == 2 ? k : 0];
         }
-        mp_fft<LOGN, R>(za, S, wb, t);                // ends with a barrier: red[] is visible too
-        double fsum = 0.0;
-        for (int i = 0; i < T / 32; ++i) fsum += red[ch][i];
-        const double mN2 = P.detrend ? fsum * 0.5 : 0.0;          // mean * N/2
-        double* out = P.dst + ((frame * C + c0 + ch) * (int64_t)F);
-#pragma unroll
-        for (int q = 0; q < R / 2; ++q) {
-            const int k = 1 + t + q * T, km = M - k;              // k in [1, M/2]
-            double2 zk = S[mp_pad(k)], zm = S[mp_pad(km)];
-            double2 w = __ldg(P.tw + k);
-            double e_r = zk.x + zm.x, e_i = zk.y - zm.y;          // Zk + conj(Zm)
-            double o_r = zk.y + zm.y, o_i = zm.x - zk.x;          // -i (Zk - conj(Zm))
-            double t_r = o_r * w.x - o_i * w.y, t_i = o_r * w.y + o_i * w.x;
-            double pr = e_r + t_r, pi = e_i + t_i, qr = e_r - t_r, qi = e_i - t_i;
-            if (k == 1) pr += mN2;                                // the window's spectrum at bin 1 is -N/4
-            double pk = (pr * pr + pi * pi) * sc, pm = (qr * qr + qi * qi) * sc;
-            if (DB) { pk = to_db(pk); pm = to_db(pm); }
-            __stcs(out + k, pk);
-            if (km != k) __stcs(out + km, pm);
-        }
-        if (t == 0) {
-            double2 z0 = S[0];
-            double x0v = z0.x + z0.y - mN2, xM = z0.x - z0.y;
-            double p0 = x0v * x0v * P.scale, pM = xM * xM * P.scale;
-            if (DB) { p0 = to_db(p0); pM = to_db(pM); }
-            out[0] = p0;
-            out[M] = pM;
-        }
+        mp_channel<LOGN, R, DB>(za, S, wb, t, red[ch], P.detrend, P.scale, P.tw,
+                                P.dst + ((frame * C + c0 + ch) * (int64_t)F));
         __syncthreads();                              // S is reused by the second channel
     }
+}
+
+// Overlapping frames (hop < nfft): a block owns a run of consecutive frames of a channel pair and
+// keeps their rows de-interleaved in a shared-memory ring of exactly one frame; every step only
+// the `hop` new rows are loaded (16-byte loads of both channels) and overwrite the oldest ones
+// between two barriers.  Each input row is then read once per run instead of nfft/hop times --
+// the row-strided loads are what bounds the frame-per-block kernel above.
+template <int LOGN, int R, bool DB>
+__global__ void __launch_bounds__((1 << (LOGN - 1)) / R)
+spectrogram_mpr_kernel(const __grid_constant__ SpecMArgs P, int32_t frun) {
+    constexpr int N = 1 << LOGN, M = N / 2, T = M / R, F = M + 1;
+    constexpr int RS = N + 4;                                    // channel arrays 4 doubles apart
+    extern __shared__ __align__(16) double sbuf[];
+    double2* S = reinterpret_cast<double2*>(sbuf);               // M + M/8 (+8) complex
+    double* xs = sbuf + 2 * (M + M / 8 + 8);                     // [2][RS]
+    __shared__ double red[2][32];
+    const int t = threadIdx.x;
+    const int pair = blockIdx.x % P.npair;
+    const int64_t f0 = (int64_t)(blockIdx.x / P.npair) * frun;
+    const int nfr = (int)min((int64_t)frun, P.nframes - f0);
+    const int C = P.C, hop = P.hop;
+    const int c0 = 2 * pair;
+    const double* x0 = P.src + (f0 * hop) * (int64_t)C + c0;
+
+    auto stage = [&](int r_first, int nrows) {                   // rows r_first .. of the run -> ring
+        for (int r = t; r < nrows; r += T) {
+            double2 v = __ldg(reinterpret_cast<const double2*>(x0 + (int64_t)(r_first + r) * C));
+            const int pos = (r_first + r) & (N - 1);
+            xs[pos] = v.x;
+            xs[RS + pos] = v.y;
+        }
+    };
+    stage(0, N);
+    double2 wb[5];
+    mp_twiddles<LOGN, R>(wb, P.tw, t);
+    __syncthreads();
+
+    for (int s = 0; s < nfr; ++s) {
+        if (t == 0 && s + 1 < nfr) {                             // next rows on their way to L2
+            const double* a0 = P.src + ((f0 + s) * hop + N) * (int64_t)C;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0),
+                         "r"((uint32_t)(hop * C * 8)) : "memory");
+        }
+        const int start = (s * hop) & (N - 1);
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ++ch) {
+            const double* xc = xs + ch * RS;
+            double2 za[R];
+            double sa = 0.0;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                za[k] = *reinterpret_cast<const double2*>(xc + ((start + 2 * (t + k * T)) & (N - 1)));
+                sa += za[k].x + za[k].y;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sa += __shfl_xor_sync(0xffffffffu, sa, o);
+            if ((t & 31) == 0) red[ch][t >> 5] = sa;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                double2 w = __ldg(reinterpret_cast<const double2*>(P.win) + (t + k * T));
+                za[k].x *= w.x;
+                za[k].y *= w.y;
+            }
+            mp_channel<LOGN, R, DB>(za, S, wb, t, red[ch], P.detrend, P.scale, P.tw,
+                                    P.dst + (((f0 + s) * C + c0 + ch) * (int64_t)F));
+            __syncthreads();                                     // S (and red) free again
+        }
+        if (s + 1 < nfr) {
+            stage(s * hop + N, hop);                             // replaces rows [s hop, (s+1) hop)
+            __syncthreads();
+        }
+    }
+}
+
+template <int LOGN, int R>
+int32_t launch_mpr(SpecMArgs& P, int64_t nf, int out_db, cudaStream_t st) {
+    constexpr int M = 1 << (LOGN - 1), T = M / R, N = 2 * M;
+    P.npair = P.C / 2;
+    const size_t smem = (size_t)(M + M / 8 + 8) * 16 + (size_t)2 * (N + 4) * 8;
+    auto k0 = spectrogram_mpr_kernel<LOGN, R, false>;
+    auto k1 = spectrogram_mpr_kernel<LOGN, R, true>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        ADN_CK(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ADN_CK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done = true;
+    }
+    int bps = 1;
+    ADN_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k0, T, smem));
+    if (bps < 1) return ADN_ERR_UNSUPPORTED;
+    // about two resident waves of blocks, runs of at least 8 frames
+    int64_t nruns = (int64_t)ctx().sm_count * bps * 2 / P.npair;
+    if (nruns < 1) nruns = 1;
+    int64_t frun = (nf + nruns - 1) / nruns;
+    if (frun < 8) frun = nf < 8 ? nf : 8;
+    if (frun * P.hop + N > 0x3fffffff) return ADN_ERR_UNSUPPORTED;
+    const int64_t grid = ((nf + frun - 1) / frun) * P.npair;
+    if (grid > 0x7fffffff) return ADN_ERR_UNSUPPORTED;
+    if (out_db) k1<<<(unsigned)grid, T, smem, st>>>(P, (int32_t)frun);
+    else k0<<<(unsigned)grid, T, smem, st>>>(P, (int32_t)frun);
+    count_launch();
+    ADN_CK(cudaGetLastError());
+    return ADN_OK;
 }
 
 template <int LOGN, int R, int CP>
@@ -1695,6 +1808,15 @@ int32_t spectrogram_dev(const double* src, int64_t n_src, int32_t C, double rate
         Q.scale = 1.0 / (rate * plan.sumw2);
         // channel pairs need 16-byte aligned rows: even C and an aligned base
         const bool pairs = C % 2 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+        // overlapping frames of channel pairs: the staging ring (nfft 2048, 4096)
+        // (measured: pays from 75 % overlap on; at 50 % only for few channels, where runs are long)
+        if (pairs && hop % 2 == 0 && nf >= 4 && (4 * hop <= nfft || (2 * hop <= nfft && C <= 16)) &&
+            env_int("ADN_SPEC_MPR", 1) != 0) {
+            int32_t rr = ADN_ERR_UNSUPPORTED;
+            if (nfft == 2048) rr = launch_mpr<11, 8>(Q, nf, out_db, st);
+            if (nfft == 4096) rr = launch_mpr<12, 8>(Q, nf, out_db, st);
+            if (rr != ADN_ERR_UNSUPPORTED) return rr;
+        }
         switch (nfft) {
             case 2048: return pairs ? launch_mp<11, 8, 2>(Q, nf, out_db, st) : launch_mp<11, 8, 1>(Q, nf, out_db, st);
             case 4096: return pairs ? launch_mp<12, 8, 2>(Q, nf, out_db, st) : launch_mp<12, 8, 1>(Q, nf, out_db, st);
