@@ -315,16 +315,18 @@ def run_ours(args):
     edge = _lib.sosfiltfilt_edge(esos)
 
     def roof(op, ms, frames, launches_per_step=1, kernel=''):
+        # per LAUNCH of the kernel: its algorithmic bytes, its average duration, its share of the step
         ach = algorithmic_bytes(op, frames, C)/(ms/launches_per_step*1e-3)/1e9
         return {'kernel': kernel, 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
                 'frac': ach/peak, 'traffic': None, 'peak_kind': peak_kind,
-                'ms_per_launch': ms/launches_per_step,
-                'share_of_step': ms/(t_f + t_s + t_e)}
+                'ms_per_launch': ms/launches_per_step, 'launches_per_step': launches_per_step,
+                'share_of_step': ms/launches_per_step/(t_f + t_s + t_e)}
 
     roofs = {
         'filter': roof('filter', t_f, n, 1, 'sos_scan_kernel<S=2,FWD>'),
         'spectrogram': roof('spectrogram', t_s, n, 1, 'spectrogram_ring_kernel<10>'),
-        'envelope': roof('envelope_sweep', t_e, n + 2*edge, 2, 'sos_scan_kernel<S=1,ENVF|REV> (2 sweeps)'),
+        'envelope': roof('envelope_sweep', t_e, n + 2*edge, 2,
+                         'sos_scan_kernel<S=1,ENVF> and <S=1,REV>: the two sweeps of the envelope, each'),
     }
     traffic_file = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.isfile(traffic_file):
