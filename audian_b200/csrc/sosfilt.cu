@@ -338,21 +338,24 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
         for (int d = 0; d < D; ++d) a[d] = wagg[(j * CG + cw) * D + d];
         matvec_acc<D>(tab_wpow + (warp - 1 - j) * DD, a, pre);
     }
-    // warp 0: aggregate of the tile, look-back for the incoming state (one lane per channel)
-    if (warp == 0 && lane < CG) {
+    // warp 0: aggregate of the tile and look-back for the incoming state.  Lane (gl, cw) handles
+    // predecessor j = base + gl + 1 of channel cw, so that the records of GW predecessors are
+    // fetched in ONE round trip to L2 instead of one per predecessor; the weighted contributions
+    // are then folded over gl by shuffles.
+    if (warp == 0) {
         const double* Pt = R.tab + (size_t)R.off_tile * DD;
-        const bool ch_real = c0 + lane < C;
+        const bool ch_real = c0 + cw < C;
         double acc[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) acc[d] = 0.0;
 #pragma unroll
         for (int j = 0; j < SOS_NW; ++j) {
 #pragma unroll
-            for (int d = 0; d < D; ++d) acc[d] += wtile[(j * CG + lane) * D + d];
+            for (int d = 0; d < D; ++d) acc[d] += wtile[(j * CG + cw) * D + d];
         }
         const bool publish = tt + 1 < R.ntt;
-        const size_t rec = (size_t)tile * CG * D + (size_t)lane * D;
-        if (publish) {
+        const size_t rec = (size_t)tile * CG * D + (size_t)cw * D;
+        if (publish && gl == 0) {
 #pragma unroll
             for (int d = 0; d < D; ++d) st_relaxed(R.agg + rec + d, acc[d]);
         }
@@ -361,48 +364,85 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
         double sin[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) sin[d] = 0.0;
-        for (int j = 1; j <= R.jdecay && j <= SOS_LOOK + 1; ++j) {
+        unsigned chmask = 0;                       // the lanes of this lane's channel
+        for (int k = 0; k < GW; ++k) chmask |= 1u << (cw + CG * k);
+        const unsigned mybit = 1u << lane;
+        const int jmax = min(R.jdecay, SOS_LOOK + 1);
+        bool ch_closed = false;
+        for (int base = 0; base < jmax; base += GW) {
+            const int j = base + gl + 1;
             const int64_t b = tt - j;
+            // 0: record outstanding, 1: aggregate taken (or nothing to add), 2: closes the sum
+            int state = 0;
             double vec[D];
-            bool closed = false;
-            if (b < 0) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) vec[d] = 0.0;
+            if (j > jmax || ch_closed || b < -1) {
+                state = 1;
+            } else if (b < 0) {
 #pragma unroll
                 for (int d = 0; d < D; ++d)
-                    vec[d] = (ch_real && R.s0) ? __ldg(R.s0 + (size_t)(c0 + lane) * D + d) : 0.0;
-                closed = true;
-            } else {
-                const size_t prec = (size_t)(tile - (int64_t)j * R.ngroups) * CG * D + (size_t)lane * D;
-                unsigned ns = 0;
-                while (true) {
-                    // both records in one round trip to L2: the inclusive state closes the
-                    // look-back, else the aggregate is taken (the last slot of the window
-                    // must be an inclusive state)
-                    double va[D];
-                    const bool ok_i = read_record<D>(R.incl + prec, vec);
+                    vec[d] = (ch_real && R.s0) ? __ldg(R.s0 + (size_t)(c0 + cw) * D + d) : 0.0;
+                state = 2;
+            }
+            const size_t prec = (size_t)(tile - (int64_t)j * R.ngroups) * CG * D + (size_t)cw * D;
+            unsigned needed = chmask;
+            unsigned ns = 0;
+            while (true) {
+                if (state == 0 && (needed & mybit)) {
+                    // both records in one round trip: the inclusive state closes the look-back,
+                    // else the aggregate is taken (the last slot of the window must be inclusive)
+                    double vi[D], va[D];
+                    const bool ok_i = read_record<D>(R.incl + prec, vi);
                     const bool ok_a = read_record<D>(R.agg + prec, va);
-                    if (ok_i) { closed = true; break; }
-                    if (j <= SOS_LOOK && ok_a) {
+                    if (ok_i) {
+                        state = 2;
+#pragma unroll
+                        for (int d = 0; d < D; ++d) vec[d] = vi[d];
+                    } else if (j <= SOS_LOOK && ok_a) {
+                        state = 1;
 #pragma unroll
                         for (int d = 0; d < D; ++d) vec[d] = va[d];
-                        break;
                     }
-                    if (ns) __nanosleep(ns);
-                    ns = ns ? (ns < 256 ? ns * 2 : ns) : 32;
                 }
+                const unsigned pend = __ballot_sync(0xffffffffu, state == 0) & chmask;
+                const unsigned clos = __ballot_sync(0xffffffffu, state == 2) & chmask;
+                // predecessors up to the first closing one are needed, the others are not
+                const int fc = clos ? __ffs(clos) - 1 : 31;
+                needed = chmask & (fc >= 31 ? 0xffffffffu : ((2u << fc) - 1u));
+                const bool done = (pend & needed) == 0;
+                if (__all_sync(0xffffffffu, done)) {
+                    ch_closed = ch_closed || clos != 0;
+                    break;
+                }
+                if (ns) __nanosleep(ns);
+                ns = ns ? (ns < 256 ? ns * 2 : ns) : 32;
             }
-            matvec_acc<D>(Pt + (size_t)(j - 1) * DD, vec, sin);
-            if (closed) break;
+            double w[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) w[d] = 0.0;
+            if ((needed & mybit) && state != 0 && j <= jmax)
+                matvec_acc<D>(Pt + (size_t)(j - 1) * DD, vec, w);
+            for (int off = CG; off < 32; off <<= 1) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) w[d] += __shfl_xor_sync(0xffffffffu, w[d], off);
+            }
+#pragma unroll
+            for (int d = 0; d < D; ++d) sin[d] += w[d];
+            if (__all_sync(0xffffffffu, ch_closed)) break;
         }
+        if (gl == 0) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) sin_s[lane * D + d] = sin[d];
-        // ---- inclusive state of this tile, for the successors
-        if (publish) {
-            double inc[D];
+            for (int d = 0; d < D; ++d) sin_s[cw * D + d] = sin[d];
+            // ---- inclusive state of this tile, for the successors
+            if (publish) {
+                double inc[D];
 #pragma unroll
-            for (int d = 0; d < D; ++d) inc[d] = acc[d];
-            matvec_acc<D>(Pt + DD, sin, inc);
+                for (int d = 0; d < D; ++d) inc[d] = acc[d];
+                matvec_acc<D>(Pt + DD, sin, inc);
 #pragma unroll
-            for (int d = 0; d < D; ++d) st_relaxed(R.incl + rec + d, inc[d]);
+                for (int d = 0; d < D; ++d) st_relaxed(R.incl + rec + d, inc[d]);
+            }
         }
     }
     __syncthreads();

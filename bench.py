@@ -77,48 +77,109 @@ def designs():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """SM clock and clock-event (throttle) reasons of one GPU while the timed region runs.
+
+    Polls NVML in this process (nvidia_ml_py) every millisecond or so: the timed region of the
+    default run lasts some 10 ms, far below what an `nvidia-smi -lms` child process resolves
+    (its first row arrives after the region has ended).  Falls back to one-shot `nvidia-smi`
+    queries when NVML cannot be loaded."""
 
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
-        self.proc = None
+        self.uuid = uuid
+        self.rows = []                  # (sm_mhz, reasons bitmask or list)
+        self.mx = None
+        self.power = []
+        self.how = None
+        self._stop_evt = threading.Event()
+        self._ready = threading.Event()
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        if self.uuid:
+            for u in (self.uuid, self.uuid.encode()):
+                try:
+                    return pynvml, pynvml.nvmlDeviceGetHandleByUUID(u)
+                except Exception:
+                    pass
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+        idx = self.index
+        try:
+            if vis:
+                idx = int(vis.split(',')[self.index])
+        except Exception:
+            pass
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(
-                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                 '--format=csv,noheader,nounits', '-lms', '100'],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(',')])
+            nv, h = self._nvml_handle()
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            masks = {'hw_slowdown': nv.nvmlClocksEventReasonHwSlowdown,
+                     'hw_thermal_slowdown': nv.nvmlClocksEventReasonHwThermalSlowdown,
+                     'sw_thermal_slowdown': nv.nvmlClocksEventReasonSwThermalSlowdown,
+                     'sw_power_cap': nv.nvmlClocksEventReasonSwPowerCap}
+            self.how = 'nvml'
+            self._ready.set()
+            while not self._stop_evt.is_set():
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(h)/1000.0)
+                except Exception:
+                    pass
+                self.rows.append((time.perf_counter(), sm, [k for k, m in masks.items() if bits & m]))
+                time.sleep(0.001)
+            return
         except Exception:
             pass
-
-    def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-        self.join(timeout=2)
-        sm = []
-        mx = None
-        reasons = set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        # fallback: repeated one-shot nvidia-smi queries (each takes tens of milliseconds)
+        self.how = 'nvidia-smi'
+        self._ready.set()
+        while not self._stop_evt.is_set():
             try:
-                sm.append(float(r[1]))
-                mx = float(r[2])
-                for k, nm in enumerate(names):
-                    if r[5 + k].lower().startswith('active'):
-                        reasons.add(nm)
+                out = subprocess.run(
+                    ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                     '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=10).stdout
+                for line in out.strip().splitlines():
+                    r = [c.strip() for c in line.split(',')]
+                    self.mx = float(r[2])
+                    self.rows.append((time.perf_counter(), float(r[1]),
+                                      [nm for k, nm in enumerate(self.NAMES)
+                                       if r[5 + k].lower().startswith('active')]))
             except Exception:
-                continue
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                time.sleep(0.05)
+
+    def wait_ready(self, timeout=5.0):
+        self._ready.wait(timeout)
+
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples taken in [t0, t1] (perf_counter times; all samples if None or if
+        fewer than two fall inside)."""
+        self._stop_evt.set()
+        self.join(timeout=15)
+        rows = self.rows
+        if t0 is not None and t1 is not None:
+            inside = [r for r in rows if t0 <= r[0] <= t1]
+            if len(inside) >= 2:
+                rows = inside
+        sm = [r[1] for r in rows]
+        reasons = set()
+        for r in rows:
+            reasons.update(r[2])
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': self.mx,
+                'reasons': sorted(reasons), 'samples': len(sm), 'how': self.how,
+                'power_w_max': max(self.power) if self.power else None}
 
 
 # ------------------------------------------------------------------ reference arm
@@ -272,13 +333,18 @@ def run_ours(args):
         if int(ok.item()) == 0:
             graphs = None
     # per-op times (and, without graphs, the timed region itself) from eager steps
-    sampler = ClockSampler(local)
+    try:
+        uuid = 'GPU-' + str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local, uuid)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
+        sampler.wait_ready()
     launches0 = _lib.launch_count()
     sync_all()
     t_start, t_stop = ev(), ev()
+    wall0 = time.perf_counter()
     torch.cuda.nvtx.range_push('timed')          # ncu --nvtx --nvtx-include "timed/"
     if graphs is None:
         t_start.record()
@@ -298,12 +364,13 @@ def run_ours(args):
         sync_all()
         launches = graph_launches*args.steps
     torch.cuda.nvtx.range_pop()
+    wall1 = time.perf_counter()
     ms_total = t_start.elapsed_time(t_stop)
     tt = torch.tensor([ms_total], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms_step = float(tt.item())/args.steps
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     samples_step = n*C*world
     value = samples_step/(ms_step*1e-3)/1e6
 
