@@ -28,6 +28,7 @@ ADN_OPT_CHUNK_BYTES = 2
 ADN_OPT_RESIDENT_MIN_BYTES = 3
 ADN_OPT_RESIDENT_CAP_BYTES = 4
 ADN_OPT_ENVELOPE_CHUNK_BYTES = 5
+ADN_OPT_SCAN_RUNS = 6
 ADN_WINDOW_HANN = 0
 ADN_DETREND_NONE = 0
 ADN_DETREND_CONSTANT = 1
@@ -44,6 +45,7 @@ SIGNATURES = {
     'adn_last_error': (C.c_char_p, []),
     'adn_version': (_i32, []),
     'adn_launch_count': (_i64, []),
+    'adn_scan_run_count': (_i64, []),
     'adn_synchronize': (_i32, []),
     'adn_host_register': (_i32, [_dp, _i64]),
     'adn_host_unregister': (_i32, [_dp]),
@@ -157,6 +159,11 @@ def init(device=-1):
 
 def launch_count():
     return int(lib().adn_launch_count())
+
+
+def scan_run_count():
+    """Launches of the SOS run kernel so far (the look-back kernel is the other scan kernel)."""
+    return int(lib().adn_scan_run_count())
 
 
 def minmax(src, step, dst=None):

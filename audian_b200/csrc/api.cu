@@ -115,7 +115,7 @@ static std::vector<DevBuf> g_pool;            // released device buffers, reused
 static DevBuf g_vbuf;                         // samples of a resident copy for verification
 static uint64_t g_stamp = 0;
 static int64_t g_opt[ADN_OPT_COUNT] = {0, 1, (int64_t)32 << 20, (int64_t)8 << 20, (int64_t)16 << 30,
-                                       0};
+                                       0, 1};
 int64_t option(int32_t which) { return g_opt[which]; }
 static cudaStream_t g_h2d = nullptr, g_d2h = nullptr;
 static std::vector<cudaEvent_t> g_events;
@@ -360,6 +360,7 @@ int32_t adn_shutdown(void) {
 const char* adn_last_error(void) { return g_err.c_str(); }
 int32_t adn_version(void) { return 100; }
 int64_t adn_launch_count(void) { return g_ctx.launches.load(); }
+int64_t adn_scan_run_count(void) { return adn::scan_run_launches(); }
 
 int32_t adn_synchronize(void) {
     int32_t rc = ensure_init();

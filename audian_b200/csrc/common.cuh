@@ -39,6 +39,7 @@ struct Ctx {
 
 Ctx& ctx();
 int64_t option(int32_t which);         // adn_set_option() values
+int64_t scan_run_launches();           // sosfilt.cu: launches of sos_run_kernel
 int32_t ensure_init();
 // *_dev entry points: the caller's stream as is (NULL = CUDA's default stream, which is
 // what torch.cuda.current_stream().cuda_stream is unless a side stream is active)

@@ -25,6 +25,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <mutex>
+#include <atomic>
 
 namespace adn {
 
@@ -79,6 +80,9 @@ struct SosRun {
     int32_t vec_in, vec_out;       // 16-byte granules allowed
     int32_t pf_tiles;              // L2 prefetch distance in time tiles (0 = off)
     int32_t lc;                    // log2(CG), or -1: no fast path
+    // sos_run_kernel: a block walks over run_tiles consecutive time tiles, after pre_tiles
+    // tiles of run-in from zero state; nbuf tile buffers (nbuf - 1 tiles prefetched)
+    int32_t run_tiles, pre_tiles, nbuf;
 };
 
 __device__ __forceinline__ double ld_relaxed(const double* p) {
@@ -142,6 +146,262 @@ __device__ __forceinline__ void st_out(T* p, T v) {
     if (MODE == MODE_ENVF && ENVF_PLAIN_STORE) *p = v; else __stcs(p, v);
 }
 
+// ---- stage one tile (rows [t0, t0 + T) of channel group c0 .. c0 + Cw) in shared memory with
+// cp.async (the caller commits / waits).  Returns true when the tile holds RAW input that the
+// passes have to rectify on the fly (MODE_ENVF, tile clear of the odd extension).
+template <int MODE>
+__device__ __forceinline__ bool sos_load_tile(const SosRun& R, double* tile_s, int64_t t0, int c0,
+                                              int Cw, int tid) {
+    const int CG = R.CG, C = R.C, T = R.T;
+    const int pad = CG < 16 ? CG : 0;
+    const int GS = SOS_L * Cw + pad;
+    // MODE_ENVF: tiles that do not touch the odd extension are loaded raw and
+    // rectified on the fly; the two edge tiles are built element by element
+    bool xform = false;
+    int64_t shift = 0;
+    if (ADN_EXT(MODE)) {
+        xform = t0 >= R.edge && t0 + T <= R.edge + R.nx;
+        shift = R.edge;
+    }
+    // fast path (block-uniform): a full channel group (CG = 2^k channels), every row of the
+    // tile inside the source: the addresses of the granules a thread copies are shifts and adds
+    const int lc = Cw == CG ? R.lc : -1;                   // log2(CG) when the group is full
+    const int64_t nlim = ADN_EXT(MODE) ? R.edge + R.nx : R.n;
+    const bool fast_in = lc >= 0 && t0 + T <= nlim && !(ADN_EXT(MODE) && !xform);
+    if (fast_in) {
+        const int64_t rowbase = MODE == MODE_REV ? R.n - 1 - t0 : t0 - shift;   // physical row of tile row 0
+        if (R.vec_in) {
+            // granule k of a thread: flat index f = 2 (tid + NT k), row r0 + k DRk (DRk = 2 NT / CG
+            // rows, a multiple of 32 whenever the tile is padded): both addresses advance by
+            // constants
+            const int f0 = 2 * tid, r0 = f0 >> lc;
+            const int DRk = (2 * SOS_NT) >> lc;
+            const int64_t gstr = (MODE == MODE_REV ? -(int64_t)DRk : (int64_t)DRk) * C;
+            const double* gp = R.src + (MODE == MODE_REV ? rowbase - r0 : rowbase + r0) * C + c0 + (f0 & (CG - 1));
+            double* sp = tile_s + f0 + (r0 >> 5) * pad;
+            if (pad) {
+#pragma unroll
+                for (int k = 0; k < SOS_L / 2; ++k) {
+                    cp_async16(sp + k * (2 * SOS_NT + 8), gp, 16);
+                    gp += gstr;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < SOS_L / 2; ++k) {
+                    cp_async16(sp + k * (2 * SOS_NT), gp, 16);
+                    gp += gstr;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < SOS_L; ++k) {
+                const int f = tid + SOS_NT * k;
+                const int r = f >> lc, c = c0 + (f & (CG - 1));
+                const int64_t grow = MODE == MODE_REV ? rowbase - r : rowbase + r;
+                cp_async8(tile_s + f + (r >> 5) * pad, R.src + grow * C + c, 8);
+            }
+        }
+    } else
+    if (ADN_EXT(MODE) && !xform) {
+        const int64_t nx = R.nx, edge = R.edge;
+        const int total = T * Cw;
+        for (int q = tid; q < total; q += SOS_NT) {
+            int row = q / Cw, col = q - row * Cw;
+            int64_t e = t0 + row;
+            double val = 0.0;
+            if (e < R.n) {
+                const double* xc = R.src + c0 + col;
+                if (e < edge) {
+                    double r0 = pre_x<MODE>(__ldg(xc));
+                    double rk = pre_x<MODE>(__ldg(xc + (edge - e) * C));
+                    val = 2.0 * r0 - rk;
+                } else if (e < edge + nx) {
+                    val = pre_x<MODE>(__ldg(xc + (e - edge) * C));
+                } else {
+                    int64_t k = e - edge - nx;
+                    double r1 = pre_x<MODE>(__ldg(xc + (nx - 1) * C));
+                    double rk = pre_x<MODE>(__ldg(xc + (nx - 2 - k) * C));
+                    val = 2.0 * r1 - rk;
+                }
+            }
+            tile_s[(row / SOS_L) * GS + (row % SOS_L) * Cw + col] = val;
+        }
+    } else {
+        const int gw = R.vec_in ? 2 : 1;                 // doubles per granule
+        const int gpr = Cw / gw;                         // granules per row
+        const int total = T * gpr;
+        int row = tid / gpr, col = tid - row * gpr;
+        const int drow = SOS_NT / gpr, dcol = SOS_NT - drow * gpr;
+        for (int q = tid; q < total; q += SOS_NT) {
+            int64_t tau = t0 + row;
+            bool ok = tau < nlim;
+            int64_t phys = MODE == MODE_REV ? R.n - 1 - tau : tau - shift;
+            const double* gp = ok ? R.src + phys * C + c0 + col * gw : R.src;
+            double* sp = tile_s + (row / SOS_L) * GS + (row % SOS_L) * Cw + col * gw;
+            if (gw == 2) cp_async16(sp, gp, ok ? 16 : 0);
+            else cp_async8(sp, gp, ok ? 8 : 0);
+            row += drow;
+            col += dcol;
+            if (col >= gpr) { col -= gpr; ++row; }
+        }
+    }
+    return xform;
+}
+
+// ---- write the finished tile back (clamp fused), coalesced
+template <int MODE>
+__device__ __forceinline__ void sos_store_tile(const SosRun& R, const double* tile_s, int64_t t0,
+                                               int c0, int Cw, int tid) {
+    const int CG = R.CG, C = R.C, T = R.T;
+    const int pad = CG < 16 ? CG : 0;
+    const int GS = SOS_L * Cw + pad;
+    const int lc = Cw == CG ? R.lc : -1;
+    // ---------------------------------------------------------------- store
+    // fast path: contiguous tile, every row lands inside dst
+    bool fast_out = lc >= 0 && t0 + T <= R.n;
+    if (fast_out) {
+        const int64_t lo = MODE == MODE_REV ? R.n - t0 - T : t0, hi = lo + T;   // physical rows
+        fast_out = lo >= R.out_skip && hi <= R.out_skip + R.n_dst;
+    }
+    if (fast_out) {
+        const int64_t rowbase = (MODE == MODE_REV ? R.n - 1 - t0 : t0) - R.out_skip;
+        if (R.vec_out) {
+            // the same constant strides as in sos_load_tile
+            const int f0 = 2 * tid, r0 = f0 >> lc;
+            const int DRk = (2 * SOS_NT) >> lc;
+            const int64_t gstr = (MODE == MODE_REV ? -(int64_t)DRk : (int64_t)DRk) * C;
+            double* gp = R.dst + (MODE == MODE_REV ? rowbase - r0 : rowbase + r0) * C + c0 + (f0 & (CG - 1));
+            const double* sp = tile_s + f0 + (r0 >> 5) * pad;
+            const int sstr = 2 * SOS_NT + (pad ? 8 : 0);
+            if (R.clamp) {
+#pragma unroll
+                for (int k = 0; k < SOS_L / 2; ++k) {
+                    double2 o = *reinterpret_cast<const double2*>(sp + k * sstr);
+                    o.x = o.x < 0.0 ? 0.0 : o.x;
+                    o.y = o.y < 0.0 ? 0.0 : o.y;
+                    st_out<MODE>(reinterpret_cast<double2*>(gp), o);
+                    gp += gstr;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < SOS_L / 2; ++k) {
+                    st_out<MODE>(reinterpret_cast<double2*>(gp), *reinterpret_cast<const double2*>(sp + k * sstr));
+                    gp += gstr;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < SOS_L; ++k) {
+                const int f = tid + SOS_NT * k;
+                const int r = f >> lc, c = c0 + (f & (CG - 1));
+                const int64_t orow = MODE == MODE_REV ? rowbase - r : rowbase + r;
+                double o = tile_s[f + (r >> 5) * pad];
+                if (R.clamp) o = o < 0.0 ? 0.0 : o;
+                st_out<MODE>(R.dst + orow * C + c, o);
+            }
+        }
+        return;
+    }
+    {
+        const int gw = R.vec_out ? 2 : 1;
+        const int gpr = Cw / gw;
+        const int total = T * gpr;
+        int row = tid / gpr, col = tid - row * gpr;
+        const int drow = SOS_NT / gpr, dcol = SOS_NT - drow * gpr;
+        for (int q = tid; q < total; q += SOS_NT) {
+            int64_t tau = t0 + row;
+            int64_t phys = MODE == MODE_REV ? R.n - 1 - tau : tau;
+            int64_t orow = phys - R.out_skip;
+            if (tau < R.n && orow >= 0 && orow < R.n_dst) {
+                const double* sp = tile_s + (row / SOS_L) * GS + (row % SOS_L) * Cw + col * gw;
+                double* gp = R.dst + orow * C + c0 + col * gw;
+                if (gw == 2) {
+                    double2 o = *reinterpret_cast<const double2*>(sp);
+                    if (R.clamp) { o.x = o.x < 0.0 ? 0.0 : o.x; o.y = o.y < 0.0 ? 0.0 : o.y; }
+                    st_out<MODE>(reinterpret_cast<double2*>(gp), o);
+                } else {
+                    double o = *sp;
+                    if (R.clamp) o = o < 0.0 ? 0.0 : o;
+                    st_out<MODE>(gp, o);
+                }
+            }
+            row += drow;
+            col += dcol;
+            if (col >= gpr) { col -= gpr; ++row; }
+        }
+    }
+}
+
+// ---- pass B of one thread: the exact DF2T recurrence over its SOS_L samples from state z,
+// outputs written in place; z leaves as the state after the last sample
+template <int S, int MODE>
+__device__ __forceinline__ void sos_recurrence(const SosK<S>& K, const SosRun& R, double* xp, int Cw,
+                                               double (&z)[2 * S], bool xform, bool want_state,
+                                               int ilast_in, int chan) {
+    constexpr int D = 2 * S;
+        if (!want_state && S > 4) {
+            const double* xr = xp;
+#pragma unroll
+            for (int i = 0; i < SOS_L; ++i) {
+                double x = *xr;
+                if (MODE == MODE_ENVF && xform) x = pre_x<MODE>(x);
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    double y = fma(K.coef[s][0], x, z[2 * s]);
+                    z[2 * s] = fma(K.coef[s][1], x, z[2 * s + 1]) - K.coef[s][3] * y;
+                    z[2 * s + 1] = K.coef[s][2] * x - K.coef[s][4] * y;
+                    x = y;
+                }
+                *const_cast<double*>(xr) = x;
+                xr += Cw;
+            }
+        } else if (!want_state) {
+            // the sections run skewed by one sample each (section s works on sample j - s in
+            // step j): the S recurrences of a step are independent of each other, which hides
+            // the latency of the dependent fp64 operations; the arithmetic per sample is unchanged
+            double xin[S + 1];
+#pragma unroll
+            for (int j = 0; j < SOS_L + S - 1; ++j) {
+#pragma unroll
+                for (int s = S - 1; s >= 0; --s) {
+                    const int i = j - s;
+                    if (i < 0 || i >= SOS_L) continue;
+                    double x;
+                    if (s == 0) {
+                        x = xp[i * Cw];
+                        if (MODE == MODE_ENVF && xform) x = pre_x<MODE>(x);
+                    } else {
+                        x = xin[s];
+                    }
+                    double y = fma(K.coef[s][0], x, z[2 * s]);
+                    z[2 * s] = fma(K.coef[s][1], x, z[2 * s + 1]) - K.coef[s][3] * y;
+                    z[2 * s + 1] = K.coef[s][2] * x - K.coef[s][4] * y;
+                    if (s == S - 1) xp[i * Cw] = y; else xin[s + 1] = y;
+                }
+            }
+        } else {
+            // the one sub-chunk per channel that contains the last sample: plain loop, state
+            // captured right after that sample
+            const int ilast = ilast_in;
+            for (int i = 0; i < SOS_L; ++i) {
+                double x = xp[i * Cw];
+                if (MODE == MODE_ENVF && xform) x = pre_x<MODE>(x);
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    double y = fma(K.coef[s][0], x, z[2 * s]);
+                    z[2 * s] = fma(K.coef[s][1], x, z[2 * s + 1]) - K.coef[s][3] * y;
+                    z[2 * s + 1] = K.coef[s][2] * x - K.coef[s][4] * y;
+                    x = y;
+                }
+                xp[i * Cw] = x;
+                if (i == ilast) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) R.zf[(size_t)chan * D + d] = z[d];
+                }
+            }
+        }
+}
+
 template <int S, int MODE>
 __global__ void __launch_bounds__(SOS_NT, S <= 2 ? 6 : (S <= 4 ? 4 : 1))
 sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRun R) {
@@ -202,82 +462,7 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
         const int ngran = R.n_staged * DD / 2;
         for (int q = tid; q < ngran; q += SOS_NT) cp_async16(tab_s + 2 * q, R.tab + 2 * q, 16);
     }
-    // MODE_ENVF: tiles that do not touch the odd extension are loaded raw and
-    // rectified on the fly; the two edge tiles are built element by element
-    bool xform = false;
-    int64_t shift = 0;
-    if (ADN_EXT(MODE)) {
-        xform = t0 >= R.edge && t0 + T <= R.edge + R.nx;
-        shift = R.edge;
-    }
-    // fast path (block-uniform): a full channel group (CG = 2^k channels), every row of the
-    // tile inside the source: the addresses of the granules a thread copies are shifts and adds
-    const int lc = Cw == CG ? R.lc : -1;                   // log2(CG) when the group is full
-    const int64_t nlim = ADN_EXT(MODE) ? R.edge + R.nx : R.n;
-    const bool fast_in = lc >= 0 && t0 + T <= nlim && !(ADN_EXT(MODE) && !xform);
-    if (fast_in) {
-        const int64_t rowbase = MODE == MODE_REV ? R.n - 1 - t0 : t0 - shift;   // physical row of tile row 0
-        if (R.vec_in) {
-#pragma unroll
-            for (int k = 0; k < SOS_L / 2; ++k) {
-                const int f = 2 * (tid + SOS_NT * k);      // flat double index in the tile
-                const int r = f >> lc, c = c0 + (f & (CG - 1));
-                const int64_t grow = MODE == MODE_REV ? rowbase - r : rowbase + r;
-                cp_async16(tile_s + f + (r >> 5) * pad, R.src + grow * C + c, 16);
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < SOS_L; ++k) {
-                const int f = tid + SOS_NT * k;
-                const int r = f >> lc, c = c0 + (f & (CG - 1));
-                const int64_t grow = MODE == MODE_REV ? rowbase - r : rowbase + r;
-                cp_async8(tile_s + f + (r >> 5) * pad, R.src + grow * C + c, 8);
-            }
-        }
-    } else
-    if (ADN_EXT(MODE) && !xform) {
-        const int64_t nx = R.nx, edge = R.edge;
-        const int total = T * Cw;
-        for (int q = tid; q < total; q += SOS_NT) {
-            int row = q / Cw, col = q - row * Cw;
-            int64_t e = t0 + row;
-            double val = 0.0;
-            if (e < R.n) {
-                const double* xc = R.src + c0 + col;
-                if (e < edge) {
-                    double r0 = pre_x<MODE>(__ldg(xc));
-                    double rk = pre_x<MODE>(__ldg(xc + (edge - e) * C));
-                    val = 2.0 * r0 - rk;
-                } else if (e < edge + nx) {
-                    val = pre_x<MODE>(__ldg(xc + (e - edge) * C));
-                } else {
-                    int64_t k = e - edge - nx;
-                    double r1 = pre_x<MODE>(__ldg(xc + (nx - 1) * C));
-                    double rk = pre_x<MODE>(__ldg(xc + (nx - 2 - k) * C));
-                    val = 2.0 * r1 - rk;
-                }
-            }
-            tile_s[(row / SOS_L) * GS + (row % SOS_L) * Cw + col] = val;
-        }
-    } else {
-        const int gw = R.vec_in ? 2 : 1;                 // doubles per granule
-        const int gpr = Cw / gw;                         // granules per row
-        const int total = T * gpr;
-        int row = tid / gpr, col = tid - row * gpr;
-        const int drow = SOS_NT / gpr, dcol = SOS_NT - drow * gpr;
-        for (int q = tid; q < total; q += SOS_NT) {
-            int64_t tau = t0 + row;
-            bool ok = tau < nlim;
-            int64_t phys = MODE == MODE_REV ? R.n - 1 - tau : tau - shift;
-            const double* gp = ok ? R.src + phys * C + c0 + col * gw : R.src;
-            double* sp = tile_s + (row / SOS_L) * GS + (row % SOS_L) * Cw + col * gw;
-            if (gw == 2) cp_async16(sp, gp, ok ? 16 : 0);
-            else cp_async8(sp, gp, ok ? 8 : 0);
-            row += drow;
-            col += dcol;
-            if (col >= gpr) { col -= gpr; ++row; }
-        }
-    }
+    const bool xform = sos_load_tile<MODE>(R, tile_s, t0, c0, Cw, tid);
     cp_async_wait_all();
     __syncthreads();
 
@@ -468,130 +653,172 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
                 matvec_acc<D>(tab_fix + gl * DD, pre, z);
             }
         }
-        if (!want_state && S > 4) {
-            const double* xr = xp;
-#pragma unroll
-            for (int i = 0; i < SOS_L; ++i) {
-                double x = *xr;
-                if (MODE == MODE_ENVF && xform) x = pre_x<MODE>(x);
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    double y = fma(K.coef[s][0], x, z[2 * s]);
-                    z[2 * s] = fma(K.coef[s][1], x, z[2 * s + 1]) - K.coef[s][3] * y;
-                    z[2 * s + 1] = K.coef[s][2] * x - K.coef[s][4] * y;
-                    x = y;
-                }
-                *const_cast<double*>(xr) = x;
-                xr += Cw;
-            }
-        } else if (!want_state) {
-            // the sections run skewed by one sample each (section s works on sample j - s in
-            // step j): the S recurrences of a step are independent of each other, which hides
-            // the latency of the dependent fp64 operations; the arithmetic per sample is unchanged
-            double xin[S + 1];
-#pragma unroll
-            for (int j = 0; j < SOS_L + S - 1; ++j) {
-#pragma unroll
-                for (int s = S - 1; s >= 0; --s) {
-                    const int i = j - s;
-                    if (i < 0 || i >= SOS_L) continue;
-                    double x;
-                    if (s == 0) {
-                        x = xp[i * Cw];
-                        if (MODE == MODE_ENVF && xform) x = pre_x<MODE>(x);
-                    } else {
-                        x = xin[s];
-                    }
-                    double y = fma(K.coef[s][0], x, z[2 * s]);
-                    z[2 * s] = fma(K.coef[s][1], x, z[2 * s + 1]) - K.coef[s][3] * y;
-                    z[2 * s + 1] = K.coef[s][2] * x - K.coef[s][4] * y;
-                    if (s == S - 1) xp[i * Cw] = y; else xin[s + 1] = y;
-                }
-            }
-        } else {
-            // the one sub-chunk per channel that contains the last sample: plain loop, state
-            // captured right after that sample
-            const int ilast = (int)(last - tau0);
-            for (int i = 0; i < SOS_L; ++i) {
-                double x = xp[i * Cw];
-                if (MODE == MODE_ENVF && xform) x = pre_x<MODE>(x);
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    double y = fma(K.coef[s][0], x, z[2 * s]);
-                    z[2 * s] = fma(K.coef[s][1], x, z[2 * s + 1]) - K.coef[s][3] * y;
-                    z[2 * s + 1] = K.coef[s][2] * x - K.coef[s][4] * y;
-                    x = y;
-                }
-                xp[i * Cw] = x;
-                if (i == ilast) {
-#pragma unroll
-                    for (int d = 0; d < D; ++d) R.zf[(size_t)(c0 + cw) * D + d] = z[d];
-                }
-            }
-        }
+        sos_recurrence<S, MODE>(K, R, xp, Cw, z, xform, want_state, (int)(last - tau0), c0 + cw);
     }
     if (R.dst == nullptr) return;
     __syncthreads();
 
-    // ---------------------------------------------------------------- store
-    // fast path: contiguous tile, every row lands inside dst
-    bool fast_out = lc >= 0 && t0 + T <= R.n;
-    if (fast_out) {
-        const int64_t lo = MODE == MODE_REV ? R.n - t0 - T : t0, hi = lo + T;   // physical rows
-        fast_out = lo >= R.out_skip && hi <= R.out_skip + R.n_dst;
+    sos_store_tile<MODE>(R, tile_s, t0, c0, Cw, tid);
+}
+
+// ======================================================================================
+// Run variant of the scan for cascades that forget quickly (the usual case: every cut-off
+// audian offers at audio rates decays below 1e-20 within one or two tiles).  A block owns a
+// RUN of consecutive time tiles of one channel group and walks along time, the state handed
+// from tile to tile through shared memory: no tile records, no look-back, no waiting on
+// other blocks.  A run that does not start at row 0 first runs over the `pre_tiles` tiles
+// before it from zero state without storing anything: by then the unknown state that entered
+// those tiles has decayed below 1e-20 of its size, far under the rounding of the state
+// itself (the look-back kernel truncates in the same way at 1e-30).  The tiles of a run are
+// prefetched nbuf - 1 ahead with cp.async into a ring of tile buffers, so the loads of the
+// next tile overlap both passes over the current one.  Passes A and B and the scans inside
+// the tile are those of sos_scan_kernel.
+constexpr int SOS_RUN_BLOCKS = 3;
+
+template <int S, int MODE>
+__global__ void __launch_bounds__(SOS_NT, SOS_RUN_BLOCKS)
+sos_run_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRun R) {
+    constexpr int D = 2 * S;
+    constexpr int DD = D * D;
+    extern __shared__ __align__(16) double smem[];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = (int)(blockIdx.x % R.ngroups);
+    const int64_t run = blockIdx.x / R.ngroups;
+    const int CG = R.CG, C = R.C;
+    const int c0 = grp * CG;
+    const int Cw = min(CG, C - c0);
+    const int GW = 32 / CG;
+    const int gl = lane / CG, cw = lane % CG;
+    const int g = warp * GW + gl;
+    const bool chan_ok = cw < Cw;
+    const int T = R.T;
+    const int pad = CG < 16 ? CG : 0;
+    const int GS = SOS_L * Cw + pad;
+    const int G = SOS_NT / CG;
+    const int nbuf = R.nbuf;
+    const size_t TS = (size_t)G * (SOS_L * CG + pad);        // doubles per tile buffer
+
+    double* bufs = smem;                                     // nbuf * TS
+    double* wagg = bufs + (size_t)nbuf * TS;                 // [NW][CG][D]
+    double* sin_s = wagg + SOS_NW * CG * D;                  // [2][CG][D]
+    double* tab_s = sin_s + 2 * CG * D;                      // n_staged * DD
+    const double* tab = tab_s;
+    const double* tab_fix = tab + R.off_fix * DD;
+    const double* tab_wpow = tab + R.off_wpow * DD;
+
+    const int64_t tt_first = run * R.run_tiles;
+    const int64_t tt_last = min(tt_first + (int64_t)R.run_tiles, R.ntt);
+    const int64_t tt_start = max((int64_t)0, tt_first - R.pre_tiles);
+    if (tt_first >= tt_last) return;
+
+    // ---- prologue: tables, the first nbuf - 1 tiles, the state entering the run
+    {
+        const int ngran = R.n_staged * DD / 2;
+        for (int q = tid; q < ngran; q += SOS_NT) cp_async16(tab_s + 2 * q, R.tab + 2 * q, 16);
     }
-    if (fast_out) {
-        const int64_t rowbase = (MODE == MODE_REV ? R.n - 1 - t0 : t0) - R.out_skip;
-        if (R.vec_out) {
+    for (int k = 0; k < nbuf - 1; ++k) {
+        if (tt_start + k < tt_last) sos_load_tile<MODE>(R, bufs + (size_t)k * TS, (tt_start + k) * T, c0, Cw, tid);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    if (tid < CG * D) {
+        const int ch = tid / D;
+        double v0 = 0.0;
+        if (tt_start == 0 && R.s0 && c0 + ch < C) v0 = __ldg(R.s0 + (size_t)c0 * D + tid);
+        sin_s[tid] = v0;
+    }
+
+    const int64_t last = R.n - 1;
+    int it = 0;
+    for (int64_t tt = tt_start; tt < tt_last; ++tt, ++it) {
+        double* tile_s = bufs + (size_t)(it % nbuf) * TS;
+        const int64_t t0 = tt * T;
+        const bool xform = ADN_EXT(MODE) && t0 >= R.edge && t0 + T <= R.edge + R.nx;
+        // the current tile has landed when at most nbuf - 2 younger groups are outstanding
+        if (nbuf == 2) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        else asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        // the tile nbuf - 1 ahead goes into the buffer the previous iteration stored from (every
+        // thread has crossed the barrier above, which it reaches after that store); one group
+        // per iteration, empty at the end of the run
+        if (tt + nbuf - 1 < tt_last)
+            sos_load_tile<MODE>(R, bufs + (size_t)((it + nbuf - 1) % nbuf) * TS, (tt + nbuf - 1) * T, c0, Cw, tid);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+
+        // ------------------------------------------------------------ pass A
+        double* xp = tile_s + g * GS + cw;
+        double v[D];
 #pragma unroll
-            for (int k = 0; k < SOS_L / 2; ++k) {
-                const int f = 2 * (tid + SOS_NT * k);
-                const int r = f >> lc, c = c0 + (f & (CG - 1));
-                const int64_t orow = MODE == MODE_REV ? rowbase - r : rowbase + r;
-                double2 o = *reinterpret_cast<const double2*>(tile_s + f + (r >> 5) * pad);
-                if (R.clamp) { o.x = o.x < 0.0 ? 0.0 : o.x; o.y = o.y < 0.0 ? 0.0 : o.y; }
-                st_out<MODE>(reinterpret_cast<double2*>(R.dst + orow * C + c), o);
-            }
-        } else {
+        for (int d = 0; d < D; ++d) v[d] = 0.0;
+        if (chan_ok) {
 #pragma unroll
-            for (int k = 0; k < SOS_L; ++k) {
-                const int f = tid + SOS_NT * k;
-                const int r = f >> lc, c = c0 + (f & (CG - 1));
-                const int64_t orow = MODE == MODE_REV ? rowbase - r : rowbase + r;
-                double o = tile_s[f + (r >> 5) * pad];
-                if (R.clamp) o = o < 0.0 ? 0.0 : o;
-                st_out<MODE>(R.dst + orow * C + c, o);
+            for (int i = 0; i < SOS_L; ++i) {
+                double x = xp[i * Cw];
+                if (MODE == MODE_ENVF && xform) x = pre_x<MODE>(x);
+#pragma unroll
+                for (int d = 0; d < D; ++d) v[d] = fma(K.W[d][i], x, v[d]);
             }
         }
-        return;
-    }
-    {
-        const int gw = R.vec_out ? 2 : 1;
-        const int gpr = Cw / gw;
-        const int total = T * gpr;
-        int row = tid / gpr, col = tid - row * gpr;
-        const int drow = SOS_NT / gpr, dcol = SOS_NT - drow * gpr;
-        for (int q = tid; q < total; q += SOS_NT) {
-            int64_t tau = t0 + row;
-            int64_t phys = MODE == MODE_REV ? R.n - 1 - tau : tau;
-            int64_t orow = phys - R.out_skip;
-            if (tau < R.n && orow >= 0 && orow < R.n_dst) {
-                const double* sp = tile_s + (row / SOS_L) * GS + (row % SOS_L) * Cw + col * gw;
-                double* gp = R.dst + orow * C + c0 + col * gw;
-                if (gw == 2) {
-                    double2 o = *reinterpret_cast<const double2*>(sp);
-                    if (R.clamp) { o.x = o.x < 0.0 ? 0.0 : o.x; o.y = o.y < 0.0 ? 0.0 : o.y; }
-                    st_out<MODE>(reinterpret_cast<double2*>(gp), o);
+        // ------------------------------------------------------------ warp scan over gl
+        {
+            int k = 0;
+            for (int off = CG; off < 32; off <<= 1, ++k) {
+                double u[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) u[d] = __shfl_up_sync(0xffffffffu, v[d], off);
+                if (lane >= off) matvec_acc<D>(tab + k * DD, u, v);
+            }
+        }
+        double ex[D];                         // exclusive prefix inside the warp
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            double t = __shfl_up_sync(0xffffffffu, v[d], CG & 31);
+            ex[d] = gl == 0 ? 0.0 : t;
+        }
+        if (gl == GW - 1) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) wagg[(warp * CG + cw) * D + d] = v[d];
+        }
+        __syncthreads();
+
+        // ------------------------------------------------------------ state entering the thread
+        double pre[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) pre[d] = 0.0;
+        for (int j = 0; j < warp; ++j) {
+            double a[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) a[d] = wagg[(j * CG + cw) * D + d];
+            matvec_acc<D>(tab_wpow + (warp - 1 - j) * DD, a, pre);
+        }
+        const int64_t tau0 = t0 + (int64_t)g * SOS_L;
+        const bool own = tt >= tt_first;
+        const bool want_state = own && R.zf != nullptr && last >= tau0 && last < tau0 + SOS_L;
+        if (chan_ok) {
+            double z[D];
+            {
+                double sv[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) sv[d] = sin_s[(it & 1) * CG * D + cw * D + d];
+                matvec_acc<D>(tab_wpow + warp * DD, sv, pre);
+#pragma unroll
+                for (int d = 0; d < D; ++d) z[d] = ex[d];
+                if (gl == 0) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) z[d] += pre[d];
                 } else {
-                    double o = *sp;
-                    if (R.clamp) o = o < 0.0 ? 0.0 : o;
-                    st_out<MODE>(gp, o);
+                    matvec_acc<D>(tab_fix + gl * DD, pre, z);
                 }
             }
-            row += drow;
-            col += dcol;
-            if (col >= gpr) { col -= gpr; ++row; }
+            // -------------------------------------------------------- pass B
+            sos_recurrence<S, MODE>(K, R, xp, Cw, z, xform, want_state, (int)(last - tau0), c0 + cw);
+            if (g == G - 1) {                 // state after the tile's last row: enters the next tile
+#pragma unroll
+                for (int d = 0; d < D; ++d) sin_s[((it + 1) & 1) * CG * D + cw * D + d] = z[d];
+            }
         }
+        __syncthreads();
+        if (own && R.dst != nullptr) sos_store_tile<MODE>(R, tile_s, t0, c0, Cw, tid);
     }
 }
 
@@ -679,6 +906,7 @@ struct Plan {
     std::vector<double> sos;      // key
     int S = 0, CG = 0;
     int jdecay = SOS_LOOK + 1;
+    int jpre = SOS_LOOK + 1;      // tiles after which the cascade has forgotten its state (< 1e-20)
     int off_fix = 0, off_wpow = 0, off_tile = 0, n_staged = 0;
     std::vector<double> W;        // [D][L]
     double* dtab = nullptr;       // device tables
@@ -752,6 +980,7 @@ int32_t get_plan(const double* sos, int S, int CG, cudaStream_t st, Plan** out) 
             ld mx = 0.0L;
             for (auto x : m.a) mx = fmaxl(mx, fabsl(x));
             if (j >= 1 && mx < 1e-30L && p.jdecay > SOS_LOOK) p.jdecay = j;
+            if (j >= 1 && mx < 1e-20L && p.jpre > SOS_LOOK) p.jpre = j;
             m = mul(m, AT);
         }
     }
@@ -808,6 +1037,78 @@ int32_t launch_S(int mode, const Plan& plan, SosRun& R, size_t smem, unsigned gr
     }
 }
 
+std::atomic<int64_t> g_run_launches{0};
+
+template <int S, int MODE>
+int32_t launch_run_mode(const Plan& plan, SosRun& R, size_t smem_bytes, unsigned grid, cudaStream_t st) {
+    SosK<S> K;
+    for (int s = 0; s < S; ++s) {
+        const double* q = plan.sos.data() + 6 * s;
+        K.coef[s][0] = q[0]; K.coef[s][1] = q[1]; K.coef[s][2] = q[2];
+        K.coef[s][3] = q[4]; K.coef[s][4] = q[5];
+    }
+    memcpy(K.W, plan.W.data(), sizeof(double) * 2 * S * SOS_L);
+    auto kern = sos_run_kernel<S, MODE>;
+    static bool attr_done = false;               // per instantiation
+    if (!attr_done) {
+        ADN_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    kern<<<grid, SOS_NT, smem_bytes, st>>>(K, R);
+    count_launch();
+    g_run_launches.fetch_add(1);
+    ADN_CK(cudaGetLastError());
+    return ADN_OK;
+}
+
+template <int S>
+int32_t launch_run_S(int mode, const Plan& plan, SosRun& R, size_t smem, unsigned grid, cudaStream_t st) {
+    switch (mode) {
+        case MODE_FWD: return launch_run_mode<S, MODE_FWD>(plan, R, smem, grid, st);
+        case MODE_ENVF: return launch_run_mode<S, MODE_ENVF>(plan, R, smem, grid, st);
+        case MODE_ZPF: return launch_run_mode<S, MODE_ZPF>(plan, R, smem, grid, st);
+        default: return launch_run_mode<S, MODE_REV>(plan, R, smem, grid, st);
+    }
+}
+
+// the run kernel when the cascade forgets fast enough for its run-in to be cheap; false: use the
+// look-back kernel
+bool plan_runs(const Plan& plan, SosRun& R, int S, size_t* smem_out, unsigned* grid_out) {
+    static int enabled = -1, nbuf_env = 0;
+    if (enabled < 0) {
+        const char* e = getenv("ADN_SOS_RUN");           // development switch; the option rules
+        enabled = e ? atoi(e) : 1;
+        const char* b = getenv("ADN_SOS_NBUF");
+        nbuf_env = b ? atoi(b) : 2;
+        if (nbuf_env < 2) nbuf_env = 2;
+        if (nbuf_env > 3) nbuf_env = 3;
+    }
+    if (!enabled || !option(ADN_OPT_SCAN_RUNS) || S > 4 || R.dst == nullptr || plan.jpre > SOS_LOOK) return false;
+    const int CG = R.CG, D = 2 * S;
+    const int pad = CG < 16 ? CG : 0;
+    const size_t TS = (size_t)(SOS_NT / CG) * (SOS_L * CG + pad);
+    const size_t smem = ((size_t)nbuf_env * TS + (size_t)(SOS_NW + 2) * CG * D +
+                         (size_t)plan.n_staged * D * D) * 8;
+    int bps = (int)((227 * 1024) / (smem + 1024));
+    if (bps > SOS_RUN_BLOCKS) bps = SOS_RUN_BLOCKS;
+    if (bps < 1) return false;
+    const int64_t resident = (int64_t)ctx().sm_count * bps;
+    int64_t runs = resident / R.ngroups;                     // per channel group
+    if (runs < 1) runs = 1;
+    int64_t run_tiles = (R.ntt + runs - 1) / runs;
+    // the run-in may cost a quarter of a run at most
+    if (run_tiles < 4 * (int64_t)plan.jpre) run_tiles = 4 * (int64_t)plan.jpre;
+    runs = (R.ntt + run_tiles - 1) / run_tiles;
+    if (runs * R.ngroups * 2 < resident) return false;       // too short to fill the device this way
+    if (run_tiles > 0x3fffffff || runs * R.ngroups > 0x7fffffff) return false;
+    R.run_tiles = (int32_t)run_tiles;
+    R.pre_tiles = plan.jpre;
+    R.nbuf = nbuf_env;
+    *smem_out = smem;
+    *grid_out = (unsigned)(runs * R.ngroups);
+    return true;
+}
+
 // one sweep of the scan kernel
 int32_t run_scan(int mode, const double* sos, int S, const double* src, int64_t n, int64_t nx,
                  int edge, int32_t C, double* dst, int64_t out_skip, int64_t n_dst, int clamp,
@@ -842,6 +1143,18 @@ int32_t run_scan(int mode, const double* sos, int S, const double* src, int64_t 
     if (ntiles > 0x7fffffff) return fail(ADN_ERR_UNSUPPORTED, "sos scan: %lld tiles", (long long)ntiles);
     R.off_fix = plan->off_fix; R.off_wpow = plan->off_wpow; R.off_tile = plan->off_tile;
     R.n_staged = plan->n_staged;
+    {
+        size_t rsmem = 0;
+        unsigned rgrid = 0;
+        if (plan_runs(*plan, R, S, &rsmem, &rgrid)) {
+            switch (S) {
+                case 1: return launch_run_S<1>(mode, *plan, R, rsmem, rgrid, st);
+                case 2: return launch_run_S<2>(mode, *plan, R, rsmem, rgrid, st);
+                case 3: return launch_run_S<3>(mode, *plan, R, rsmem, rgrid, st);
+                case 4: return launch_run_S<4>(mode, *plan, R, rsmem, rgrid, st);
+            }
+        }
+    }
     // tile records: agg | incl, every word SOS_EMPTY until published
     const size_t recs = (size_t)ntiles * CG * D;
     DevBuf& tb = scratch(tile_slot);
@@ -867,6 +1180,8 @@ int32_t run_scan(int mode, const double* sos, int S, const double* src, int64_t 
 }
 
 }  // namespace
+
+int64_t scan_run_launches() { return g_run_launches.load(); }
 
 int32_t sosfilt_dev(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
                     int64_t nbefore, double* dst, int64_t n_dst, const double* zi, double* zf,

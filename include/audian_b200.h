@@ -68,7 +68,11 @@ extern "C" {
                                           sweeps: measured on B200 the scan kernel is not HBM
                                           bound enough for the saved traffic to pay for the
                                           extra launches (16 MiB chunks: 0.74 ms vs 0.25 ms) */
-#define ADN_OPT_COUNT               6
+#define ADN_OPT_SCAN_RUNS           6  /* 1 (default): SOS cascades that forget their state within
+                                          a few tiles are filtered by the run kernel (a block walks
+                                          along time, state handed on in shared memory, run-in from
+                                          zero state); 0: always the look-back kernel */
+#define ADN_OPT_COUNT               7
 
 #define ADN_WINDOW_HANN      0   /* periodic Hann == scipy get_window('hann', nfft) */
 #define ADN_DETREND_NONE     0
@@ -80,6 +84,7 @@ int32_t adn_shutdown(void);
 const char* adn_last_error(void);
 int32_t adn_version(void);
 int64_t adn_launch_count(void);        /* kernels launched by this library so far */
+int64_t adn_scan_run_count(void);      /* of these: launches of the SOS run kernel (ADN_OPT_SCAN_RUNS) */
 int32_t adn_synchronize(void);         /* waits for the library's stream */
 /* page-lock a host range so that the host-pointer entry points copy at full
  * PCIe rate (optional; plain pageable memory works too) */

@@ -232,6 +232,123 @@ def test_sosfilt_impulse_response():
     assert np.max(np.abs(got - ref)) <= 1e-12
 
 
+# ---------------------------------------------------------------- run kernel vs look-back kernel
+
+def _both_scan_kernels(call):
+    """call() once with the run kernel allowed and once with the look-back kernel only;
+    returns (result with runs, result with look-back, run-kernel launches of the first call)."""
+    _lib.set_option(_lib.ADN_OPT_SCAN_RUNS, 1)
+    chunk = _lib.get_option(_lib.ADN_OPT_CHUNK_BYTES)
+    _lib.set_option(_lib.ADN_OPT_CHUNK_BYTES, 1 << 30)      # the whole trace in one piece
+    try:
+        r0 = _lib.scan_run_count()
+        a = call()
+        nrun = _lib.scan_run_count() - r0
+        _lib.set_option(_lib.ADN_OPT_SCAN_RUNS, 0)
+        r1 = _lib.scan_run_count()
+        b = call()
+        assert _lib.scan_run_count() == r1, 'look-back only: the run kernel must not launch'
+    finally:
+        _lib.set_option(_lib.ADN_OPT_SCAN_RUNS, 1)
+        _lib.set_option(_lib.ADN_OPT_CHUNK_BYTES, chunk)
+    return a, b, nrun
+
+
+@pytest.mark.parametrize('C,n,filt', [
+    (8, 1200000, 'bp2'), (8, 600001, 'lp2'), (8, 1800123, 'bp4'), (64, 200000, 'bp2'),
+    (3, 2000003, 'bp2'), (1, 8000000, 'lp4'), (2, 4000000, 'hp2'), (24, 500000, 'bp3'),
+    (4, 3500000, 'bp4'), (16, 600000, 'lp2'),
+])
+def test_sosfilt_run_kernel(C, n, filt):
+    """Long traces take the run kernel (a block per run of tiles, run-in from zero state): same
+    result as the look-back kernel (to rounding) and as scipy (to the parity tolerance)."""
+    fs = 48000.
+    x = synth(5, n, C, fs, seed=C + n % 97)
+    sos = FILTERS[filt](fs)
+    nbefore = 37
+
+    def call():
+        got = np.empty((n - nbefore, C))
+        _lib.sosfilt(sos, x, got, nbefore)
+        return got
+
+    a, b, nrun = _both_scan_kernels(call)
+    assert nrun >= 1, 'this shape is meant to take the run kernel'
+    assert np.max(np.abs(a - b)) <= 1e-12*max(1.0, np.max(np.abs(b)))
+    ref = np.empty((n - nbefore, C))
+    orc.filter_process(sos, x, ref, nbefore)
+    assert_trace_close(a, ref, f'run kernel {filt} C={C}')
+    assert np.max(np.abs(a - ref)) <= 1e-11*max(1.0, np.max(np.abs(ref)))
+
+
+def test_sosfilt_run_kernel_streaming_state():
+    """zi/zf through the run kernel: chunks long enough for it, state carried between them."""
+    fs = 96000.
+    C, n = 4, 3000000
+    x = synth(0, n, C, fs, seed=15)
+    sos = FILTERS['bp2'](fs)
+    S = sos.shape[0]
+    ref = np.empty((n, C))
+    orc.filter_process(sos, x, ref, 0)
+    zi = np.zeros((C, S, 2))
+    got = np.empty((n, C))
+    r0 = _lib.scan_run_count()
+    pos = 0
+    old = _lib.get_option(_lib.ADN_OPT_CHUNK_BYTES)
+    _lib.set_option(_lib.ADN_OPT_CHUNK_BYTES, 1 << 30)
+    try:
+        for chunk in (1200000, 1000001, n):
+            stop = min(n, pos + chunk)
+            _lib.sosfilt(sos, x[pos:stop], got[pos:stop], 0, zi=zi)
+            pos = stop
+    finally:
+        _lib.set_option(_lib.ADN_OPT_CHUNK_BYTES, old)
+    assert _lib.scan_run_count() - r0 >= 1
+    assert_trace_close(got, ref, 'streamed through the run kernel')
+    assert np.max(np.abs(got - ref)) <= 1e-11
+    for c in range(C):
+        _, zf = sosfilt(sos, x[:, c], zi=np.zeros((S, 2)))
+        assert np.max(np.abs(zi[c] - zf)) <= 1e-9*max(1.0, np.max(np.abs(zf)))
+
+
+def test_sosfilt_slow_cascade_keeps_look_back():
+    """A cascade that needs tens of tiles to forget its state is not given a run-in."""
+    fs = 96000.
+    n, C = 800000, 8
+    x = synth(1, n, C, fs, seed=3) + 0.25            # offset: large slowly decaying state
+    sos = FILTERS['hp_low'](fs)
+    r0 = _lib.scan_run_count()
+    got = np.empty((n, C))
+    _lib.sosfilt(sos, x, got, 0)
+    assert _lib.scan_run_count() == r0
+    ref = np.empty((n, C))
+    orc.filter_process(sos, x, ref, 0)
+    assert_trace_close(got, ref, 'hp_low')
+
+
+@pytest.mark.parametrize('C,n,order,hp', [(8, 1500000, 2, 0), (64, 300000, 2, 0), (2, 5000000, 4, 0),
+                                          (3, 1200000, 2, 50.), (8, 700001, 4, 20.)])
+def test_envelope_run_kernel(C, n, order, hp):
+    fs = 48000.
+    x = synth(9, n, C, fs, seed=C + 200)
+    sos = orc.envelope_design(fs, 500., hp, order)
+    nbefore = 11
+
+    def call():
+        got = np.empty((n - nbefore, C))
+        _lib.envelope(sos, x, got, nbefore, hp == 0)
+        return got
+
+    a, b, nrun = _both_scan_kernels(call)
+    if hp == 0:
+        assert nrun >= 2, 'both sweeps are meant to take the run kernel'
+    assert np.max(np.abs(a - b)) <= 1e-11*max(1.0, np.max(np.abs(b)))
+    ref = np.empty((n - nbefore, C))
+    orc.envelope_process(sos, x, ref, nbefore, hp)
+    assert_trace_close(a, ref, f'envelope run kernel C={C} order={order} hp={hp}')
+    assert np.max(np.abs(a - ref)) <= 1e-10*max(1.0, np.max(np.abs(ref)))
+
+
 # ---------------------------------------------------------------- envelope
 
 @pytest.mark.parametrize('C', [1, 2, 3, 8, 32, 64])
