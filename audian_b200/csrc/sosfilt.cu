@@ -203,28 +203,45 @@ __device__ __forceinline__ bool sos_load_tile(const SosRun& R, double* tile_s, i
         }
     } else
     if (ADN_EXT(MODE) && !xform) {
+        // element by element, in batches whose loads are all issued before the first use (a run
+        // whose first tile is an edge tile would otherwise start some 30 load latencies late)
         const int64_t nx = R.nx, edge = R.edge;
         const int total = T * Cw;
-        for (int q = tid; q < total; q += SOS_NT) {
-            int row = q / Cw, col = q - row * Cw;
-            int64_t e = t0 + row;
-            double val = 0.0;
-            if (e < R.n) {
-                const double* xc = R.src + c0 + col;
-                if (e < edge) {
-                    double r0 = pre_x<MODE>(__ldg(xc));
-                    double rk = pre_x<MODE>(__ldg(xc + (edge - e) * C));
-                    val = 2.0 * r0 - rk;
-                } else if (e < edge + nx) {
-                    val = pre_x<MODE>(__ldg(xc + (e - edge) * C));
-                } else {
-                    int64_t k = e - edge - nx;
-                    double r1 = pre_x<MODE>(__ldg(xc + (nx - 1) * C));
-                    double rk = pre_x<MODE>(__ldg(xc + (nx - 2 - k) * C));
-                    val = 2.0 * r1 - rk;
+        constexpr int UB = 8;
+        for (int q0 = tid; q0 < total; q0 += SOS_NT * UB) {
+            double va[UB], vb[UB];
+            int kind[UB], sidx[UB];          // 0: beyond the end, 1: plain row, 2: reflected, -1: no element
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int q = q0 + u * SOS_NT;
+                kind[u] = -1;
+                va[u] = vb[u] = 0.0;
+                sidx[u] = 0;
+                if (q < total) {
+                    const int row = q / Cw, col = q - row * Cw;
+                    const int64_t e = t0 + row;
+                    sidx[u] = (row / SOS_L) * GS + (row % SOS_L) * Cw + col;
+                    const double* xc = R.src + c0 + col;
+                    kind[u] = 0;
+                    if (e < R.n) {
+                        int64_t ra, rb = -1;
+                        if (e < edge) { ra = 0; rb = edge - e; }
+                        else if (e < edge + nx) { ra = e - edge; }
+                        else { ra = nx - 1; rb = nx - 2 - (e - edge - nx); }
+                        va[u] = __ldg(xc + ra * C);
+                        kind[u] = 1;
+                        if (rb >= 0) { vb[u] = __ldg(xc + rb * C); kind[u] = 2; }
+                    }
                 }
             }
-            tile_s[(row / SOS_L) * GS + (row % SOS_L) * Cw + col] = val;
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                if (kind[u] < 0) continue;
+                double val = 0.0;
+                if (kind[u] == 1) val = pre_x<MODE>(va[u]);
+                else if (kind[u] == 2) val = 2.0 * pre_x<MODE>(va[u]) - pre_x<MODE>(vb[u]);
+                tile_s[sidx[u]] = val;
+            }
         }
     } else {
         const int gw = R.vec_in ? 2 : 1;                 // doubles per granule

@@ -389,11 +389,13 @@ def run_ours(args):
                 'ms_per_launch': ms/launches_per_step, 'launches_per_step': launches_per_step,
                 'share_of_step': ms/launches_per_step/(t_f + t_s + t_e)}
 
+    # which scan kernel ran: the run kernel (cascades that forget fast) or the look-back kernel
+    scan_name = 'sos_run_kernel' if _lib.scan_run_count() > 0 else 'sos_scan_kernel'
     roofs = {
-        'filter': roof('filter', t_f, n, 1, 'sos_scan_kernel<S=2,FWD>'),
+        'filter': roof('filter', t_f, n, 1, scan_name + '<S=2,FWD>'),
         'spectrogram': roof('spectrogram', t_s, n, 1, 'spectrogram_ring_kernel<10>'),
         'envelope': roof('envelope_sweep', t_e, n + 2*edge, 2,
-                         'sos_scan_kernel<S=1,ENVF> and <S=1,REV>: the two sweeps of the envelope, each'),
+                         scan_name + '<S=1,ENVF> and <S=1,REV>: the two sweeps of the envelope, each'),
     }
     traffic_file = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.isfile(traffic_file):
