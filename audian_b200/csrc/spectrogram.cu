@@ -581,6 +581,15 @@ constexpr int SR_MAXNT = 128;
 #define SR_WIN_SMEM 1
 #endif
 constexpr int SR_PF = 8;            // 16-byte vectors in flight per thread and step
+// SR_ASYNC: the rows of the next step go straight into the ring with 8-byte cp.async, issued as
+// soon as every warp holds its frame of this step in registers (one barrier after the frame
+// loads): the copies land while the transforms run and no register stages them.  Needs one
+// item per warp and step (the launcher sees to it).  Measured on B200 (nfft 1024, hop 512):
+// 8 ch 178 us against 172 us with register staging, 1 ch 155 / 145 us, 64 ch 396 / 407 us: the
+// barrier in the middle of the step costs what the hidden load latency gains, so off.
+#ifndef SR_ASYNC
+#define SR_ASYNC 0
+#endif
 
 struct SpecRArgs {
     const double* src;
@@ -654,6 +663,7 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
     const int64_t gstep = (int64_t)DR * C, gchunk = (int64_t)CH * C;
     const double* gnext = gp0 + (int64_t)(span0 + r0) * C;   // this thread's first vector of the next chunk
     const int64_t rows_run = P.nrows - f0 * hop;             // source rows from the start of the run
+    const int rmax_async = (int)min((int64_t)0x3fffffff, rows_run - 1);
     auto put = [&](double2 v, int pos) {
         pos &= RM;
         if (W == 1) {
@@ -737,14 +747,20 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
             const int it = (warp + NW * iter) * FPW + sub;
             int fi = it >> LW, ci = it & (W - 1);
             const bool live = it < nitems && s * FSTEP + fi < FRa;
-            if (!__any_sync(0xffffffffu, live)) continue;
-            const bool last_iter = more && iter == niter - 1;
+            const bool any_live = __any_sync(0xffffffffu, live);
+            if (!SR_ASYNC && !any_live) continue;
+            const bool last_iter = !SR_ASYNC && more && iter == niter - 1;
             if (!live) { fi = 0; ci = 0; }
             const int start = ws + fi * hop + 2 * t;
             const double* xr = xs + ci * RS;
 
             // ---- load, window; the frame sum for the mean goes on in the background
             double2 a[16];
+            if (SR_ASYNC && !any_live) {
+                // no frame for this warp: it only takes part in the hand-over of the ring
+#pragma unroll
+                for (int p = 0; p < 16; ++p) a[p] = make_double2(0.0, 0.0);
+            } else
             if (T == 32 && rot_ok) {
                 const double* xb = xr + 2 * t;
                 switch (((ws + fi * hop) >> 6) & 15) {
@@ -758,6 +774,21 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
 #pragma unroll
                 for (int p = 0; p < 16; ++p)
                     a[p] = *reinterpret_cast<const double2*>(xr + ((start + 2 * T * p) & RM));
+            }
+            if (SR_ASYNC) {
+                // every warp holds its frame: the oldest rows of the ring are free for the chunk
+                // of the next step
+                __syncthreads();
+                if (more) {
+                    const int total = CH << LW;                      // doubles of the chunk (CH rows x W)
+                    for (int e = tid; e < total; e += NT) {
+                        const int r = e >> LW, ch = e & (W - 1);
+                        const double* g = P.src + ((f0 * hop + min(nrow + r, rmax_async)) * (int64_t)C + c0 + ch);
+                        cp_async8(xs + ch * RS + ((npos + r) & RM), g);
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                }
+                if (!any_live) continue;
             }
             double sm = 0.0;
             {
@@ -937,6 +968,12 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
             __syncwarp();
         }
 
+        if (SR_ASYNC) {
+            if (more) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncthreads();
+            }
+        } else
         if (more) {
             if (!loaded) issue_loads();     // warps without an item in the last iteration
             __syncthreads();            // every warp is done with the rows the chunk replaces
@@ -987,6 +1024,7 @@ int32_t launch_ring_kernel(SpecRArgs& P, int64_t nf, cudaStream_t st) {
         if (smem <= limit || P.FSTEP == 1) break;
     }
     if (smem > limit) return ADN_ERR_UNSUPPORTED;
+    if (SR_ASYNC && P.FSTEP * P.CB > items) return ADN_ERR_UNSUPPORTED;    // one item per warp and step
     auto kern = spectrogram_ring_kernel<LOGN, DB>;
     static bool attr_done = false;
     if (!attr_done) {
