@@ -351,10 +351,10 @@ __device__ __forceinline__ void sos_store_tile(const SosRun& R, const double* ti
 
 // ---- pass B of one thread: the exact DF2T recurrence over its SOS_L samples from state z,
 // outputs written in place; z leaves as the state after the last sample
-template <int S, int MODE>
-__device__ __forceinline__ void sos_recurrence(const SosK<S>& K, const SosRun& R, double* xp, int Cw,
-                                               double (&z)[2 * S], bool xform, bool want_state,
-                                               int ilast_in, int chan) {
+template <int S, int MODE, bool xform>
+__device__ __forceinline__ void sos_recurrence_x(const SosK<S>& K, const SosRun& R, double* xp, int Cw,
+                                                 double (&z)[2 * S], bool want_state,
+                                                 int ilast_in, int chan) {
     constexpr int D = 2 * S;
         if (!want_state && S > 4) {
             const double* xr = xp;
@@ -417,6 +417,35 @@ __device__ __forceinline__ void sos_recurrence(const SosK<S>& K, const SosRun& R
                 }
             }
         }
+}
+
+// the rectification flag of a tile is block-uniform: one branch per tile instead of a select per
+// sample (only the two edge tiles of an envelope sweep take the second copy)
+template <int S, int MODE>
+__device__ __forceinline__ void sos_recurrence(const SosK<S>& K, const SosRun& R, double* xp, int Cw,
+                                               double (&z)[2 * S], bool xform, bool want_state,
+                                               int ilast_in, int chan) {
+    if (MODE == MODE_ENVF && !xform) sos_recurrence_x<S, MODE, false>(K, R, xp, Cw, z, want_state, ilast_in, chan);
+    else sos_recurrence_x<S, MODE, true>(K, R, xp, Cw, z, want_state, ilast_in, chan);
+}
+
+// pass A of one thread: zero-state end state of its SOS_L samples (dot products against K.W)
+template <int S, int MODE, bool xform>
+__device__ __forceinline__ void sos_pass_a_x(const SosK<S>& K, const double* xp, int Cw, double (&v)[2 * S]) {
+    constexpr int D = 2 * S;
+#pragma unroll
+    for (int i = 0; i < SOS_L; ++i) {
+        double x = xp[i * Cw];
+        if (MODE == MODE_ENVF && xform) x = pre_x<MODE>(x);
+#pragma unroll
+        for (int d = 0; d < D; ++d) v[d] = fma(K.W[d][i], x, v[d]);
+    }
+}
+template <int S, int MODE>
+__device__ __forceinline__ void sos_pass_a(const SosK<S>& K, const double* xp, int Cw, double (&v)[2 * S],
+                                           bool xform) {
+    if (MODE == MODE_ENVF && !xform) sos_pass_a_x<S, MODE, false>(K, xp, Cw, v);
+    else sos_pass_a_x<S, MODE, true>(K, xp, Cw, v);
 }
 
 template <int S, int MODE>
@@ -489,13 +518,7 @@ sos_scan_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRu
 #pragma unroll
     for (int d = 0; d < D; ++d) v[d] = 0.0;
     if (chan_ok) {
-#pragma unroll
-        for (int i = 0; i < SOS_L; ++i) {
-            double x = xp[i * Cw];
-            if (MODE == MODE_ENVF && xform) x = pre_x<MODE>(x);
-#pragma unroll
-            for (int d = 0; d < D; ++d) v[d] = fma(K.W[d][i], x, v[d]);
-        }
+        sos_pass_a<S, MODE>(K, xp, Cw, v, xform);
     }
 
     // ---------------------------------------------------------------- warp scan over gl
@@ -768,13 +791,7 @@ sos_run_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRun
 #pragma unroll
         for (int d = 0; d < D; ++d) v[d] = 0.0;
         if (chan_ok) {
-#pragma unroll
-            for (int i = 0; i < SOS_L; ++i) {
-                double x = xp[i * Cw];
-                if (MODE == MODE_ENVF && xform) x = pre_x<MODE>(x);
-#pragma unroll
-                for (int d = 0; d < D; ++d) v[d] = fma(K.W[d][i], x, v[d]);
-            }
+            sos_pass_a<S, MODE>(K, xp, Cw, v, xform);
         }
         // ------------------------------------------------------------ warp scan over gl
         {
