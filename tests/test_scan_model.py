@@ -168,3 +168,51 @@ def test_sosfiltfilt_edge():
                             (2, (100., 500.), 'bandpass'), (3, 2000., 'highpass')]:
         sos = butter(order, wn, kind, fs=48000., output='sos')
         assert _lib.sosfiltfilt_edge(sos) == sosfiltfilt_edge(sos)
+
+
+# ---------------------------------------------------------------- run kernel: run-in from zero state
+
+def run_in_tiles(sos, T, tol=1e-20, look=32):
+    """Plan::jpre of sosfilt.cu: tiles after which max|A^(T j)| < tol, or None."""
+    for j in range(1, look + 1):
+        if np.max(np.abs(_lib.sos_state_space(sos, T*j)[2])) < tol:
+            return j
+    return None
+
+
+@pytest.mark.parametrize('design', [
+    lambda fs: butter(2, (1000., 15000.), 'bandpass', fs=fs, output='sos'),
+    lambda fs: butter(4, (1000., 15000.), 'bandpass', fs=fs, output='sos'),
+    lambda fs: butter(2, 500., 'lowpass', fs=fs, output='sos'),
+    lambda fs: butter(4, 500., 'lowpass', fs=fs, output='sos'),
+    lambda fs: butter(2, 0.02*fs, 'highpass', fs=fs, output='sos'),
+])
+@pytest.mark.parametrize('CG', [1, 8])
+def test_run_in_from_zero_state_is_exact_to_rounding(design, CG):
+    """sos_run_kernel starts a run `jpre` tiles early from ZERO state instead of taking the true
+    state from its predecessors: with the kernel's criterion (max|A^(T jpre)| < 1e-20) what it
+    stores equals sosfilt over the whole trace to rounding, even with a DC offset that loads the
+    states (worst case for a high-pass)."""
+    fs = 48000.
+    sos = design(fs)
+    T = (NT//CG)*L
+    jpre = run_in_tiles(sos, T)
+    assert jpre is not None and jpre <= 8, 'the audio-rate designs of the bench take the run kernel'
+    rng = np.random.default_rng(CG)
+    run_tiles = 4*jpre
+    n = (jpre + run_tiles + 3)*T
+    x = rng.standard_normal(n)*0.1 + 0.7
+    ref = sosfilt(sos, x)
+    start = 3*T + jpre*T                    # first stored row of the run
+    y, _ = df2t_chunk(sos, x[start - jpre*T:start + run_tiles*T], np.zeros(2*sos.shape[0]))
+    got = y[jpre*T:]
+    # two rounding trajectories of a narrow low-pass differ by ~1e-14 before they lock in; a
+    # run-in that is too short would leave 1e-20^(fraction) of an O(1) state, orders above this
+    assert np.max(np.abs(got - ref[start:start + run_tiles*T])) <= 1e-12*max(1.0, np.max(np.abs(ref)))
+
+
+def test_slow_cascade_gets_no_run_in():
+    """A 30-Hz high-pass at 96 kHz needs far more than the look-back window to forget: the host
+    logic must keep the look-back kernel for it (Plan::jpre > SOS_LOOK)."""
+    sos = butter(2, 0.0006*96000., 'highpass', fs=96000., output='sos')
+    assert run_in_tiles(sos, (NT//8)*L) is None
