@@ -20,7 +20,10 @@ namespace adn {
 namespace {
 
 constexpr int MM_THREADS = 256;
-constexpr int MM_UNROLL = 4;
+// independent 16-byte loads in flight per thread: 8 for full-size blocks and the warp kernel
+// (measured on B200: config 4 73.8 -> 75.6 %, 64 channels 82 -> 85 %, one channel 71 -> 81 % of the
+// HBM roofline), 4 where a block only has a few iterations (step 1920 x 8 channels: 65 against 63 %)
+constexpr int MM_UNROLL = 8;
 
 struct Best {          // running min or max with the row it came from (-1 = empty)
     double v;
@@ -63,10 +66,13 @@ struct Fast {
         mx = __longlong_as_double(0xfff0000000000000ll);      // -inf
         special = 0.0; nanv = 0.0; zrow = -1; nrow = -1; any = -1;
     }
+    // compare-and-select instead of fmin / fmax (a NaN fails both compares and is skipped just
+    // the same; which of two equal zeros stays does not matter, resolve() overrides it): three
+    // instructions per update where fmin / fmax cost eight on sm_100, which made the kernels
+    // issue bound.  `any` (>= 0: the thread saw an element) is set once after the loops.
     __device__ __forceinline__ void feed(double v, int32_t row) {
-        mn = fmin(mn, v);
-        mx = fmax(mx, v);
-        any = row;
+        mn = v < mn ? v : mn;
+        mx = v > mx ? v : mx;
         if (!(fabs(v) > 0.0)) {                                // zero or NaN: rare
             if (v != v) { nanv = v; nrow = row; }
             else { special = v; zrow = row; }
@@ -104,7 +110,7 @@ __device__ __forceinline__ void unpack(double2 v, double* e) { e[0] = v.x; e[1] 
 // One block reduces rows [row0, row1) of one segment (all channels) to one
 // (min, max) pair per channel.  active = threads whose flat stride keeps their
 // channel fixed: (active*VEC) % C == 0.
-template <int VEC>
+template <int VEC, int UN>
 __global__ void __launch_bounds__(MM_THREADS)
 minmax_split_kernel(const double* __restrict__ src, int64_t n, int32_t C, int64_t step,
                     int64_t rows_per_split, int32_t nsplit, int32_t active,
@@ -141,20 +147,20 @@ minmax_split_kernel(const double* __restrict__ src, int64_t n, int32_t C, int64_
 #pragma unroll
         for (int e = 0; e < VEC; ++e) r[e] = (tid * VEC + e) / C;
         int64_t u = tid;
-        // main loop: MM_UNROLL independent loads in flight per thread
-        for (; u + (int64_t)(MM_UNROLL - 1) * active < nunits; u += (int64_t)MM_UNROLL * active) {
-            V v[MM_UNROLL];
+        // main loop: UN independent loads in flight per thread
+        for (; u + (int64_t)(UN - 1) * active < nunits; u += (int64_t)UN * active) {
+            V v[UN];
 #pragma unroll
-            for (int k = 0; k < MM_UNROLL; ++k) v[k] = __ldcs(base + u + (int64_t)k * active);
+            for (int k = 0; k < UN; ++k) v[k] = __ldcs(base + u + (int64_t)k * active);
 #pragma unroll
-            for (int k = 0; k < MM_UNROLL; ++k) {
+            for (int k = 0; k < UN; ++k) {
                 double el[VEC];
                 unpack(v[k], el);
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) acc[e].feed(el[e], r[e] + k * rpi);
             }
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) r[e] += MM_UNROLL * rpi;
+            for (int e = 0; e < VEC; ++e) r[e] += UN * rpi;
         }
         for (; u < nunits; u += active) {
             double el[VEC];
@@ -162,9 +168,15 @@ minmax_split_kernel(const double* __restrict__ src, int64_t n, int32_t C, int64_
 #pragma unroll
             for (int e = 0; e < VEC; ++e) { acc[e].feed(el[e], r[e]); r[e] += rpi; }
         }
+        if (tid < nunits) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[e].any = r[e] - rpi;        // the last row fed
+        }
         // single channel read as pairs of rows: an odd row count leaves one element over
-        if (VEC == 2 && (nflat & 1) && tid == (int)(nunits % active))
+        if (VEC == 2 && (nflat & 1) && tid == (int)(nunits % active)) {
             acc[0].feed(src[row0 * C + nflat - 1], (int32_t)(nflat - 1));
+            acc[0].any = (int32_t)(nflat - 1);
+        }
     }
 #pragma unroll
     for (int e = 0; e < VEC; ++e) acc[e].resolve(mn[e], mx[e]);
@@ -304,8 +316,14 @@ minmax_warp_kernel(const double* __restrict__ src, int64_t n, int32_t C, int64_t
 #pragma unroll
         for (int e = 0; e < VEC; ++e) { acc[e].feed(el[e], r[e]); r[e] += rpi; }
     }
-    if (VEC == 2 && (nflat & 1) && lane == (int)(nunits & 31))
+    if (lane < nunits) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[e].any = r[e] - rpi;            // the last row fed
+    }
+    if (VEC == 2 && (nflat & 1) && lane == (int)(nunits & 31)) {
         acc[0].feed(src[seg0 * C + nflat - 1], (int32_t)(nflat - 1));
+        acc[0].any = (int32_t)(nflat - 1);
+    }
     Best mn[VEC], mx[VEC];
 #pragma unroll
     for (int e = 0; e < VEC; ++e) acc[e].resolve(mn[e], mx[e]);
@@ -465,10 +483,16 @@ int32_t minmax_dev(const double* src, int64_t n, int32_t C, int64_t step, double
         part = sb.as<double>();
     }
     unsigned grid = (unsigned)(nseg * nsplit);
-    if (vec2)
-        minmax_split_kernel<2><<<grid, MM_THREADS, 0, st>>>(src, n, C, step, rows, nsplit, active, dst, part);
+    // deep unrolling pays when a thread has at least a few rounds of it
+    const bool deep = rows * (int64_t)C >= (int64_t)4 * MM_THREADS * VEC * MM_UNROLL;
+    if (vec2 && deep)
+        minmax_split_kernel<2, MM_UNROLL><<<grid, MM_THREADS, 0, st>>>(src, n, C, step, rows, nsplit, active, dst, part);
+    else if (vec2)
+        minmax_split_kernel<2, 4><<<grid, MM_THREADS, 0, st>>>(src, n, C, step, rows, nsplit, active, dst, part);
+    else if (deep)
+        minmax_split_kernel<1, MM_UNROLL><<<grid, MM_THREADS, 0, st>>>(src, n, C, step, rows, nsplit, active, dst, part);
     else
-        minmax_split_kernel<1><<<grid, MM_THREADS, 0, st>>>(src, n, C, step, rows, nsplit, active, dst, part);
+        minmax_split_kernel<1, 4><<<grid, MM_THREADS, 0, st>>>(src, n, C, step, rows, nsplit, active, dst, part);
     count_launch();
     ADN_CK(cudaGetLastError());
     if (nsplit > 1) {
