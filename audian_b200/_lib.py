@@ -29,6 +29,7 @@ ADN_OPT_RESIDENT_MIN_BYTES = 3
 ADN_OPT_RESIDENT_CAP_BYTES = 4
 ADN_OPT_ENVELOPE_CHUNK_BYTES = 5
 ADN_OPT_SCAN_RUNS = 6
+ADN_OPT_ZERO_PHASE_ONEPASS = 7
 ADN_WINDOW_HANN = 0
 ADN_DETREND_NONE = 0
 ADN_DETREND_CONSTANT = 1
@@ -46,11 +47,15 @@ SIGNATURES = {
     'adn_version': (_i32, []),
     'adn_launch_count': (_i64, []),
     'adn_scan_run_count': (_i64, []),
+    'adn_zero_phase_count': (_i64, []),
     'adn_synchronize': (_i32, []),
     'adn_host_register': (_i32, [_dp, _i64]),
     'adn_host_unregister': (_i32, [_dp]),
     'adn_set_option': (_i32, [_i32, _i64]),
     'adn_get_option': (_i64, [_i32]),
+    'adn_mirror_create': (_i32, [C.POINTER(_i64)]),
+    'adn_mirror_release': (_i32, [_i64]),
+    'adn_mirror_invalidate': (_i32, [_i64]),
     'adn_invalidate': (_i32, [_dp, _i64]),
     'adn_resident_hits': (_i64, []),
     'adn_transfer_bytes': (_i32, [C.POINTER(_i64), C.POINTER(_i64)]),
@@ -61,6 +66,20 @@ SIGNATURES = {
                                    _dp, _i64, _i32, C.POINTER(_i64)]),
     'adn_decibel_f64': (_i32, [_dp, _i64, _f64, _f64, _dp]),
     'adn_sosfiltfilt_f64': (_i32, [_dp, _i32, _dp, _i64, _i32, _dp, _i64]),
+    'adn_minmax_f64_m': (_i32, [_dp, _i64, _i32, _i64, _dp, _i64]),
+    'adn_sosfilt_f64_m': (_i32, [_dp, _i32, _dp, _i64, _i32, _i64, _dp, _i64, _dp, _i64, _i64]),
+    'adn_envelope_f64_m': (_i32, [_dp, _i32, _dp, _i64, _i32, _i64, _dp, _i64, _i32, _i64, _i64]),
+    'adn_spectrogram_f64_m': (_i32, [_dp, _i64, _i32, _f64, _i32, _i32, _i32, _i32,
+                                     _dp, _i64, _i32, C.POINTER(_i64), _i64, _i64]),
+    'adn_spec_image_db_f64_m': (_i32, [_dp, _i64, _i32, _i32, _i32, _dp, _i64]),
+    'adn_minmax_channel_f64_m': (_i32, [_dp, _i64, _i32, _i32, _i64, _dp, _i64]),
+    'adn_unwrap_f64': (_i32, [_dp, _i64, _i32, _f64, _i32]),
+    'adn_unwrap_f64_dev': (_i32, [_dp, _i64, _i32, _f64, _i32, _dp, _dp]),
+    'adn_play_region_f64_m': (_i32, [_dp, _i64, _i32, _dp, _i32, _dp, _i32, _f64, _f64, _dp, _i32, _i64,
+                                     _dp, _i64]),
+    'adn_play_region_f64_dev': (_i32, [_dp, _i64, _i32, _dp, _i32, _dp, _i32, _f64, _f64, _dp, _i32, _i64,
+                                       _dp, _dp]),
+    'adn_mean_power_db_f64_m': (_i32, [_dp, _i64, _i32, _i32, _i32, _i64, _i64, _f64, _dp, _i64]),
     'adn_sosfiltfilt_f64_dev': (_i32, [_dp, _i32, _dp, _i64, _i32, _dp, _i64, _dp]),
     'adn_spec_image_db_f64': (_i32, [_dp, _i64, _i32, _i32, _i32, _dp]),
     'adn_mean_power_db_f64': (_i32, [_dp, _i64, _i32, _i32, _i32, _i64, _i64, _f64, _dp]),
@@ -151,6 +170,38 @@ def sos_array(sos):
     return sos, sos.shape[0]
 
 
+# ---------------------------------------------------------------- mirrors
+
+class Mirror(object):
+    """Device copy of (part of) one host buffer, handed explicitly from the call that
+    fills the buffer (`dst_mirror=`) to the calls that read it (`src_mirror=`).  The
+    owner invalidates it whenever the host buffer changes by other means."""
+
+    def __init__(self):
+        h = _i64(0)
+        check(lib().adn_mirror_create(C.byref(h)))
+        self.handle = h.value
+
+    def invalidate(self):
+        if self.handle:
+            lib().adn_mirror_invalidate(self.handle)
+
+    def release(self):
+        if self.handle and _lib is not None:
+            _lib.adn_mirror_release(self.handle)
+        self.handle = 0
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+def _h(mirror):
+    return 0 if mirror is None else int(mirror.handle)
+
+
 # ---------------------------------------------------------------- host arrays
 
 def init(device=-1):
@@ -166,7 +217,12 @@ def scan_run_count():
     return int(lib().adn_scan_run_count())
 
 
-def minmax(src, step, dst=None):
+def zero_phase_count():
+    """Launches of the one-pass zero-phase kernel so far (csrc/zerophase.cu)."""
+    return int(lib().adn_zero_phase_count())
+
+
+def minmax(src, step, dst=None, src_mirror=None):
     """dst (2*ceil(n/step), C): rows 2j / 2j+1 = min / max of source rows
     [j*step, (j+1)*step).  compresseddata.py:49-52,97-100; traceitem.py:58-61."""
     src = _f64_array(src, 'src')
@@ -179,11 +235,61 @@ def minmax(src, step, dst=None):
     dst = _f64_array(dst, 'dst')
     if dst.shape != (2*nseg, ch):
         raise ValueError(f'dst must have shape {(2*nseg, ch)}')
-    check(lib().adn_minmax_f64(ptr(src), n, ch, int(step), ptr(dst)))
+    check(lib().adn_minmax_f64_m(ptr(src), n, ch, int(step), ptr(dst), _h(src_mirror)))
     return dst
 
 
-def sosfilt(sos, src, dst, nbefore=0, zi=None):
+def minmax_channel(src, channel, step, src_mirror=None):
+    """Interleaved min / max of `step` rows of one column of a (frames, channels) trace:
+    what TraceItem.update_plot draws (traceitem.py:58-61).  Returns (2*ceil(n/step),)."""
+    src = _f64_array(src, 'src')
+    if src.ndim != 2:
+        raise ValueError('src must be (frames, channels)')
+    n, ch = src.shape
+    nseg = (n + step - 1)//step if n > 0 else 0
+    dst = np.empty(2*nseg)
+    check(lib().adn_minmax_channel_f64_m(ptr(src), n, ch, int(channel), int(step), ptr(dst),
+                                         _h(src_mirror)))
+    return dst
+
+
+def unwrap(data, thresh, clips=False):
+    """audioio's unwrap(data, thresh, clips) in place on a (frames, channels) array
+    (the loader option of Data.open, data.py:180)."""
+    data = _f64_array(data, 'data')
+    if data.ndim == 1:
+        n, ch = data.shape[0], 1
+    else:
+        n, ch = data.shape
+    check(lib().adn_unwrap_f64(ptr(data), n, ch, float(thresh), 1 if clips else 0))
+    return data
+
+
+def play_region(src, left, right, rate, het_freq=0.0, cutoff=20000.0, src_mirror=None):
+    """(playdata, rate) as DataBrowser.play_region computes them before the fade
+    (databrowser.py:1711-1728): means over the channel groups `left` / `right` (right may be
+    empty: one column), heterodyne + butter(2, cutoff) sosfiltfilt + [::nstep] if het_freq > 0."""
+    from scipy.signal import butter
+    src = _f64_array(src, 'src')
+    n, ch = src.shape
+    left = np.ascontiguousarray(left, dtype=np.int32)
+    right = np.ascontiguousarray(right, dtype=np.int32)
+    ncols = 2 if right.size > 0 else 1
+    sos, S, nstep = None, 0, 1
+    if het_freq > 0:
+        sos = np.ascontiguousarray(butter(2, cutoff, 'low', output='sos', fs=rate))
+        S = sos.shape[0]
+        nstep = max(1, int(np.round(rate/(2*cutoff))))
+    out = np.empty(((n + nstep - 1)//nstep, ncols))
+    check(lib().adn_play_region_f64_m(ptr(src), n, ch, left.ctypes.data, left.size,
+                                      right.ctypes.data if right.size else None, right.size,
+                                      float(rate), float(het_freq),
+                                      None if sos is None else sos.ctypes.data, S, nstep,
+                                      ptr(out), _h(src_mirror)))
+    return out, rate/nstep
+
+
+def sosfilt(sos, src, dst, nbefore=0, zi=None, src_mirror=None, dst_mirror=None):
     """dst[i, c] = scipy.signal.sosfilt(sos, src[:, c])[nbefore + i].
     zi: None or (C, S, 2) float64, updated in place.  bufferedfilter.py:31-36."""
     src = _f64_array(src, 'src')
@@ -195,14 +301,15 @@ def sosfilt(sos, src, dst, nbefore=0, zi=None):
         zi = _f64_array(zi, 'zi')
         if zi.shape != (src.shape[1], S, 2):
             raise ValueError('zi must have shape (channels, sections, 2)')
-    check(lib().adn_sosfilt_f64(None if sos is None else sos.ctypes.data, S,
-                                ptr(src), src.shape[0], src.shape[1], int(nbefore),
-                                ptr(dst), dst.shape[0],
-                                None if zi is None else zi.ctypes.data))
+    check(lib().adn_sosfilt_f64_m(None if sos is None else sos.ctypes.data, S,
+                                  ptr(src), src.shape[0], src.shape[1], int(nbefore),
+                                  ptr(dst), dst.shape[0],
+                                  None if zi is None else zi.ctypes.data,
+                                  _h(src_mirror), _h(dst_mirror)))
     return dst
 
 
-def envelope(sos, src, dst, nbefore=0, clamp_negative=True):
+def envelope(sos, src, dst, nbefore=0, clamp_negative=True, src_mirror=None, dst_mirror=None):
     """dst = sosfiltfilt(sos, (pi/2)|src|, axis=0)[nbefore:], negatives clamped.
     bufferedenvelope.py:34-41."""
     src = _f64_array(src, 'src')
@@ -210,9 +317,10 @@ def envelope(sos, src, dst, nbefore=0, clamp_negative=True):
     sos, S = sos_array(sos)
     if src.ndim != 2 or dst.ndim != 2 or src.shape[1] != dst.shape[1]:
         raise ValueError('src and dst must be (frames, channels) with equal channels')
-    check(lib().adn_envelope_f64(None if sos is None else sos.ctypes.data, S,
-                                 ptr(src), src.shape[0], src.shape[1], int(nbefore),
-                                 ptr(dst), dst.shape[0], 1 if clamp_negative else 0))
+    check(lib().adn_envelope_f64_m(None if sos is None else sos.ctypes.data, S,
+                                   ptr(src), src.shape[0], src.shape[1], int(nbefore),
+                                   ptr(dst), dst.shape[0], 1 if clamp_negative else 0,
+                                   _h(src_mirror), _h(dst_mirror)))
     return dst
 
 
@@ -229,7 +337,7 @@ def sosfiltfilt(sos, src, dst=None):
 
 
 def spectrogram(src, rate, nfft, hop, dst, window=ADN_WINDOW_HANN,
-                detrend=ADN_DETREND_CONSTANT, out_db=False):
+                detrend=ADN_DETREND_CONSTANT, out_db=False, src_mirror=None, dst_mirror=None):
     """Fills dst (n_dst, C, nfft//2+1) like BufferedSpectrogram.process
     (bufferedspectrogram.py:45-62); returns the number of computed frames."""
     src = _f64_array(src, 'src')
@@ -238,9 +346,10 @@ def spectrogram(src, rate, nfft, hop, dst, window=ADN_WINDOW_HANN,
        dst.shape[2] != nfft//2 + 1:
         raise ValueError('src must be (frames, C) and dst (n, C, nfft//2+1)')
     n = _i64(0)
-    check(lib().adn_spectrogram_f64(ptr(src), src.shape[0], src.shape[1], float(rate),
-                                    int(nfft), int(hop), window, detrend, ptr(dst),
-                                    dst.shape[0], 1 if out_db else 0, C.byref(n)))
+    check(lib().adn_spectrogram_f64_m(ptr(src), src.shape[0], src.shape[1], float(rate),
+                                      int(nfft), int(hop), window, detrend, ptr(dst),
+                                      dst.shape[0], 1 if out_db else 0, C.byref(n),
+                                      _h(src_mirror), _h(dst_mirror)))
     return n.value
 
 
@@ -253,24 +362,24 @@ def decibel(power, ref_power=1.0, min_power=1e-20):
     return out
 
 
-def spec_image_db(spec, channel):
+def spec_image_db(spec, channel, src_mirror=None):
     """decibel(spec[:, channel, :].T) as a new (F, n) array (specitem.py:33-39)."""
     spec = _f64_array(spec, 'spec')
     if spec.ndim != 3:
         raise ValueError('spec must be (frames, channels, bins)')
     n, ch, F = spec.shape
     out = np.empty((F, n))
-    check(lib().adn_spec_image_db_f64(ptr(spec), n, ch, F, int(channel), ptr(out)))
+    check(lib().adn_spec_image_db_f64_m(ptr(spec), n, ch, F, int(channel), ptr(out), _h(src_mirror)))
     return out
 
 
-def mean_power_db(spec, channel, i0, i1, floor_db=-200.0):
+def mean_power_db(spec, channel, i0, i1, floor_db=-200.0, src_mirror=None):
     """max(decibel(mean(spec[i0:i1, channel, :], axis=0)), floor_db) (spectrogramplot.py:158-160)."""
     spec = _f64_array(spec, 'spec')
     n, ch, F = spec.shape
     out = np.empty(F)
-    check(lib().adn_mean_power_db_f64(ptr(spec), n, ch, F, int(channel), int(i0), int(i1),
-                                      float(floor_db), ptr(out)))
+    check(lib().adn_mean_power_db_f64_m(ptr(spec), n, ch, F, int(channel), int(i0), int(i1),
+                                        float(floor_db), ptr(out), _h(src_mirror)))
     return out
 
 
@@ -321,15 +430,13 @@ def get_option(option):
 
 
 def enable_resident(on=True):
-    """Results of the host-array calls stay on the device for the traces that
-    consume them (the trace classes invalidate them when audioio moves or
-    replaces a buffer).  Needs no GPU: only flips an option."""
+    """Whether mirrors are honoured at all (default on).  Needs no GPU: only flips an option."""
     lib().adn_set_option(ADN_OPT_RESIDENT, 1 if on else 0)
 
 
 def invalidate(a):
-    """Forget device copies of the host array `a` (it was changed by other
-    means than a call into the library)."""
+    """Invalidate every mirror that overlaps the host array `a` (it was changed by
+    other means than a call into the library)."""
     if a is not None and a.size > 0:
         lib().adn_invalidate(a.ctypes.data, a.nbytes)
 

@@ -57,6 +57,29 @@ class BufferedData(BufferedArray):
         self.dests = []
         self.need_update = False
         self.verbose = 0
+        self._mirror = None
+
+    # ------------------------------------------------------------ device copies
+    # process() of a subclass names `self.mirror()` as the destination mirror of the
+    # library call that fills (part of) self.buffer, and `self.source_mirror()` as the
+    # source mirror: the consumers of a trace (reference buffereddata.py:149-153 walks
+    # filtered -> spectrogram, envelope) read the device copy their source left behind
+    # instead of uploading the buffer again.  Explicit hand-over: only buffers owned by
+    # a trace are ever kept, and the owner invalidates its mirror whenever audioio moves,
+    # replaces or reloads the buffer (move_buffer / allocate_buffer / reload_buffer).
+    def mirror(self):
+        if self._mirror is None:
+            self._mirror = _lib.Mirror()
+        return self._mirror
+
+    def source_mirror(self):
+        src = self.source
+        return getattr(src, '_mirror', None) if src is not None else None
+
+    def invalidate_device(self):
+        """The host buffer was changed by other means than process(): forget its device copy."""
+        if self._mirror is not None:
+            self._mirror.invalidate()
 
     # ------------------------------------------------------------ wiring
     def expand_times(self, tbefore, tafter):
@@ -83,7 +106,6 @@ class BufferedData(BufferedArray):
         self.follow = 0
 
     def open(self, source, step=1, more_shape=None):
-        _lib.enable_resident()
         self.source = source
         source.dests.append(self)
         self.ampl_min = source.ampl_min
@@ -99,18 +121,21 @@ class BufferedData(BufferedArray):
         self.update_step(step, more_shape)
 
     # ------------------------------------------------------------ buffers
-    # The library may keep the result of process() on the device, remembered by
-    # the host range of `dest` (ADN_OPT_RESIDENT), so that the traces further
-    # down the chain do not upload it again.  audioio moves the contents of
-    # `self.buffer` around (move_buffer recycles the overlap) and replaces the
-    # array (allocate_buffer): tell the library before that happens.
+    # audioio moves the contents of `self.buffer` around (move_buffer recycles the
+    # overlap), replaces the array (allocate_buffer) and refills it (reload_buffer):
+    # the device copy is invalid from that moment on; the process() calls those methods
+    # trigger make it valid again for the rows they fill.
     def move_buffer(self, offset, nframes):
-        _lib.invalidate(self.buffer)
+        self.invalidate_device()
         super().move_buffer(offset, nframes)
 
     def allocate_buffer(self, *args, **kwargs):
-        _lib.invalidate(self.buffer)
+        self.invalidate_device()
         super().allocate_buffer(*args, **kwargs)
+
+    def reload_buffer(self):
+        self.invalidate_device()
+        super().reload_buffer()
 
     def align_buffer(self):
         src = self.source
@@ -193,14 +218,15 @@ class BufferedData(BufferedArray):
                 trace = up
 
     # ------------------------------------------------------------ stand-alone use
-    def configure_standalone(self, rate, channels, **params):
+    def configure_standalone(self, rate, channels, source=None, **params):
         """Use `process()` directly on arrays without audian's data graph
         (bench / scripts): sets the attributes `open()` would take from a
-        source, applies `params` and designs filters via `update()`."""
-        _lib.enable_resident()
+        source, applies `params` and designs filters via `update()`.  `source`: the
+        trace whose process() fills the arrays this one reads (its device copy is
+        then used instead of an upload)."""
         self.rate = float(rate)
         self.channels = int(channels)
-        self.source = _Standalone(rate, channels)
+        self.source = source if source is not None else _Standalone(rate, channels)
         for k, v in params.items():
             setattr(self, k, v)
         self._standalone_update()

@@ -53,4 +53,5 @@ class BufferedEnvelope(BufferedData):
 
     def process(self, source, dest, nbefore):
         _lib.envelope(self.sos, source, dest, nbefore,
-                      clamp_negative=(self.highpass_cutoff == 0))
+                      clamp_negative=(self.highpass_cutoff == 0),
+                      src_mirror=self.source_mirror(), dst_mirror=self.mirror())

@@ -60,4 +60,5 @@ class BufferedFilter(BufferedData):
 
     def process(self, source, dest, nbefore):
         # sos None -> the library copies source[nbefore:] (bufferedfilter.py:32-33)
-        _lib.sosfilt(self.sos, source, dest, nbefore)
+        _lib.sosfilt(self.sos, source, dest, nbefore, src_mirror=self.source_mirror(),
+                     dst_mirror=self.mirror())

@@ -78,7 +78,8 @@ class BufferedSpectrogram(BufferedData):
         self.hop = int(self.nfft*(1 - self.overlap_frac))
 
     def process(self, source, dest, nbefore):
-        n = _lib.spectrogram(source, self.source.rate, self.nfft, self.hop, dest)
+        n = _lib.spectrogram(source, self.source.rate, self.nfft, self.hop, dest,
+                             src_mirror=self.source_mirror(), dst_mirror=self.mirror())
         if n > 0:
             # what scipy returns as `freq` (bufferedspectrogram.py:60)
             self.frequencies = np.fft.rfftfreq(self.nfft, 1/self.source.rate)
@@ -91,7 +92,7 @@ class BufferedSpectrogram(BufferedData):
             return None, None
         nf = max(1, self.buffer.shape[2]//16)
         # (bins, frames) decibel image of the channel, from the device copy of the buffer
-        db = _lib.spec_image_db(self.buffer, channel)
+        db = _lib.spec_image_db(self.buffer, channel, src_mirror=self._mirror)
         with np.errstate(all='ignore'):
             zmin = np.percentile(db[-nf:, :], 95)
         zmax = np.max(db)

@@ -1,10 +1,12 @@
 // C ABI of libaudian_b200.so: context, error state, host-pointer entry points.
 // Declarations and the reference functions each entry replaces: include/audian_b200.h
-#include "common.cuh"
+#include "sos_common.cuh"
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <map>
+#include <array>
 
 namespace adn {
 
@@ -45,11 +47,17 @@ void DevBuf::release() {
 }
 
 static Ctx g_ctx;
-static DevBuf g_scratch[SCR_COUNT];
+// scratch memory of the kernels' launchers, one set per stream: work on different streams
+// never shares tile records or work buffers (a std::map never moves its elements)
+static std::map<cudaStream_t, std::array<DevBuf, SCR_COUNT>> g_scratch;
+static std::mutex g_scratch_mu;
 static std::mutex g_mu;
 
 Ctx& ctx() { return g_ctx; }
-DevBuf& scratch(int slot) { return g_scratch[slot]; }
+DevBuf& scratch(int slot, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    return g_scratch[st][slot];
+}
 
 static int32_t init_locked(int32_t device) {
     if (g_ctx.ready && (device < 0 || device == g_ctx.device)) return ADN_OK;
@@ -95,33 +103,40 @@ int32_t ensure_init() {
 //
 // Host-pointer entry points move data on three streams -- uploads, kernels, downloads -- in
 // chunks, so that on pinned host memory the two PCIe directions and the kernels overlap.
-// Outputs of at least `resident_min` bytes can stay on the device, remembered by the host
-// range they were copied to (option ADN_OPT_RESIDENT, off by default): a later call whose
-// source lies inside such a range reads the device copy instead of uploading it again
-// (filtered -> spectrogram / envelope).  The caller owns the discipline: whoever changes such
-// a host buffer by other means calls adn_invalidate() -- the trace classes of audian_b200 do so
-// whenever audioio moves or reallocates a buffer.  As a safety net a hit is verified on a few
-// dozen sampled values before it is trusted (ADN_OPT_VERIFY, on by default).
+//
+// Device copies of results are handed from a producer to its consumers EXPLICITLY: a caller
+// that owns a buffer (a derived trace of audian_b200) creates a mirror (adn_mirror_create) and
+// passes its handle as `dst_mirror` to the call that fills the buffer; the result then also
+// stays in the mirror's device buffer, tagged with the host range it was copied to.  A consumer
+// passes the same handle as `src_mirror` together with its host source pointer: if the source
+// range lies inside the mirror's valid range the upload is skipped.  The owner invalidates the
+// mirror (adn_mirror_invalidate) whenever the host buffer changes by other means -- the trace
+// classes do so in move_buffer / allocate_buffer / reload_buffer.  Calls without a mirror
+// (handle 0: every plain entry point) never look at device copies, so an array that was freed
+// and reallocated, or edited in place, can never be served from stale device data.  A mirror
+// is marked valid only after the computation and the download succeeded.
 
-struct Resident {
-    const char* host = nullptr;
-    size_t bytes = 0;
+struct Mirror {
     DevBuf buf;
-    uint64_t stamp = 0;
+    const char* host = nullptr;        // host range the device buffer mirrors
+    size_t bytes = 0;
+    bool valid = false;
 };
 
-static std::vector<Resident> g_res;
-static std::vector<DevBuf> g_pool;            // released device buffers, reused by size
-static DevBuf g_vbuf;                         // samples of a resident copy for verification
-static uint64_t g_stamp = 0;
-static int64_t g_opt[ADN_OPT_COUNT] = {0, 1, (int64_t)32 << 20, (int64_t)8 << 20, (int64_t)16 << 30,
-                                       0, 1};
+static std::map<int64_t, Mirror> g_mirrors;
+static int64_t g_next_mirror = 1;
+static int64_t g_opt[ADN_OPT_COUNT] = {1, 0, (int64_t)32 << 20, (int64_t)1 << 20, (int64_t)16 << 30,
+                                       0, 1, 1};
 int64_t option(int32_t which) { return g_opt[which]; }
 static cudaStream_t g_h2d = nullptr, g_d2h = nullptr;
 static std::vector<cudaEvent_t> g_events;
 static size_t g_event_next = 0;
 static int64_t g_res_hits = 0, g_res_misses = 0;
 static int64_t g_bytes_h2d = 0, g_bytes_d2h = 0;   // moved by the host-pointer entry points
+// host-pointer entry points share the staging buffers, the three streams and the mirrors:
+// one call at a time (ctypes releases the GIL, so Python threads do get here concurrently)
+static std::recursive_mutex g_api_mu;
+#define ADN_API_LOCK std::lock_guard<std::recursive_mutex> api_lock__(g_api_mu)
 
 
 static cudaError_t h2d(void* dev, const void* host, size_t bytes, cudaStream_t st) {
@@ -160,89 +175,38 @@ static int32_t chain(cudaStream_t a, cudaStream_t b) {
     return ADN_OK;
 }
 
-static void pool_put(DevBuf& b) {
-    if (!b.p) return;
-    if (g_pool.size() >= 8) {                  // bounded: free the smallest
-        size_t k = 0;
-        for (size_t i = 1; i < g_pool.size(); ++i) if (g_pool[i].cap < g_pool[k].cap) k = i;
-        g_pool[k].release();
-        g_pool.erase(g_pool.begin() + k);
-    }
-    g_pool.push_back(b);
-    b.p = nullptr;
-    b.cap = 0;
-}
-
-static int32_t pool_get(size_t bytes, DevBuf* out) {
-    size_t best = g_pool.size();
-    for (size_t i = 0; i < g_pool.size(); ++i)
-        if (g_pool[i].cap >= bytes && g_pool[i].cap <= 2 * bytes + 4096 &&
-            (best == g_pool.size() || g_pool[i].cap < g_pool[best].cap))
-            best = i;
-    if (best < g_pool.size()) {
-        *out = g_pool[best];
-        g_pool.erase(g_pool.begin() + best);
-        return ADN_OK;
-    }
-    DevBuf b;
-    int32_t rc = b.reserve(bytes);
-    if (rc) return rc;
-    *out = b;
-    return ADN_OK;
-}
-
-static void drop_overlapping(const void* host, size_t bytes) {
-    const char* lo = static_cast<const char*>(host);
-    const char* hi = lo + bytes;
-    for (size_t i = 0; i < g_res.size();) {
-        Resident& r = g_res[i];
-        if (r.host < hi && lo < r.host + r.bytes) {
-            pool_put(r.buf);
-            g_res.erase(g_res.begin() + i);
-        } else {
-            ++i;
-        }
-    }
+static Mirror* mirror_of(int64_t handle) {
+    if (handle <= 0 || !g_opt[ADN_OPT_RESIDENT]) return nullptr;
+    auto it = g_mirrors.find(handle);
+    return it == g_mirrors.end() ? nullptr : &it->second;
 }
 
 static void release_residents() {
-    for (auto& r : g_res) r.buf.release();
-    g_res.clear();
-    for (auto& b : g_pool) b.release();
-    g_pool.clear();
-    g_vbuf.release();
+    for (auto& kv : g_mirrors) kv.second.buf.release();
+    g_mirrors.clear();
     for (auto e : g_events) cudaEventDestroy(e);
     g_events.clear();
     if (g_h2d) { cudaStreamDestroy(g_h2d); g_h2d = nullptr; }
     if (g_d2h) { cudaStreamDestroy(g_d2h); g_d2h = nullptr; }
 }
 
-// Device buffer the result for host range [dst, dst + bytes) is computed into: a resident
-// one (registered under that range) or the shared staging buffer.
-static int32_t out_buffer(void* dst, size_t bytes, double** dev) {
+// Device buffer the result for host range [dst, dst + bytes) is computed into: the mirror's
+// (left INVALID until mirror_commit) or the shared staging buffer.
+static int32_t out_buffer(int64_t dst_mirror, void* dst, size_t bytes, double** dev) {
     Ctx& c = ctx();
-    drop_overlapping(dst, bytes);
-    if (g_opt[ADN_OPT_RESIDENT] && (int64_t)bytes >= g_opt[ADN_OPT_RESIDENT_MIN_BYTES]) {
-        size_t total = bytes;
-        for (auto& r : g_res) total += r.bytes;
-        while (!g_res.empty() && (int64_t)total > g_opt[ADN_OPT_RESIDENT_CAP_BYTES]) {
-            size_t k = 0;
-            for (size_t i = 1; i < g_res.size(); ++i) if (g_res[i].stamp < g_res[k].stamp) k = i;
-            total -= g_res[k].bytes;
-            pool_put(g_res[k].buf);
-            g_res.erase(g_res.begin() + k);
+    Mirror* m = mirror_of(dst_mirror);
+    if (m) {
+        m->valid = false;
+        if ((int64_t)bytes >= g_opt[ADN_OPT_RESIDENT_MIN_BYTES]) {
+            size_t total = 0;
+            for (auto& kv : g_mirrors) if (&kv.second != m) total += kv.second.buf.cap;
+            if ((int64_t)(total + bytes) <= g_opt[ADN_OPT_RESIDENT_CAP_BYTES] &&
+                m->buf.reserve(bytes) == ADN_OK) {
+                *dev = m->buf.as<double>();
+                return ADN_OK;
+            }
+            cudaGetLastError();          // out of device memory for a kept copy: staging buffer
         }
-        Resident r;
-        int32_t rc = pool_get(bytes, &r.buf);
-        if (rc == ADN_OK) {
-            r.host = static_cast<const char*>(dst);
-            r.bytes = bytes;
-            r.stamp = ++g_stamp;
-            *dev = r.buf.as<double>();
-            g_res.push_back(r);
-            return ADN_OK;
-        }
-        // out of device memory for a resident copy: fall through to the staging buffer
     }
     int32_t rc = c.out.reserve(bytes ? bytes : 16);
     if (rc) return rc;
@@ -250,50 +214,27 @@ static int32_t out_buffer(void* dst, size_t bytes, double** dev) {
     return ADN_OK;
 }
 
-__global__ void sample_kernel(const double* __restrict__ p, int64_t n, int32_t k, double* __restrict__ out) {
-    int i = threadIdx.x;
-    if (i < k) out[i] = p[(int64_t)((unsigned long long)i * 0x9E3779B97F4A7C15ull % (unsigned long long)n)];
+// the result in `dev` has reached the host range: from now on the mirror may serve it
+static void mirror_commit(int64_t dst_mirror, const void* dst, size_t bytes, const double* dev) {
+    Mirror* m = mirror_of(dst_mirror);
+    if (!m || m->buf.p != dev || bytes == 0) return;
+    m->host = static_cast<const char*>(dst);
+    m->bytes = bytes;
+    m->valid = true;
 }
 
-// Device copy of the host range [src, src + bytes) if a verified resident one exists.
-static int32_t in_resident(const void* src, size_t bytes, const double** dev) {
+// Device copy of the host range [src, src + bytes) if the mirror holds it.
+static int32_t in_resident(int64_t src_mirror, const void* src, size_t bytes, const double** dev) {
     *dev = nullptr;
-    if (!g_opt[ADN_OPT_RESIDENT] || (int64_t)bytes < g_opt[ADN_OPT_RESIDENT_MIN_BYTES]) return ADN_OK;
+    Mirror* m = mirror_of(src_mirror);
+    if (!m) return ADN_OK;
     const char* lo = static_cast<const char*>(src);
-    for (size_t i = 0; i < g_res.size(); ++i) {
-        Resident& r = g_res[i];
-        if (lo < r.host || lo + bytes > r.host + r.bytes) continue;
-        const double* d = reinterpret_cast<const double*>(static_cast<const char*>(r.buf.p) + (lo - r.host));
-        if (g_opt[ADN_OPT_VERIFY]) {
-            Ctx& c = ctx();
-            const int K = 48;
-            const int64_t n = (int64_t)(bytes / 8);
-            int32_t rc = g_vbuf.reserve(4096);
-            if (rc) return rc;
-            sample_kernel<<<1, 64, 0, c.stream>>>(d, n, K, g_vbuf.as<double>());
-            count_launch();
-            double got[K];
-            ADN_CK(d2h(got, g_vbuf.p, sizeof got, c.stream));
-            ADN_CK(cudaStreamSynchronize(c.stream));
-            const double* h = static_cast<const double*>(src);
-            bool same = true;
-            for (int j = 0; j < K && same; ++j) {
-                int64_t idx = (int64_t)((unsigned long long)j * 0x9E3779B97F4A7C15ull % (unsigned long long)n);
-                same = memcmp(&got[j], &h[idx], 8) == 0;
-            }
-            if (!same) {                        // the host buffer changed behind our back
-                pool_put(r.buf);
-                g_res.erase(g_res.begin() + i);
-                ++g_res_misses;
-                return ADN_OK;
-            }
-        }
-        r.stamp = ++g_stamp;
+    if (m->valid && lo >= m->host && lo + bytes <= m->host + m->bytes) {
+        *dev = reinterpret_cast<const double*>(static_cast<const char*>(m->buf.p) + (lo - m->host));
         ++g_res_hits;
-        *dev = d;
-        return ADN_OK;
+    } else {
+        ++g_res_misses;
     }
-    ++g_res_misses;
     return ADN_OK;
 }
 
@@ -307,8 +248,8 @@ static int32_t stage_in(const void* host, size_t bytes) {
 }
 
 // Source of a host-pointer call: the resident copy, or a whole upload.
-static int32_t source_dev(const void* host, size_t bytes, const double** dev) {
-    int32_t rc = in_resident(host, bytes, dev);
+static int32_t source_dev(int64_t src_mirror, const void* host, size_t bytes, const double** dev) {
+    int32_t rc = in_resident(src_mirror, host, bytes, dev);
     if (rc || *dev) return rc;
     if ((rc = stage_in(host, bytes))) return rc;
     *dev = ctx().in.as<double>();
@@ -341,6 +282,7 @@ int32_t adn_init(int32_t device) {
 }
 
 int32_t adn_shutdown(void) {
+    ADN_API_LOCK;
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_ctx.ready) return ADN_OK;
     cudaSetDevice(g_ctx.device);
@@ -349,7 +291,11 @@ int32_t adn_shutdown(void) {
     g_ctx.out.release();
     g_ctx.aux.release();
     release_residents();
-    for (int i = 0; i < SCR_COUNT; ++i) g_scratch[i].release();
+    {
+        std::lock_guard<std::mutex> lk2(g_scratch_mu);
+        for (auto& kv : g_scratch) for (auto& b : kv.second) b.release();
+        g_scratch.clear();
+    }
     cudaStreamDestroy(g_ctx.stream);
     g_ctx.stream = nullptr;
     g_ctx.ready = false;
@@ -361,6 +307,7 @@ const char* adn_last_error(void) { return g_err.c_str(); }
 int32_t adn_version(void) { return 100; }
 int64_t adn_launch_count(void) { return g_ctx.launches.load(); }
 int64_t adn_scan_run_count(void) { return adn::scan_run_launches(); }
+int64_t adn_zero_phase_count(void) { return adn::zp_launches(); }
 
 int32_t adn_synchronize(void) {
     int32_t rc = ensure_init();
@@ -388,14 +335,10 @@ int32_t adn_host_unregister(void* ptr) {
 
 int32_t adn_set_option(int32_t option, int64_t value) {
     if (option < 0 || option >= ADN_OPT_COUNT) return fail(ADN_ERR_INVALID, "adn_set_option: option %d", option);
-    std::lock_guard<std::mutex> lk(g_mu);
+    ADN_API_LOCK;
     g_opt[option] = value;
-    if (option == ADN_OPT_RESIDENT && value == 0 && g_ctx.ready) {
-        cudaSetDevice(g_ctx.device);
-        cudaStreamSynchronize(g_ctx.stream);
-        for (auto& r : g_res) pool_put(r.buf);
-        g_res.clear();
-    }
+    if (option == ADN_OPT_RESIDENT && value == 0)
+        for (auto& kv : g_mirrors) kv.second.valid = false;
     return ADN_OK;
 }
 
@@ -404,9 +347,43 @@ int64_t adn_get_option(int32_t option) {
     return g_opt[option];
 }
 
+int32_t adn_mirror_create(int64_t* handle) {
+    if (!handle) return fail(ADN_ERR_INVALID, "adn_mirror_create: NULL pointer");
+    ADN_API_LOCK;
+    *handle = g_next_mirror++;
+    g_mirrors[*handle] = Mirror();
+    return ADN_OK;
+}
+
+int32_t adn_mirror_release(int64_t handle) {
+    ADN_API_LOCK;
+    auto it = g_mirrors.find(handle);
+    if (it == g_mirrors.end()) return ADN_OK;
+    if (it->second.buf.p && g_ctx.ready) {
+        cudaSetDevice(g_ctx.device);
+        cudaStreamSynchronize(g_ctx.stream);
+    }
+    it->second.buf.release();
+    g_mirrors.erase(it);
+    return ADN_OK;
+}
+
+int32_t adn_mirror_invalidate(int64_t handle) {
+    ADN_API_LOCK;
+    auto it = g_mirrors.find(handle);
+    if (it != g_mirrors.end()) it->second.valid = false;
+    return ADN_OK;
+}
+
 int32_t adn_invalidate(const void* host, int64_t bytes) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (host && bytes > 0 && !g_res.empty()) drop_overlapping(host, (size_t)bytes);
+    ADN_API_LOCK;
+    if (!host || bytes <= 0) return ADN_OK;
+    const char* lo = static_cast<const char*>(host);
+    const char* hi = lo + bytes;
+    for (auto& kv : g_mirrors) {
+        Mirror& m = kv.second;
+        if (m.valid && m.host < hi && lo < m.host + m.bytes) m.valid = false;
+    }
     return ADN_OK;
 }
 
@@ -418,19 +395,20 @@ int32_t adn_transfer_bytes(int64_t* h2d_bytes, int64_t* d2h_bytes) {
     return ADN_OK;
 }
 
-int32_t adn_minmax_f64(const double* src, int64_t n, int32_t C, int64_t step, double* dst) {
+int32_t adn_minmax_f64_m(const double* src, int64_t n, int32_t C, int64_t step, double* dst,
+                         int64_t src_mirror) {
     if (n < 0 || C < 1 || step < 1) return fail(ADN_ERR_INVALID, "adn_minmax_f64: n=%lld C=%d step=%lld",
                                                (long long)n, C, (long long)step);
     if (n == 0) return ADN_OK;
     if (!src || !dst) return fail(ADN_ERR_INVALID, "adn_minmax_f64: NULL pointer");
+    ADN_API_LOCK;
     int32_t rc = ensure_init();
     if (rc) return rc;
     Ctx& c = ctx();
     int64_t nseg = (n + step - 1) / step;
     size_t in_b = (size_t)n * C * 8, out_b = (size_t)nseg * 2 * C * 8;
     const double* dsrc = nullptr;
-    if ((rc = in_resident(src, in_b, &dsrc))) return rc;
-    drop_overlapping(dst, out_b);
+    if ((rc = in_resident(src_mirror, src, in_b, &dsrc))) return rc;
     if ((rc = c.out.reserve(out_b))) return rc;
     if (dsrc) {
         if ((rc = minmax_dev(dsrc, n, C, step, c.out.as<double>(), c.stream))) return rc;
@@ -453,8 +431,13 @@ int32_t adn_minmax_f64(const double* src, int64_t n, int32_t C, int64_t step, do
     return copy_out(dst, c.out.as<double>(), out_b);
 }
 
-int32_t adn_sosfilt_f64(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
-                        int64_t nbefore, double* dst, int64_t n_dst, double* zi_inout) {
+int32_t adn_minmax_f64(const double* src, int64_t n, int32_t C, int64_t step, double* dst) {
+    return adn_minmax_f64_m(src, n, C, step, dst, 0);
+}
+
+int32_t adn_sosfilt_f64_m(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
+                          int64_t nbefore, double* dst, int64_t n_dst, double* zi_inout,
+                          int64_t src_mirror, int64_t dst_mirror) {
     if (S < 0 || S > ADN_MAX_SECTIONS || C < 1 || n_src < 0 || n_dst < 0 || nbefore < 0)
         return fail(ADN_ERR_INVALID, "adn_sosfilt_f64: S=%d C=%d n_src=%lld n_dst=%lld nbefore=%lld",
                     S, C, (long long)n_src, (long long)n_dst, (long long)nbefore);
@@ -464,9 +447,10 @@ int32_t adn_sosfilt_f64(const double* sos, int32_t S, const double* src, int64_t
     if ((S > 0 && !sos) || (n_src > 0 && !src) || (n_dst > 0 && !dst))
         return fail(ADN_ERR_INVALID, "adn_sosfilt_f64: NULL pointer");
     if (n_src == 0) return ADN_OK;
+    ADN_API_LOCK;
     size_t in_b = (size_t)n_src * C * 8, out_b = (size_t)n_dst * C * 8;
     if (S == 0) {                               // reference: sos is None -> dest = source[nbefore:]
-        { std::lock_guard<std::mutex> lk(g_mu); if (!g_res.empty()) drop_overlapping(dst, out_b); }
+        adn_mirror_invalidate(dst_mirror);
         if (n_dst > 0) memmove(dst, src + nbefore * C, out_b);
         return ADN_OK;
     }
@@ -481,15 +465,17 @@ int32_t adn_sosfilt_f64(const double* sos, int32_t S, const double* src, int64_t
     double* d_state[2] = {d_zi + (size_t)C * S * 2, d_zi + (size_t)C * S * 4};
     if (zi_inout) ADN_CK(h2d(d_zi, zi_inout, z_b, c.stream));
     const double* dsrc = nullptr;
-    if ((rc = in_resident(src, in_b, &dsrc))) return rc;
+    if ((rc = in_resident(src_mirror, src, in_b, &dsrc))) return rc;
     double* dout = nullptr;
-    if ((rc = out_buffer(dst, out_b, &dout))) return rc;
+    if ((rc = out_buffer(dst_mirror, dst, out_b, &dout))) return rc;
     if (dsrc) {
         if ((rc = sosfilt_dev(sos, S, dsrc, n_src, C, nbefore, n_dst > 0 ? dout : nullptr, n_dst,
                               zi_inout ? d_zi : nullptr, zi_inout ? d_state[0] : nullptr, c.stream)))
             return rc;
         if (zi_inout) ADN_CK(d2h(zi_inout, d_state[0], z_b, c.stream));
-        return copy_out(dst, dout, out_b);
+        if ((rc = copy_out(dst, dout, out_b))) return rc;
+        mirror_commit(dst_mirror, dst, out_b, dout);
+        return ADN_OK;
     }
     // chunks of rows: upload k+1, filter k (state carried from chunk to chunk: equal to one pass,
     // the streamed == one-shot property of the scan), download k-1
@@ -525,11 +511,19 @@ int32_t adn_sosfilt_f64(const double* sos, int32_t S, const double* src, int64_t
         if (last && zi_inout)
             ADN_CK(d2h(zi_inout, zout, z_b, c.stream));
     }
-    return sync_pipeline();
+    if ((rc = sync_pipeline())) return rc;
+    mirror_commit(dst_mirror, dst, out_b, dout);
+    return ADN_OK;
 }
 
-int32_t adn_envelope_f64(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
-                         int64_t nbefore, double* dst, int64_t n_dst, int32_t clamp_negative) {
+int32_t adn_sosfilt_f64(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
+                        int64_t nbefore, double* dst, int64_t n_dst, double* zi_inout) {
+    return adn_sosfilt_f64_m(sos, S, src, n_src, C, nbefore, dst, n_dst, zi_inout, 0, 0);
+}
+
+int32_t adn_envelope_f64_m(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
+                           int64_t nbefore, double* dst, int64_t n_dst, int32_t clamp_negative,
+                           int64_t src_mirror, int64_t dst_mirror) {
     if (S < 0 || S > ADN_MAX_SECTIONS || C < 1 || n_src < 0 || n_dst < 0 || nbefore < 0)
         return fail(ADN_ERR_INVALID, "adn_envelope_f64: S=%d C=%d n_src=%lld n_dst=%lld nbefore=%lld",
                     S, C, (long long)n_src, (long long)n_dst, (long long)nbefore);
@@ -538,9 +532,10 @@ int32_t adn_envelope_f64(const double* sos, int32_t S, const double* src, int64_
                     (long long)n_dst, (long long)(n_src - nbefore));
     if ((S > 0 && !sos) || (n_src > 0 && !src) || (n_dst > 0 && !dst))
         return fail(ADN_ERR_INVALID, "adn_envelope_f64: NULL pointer");
+    ADN_API_LOCK;
     size_t in_b = (size_t)n_src * C * 8, out_b = (size_t)n_dst * C * 8;
     if (S == 0) {                               // reference: sos is None -> zeros
-        { std::lock_guard<std::mutex> lk(g_mu); if (!g_res.empty()) drop_overlapping(dst, out_b); }
+        adn_mirror_invalidate(dst_mirror);
         if (n_dst > 0) memset(dst, 0, out_b);
         return ADN_OK;
     }
@@ -550,13 +545,20 @@ int32_t adn_envelope_f64(const double* sos, int32_t S, const double* src, int64_
     int32_t rc = ensure_init();
     if (rc) return rc;
     const double* dsrc = nullptr;
-    if ((rc = source_dev(src, in_b, &dsrc))) return rc;
+    if ((rc = source_dev(src_mirror, src, in_b, &dsrc))) return rc;
     double* dout = nullptr;
-    if ((rc = out_buffer(dst, out_b, &dout))) return rc;
+    if ((rc = out_buffer(dst_mirror, dst, out_b, &dout))) return rc;
     if (n_dst > 0 &&
         (rc = envelope_dev(sos, S, dsrc, n_src, C, nbefore, dout, n_dst, clamp_negative, ctx().stream)))
         return rc;
-    return copy_out(dst, dout, out_b);
+    if ((rc = copy_out(dst, dout, out_b))) return rc;
+    mirror_commit(dst_mirror, dst, out_b, dout);
+    return ADN_OK;
+}
+
+int32_t adn_envelope_f64(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
+                         int64_t nbefore, double* dst, int64_t n_dst, int32_t clamp_negative) {
+    return adn_envelope_f64_m(sos, S, src, n_src, C, nbefore, dst, n_dst, clamp_negative, 0, 0);
 }
 
 int32_t adn_sosfiltfilt_f64(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
@@ -570,20 +572,22 @@ int32_t adn_sosfiltfilt_f64(const double* sos, int32_t S, const double* src, int
         return fail(ADN_ERR_SHORT, "adn_sosfiltfilt_f64: the length of the input (%lld) must be greater "
                     "than the pad length %d", (long long)n_src, adn_sosfiltfilt_edge(sos, S));
     if (n_dst == 0) return ADN_OK;
+    ADN_API_LOCK;
     int32_t rc = ensure_init();
     if (rc) return rc;
     size_t in_b = (size_t)n_src * C * 8, out_b = (size_t)n_dst * C * 8;
     const double* dsrc = nullptr;
-    if ((rc = source_dev(src, in_b, &dsrc))) return rc;
+    if ((rc = source_dev(0, src, in_b, &dsrc))) return rc;
     double* dout = nullptr;
-    if ((rc = out_buffer(dst, out_b, &dout))) return rc;
+    if ((rc = out_buffer(0, dst, out_b, &dout))) return rc;
     if ((rc = sosfiltfilt_dev(sos, S, dsrc, n_src, C, 0, dout, n_dst, ctx().stream))) return rc;
     return copy_out(dst, dout, out_b);
 }
 
-int32_t adn_spectrogram_f64(const double* src, int64_t n_src, int32_t C, double rate, int32_t nfft,
-                            int32_t hop, int32_t window_id, int32_t detrend_id, double* dst,
-                            int64_t n_dst, int32_t out_db, int64_t* n_computed) {
+int32_t adn_spectrogram_f64_m(const double* src, int64_t n_src, int32_t C, double rate, int32_t nfft,
+                              int32_t hop, int32_t window_id, int32_t detrend_id, double* dst,
+                              int64_t n_dst, int32_t out_db, int64_t* n_computed,
+                              int64_t src_mirror, int64_t dst_mirror) {
     if (C < 1 || n_src < 0 || n_dst < 0 || nfft < 1 || hop < 1 || hop > nfft || !(rate > 0))
         return fail(ADN_ERR_INVALID, "adn_spectrogram_f64: C=%d n_src=%lld n_dst=%lld nfft=%d hop=%d rate=%g",
                     C, (long long)n_src, (long long)n_dst, nfft, hop, rate);
@@ -591,10 +595,11 @@ int32_t adn_spectrogram_f64(const double* src, int64_t n_src, int32_t C, double 
         return fail(ADN_ERR_INVALID, "adn_spectrogram_f64: NULL pointer");
     if (n_computed) *n_computed = 0;
     if (n_dst == 0) return ADN_OK;
+    ADN_API_LOCK;
     int64_t nf = spectrogram_frames(n_src, n_dst, nfft, hop);
     size_t F = (size_t)nfft / 2 + 1;
     if (nf == 0) {                              // reference: dest[:] = 0
-        { std::lock_guard<std::mutex> lk(g_mu); if (!g_res.empty()) drop_overlapping(dst, (size_t)n_dst * C * F * 8); }
+        adn_mirror_invalidate(dst_mirror);
         memset(dst, 0, (size_t)n_dst * C * F * 8);
         return ADN_OK;
     }
@@ -605,9 +610,10 @@ int32_t adn_spectrogram_f64(const double* src, int64_t n_src, int32_t C, double 
     int64_t nsource = (nf - 1) * (int64_t)hop + nfft;      // rows the frames actually read
     size_t in_b = (size_t)nsource * C * 8, out_b = (size_t)nf * C * F * 8;
     const double* dsrc = nullptr;
-    if ((rc = in_resident(src, in_b, &dsrc))) return rc;
+    if ((rc = in_resident(src_mirror, src, in_b, &dsrc))) return rc;
     double* dout = nullptr;
-    if ((rc = out_buffer(dst, out_b, &dout))) return rc;
+    // the mirror keeps all n_dst frames (the zero-filled ones too): consumers ask for the whole buffer
+    if ((rc = out_buffer(dst_mirror, dst, (size_t)n_dst * C * F * 8, &dout))) return rc;
     // chunks of frames: upload the rows chunk k adds, transform chunk k, download chunk k-1
     const bool upload = dsrc == nullptr;
     if (upload) {
@@ -632,10 +638,20 @@ int32_t adn_spectrogram_f64(const double* src, int64_t n_src, int32_t C, double 
         if ((rc = chain(c.stream, g_d2h))) return rc;
         ADN_CK(d2h(dst + (size_t)f0 * C * F, dout + (size_t)f0 * C * F, (size_t)fc * C * F * 8, g_d2h));
     }
+    if (n_dst > nf && mirror_of(dst_mirror) && dout == mirror_of(dst_mirror)->buf.p)
+        ADN_CK(cudaMemsetAsync(dout + (size_t)nf * C * F, 0, (size_t)(n_dst - nf) * C * F * 8, c.stream));
     if ((rc = sync_pipeline())) return rc;
     if (n_dst > nf) memset(dst + (size_t)nf * C * F, 0, (size_t)(n_dst - nf) * C * F * 8);
+    mirror_commit(dst_mirror, dst, (size_t)n_dst * C * F * 8, dout);
     if (n_computed) *n_computed = nf;
     return ADN_OK;
+}
+
+int32_t adn_spectrogram_f64(const double* src, int64_t n_src, int32_t C, double rate, int32_t nfft,
+                            int32_t hop, int32_t window_id, int32_t detrend_id, double* dst,
+                            int64_t n_dst, int32_t out_db, int64_t* n_computed) {
+    return adn_spectrogram_f64_m(src, n_src, C, rate, nfft, hop, window_id, detrend_id, dst, n_dst, out_db,
+                                 n_computed, 0, 0);
 }
 
 int32_t adn_decibel_f64(const double* power, int64_t n, double ref_power, double min_power,
@@ -643,24 +659,24 @@ int32_t adn_decibel_f64(const double* power, int64_t n, double ref_power, double
     if (n < 0) return fail(ADN_ERR_INVALID, "adn_decibel_f64: n=%lld", (long long)n);
     if (n == 0) return ADN_OK;
     if (!power || !dst) return fail(ADN_ERR_INVALID, "adn_decibel_f64: NULL pointer");
+    ADN_API_LOCK;
     int32_t rc = ensure_init();
     if (rc) return rc;
     Ctx& c = ctx();
     const double* dsrc = nullptr;
-    if ((rc = source_dev(power, (size_t)n * 8, &dsrc))) return rc;
-    drop_overlapping(dst, (size_t)n * 8);
+    if ((rc = source_dev(0, power, (size_t)n * 8, &dsrc))) return rc;
     if ((rc = c.out.reserve((size_t)n * 8))) return rc;
     if ((rc = decibel_dev(dsrc, n, ref_power, min_power, c.out.as<double>(), c.stream)))
         return rc;
     return copy_out(dst, c.out.as<double>(), (size_t)n * 8);
 }
 
-// one channel of a (n, C, F) spectrogram buffer on the device: the resident copy of the whole
+// one channel of a (n, C, F) spectrogram buffer on the device: the mirror's copy of the whole
 // buffer if there is one (then *Cd = C, *chd = channel), else only that channel's rows are
 // uploaded with a strided copy (*Cd = 1, *chd = 0)
-static int32_t spec_channel_dev(const double* spec, int64_t n, int32_t C, int32_t F, int32_t channel,
-                                const double** dev, int32_t* Cd, int32_t* chd) {
-    int32_t rc = in_resident(spec, (size_t)n * C * F * 8, dev);
+static int32_t spec_channel_dev(int64_t src_mirror, const double* spec, int64_t n, int32_t C, int32_t F,
+                                int32_t channel, const double** dev, int32_t* Cd, int32_t* chd) {
+    int32_t rc = in_resident(src_mirror, spec, (size_t)n * C * F * 8, dev);
     if (rc) return rc;
     if (*dev) { *Cd = C; *chd = channel; return ADN_OK; }
     Ctx& c = ctx();
@@ -674,41 +690,47 @@ static int32_t spec_channel_dev(const double* spec, int64_t n, int32_t C, int32_
     return ADN_OK;
 }
 
-int32_t adn_spec_image_db_f64(const double* spec, int64_t n, int32_t C, int32_t F, int32_t channel,
-                              double* dst) {
+int32_t adn_spec_image_db_f64_m(const double* spec, int64_t n, int32_t C, int32_t F, int32_t channel,
+                                double* dst, int64_t src_mirror) {
     if (n < 0 || C < 1 || F < 1 || channel < 0 || channel >= C)
         return fail(ADN_ERR_INVALID, "adn_spec_image_db_f64: n=%lld C=%d F=%d channel=%d", (long long)n, C, F, channel);
     if (n == 0) return ADN_OK;
     if (!spec || !dst) return fail(ADN_ERR_INVALID, "adn_spec_image_db_f64: NULL pointer");
+    ADN_API_LOCK;
     int32_t rc = ensure_init();
     if (rc) return rc;
     Ctx& c = ctx();
     const double* d = nullptr;
     int32_t Cd = C, chd = channel;
-    if ((rc = spec_channel_dev(spec, n, C, F, channel, &d, &Cd, &chd))) return rc;
-    drop_overlapping(dst, (size_t)n * F * 8);
+    if ((rc = spec_channel_dev(src_mirror, spec, n, C, F, channel, &d, &Cd, &chd))) return rc;
     if ((rc = c.out.reserve((size_t)n * F * 8))) return rc;
     if ((rc = spec_image_dev(d, n, Cd, F, chd, c.out.as<double>(), c.stream))) return rc;
     return copy_out(dst, c.out.as<double>(), (size_t)n * F * 8);
 }
 
-int32_t adn_mean_power_db_f64(const double* spec, int64_t n, int32_t C, int32_t F, int32_t channel,
-                              int64_t i0, int64_t i1, double floor_db, double* dst) {
+int32_t adn_spec_image_db_f64(const double* spec, int64_t n, int32_t C, int32_t F, int32_t channel,
+                              double* dst) {
+    return adn_spec_image_db_f64_m(spec, n, C, F, channel, dst, 0);
+}
+
+int32_t adn_mean_power_db_f64_m(const double* spec, int64_t n, int32_t C, int32_t F, int32_t channel,
+                                int64_t i0, int64_t i1, double floor_db, double* dst, int64_t src_mirror) {
     if (n < 1 || C < 1 || F < 1 || channel < 0 || channel >= C || i0 < 0 || i1 <= i0 || i1 > n)
         return fail(ADN_ERR_INVALID, "adn_mean_power_db_f64: n=%lld C=%d F=%d channel=%d i0=%lld i1=%lld",
                     (long long)n, C, F, channel, (long long)i0, (long long)i1);
     if (!spec || !dst) return fail(ADN_ERR_INVALID, "adn_mean_power_db_f64: NULL pointer");
+    ADN_API_LOCK;
     int32_t rc = ensure_init();
     if (rc) return rc;
     Ctx& c = ctx();
     const double* d = nullptr;
     int32_t Cd = C, chd = channel;
-    // without a resident copy only the rows i0..i1 of the channel go up
-    rc = in_resident(spec, (size_t)n * C * F * 8, &d);
+    // without a device copy only the rows i0..i1 of the channel go up
+    rc = in_resident(src_mirror, spec, (size_t)n * C * F * 8, &d);
     if (rc) return rc;
     int64_t a0 = i0, a1 = i1;
     if (!d) {
-        if ((rc = spec_channel_dev(spec + (size_t)i0 * C * F, i1 - i0, C, F, channel, &d, &Cd, &chd))) return rc;
+        if ((rc = spec_channel_dev(0, spec + (size_t)i0 * C * F, i1 - i0, C, F, channel, &d, &Cd, &chd))) return rc;
         a0 = 0;
         a1 = i1 - i0;
     }
@@ -717,20 +739,128 @@ int32_t adn_mean_power_db_f64(const double* spec, int64_t n, int32_t C, int32_t 
     return copy_out(dst, c.out.as<double>(), (size_t)F * 8);
 }
 
+int32_t adn_mean_power_db_f64(const double* spec, int64_t n, int32_t C, int32_t F, int32_t channel,
+                              int64_t i0, int64_t i1, double floor_db, double* dst) {
+    return adn_mean_power_db_f64_m(spec, n, C, F, channel, i0, i1, floor_db, dst, 0);
+}
+
 int32_t adn_pcm_to_f64(const void* pcm, int64_t n, int32_t bits, double gain, double* dst) {
     if (n < 0 || (bits != 16 && bits != 24 && bits != 32))
         return fail(ADN_ERR_INVALID, "adn_pcm_to_f64: n=%lld bits=%d (16, 24 or 32)", (long long)n, bits);
     if (n == 0) return ADN_OK;
     if (!pcm || !dst) return fail(ADN_ERR_INVALID, "adn_pcm_to_f64: NULL pointer");
+    ADN_API_LOCK;
     int32_t rc = ensure_init();
     if (rc) return rc;
     Ctx& c = ctx();
     const size_t in_b = (size_t)n * (bits / 8), out_b = (size_t)n * 8;
     if ((rc = stage_in(pcm, in_b))) return rc;
     double* dout = nullptr;
-    if ((rc = out_buffer(dst, out_b, &dout))) return rc;       // the decoded trace can stay resident
+    if ((rc = out_buffer(0, dst, out_b, &dout))) return rc;
     if ((rc = pcm_dev(c.in.p, n, bits, gain, dout, c.stream))) return rc;
     return copy_out(dst, dout, out_b);
+}
+
+int32_t adn_minmax_channel_f64_m(const double* src, int64_t n, int32_t C, int32_t channel, int64_t step,
+                                 double* dst, int64_t src_mirror) {
+    if (n < 0 || C < 1 || step < 1 || channel < 0 || channel >= C)
+        return fail(ADN_ERR_INVALID, "adn_minmax_channel_f64: n=%lld C=%d channel=%d step=%lld",
+                    (long long)n, C, channel, (long long)step);
+    if (n == 0) return ADN_OK;
+    if (!src || !dst) return fail(ADN_ERR_INVALID, "adn_minmax_channel_f64: NULL pointer");
+    ADN_API_LOCK;
+    int32_t rc = ensure_init();
+    if (rc) return rc;
+    Ctx& c = ctx();
+    const int64_t nseg = (n + step - 1) / step;
+    const size_t col_b = (size_t)n * 8, out_b = (size_t)nseg * 2 * 8;
+    const double* dsrc = nullptr;
+    if ((rc = in_resident(src_mirror, src, (size_t)n * C * 8, &dsrc))) return rc;
+    if ((rc = c.in.reserve(col_b))) return rc;
+    if ((rc = c.out.reserve(out_b))) return rc;
+    if (dsrc) {
+        // the trace is on the device: gather the column there
+        if ((rc = gather_channel_dev(dsrc, n, C, channel, c.in.as<double>(), c.stream))) return rc;
+    } else {
+        // only the column goes up (strided copy): n x 8 bytes instead of n x C x 8
+        g_bytes_h2d += (int64_t)col_b;
+        ADN_CK(cudaMemcpy2DAsync(c.in.p, 8, src + channel, (size_t)C * 8, 8, (size_t)n,
+                                 cudaMemcpyHostToDevice, c.stream));
+    }
+    if ((rc = minmax_dev(c.in.as<double>(), n, 1, step, c.out.as<double>(), c.stream))) return rc;
+    return copy_out(dst, c.out.as<double>(), out_b);
+}
+
+int32_t adn_unwrap_f64(double* data, int64_t n, int32_t C, double thresh, int32_t clips) {
+    if (n < 0 || C < 1) return fail(ADN_ERR_INVALID, "adn_unwrap_f64: n=%lld C=%d", (long long)n, C);
+    if (n == 0 || !(thresh > 0.0)) return ADN_OK;          // audioio: thresh <= 0 switches it off
+    if (!data) return fail(ADN_ERR_INVALID, "adn_unwrap_f64: NULL pointer");
+    ADN_API_LOCK;
+    int32_t rc = ensure_init();
+    if (rc) return rc;
+    Ctx& c = ctx();
+    const size_t b = (size_t)n * C * 8;
+    if ((rc = stage_in(data, b))) return rc;
+    if ((rc = c.out.reserve(b))) return rc;
+    if ((rc = unwrap_dev(c.in.as<double>(), n, C, thresh, clips, c.out.as<double>(), c.stream))) return rc;
+    return copy_out(data, c.out.as<double>(), b);
+}
+
+static int32_t play_region_impl(const double* dsrc, int64_t n, int32_t C, const int32_t* left, int32_t nleft,
+                                const int32_t* right, int32_t nright, double rate, double het_freq,
+                                const double* sos, int32_t S, int64_t nstep, double* work, double* dout,
+                                cudaStream_t st) {
+    const int ncols = nright > 0 ? 2 : 1;
+    const bool het = het_freq > 0.0;
+    int32_t rc;
+    if (!het) return play_mix_dev(dsrc, n, C, left, nleft, right, nright, rate, 0.0, dout, st);
+    double* mixed = work;
+    double* filt = work + (size_t)n * ncols;
+    if ((rc = play_mix_dev(dsrc, n, C, left, nleft, right, nright, rate, het_freq, mixed, st))) return rc;
+    if ((rc = sosfiltfilt_dev(sos, S, mixed, n, ncols, 0, filt, n, st))) return rc;
+    return decimate_dev(filt, (n + nstep - 1) / nstep, ncols, nstep, dout, st);
+}
+
+static int32_t play_region_check(int64_t n, int32_t C, const int32_t* left, int32_t nleft, const int32_t* right,
+                                 int32_t nright, double rate, double het_freq, const double* sos, int32_t S,
+                                 int64_t nstep) {
+    if (n < 0 || C < 1 || nleft < 1 || nleft > 64 || nright < 0 || nright > 64 || !left ||
+        (nright > 0 && !right) || !(rate > 0) || nstep < 1)
+        return fail(ADN_ERR_INVALID, "adn_play_region_f64: n=%lld C=%d nleft=%d nright=%d nstep=%lld",
+                    (long long)n, C, nleft, nright, (long long)nstep);
+    for (int i = 0; i < nleft; ++i) if (left[i] < 0 || left[i] >= C) return fail(ADN_ERR_INVALID, "adn_play_region_f64: channel %d", left[i]);
+    for (int i = 0; i < nright; ++i) if (right[i] < 0 || right[i] >= C) return fail(ADN_ERR_INVALID, "adn_play_region_f64: channel %d", right[i]);
+    if (het_freq > 0.0) {
+        if (!sos || S < 1 || S > ADN_MAX_SECTIONS) return fail(ADN_ERR_INVALID, "adn_play_region_f64: heterodyne needs the low-pass sos");
+        if (n <= adn_sosfiltfilt_edge(sos, S))
+            return fail(ADN_ERR_SHORT, "adn_play_region_f64: the length of the input (%lld) must be greater "
+                        "than the sosfiltfilt pad length %d", (long long)n, adn_sosfiltfilt_edge(sos, S));
+    }
+    return ADN_OK;
+}
+
+int32_t adn_play_region_f64_m(const double* src, int64_t n, int32_t C, const int32_t* left, int32_t nleft,
+                              const int32_t* right, int32_t nright, double rate, double het_freq,
+                              const double* sos, int32_t S, int64_t nstep, double* dst, int64_t src_mirror) {
+    int32_t rc = play_region_check(n, C, left, nleft, right, nright, rate, het_freq, sos, S, nstep);
+    if (rc) return rc;
+    if (n == 0) return ADN_OK;
+    if (!src || !dst) return fail(ADN_ERR_INVALID, "adn_play_region_f64: NULL pointer");
+    ADN_API_LOCK;
+    if ((rc = ensure_init())) return rc;
+    Ctx& c = ctx();
+    const int ncols = nright > 0 ? 2 : 1;
+    if (!(het_freq > 0.0)) nstep = 1;
+    const int64_t no = (n + nstep - 1) / nstep;
+    const double* dsrc = nullptr;
+    if ((rc = source_dev(src_mirror, src, (size_t)n * C * 8, &dsrc))) return rc;
+    if ((rc = c.out.reserve((size_t)no * ncols * 8))) return rc;
+    DevBuf& wb = scratch(SCR_PLAY, c.stream);
+    if ((rc = wb.reserve((size_t)2 * n * ncols * 8 + 16))) return rc;
+    if ((rc = play_region_impl(dsrc, n, C, left, nleft, right, nright, rate, het_freq, sos, S, nstep,
+                               wb.as<double>(), c.out.as<double>(), c.stream)))
+        return rc;
+    return copy_out(dst, c.out.as<double>(), (size_t)no * ncols * 8);
 }
 
 // ---------------------------------------------------------------- device entry points
@@ -763,6 +893,36 @@ int32_t adn_pcm_to_f64_dev(const void* pcm, int64_t n, int32_t bits, double gain
     return pcm_dev(pcm, n, bits, gain, dst, pick(stream));
 }
 
+
+int32_t adn_unwrap_f64_dev(const double* src, int64_t n, int32_t C, double thresh, int32_t clips, double* dst,
+                           void* stream) {
+    if (n < 0 || C < 1 || (n > 0 && (!src || !dst)) || src == dst)
+        return fail(ADN_ERR_INVALID, "adn_unwrap_f64_dev: bad arguments (out of place only)");
+    if (n == 0) return ADN_OK;
+    int32_t rc = ensure_init();
+    if (rc) return rc;
+    if (!(thresh > 0.0)) {
+        ADN_CK(cudaMemcpyAsync(dst, src, (size_t)n * C * 8, cudaMemcpyDeviceToDevice, pick(stream)));
+        return ADN_OK;
+    }
+    return unwrap_dev(src, n, C, thresh, clips, dst, pick(stream));
+}
+
+int32_t adn_play_region_f64_dev(const double* src, int64_t n, int32_t C, const int32_t* left, int32_t nleft,
+                                const int32_t* right, int32_t nright, double rate, double het_freq,
+                                const double* sos, int32_t S, int64_t nstep, double* dst, void* stream) {
+    int32_t rc = play_region_check(n, C, left, nleft, right, nright, rate, het_freq, sos, S, nstep);
+    if (rc) return rc;
+    if (n == 0) return ADN_OK;
+    if (!src || !dst) return fail(ADN_ERR_INVALID, "adn_play_region_f64_dev: NULL pointer");
+    if ((rc = ensure_init())) return rc;
+    const int ncols = nright > 0 ? 2 : 1;
+    if (!(het_freq > 0.0)) nstep = 1;
+    DevBuf& wb = scratch(SCR_PLAY, pick(stream));
+    if ((rc = wb.reserve((size_t)2 * n * ncols * 8 + 16))) return rc;
+    return play_region_impl(src, n, C, left, nleft, right, nright, rate, het_freq, sos, S, nstep,
+                            wb.as<double>(), dst, pick(stream));
+}
 
 int32_t adn_minmax_f64_dev(const double* src, int64_t n, int32_t C, int64_t step, double* dst,
                            void* stream) {

@@ -46,11 +46,12 @@ int32_t ensure_init();
 inline cudaStream_t pick(void* s) { return static_cast<cudaStream_t>(s); }
 inline void count_launch(int n = 1) { ctx().launches += n; }
 
-// per-stream scratch that must outlive an asynchronous launch: handed out from a
-// small pool keyed by purpose; grown (never shrunk) under the caller's stream order.
-DevBuf& scratch(int slot);
+// scratch that must outlive an asynchronous launch: one set of grow-only buffers per
+// stream, keyed by purpose.  Calls on different streams never share scratch; calls on one
+// stream are ordered by the stream.
+DevBuf& scratch(int slot, cudaStream_t st);
 enum { SCR_SOS_TILES = 0, SCR_SOS_TABLES, SCR_SOS_MISC, SCR_ENV_FWD, SCR_ENV_MISC,
-       SCR_MINMAX_PART, SCR_SPEC_TABLES, SCR_SPEC_WORK, SCR_COUNT };
+       SCR_MINMAX_PART, SCR_SPEC_TABLES, SCR_SPEC_WORK, SCR_UNWRAP, SCR_PLAY, SCR_COUNT };
 
 // ---- kernels' host launchers (device pointers, asynchronous) ----
 int32_t minmax_dev(const double* src, int64_t n, int32_t C, int64_t step, double* dst,
@@ -85,6 +86,15 @@ int32_t mean_power_dev(const double* spec, int32_t C, int32_t F, int32_t channel
 int32_t pcm_dev(const void* pcm, int64_t n, int32_t bits, double gain, double* dst, cudaStream_t st);
 int32_t synth_dev(double* dst, int64_t t0, int64_t n, int32_t C, double rate, uint64_t seed,
                   cudaStream_t st);
+// ingest.cu
+int32_t unwrap_dev(const double* src, int64_t n, int32_t C, double thresh, int32_t clips, double* dst,
+                   cudaStream_t st);
+int32_t gather_channel_dev(const double* src, int64_t n, int32_t C, int32_t channel, double* dst,
+                           cudaStream_t st);
+int32_t play_mix_dev(const double* src, int64_t n, int32_t C, const int32_t* left, int32_t nleft,
+                     const int32_t* right, int32_t nright, double rate, double het_freq, double* dst,
+                     cudaStream_t st);
+int32_t decimate_dev(const double* src, int64_t n_out, int32_t C, int64_t nstep, double* dst, cudaStream_t st);
 
 // number of spectrogram frames the reference computes (bufferedspectrogram.py:46-57)
 inline int64_t spectrogram_frames(int64_t n_src, int64_t n_dst, int32_t nfft, int32_t hop) {

@@ -477,7 +477,7 @@ int32_t minmax_dev(const double* src, int64_t n, int32_t C, int64_t step, double
     int32_t nsplit = (int32_t)nsplit64;
     double* part = nullptr;
     if (nsplit > 1) {
-        DevBuf& sb = scratch(SCR_MINMAX_PART);
+        DevBuf& sb = scratch(SCR_MINMAX_PART, st);
         int32_t rc = sb.reserve((size_t)nseg * nsplit * 2 * C * 8);
         if (rc) return rc;
         part = sb.as<double>();

@@ -20,7 +20,7 @@
 //   pass B   the exact DF2T recurrence from the true incoming state, outputs
 //            written in place into the staged tile, tile stored coalesced
 // HBM traffic: 8 B read + 8 B written per sample; state carried in fp64.
-#include "common.cuh"
+#include "sos_common.cuh"
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
@@ -30,34 +30,6 @@
 namespace adn {
 
 namespace {
-
-constexpr int SOS_L = 32;          // samples per thread
-constexpr int SOS_NT = 128;        // threads per block
-constexpr int SOS_NW = SOS_NT / 32;
-constexpr int SOS_LOOK = 32;       // look-back window (tiles)
-
-// MODE_ENVF: forward sweep of the envelope (rectified input, odd extension); MODE_ZPF: the same
-// without the rectification = forward sweep of a plain sosfiltfilt
-enum { MODE_FWD = 0, MODE_ENVF = 1, MODE_REV = 2, MODE_ZPF = 3 };
-#define ADN_EXT(MODE) ((MODE) == MODE_ENVF || (MODE) == MODE_ZPF)
-
-// table layout (D x D row-major matrices, DD = D*D doubles each), packed per channel-group
-// width CG (GW = 32/CG sub-chunks per warp):
-//   [0, nscan)                 A^(L 2^k),  k < log2(GW)     warp scan
-//   [off_fix, off_fix+GW)      A^(L j),    j < GW           fix-up inside the warp
-//   [off_wpow, off_wpow+NW+1)  A^(L GW k), k <= NW          warp prefixes
-//   -- the slots above are staged in shared memory (n_staged of them) --
-//   [off_tile, off_tile+33)    (A^T)^j,    j <= 32          look-back over tiles
-// tile records are self-validating: every double of an aggregate / inclusive state is
-// published with a plain 8-byte store and read back until it differs from this pattern
-// (a NaN payload no arithmetic produces), so no flag, fence or L1 invalidation is needed
-constexpr unsigned long long SOS_EMPTY = 0xFFFFFFFFFFFFFFFFull;
-
-template <int S>
-struct SosK {                      // lives in the kernel's constant bank
-    double coef[S][5];             // b0 b1 b2 a1 a2
-    double W[2 * S][SOS_L];        // pass-A weights
-};
 
 struct SosRun {
     const double* src;
@@ -117,20 +89,6 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
-// v += M u, M block lower triangular (section k only sees states of sections <= k)
-template <int D>
-__device__ __forceinline__ void matvec_acc(const double* __restrict__ M, const double (&u)[D],
-                                           double (&v)[D]) {
-#pragma unroll
-    for (int r = 0; r < D; ++r) {
-        double a = v[r];
-#pragma unroll
-        for (int c = 0; c <= (r | 1); ++c) a = fma(M[r * D + c], u[c], a);
-        v[r] = a;
-    }
-}
-
-constexpr double HALF_PI = 1.5707963267948966;
 // input transform of the forward sweeps: (pi/2)|x| for the envelope, identity otherwise
 template <int MODE> __device__ __forceinline__ double pre_x(double x) {
     return MODE == MODE_ENVF ? HALF_PI * fabs(x) : x;
@@ -863,7 +821,6 @@ sos_run_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ SosRun
 
 // initial states of the two sosfiltfilt sweeps: s0[c][d] = zi[d] * x0[c]
 // which = 0: x0 = ext[0] = 2 r(0) - r(edge) of the raw input;  which = 1: x0 = row[c]
-struct ZiK { double z[2 * ADN_MAX_SECTIONS]; };      // sosfilt_zi(sos), passed by value
 
 __global__ void env_s0_kernel(int which, const double* __restrict__ src, int32_t C, int32_t D,
                               int64_t edge, const __grid_constant__ ZiK zik, double* __restrict__ s0) {
@@ -941,32 +898,28 @@ void state_space(const double* sos, int S, Mat& A, std::vector<ld>& B) {
     B = z;
 }
 
-struct Plan {
-    std::vector<double> sos;      // key
-    int S = 0, CG = 0;
-    int jdecay = SOS_LOOK + 1;
-    int jpre = SOS_LOOK + 1;      // tiles after which the cascade has forgotten its state (< 1e-20)
-    int off_fix = 0, off_wpow = 0, off_tile = 0, n_staged = 0;
-    std::vector<double> W;        // [D][L]
-    double* dtab = nullptr;       // device tables
-};
+}  // namespace
 
-std::vector<Plan> g_plans;
-std::mutex g_plan_mu;
+SosPlan::~SosPlan() {
+    if (dtab) cudaFree(dtab);         // waits for kernels that still read the tables
+}
 
-int32_t get_plan(const double* sos, int S, int CG, cudaStream_t st, Plan** out) {
+static std::vector<std::shared_ptr<SosPlan>> g_plans;
+static std::mutex g_plan_mu;
+
+int32_t get_sos_plan(const double* sos, int S, int CG, cudaStream_t st, std::shared_ptr<SosPlan>* out) {
     std::lock_guard<std::mutex> lk(g_plan_mu);
-    for (auto& p : g_plans)
-        if (p.S == S && p.CG == CG && memcmp(p.sos.data(), sos, sizeof(double) * 6 * S) == 0) {
-            *out = &p;
+    for (size_t i = 0; i < g_plans.size(); ++i) {
+        auto& q = g_plans[i];
+        if (q->S == S && q->CG == CG && memcmp(q->sos.data(), sos, sizeof(double) * 6 * S) == 0) {
+            *out = q;
             return ADN_OK;
         }
-    if (g_plans.size() >= 64) {                 // bounded cache
-        for (auto& p : g_plans) cudaFree(p.dtab);
-        g_plans.clear();
     }
+    if (g_plans.size() >= 64) g_plans.erase(g_plans.begin());     // bounded cache: drop the oldest
     const int D = 2 * S, DD = D * D;
-    Plan p;
+    auto pp = std::make_shared<SosPlan>();
+    SosPlan& p = *pp;
     p.sos.assign(sos, sos + 6 * S);
     p.S = S;
     p.CG = CG;
@@ -1020,15 +973,15 @@ int32_t get_plan(const double* sos, int S, int CG, cudaStream_t st, Plan** out) 
             for (auto x : m.a) mx = fmaxl(mx, fabsl(x));
             if (j >= 1 && mx < 1e-30L && p.jdecay > SOS_LOOK) p.jdecay = j;
             if (j >= 1 && mx < 1e-20L && p.jpre > SOS_LOOK) p.jpre = j;
+            if (j >= 1 && mx < 1e-17L && p.jzp > SOS_LOOK) p.jzp = j;
             m = mul(m, AT);
         }
     }
     ADN_CK(cudaMalloc(&p.dtab, tab.size() * sizeof(double)));
     ADN_CK(cudaMemcpyAsync(p.dtab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     ADN_CK(cudaStreamSynchronize(st));           // `tab` is a stack-lifetime host buffer
-    if (g_plans.capacity() < 64) g_plans.reserve(64);
-    g_plans.push_back(std::move(p));
-    *out = &g_plans.back();
+    g_plans.push_back(pp);
+    *out = pp;
     return ADN_OK;
 }
 
@@ -1045,15 +998,12 @@ int pick_cg(int C) {
     return cg;
 }
 
+namespace {
+
 template <int S, int MODE>
-int32_t launch_mode(const Plan& plan, SosRun& R, size_t smem_bytes, unsigned grid, cudaStream_t st) {
+int32_t launch_mode(const SosPlan& plan, SosRun& R, size_t smem_bytes, unsigned grid, cudaStream_t st) {
     SosK<S> K;
-    for (int s = 0; s < S; ++s) {
-        const double* q = plan.sos.data() + 6 * s;
-        K.coef[s][0] = q[0]; K.coef[s][1] = q[1]; K.coef[s][2] = q[2];
-        K.coef[s][3] = q[4]; K.coef[s][4] = q[5];
-    }
-    memcpy(K.W, plan.W.data(), sizeof(double) * 2 * S * SOS_L);
+    fill_sosk<S>(plan, K);
     auto kern = sos_scan_kernel<S, MODE>;
     static bool attr_done = false;               // per instantiation
     if (!attr_done) {
@@ -1067,7 +1017,7 @@ int32_t launch_mode(const Plan& plan, SosRun& R, size_t smem_bytes, unsigned gri
 }
 
 template <int S>
-int32_t launch_S(int mode, const Plan& plan, SosRun& R, size_t smem, unsigned grid, cudaStream_t st) {
+int32_t launch_S(int mode, const SosPlan& plan, SosRun& R, size_t smem, unsigned grid, cudaStream_t st) {
     switch (mode) {
         case MODE_FWD: return launch_mode<S, MODE_FWD>(plan, R, smem, grid, st);
         case MODE_ENVF: return launch_mode<S, MODE_ENVF>(plan, R, smem, grid, st);
@@ -1079,14 +1029,9 @@ int32_t launch_S(int mode, const Plan& plan, SosRun& R, size_t smem, unsigned gr
 std::atomic<int64_t> g_run_launches{0};
 
 template <int S, int MODE>
-int32_t launch_run_mode(const Plan& plan, SosRun& R, size_t smem_bytes, unsigned grid, cudaStream_t st) {
+int32_t launch_run_mode(const SosPlan& plan, SosRun& R, size_t smem_bytes, unsigned grid, cudaStream_t st) {
     SosK<S> K;
-    for (int s = 0; s < S; ++s) {
-        const double* q = plan.sos.data() + 6 * s;
-        K.coef[s][0] = q[0]; K.coef[s][1] = q[1]; K.coef[s][2] = q[2];
-        K.coef[s][3] = q[4]; K.coef[s][4] = q[5];
-    }
-    memcpy(K.W, plan.W.data(), sizeof(double) * 2 * S * SOS_L);
+    fill_sosk<S>(plan, K);
     auto kern = sos_run_kernel<S, MODE>;
     static bool attr_done = false;               // per instantiation
     if (!attr_done) {
@@ -1101,7 +1046,7 @@ int32_t launch_run_mode(const Plan& plan, SosRun& R, size_t smem_bytes, unsigned
 }
 
 template <int S>
-int32_t launch_run_S(int mode, const Plan& plan, SosRun& R, size_t smem, unsigned grid, cudaStream_t st) {
+int32_t launch_run_S(int mode, const SosPlan& plan, SosRun& R, size_t smem, unsigned grid, cudaStream_t st) {
     switch (mode) {
         case MODE_FWD: return launch_run_mode<S, MODE_FWD>(plan, R, smem, grid, st);
         case MODE_ENVF: return launch_run_mode<S, MODE_ENVF>(plan, R, smem, grid, st);
@@ -1112,7 +1057,7 @@ int32_t launch_run_S(int mode, const Plan& plan, SosRun& R, size_t smem, unsigne
 
 // the run kernel when the cascade forgets fast enough for its run-in to be cheap; false: use the
 // look-back kernel
-bool plan_runs(const Plan& plan, SosRun& R, int S, size_t* smem_out, unsigned* grid_out) {
+bool plan_runs(const SosPlan& plan, SosRun& R, int S, size_t* smem_out, unsigned* grid_out) {
     static int enabled = -1, nbuf_env = 0;
     if (enabled < 0) {
         const char* e = getenv("ADN_SOS_RUN");           // development switch; the option rules
@@ -1154,8 +1099,8 @@ int32_t run_scan(int mode, const double* sos, int S, const double* src, int64_t 
                  const double* s0, double* zf, int tile_slot, cudaStream_t st) {
     const int CG = pick_cg(C);
     const int D = 2 * S;
-    Plan* plan = nullptr;
-    int32_t rc = get_plan(sos, S, CG, st, &plan);
+    std::shared_ptr<SosPlan> plan;
+    int32_t rc = get_sos_plan(sos, S, CG, st, &plan);
     if (rc) return rc;
     SosRun R;
     memset(&R, 0, sizeof R);
@@ -1196,7 +1141,7 @@ int32_t run_scan(int mode, const double* sos, int S, const double* src, int64_t 
     }
     // tile records: agg | incl, every word SOS_EMPTY until published
     const size_t recs = (size_t)ntiles * CG * D;
-    DevBuf& tb = scratch(tile_slot);
+    DevBuf& tb = scratch(tile_slot, st);
     if ((rc = tb.reserve(recs * 16))) return rc;
     R.agg = tb.as<double>();
     R.incl = R.agg + recs;
@@ -1237,7 +1182,7 @@ int32_t sosfilt_dev(const double* sos, int32_t S, const double* src, int64_t n_s
 }
 
 // zi = sosfilt_zi(sos): per section scale * lfilter_zi(b, a), scale *= sum(b)/sum(a)
-static void sosfilt_zi_host(const double* sos, int S, double* zi) {
+void sosfilt_zi_host(const double* sos, int S, double* zi) {
     double scale = 1.0;
     for (int s = 0; s < S; ++s) {
         const double* q = sos + 6 * s;
@@ -1320,75 +1265,18 @@ static int32_t zero_phase_dev(bool rect, const double* sos, int32_t S, const dou
     const int D = 2 * S;
     const int edge = adn_sosfiltfilt_edge(sos, S);
     const int64_t next = n_src + 2 * (int64_t)edge;
+    {
+        // one pass with the tile in registers when the cascade forgets fast enough (zerophase.cu)
+        bool handled = false;
+        int32_t rc1 = zero_phase_regs_dev(rect, sos, S, src, n_src, C, edge, edge, edge + nbefore, dst, n_dst,
+                                          clamp_negative, &handled, st);
+        if (rc1 || handled) return rc1;
+    }
     ZiK zik;
     sosfilt_zi_host(sos, S, zik.z);
-    DevBuf& fwd = scratch(SCR_ENV_FWD);
-    DevBuf& misc = scratch(SCR_ENV_MISC);
+    DevBuf& fwd = scratch(SCR_ENV_FWD, st);
+    DevBuf& misc = scratch(SCR_ENV_MISC, st);
     int32_t rc;
-    // Optional schedule (ADN_OPT_ENVELOPE_CHUNK_BYTES > 0, off by default: see the header):
-    // cascades that forget their state within `keep` rows (|A^keep| < 1e-30) are swept in
-    // chunks that live in L2: forward over chunk j+1, then backward over chunk j, whose
-    // incoming state comes from a zero-state reverse pass over the first `keep` rows of chunk
-    // j+1 (exact to 1e-30).  The forward result only ever exists in a three-slot ring that
-    // stays cache resident, so HBM sees the input once and the result once (16 B/sample)
-    // instead of the 32 B/sample of two full sweeps.
-    {
-        const int64_t chunk_bytes = option(ADN_OPT_ENVELOPE_CHUNK_BYTES);
-        const int64_t keep = chunk_bytes > 0 ? adn_sos_decay_length(sos, S, 1e-30) : -1;
-        int64_t rpc = chunk_bytes / ((int64_t)C * 8);             // rows per chunk
-        if (rect && keep > 0 && rpc >= 8 * keep && rpc > 4 * edge && n_src >= 3 * rpc) {
-            const int64_t nch = n_src / rpc;
-            rpc = (n_src + nch - 1) / nch;
-            const int64_t slot_rows = rpc + 2 * edge;
-            if ((rc = fwd.reserve((size_t)(3 * slot_rows) * C * 8))) return rc;
-            if ((rc = misc.reserve((size_t)(4 * C * D) * 8))) return rc;
-            double* st_f[2] = {misc.as<double>(), misc.as<double>() + (size_t)C * D};
-            double* st_b = st_f[1] + (size_t)C * D;
-            double* st_k = st_b + (size_t)C * D;
-            const int nb = (C * D + 127) / 128;
-            auto slot = [&](int64_t j) { return fwd.as<double>() + (size_t)(j % 3) * slot_rows * C; };
-            auto a_of = [&](int64_t j) { return j * rpc < n_src ? j * rpc : n_src; };
-            auto len_of = [&](int64_t j) {                        // rows of chunk j of the forward result
-                return a_of(j + 1) - a_of(j) + (j == 0 ? edge : 0) + (j == nch - 1 ? edge : 0);
-            };
-            auto forward = [&](int64_t j) -> int32_t {
-                const int64_t a = a_of(j), b = a_of(j + 1);
-                const double* zi = st_f[(j + 1) & 1];
-                if (j == 0) {
-                    env_s0_kernel<<<nb, 128, 0, st>>>(0, src, C, D, edge, zik, st_f[1]);
-                    count_launch();
-                }
-                return envelope_forward_dev(sos, S, src + a * C, b - a, C, j == 0 ? edge : 0,
-                                            j == nch - 1 ? edge : 0, zi, slot(j), st_f[j & 1], st);
-            };
-            if ((rc = forward(0))) return rc;
-            for (int64_t j = 0; j < nch; ++j) {
-                if (j + 1 < nch) {
-                    if ((rc = forward(j + 1))) return rc;
-                    // state entering chunk j from behind: the next chunk's first rows, reversed
-                    if ((rc = sosfilt_reverse_dev(sos, S, slot(j + 1), keep, C, nullptr, nullptr, 0, 0, 0,
-                                                  st_k, st)))
-                        return rc;
-                } else {
-                    env_s0_kernel<<<nb, 128, 0, st>>>(1, slot(j) + (len_of(j) - 1) * C, C, D, 0, zik, st_k);
-                    count_launch();
-                }
-                const int64_t L = len_of(j);
-                const int64_t G = j == 0 ? 0 : edge + a_of(j);    // position in the extended sequence
-                int64_t r_lo = edge + nbefore - G, r_hi = edge + nbefore + n_dst - G;
-                if (r_lo < 0) r_lo = 0;
-                if (r_hi > L) r_hi = L;
-                if (r_hi > r_lo) {
-                    if ((rc = sosfilt_reverse_dev(sos, S, slot(j), L, C, st_k,
-                                                  dst + (G + r_lo - edge - nbefore) * C, r_lo, r_hi - r_lo,
-                                                  clamp_negative, nullptr, st)))
-                        return rc;
-                }
-            }
-            ADN_CK(cudaGetLastError());
-            return ADN_OK;
-        }
-    }
     if ((rc = fwd.reserve((size_t)next * C * 8))) return rc;
     if ((rc = misc.reserve((size_t)(2 * C * D) * 8))) return rc;
     double* d_s0f = misc.as<double>();

@@ -1642,7 +1642,7 @@ int32_t spectrogram_big(const SpecPlan& plan, const double* src, int32_t C, doub
     int64_t fr = ((int64_t)1 << 30) / (M * 16 * C);
     if (fr < 1) fr = 1;
     if (fr > nf) fr = nf;
-    DevBuf& wb = scratch(SCR_SPEC_WORK);
+    DevBuf& wb = scratch(SCR_SPEC_WORK, st);
     int32_t rc = wb.reserve((size_t)(fr * C * M * 16));
     if (rc) return rc;
     double2* work = wb.as<double2>();
@@ -1753,7 +1753,7 @@ int32_t spectrogram_bluestein(const SpecPlan& plan, const double* src, int32_t C
     int64_t fr = ((int64_t)1 << 29) / (L * 16 * C);             // two buffers of at most 512 MiB
     if (fr < 1) fr = 1;
     if (fr > nf) fr = nf;
-    DevBuf& wb = scratch(SCR_SPEC_WORK);
+    DevBuf& wb = scratch(SCR_SPEC_WORK, st);
     int32_t rc = wb.reserve((size_t)(2 * fr * C * L * 16));
     if (rc) return rc;
     double2* wa = wb.as<double2>();

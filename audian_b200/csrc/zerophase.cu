@@ -1,0 +1,910 @@
+// Zero-phase SOS filtering (scipy sosfiltfilt; with the rectification in front of it:
+// BufferedEnvelope.process, src/audian/bufferedenvelope.py:34-41; without:
+// the play-back low-pass, src/audian/databrowser.py:1725) in ONE pass over the input, the
+// tile held in registers: HBM sees every input row once and every output row once
+// (16 B per sample instead of the 32 B of a forward and a backward sweep through memory).
+//
+// Geometry as in sosfilt.cu: a tile = SOS_NT threads x SOS_L consecutive samples, lane (gl, cw)
+// of warp w owns sub-chunk g = w GW + gl of channel cw of a group of CG channels.  A block
+// owns a run of consecutive tiles and walks BACKWARD along time:
+//   - the backward sweep carries its state exactly from tile to tile (the state after the
+//     first row of tile T+1 enters the last row of tile T);
+//   - the forward state entering tile T comes from the zero-state aggregates of the JJ tiles
+//     before it, sum_j (A^T)^(j-1) agg[T-j] (a cascade that forgets its state within JJ - 1
+//     tiles to 1e-20: the truncation sosfilt.cu's run kernel makes); those aggregates need
+//     pass A only (dot products), computed when a tile is visited JJ iterations ahead of its
+//     own turn ("look-ahead visit": tile read from HBM; the second read, JJ tiles later, is
+//     an L2 hit);
+//   - a main visit loads the tile into registers, runs the exact DF2T recurrence forward from
+//     the true incoming state (y1 replaces x in the registers), pass A + scan + DF2T backward
+//     over the same registers (y2 replaces y1), clamps and stores from the registers: each
+//     warp store covers GW rows x CG channels = full 32-byte sectors for CG >= 4.
+// A run starts JO tiles behind its last output tile (run-out of the backward sweep from zero
+// state) unless it reaches the end of the sequence, where scipy's zi * y1[last] applies.
+#include "sos_common.cuh"
+#include <cstring>
+#include <cstdlib>
+#include <atomic>
+
+namespace adn {
+
+namespace {
+
+constexpr int ZP_MAX_JJ = 16;
+
+struct ZpArgs {
+    const double* src;
+    double* dst;
+    const double* tab;                 // plan tables in global memory
+    int32_t off_fix, off_wpow, off_tile, n_staged;
+    int64_t nx;                        // raw rows
+    int64_t N;                         // rows of the extended sequence: edgeL + nx + edgeR
+    int64_t out_first, n_dst;          // sequence rows [out_first, out_first + n_dst) -> dst rows
+    int64_t ntt;                       // tiles of the sequence
+    int64_t t_out0, t_out1;            // output tiles [t_out0, t_out1)
+    int32_t C, CG, ngroups, T;
+    int32_t edgeL, edgeR;
+    int32_t zi_left, zi_right;         // sosfilt_zi initial conditions at that end (else zero state)
+    int32_t clamp;
+    int32_t JJ, JO;                    // look-ahead tiles of the forward state; run-out tiles
+    int32_t run_tiles;
+    int32_t pf;                        // bulk L2 prefetch of the next look-ahead tile
+    ZiK zi;
+};
+
+template <bool RECT> __device__ __forceinline__ double zp_pre(double x) {
+    return RECT ? HALF_PI * fabs(x) : x;
+}
+
+// value of the extended sequence at row e of the channel whose column starts at xc
+template <bool RECT>
+__device__ __forceinline__ double zp_ext_value(const ZpArgs& P, const double* __restrict__ xc, int64_t e) {
+    if (e < 0 || e >= P.N) return 0.0;
+    const int64_t C = P.C;
+    if (e < P.edgeL)
+        return 2.0 * zp_pre<RECT>(__ldg(xc)) - zp_pre<RECT>(__ldg(xc + (P.edgeL - e) * C));
+    e -= P.edgeL;
+    if (e < P.nx) return zp_pre<RECT>(__ldg(xc + e * C));
+    e -= P.nx;
+    return 2.0 * zp_pre<RECT>(__ldg(xc + (P.nx - 1) * C)) - zp_pre<RECT>(__ldg(xc + (P.nx - 2 - e) * C));
+}
+
+// exact DF2T recurrence over the SOS_L register-resident samples (in time order, or reversed),
+// outputs in place; the sections run skewed by one sample each so that the S recurrences of
+// a step are independent (as in sosfilt.cu)
+template <int S, bool REVERSE>
+__device__ __forceinline__ void zp_df2t(const SosK<S>& K, double (&x)[SOS_L], double (&z)[2 * S]) {
+    double xin[S + 1];
+#pragma unroll
+    for (int j = 0; j < SOS_L + S - 1; ++j) {
+#pragma unroll
+        for (int s = S - 1; s >= 0; --s) {
+            const int k = j - s;
+            if (k < 0 || k >= SOS_L) continue;
+            const int i = REVERSE ? SOS_L - 1 - k : k;
+            const double xv = s == 0 ? x[i] : xin[s];
+            const double y = fma(K.coef[s][0], xv, z[2 * s]);
+            z[2 * s] = fma(K.coef[s][1], xv, z[2 * s + 1]) - K.coef[s][3] * y;
+            z[2 * s + 1] = K.coef[s][2] * xv - K.coef[s][4] * y;
+            if (s == S - 1) x[i] = y; else xin[s + 1] = y;
+        }
+    }
+}
+
+// zero-state end state of the register-resident samples, processed forward or reversed
+template <int S, bool REVERSE>
+__device__ __forceinline__ void zp_pass_a(const SosK<S>& K, const double (&x)[SOS_L], double (&v)[2 * S]) {
+#pragma unroll
+    for (int i = 0; i < SOS_L; ++i) {
+#pragma unroll
+        for (int d = 0; d < 2 * S; ++d) v[d] = fma(K.W[d][REVERSE ? SOS_L - 1 - i : i], x[i], v[d]);
+    }
+}
+
+// one homogeneous step of the cascade (input 0)
+template <int S>
+__device__ __forceinline__ void zp_step0(const SosK<S>& K, double (&z)[2 * S]) {
+    double xv = 0.0;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const double y = fma(K.coef[s][0], xv, z[2 * s]);
+        z[2 * s] = fma(K.coef[s][1], xv, z[2 * s + 1]) - K.coef[s][3] * y;
+        z[2 * s + 1] = K.coef[s][2] * xv - K.coef[s][4] * y;
+        xv = y;
+    }
+}
+
+#ifndef ZP_BLOCKS
+#define ZP_BLOCKS 4
+#endif
+
+template <int S, bool RECT>
+__global__ void __launch_bounds__(SOS_NT, S <= 2 ? ZP_BLOCKS : 3)
+sos_zp_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ ZpArgs P) {
+    constexpr int D = 2 * S;
+    constexpr int DD = D * D;
+    extern __shared__ __align__(16) double smem[];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = (int)(blockIdx.x % P.ngroups);
+    const int64_t run = blockIdx.x / P.ngroups;
+    const int CG = P.CG, C = P.C;
+    const int c0 = grp * CG;
+    const int Cw = min(CG, C - c0);
+    const int GW = 32 / CG;
+    const int gl = lane / CG, cw = lane % CG;
+    const int g = warp * GW + gl;
+    const bool chan_ok = cw < Cw;
+    const int T = P.T;
+    const int JJ = P.JJ, NS = JJ + 1;
+
+    double* tab_s = smem;                                   // n_staged * DD
+    double* wagg = tab_s + (size_t)P.n_staged * DD;         // [NW][CG][D]
+    double* sinf_s = wagg + SOS_NW * CG * D;                // [CG][D]
+    double* sinb_s = sinf_s + CG * D;                       // [2][CG][D]
+    double* aggr = sinb_s + 2 * CG * D;                     // [NS][CG][D]   zero-state tile aggregates
+    double* etot = aggr + (size_t)NS * CG * D;              // [NS][D][NT]   per-thread zero-state offsets
+    const double* tab_fix = tab_s + P.off_fix * DD;
+    const double* tab_wpow = tab_s + P.off_wpow * DD;
+    const double* Pt = P.tab + (size_t)P.off_tile * DD;     // (A^T)^j, global
+
+    const int64_t a = P.t_out0 + run * P.run_tiles;         // output tiles [a, b)
+    const int64_t b = min(a + (int64_t)P.run_tiles, P.t_out1);
+    if (a >= b) return;
+    const int64_t top = min(b + (int64_t)P.JO, P.ntt) - 1;  // first tile of the walk
+
+    for (int q = tid; q < P.n_staged * DD; q += SOS_NT) tab_s[q] = __ldg(P.tab + q);
+    if (tid < 2 * CG * D) sinb_s[tid] = 0.0;
+
+    const double* xc = P.src + c0 + (chan_ok ? cw : 0);
+    auto slot_of = [&](int64_t t) { return (int)((t + 64 * (int64_t)NS) % NS); };
+
+    auto prefetch = [&](int64_t t) {
+        if (!P.pf || tid != 0 || grp != 0 || t < 0 || t >= P.ntt) return;
+        int64_t p0 = t * T - P.edgeL, p1 = p0 + T;
+        if (p0 < 0) p0 = 0;
+        if (p1 > P.nx) p1 = P.nx;
+        if (p1 <= p0) return;
+        const char* adr = reinterpret_cast<const char*>(P.src + p0 * C);
+        int64_t bytes = (p1 - p0) * (int64_t)C * 8;
+        const int64_t mis = reinterpret_cast<uintptr_t>(adr) & 15;
+        adr -= mis;
+        bytes = (bytes + mis + 15) & ~(int64_t)15;
+        if (adr >= reinterpret_cast<const char*>(P.src))
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(adr), "r"((uint32_t)bytes) : "memory");
+    };
+
+    __syncthreads();
+    // The walk, one tile visit per iteration: look-ahead visits L(u) of tiles u = top, top-1, ...
+    // interleaved with the main visits V(u + JJ) once JJ + 1 look-ahead visits have filled the
+    // ring: L(top) .. L(top-JJ) V(top) L(top-JJ-1) V(top-1) ... L(a-JJ) V(a).  Both kinds start
+    // with the same tile load (one copy of that code).
+    int par = 0;                                            // parity of the backward state slot
+    const int64_t nvis = 2 * (top - (a - JJ) + 1);
+    for (int64_t it = 0; it < nvis; ++it) {
+        const int64_t u = top - (it >> 1);
+        const bool is_main = it & 1;
+        const int64_t t = is_main ? u + JJ : u;
+        if (is_main && t > top) continue;
+        const int slot = slot_of(t);
+        if (!is_main && t < 0) {
+            // before the sequence: the virtual tile -1 carries the initial state of the sweep
+            if (tid < CG * D) {
+                const int ch = tid / D, d = tid - ch * D;
+                double v = 0.0;
+                if (t == -1 && P.zi_left && c0 + ch < C)
+                    v = P.zi.z[d] * zp_ext_value<RECT>(P, P.src + c0 + ch, 0);
+                aggr[(size_t)slot * CG * D + tid] = v;
+            }
+            __syncthreads();
+            continue;
+        }
+        // ---- rows of tile t of this thread's channel -> registers
+        double x[SOS_L];
+        {
+            const int64_t e0 = t * T + (int64_t)g * SOS_L;  // sequence row of x[0]
+            const bool fast = t * T >= P.edgeL && (t + 1) * (int64_t)T <= P.edgeL + P.nx;
+            if (!chan_ok) {
+#pragma unroll
+                for (int i = 0; i < SOS_L; ++i) x[i] = 0.0;
+            } else if (fast) {
+                const double* p = xc + (e0 - P.edgeL) * C;
+                if (C == 8) {
+#pragma unroll
+                    for (int i = 0; i < SOS_L; ++i) x[i] = __ldg(p + i * 8);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < SOS_L; ++i) { x[i] = __ldg(p); p += C; }
+                }
+#pragma unroll
+                for (int i = 0; i < SOS_L; ++i) x[i] = zp_pre<RECT>(x[i]);
+            } else {
+                // the two edge tiles and the tail: element by element through local memory (a
+                // rolled loop: this path is rare and must not cost code size)
+                double tmp[SOS_L];
+#pragma unroll 1
+                for (int i = 0; i < SOS_L; ++i) tmp[i] = zp_ext_value<RECT>(P, xc, e0 + i);
+#pragma unroll
+                for (int i = 0; i < SOS_L; ++i) x[i] = tmp[i];
+            }
+        }
+        if (!is_main) {
+            // ---- look-ahead visit: zero-state forward aggregate of the tile and of every
+            // thread's prefix inside it
+            double v[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) v[d] = 0.0;
+            zp_pass_a<S, false>(K, x, v);
+            {
+                int k = 0;
+                for (int off = CG; off < 32; off <<= 1, ++k) {
+                    double w[D];
+#pragma unroll
+                    for (int d = 0; d < D; ++d) w[d] = __shfl_up_sync(0xffffffffu, v[d], off);
+                    if (lane >= off) matvec_acc<D>(tab_s + k * DD, w, v);
+                }
+            }
+            double ex[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const double w = __shfl_up_sync(0xffffffffu, v[d], CG & 31);
+                ex[d] = gl == 0 ? 0.0 : w;
+            }
+            if (gl == GW - 1) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) wagg[(warp * CG + cw) * D + d] = v[d];
+            }
+            __syncthreads();
+            double pre[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) pre[d] = 0.0;
+            for (int j = 0; j < warp; ++j) {
+                double w[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) w[d] = wagg[(j * CG + cw) * D + d];
+                matvec_acc<D>(tab_wpow + (warp - 1 - j) * DD, w, pre);
+            }
+            matvec_acc<D>(tab_fix + gl * DD, pre, ex);       // ex + A^(L gl) pre
+#pragma unroll
+            for (int d = 0; d < D; ++d) etot[((size_t)slot * D + d) * SOS_NT + tid] = ex[d];
+            if (tid < CG * D) {
+                // aggregate of the tile: sum_w A^(L GW (NW-1-w)) wagg[w]
+                const int ch = tid / D, r = tid - ch * D;
+                double acc = 0.0;
+                for (int w = 0; w < SOS_NW; ++w) {
+                    const double* M = tab_wpow + (SOS_NW - 1 - w) * DD + r * D;
+                    const double* q = wagg + (w * CG + ch) * D;
+                    for (int c = 0; c < D; ++c) acc = fma(M[c], q[c], acc);
+                }
+                aggr[(size_t)slot * CG * D + tid] = acc;
+            }
+            __syncthreads();
+            continue;
+        }
+        // ---- main visit of tile t
+        const bool store = t < b;
+        const bool last = t == P.ntt - 1;
+        prefetch(t - 2 - JJ);
+        if (tid < CG * D) {
+            // forward state entering the tile: sum_{j=1..JJ} (A^T)^(j-1) agg[t-j]
+            const int ch = tid / D, r = tid - ch * D;
+            double acc = 0.0;
+            for (int j = 1; j <= JJ; ++j) {
+                const double* M = Pt + (size_t)(j - 1) * DD + r * D;
+                const double* q = aggr + (size_t)slot_of(t - j) * CG * D + ch * D;
+                for (int c = 0; c < D; ++c) acc = fma(__ldg(M + c), q[c], acc);
+            }
+            sinf_s[tid] = acc;
+        }
+        __syncthreads();
+        double z[D];
+        {
+            double sv[D], tmp[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                sv[d] = sinf_s[cw * D + d];
+                tmp[d] = 0.0;
+                z[d] = etot[((size_t)slot * D + d) * SOS_NT + tid];
+            }
+            matvec_acc<D>(tab_wpow + warp * DD, sv, tmp);
+            matvec_acc<D>(tab_fix + gl * DD, tmp, z);
+        }
+        zp_df2t<S, false>(K, x, z);                          // x <- y1
+        // ---- backward sweep over the same registers
+        double vb[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) vb[d] = 0.0;
+        int lstar = SOS_L;                                   // last tile: index of the last row in its owner
+        bool owner = false;
+        double sb0[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) sb0[d] = 0.0;
+        if (last) {
+            const int il = (int)(P.N - 1 - t * T);
+            const int gstar = il / SOS_L;
+            lstar = il - gstar * SOS_L;
+            owner = g == gstar;
+            double ylast = 0.0;
+#pragma unroll
+            for (int i = 0; i < SOS_L; ++i) {
+                if (owner && i == lstar) ylast = x[i];
+                if (g > gstar || (owner && i > lstar)) x[i] = 0.0;
+            }
+            if (owner && P.zi_right) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) sb0[d] = P.zi.z[d] * ylast;
+            }
+        }
+        zp_pass_a<S, true>(K, x, vb);
+        if (last && owner) {
+            // the state zi * y1[last] enters at row lstar: seen from the rows before, it has
+            // been carried over lstar + 1 rows
+            double h[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) h[d] = sb0[d];
+            for (int k = 0; k <= lstar; ++k) zp_step0<S>(K, h);
+#pragma unroll
+            for (int d = 0; d < D; ++d) vb[d] += h[d];
+        }
+        {
+            int k = 0;
+            for (int off = CG; off < 32; off <<= 1, ++k) {
+                double w[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) w[d] = __shfl_down_sync(0xffffffffu, vb[d], off);
+                if (lane + off < 32) matvec_acc<D>(tab_s + k * DD, w, vb);
+            }
+        }
+        double zb[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const double w = __shfl_down_sync(0xffffffffu, vb[d], CG & 31);
+            zb[d] = gl == GW - 1 ? 0.0 : w;
+        }
+        if (gl == 0) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) wagg[(warp * CG + cw) * D + d] = vb[d];
+        }
+        __syncthreads();
+        {
+            double pre[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) pre[d] = 0.0;
+            for (int j = SOS_NW - 1; j > warp; --j) {
+                double w[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) w[d] = wagg[(j * CG + cw) * D + d];
+                matvec_acc<D>(tab_wpow + (j - 1 - warp) * DD, w, pre);
+            }
+            double sv[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) sv[d] = last ? 0.0 : sinb_s[par * CG * D + cw * D + d];
+            matvec_acc<D>(tab_wpow + (SOS_NW - 1 - warp) * DD, sv, pre);
+            matvec_acc<D>(tab_fix + (GW - 1 - gl) * DD, pre, zb);
+        }
+        if (last) {
+            // rolled loop through local memory: the owner of the last row starts there from
+            // zi * y1[last]; rows behind it are not part of the sequence
+            double tmp[SOS_L];
+#pragma unroll
+            for (int i = 0; i < SOS_L; ++i) tmp[i] = x[i];
+#pragma unroll 1
+            for (int i = SOS_L - 1; i >= 0; --i) {
+                if (owner && i == lstar) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) zb[d] = sb0[d];
+                }
+                double xv = tmp[i];
+#pragma unroll
+                for (int q = 0; q < S; ++q) {
+                    const double y = fma(K.coef[q][0], xv, zb[2 * q]);
+                    zb[2 * q] = fma(K.coef[q][1], xv, zb[2 * q + 1]) - K.coef[q][3] * y;
+                    zb[2 * q + 1] = K.coef[q][2] * xv - K.coef[q][4] * y;
+                    xv = y;
+                }
+                tmp[i] = xv;
+            }
+#pragma unroll
+            for (int i = 0; i < SOS_L; ++i) x[i] = tmp[i];
+        } else {
+            zp_df2t<S, true>(K, x, zb);                      // x <- y2
+        }
+        if (g == 0 && chan_ok) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) sinb_s[(par ^ 1) * CG * D + cw * D + d] = zb[d];
+        }
+        par ^= 1;
+        if (store && chan_ok) {
+            if (P.clamp) {
+#pragma unroll
+                for (int i = 0; i < SOS_L; ++i) x[i] = x[i] < 0.0 ? 0.0 : x[i];
+            }
+            const int64_t e0 = t * T + (int64_t)g * SOS_L;
+            const bool fast = t * T >= P.out_first && (t + 1) * (int64_t)T <= P.out_first + P.n_dst;
+            double* p = P.dst + (e0 - P.out_first) * C + c0 + cw;
+            if (fast && C == 8) {
+#pragma unroll
+                for (int i = 0; i < SOS_L; ++i) __stcs(p + i * 8, x[i]);
+            } else {
+                const int64_t o0 = e0 - P.out_first;
+#pragma unroll
+                for (int i = 0; i < SOS_L; ++i) {
+                    if (fast || (o0 + i >= 0 && o0 + i < P.n_dst)) __stcs(p, x[i]);
+                    p += C;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ======================================================================================
+// Pipelined variant for cascades that forget within JJ <= ZP_NTEAM - 2 tiles: nothing is read
+// twice, not even from L2.  A block is ZP_NTEAM teams of four warps and owns ONE run; team k
+// takes the tiles top - k, top - k - NTEAM, ...  A team loads its tile into registers, computes
+// the zero-state forward aggregates (pass A) and publishes the tile aggregate; the tile then
+// STAYS in the team's registers until the teams of the JJ tiles before it have published
+// theirs (they load later: the walk goes backward), which gives the forward state entering
+// the tile; forward recurrence, backward pass A and scan follow in the same registers.  The
+// backward state is handed from tile to tile as  sin_b(T) = A^T sin_b(T+1) + agg_b(T)  by one
+// warp as soon as agg_b(T) is known, so the teams work concurrently and only that small
+// matrix-vector product is serial along the run.  The register files of the waiting teams are
+// the look-ahead window: 4 teams x 32 KB of samples per SM, more than shared memory could hold
+// next to anything else.
+constexpr int ZP_NTEAM = 4;
+constexpr int ZP_PNT = SOS_NT * ZP_NTEAM;
+
+__device__ __forceinline__ void zp_team_bar(int team) {
+    asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(SOS_NT) : "memory");
+}
+// lane 0 polls a shared-memory tile counter (counts down along the walk) until it is <= v
+__device__ __forceinline__ void zp_wait_le(const volatile long long* f, long long v, int lane) {
+    if (lane == 0) {
+        while (*f > v) __nanosleep(20);
+        __threadfence_block();
+    }
+    __syncwarp();
+}
+
+template <int S, bool RECT>
+__global__ void __launch_bounds__(ZP_PNT, 1)
+sos_zp_pipe_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ ZpArgs P) {
+    constexpr int D = 2 * S;
+    constexpr int DD = D * D;
+    extern __shared__ __align__(16) double smem[];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int team = tid >> 7, ttid = tid & (SOS_NT - 1), warp = ttid >> 5;   // warp inside the team
+    const int grp = (int)(blockIdx.x % P.ngroups);
+    const int64_t run = blockIdx.x / P.ngroups;
+    const int CG = P.CG, C = P.C;
+    const int c0 = grp * CG;
+    const int Cw = min(CG, C - c0);
+    const int GW = 32 / CG;
+    const int gl = lane / CG, cw = lane % CG;
+    const int g = warp * GW + gl;
+    const bool chan_ok = cw < Cw;
+    const int T = P.T;
+    const int JJ = P.JJ;
+
+    double* tab_s = smem;                                   // n_staged * DD
+    double* wagg_all = tab_s + (size_t)P.n_staged * DD;     // [NTEAM][2][NW][CG][D]: forward / backward phase
+    double* wagg = wagg_all + (size_t)team * 2 * SOS_NW * CG * D;
+    double* waggb = wagg + (size_t)SOS_NW * CG * D;
+    double* aggr = wagg_all + (size_t)ZP_NTEAM * 2 * SOS_NW * CG * D;   // [NTEAM][CG][D]  forward tile aggregates
+    double* sinb_s = aggr + (size_t)ZP_NTEAM * CG * D;      // [NTEAM][CG][D]  backward state leaving a team's tile
+    volatile long long* la_flag = reinterpret_cast<volatile long long*>(sinb_s + (size_t)ZP_NTEAM * CG * D);  // [NTEAM]
+    volatile long long* sb_flag = la_flag + ZP_NTEAM;       // tile whose outgoing backward state is published
+    const double* tab_fix = tab_s + P.off_fix * DD;
+    const double* tab_wpow = tab_s + P.off_wpow * DD;
+    const double* Pt = P.tab + (size_t)P.off_tile * DD;     // (A^T)^j, global
+
+    const int64_t a = P.t_out0 + run * P.run_tiles;         // output tiles [a, b)
+    const int64_t b = min(a + (int64_t)P.run_tiles, P.t_out1);
+    if (a >= b) return;
+    const int64_t top = min(b + (int64_t)P.JO, P.ntt) - 1;  // first tile of the walk
+
+    for (int q = tid; q < P.n_staged * DD; q += ZP_PNT) tab_s[q] = __ldg(P.tab + q);
+    for (int q = tid; q < ZP_NTEAM * CG * D; q += ZP_PNT) sinb_s[q] = 0.0;
+    if (tid < ZP_NTEAM) la_flag[tid] = (long long)1 << 60;
+    if (tid == 0) *sb_flag = top + 1;
+    __syncthreads();
+
+    const double* xc = P.src + c0 + (chan_ok ? cw : 0);
+
+    for (int64_t t = top - team; t >= a - JJ; t -= ZP_NTEAM) {
+        // L2 prefetch of the tile this team takes next but one (contiguous rows)
+        if (P.pf && ttid == 0 && grp == 0) {
+            const int64_t tp = t - (int64_t)P.pf * ZP_NTEAM;
+            if (tp >= 0 && tp >= a - JJ) {
+                int64_t p0 = tp * T - P.edgeL, p1 = p0 + T;
+                if (p0 < 0) p0 = 0;
+                if (p1 > P.nx) p1 = P.nx;
+                if (p1 > p0) {
+                    const char* adr = reinterpret_cast<const char*>(P.src + p0 * C);
+                    int64_t bytes = (p1 - p0) * (int64_t)C * 8;
+                    const int64_t mis = reinterpret_cast<uintptr_t>(adr) & 15;
+                    adr -= mis;
+                    bytes = (bytes + mis + 15) & ~(int64_t)15;
+                    if (adr >= reinterpret_cast<const char*>(P.src))
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(adr), "r"((uint32_t)bytes) : "memory");
+                }
+            }
+        }
+        if (t < 0) {
+            // before the sequence: the virtual tile -1 carries the initial state of the sweep
+            if (ttid < CG * D) {
+                const int ch = ttid / D, d = ttid - ch * D;
+                double v = 0.0;
+                if (t == -1 && P.zi_left && c0 + ch < C)
+                    v = P.zi.z[d] * zp_ext_value<RECT>(P, P.src + c0 + ch, 0);
+                aggr[(size_t)team * CG * D + ttid] = v;
+            }
+            zp_team_bar(team);
+            if (ttid == 0) { __threadfence_block(); la_flag[team] = t; }
+            continue;
+        }
+        // ---- rows of tile t of this thread's channel -> registers
+        double x[SOS_L];
+        {
+            const int64_t e0 = t * T + (int64_t)g * SOS_L;  // sequence row of x[0]
+            const bool fast = t * T >= P.edgeL && (t + 1) * (int64_t)T <= P.edgeL + P.nx;
+            if (!chan_ok) {
+#pragma unroll
+                for (int i = 0; i < SOS_L; ++i) x[i] = 0.0;
+            } else if (fast) {
+                const double* p = xc + (e0 - P.edgeL) * C;
+                if (C == 8) {
+#pragma unroll
+                    for (int i = 0; i < SOS_L; ++i) x[i] = __ldg(p + i * 8);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < SOS_L; ++i) { x[i] = __ldg(p); p += C; }
+                }
+#pragma unroll
+                for (int i = 0; i < SOS_L; ++i) x[i] = zp_pre<RECT>(x[i]);
+            } else {
+                double tmp[SOS_L];
+#pragma unroll 1
+                for (int i = 0; i < SOS_L; ++i) tmp[i] = zp_ext_value<RECT>(P, xc, e0 + i);
+#pragma unroll
+                for (int i = 0; i < SOS_L; ++i) x[i] = tmp[i];
+            }
+        }
+        // ---- zero-state forward aggregates of the tile
+        double z[D];                                        // this thread's zero-state prefix, then its state
+        {
+            double v[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) v[d] = 0.0;
+            zp_pass_a<S, false>(K, x, v);
+            {
+                int k = 0;
+                for (int off = CG; off < 32; off <<= 1, ++k) {
+                    double w[D];
+#pragma unroll
+                    for (int d = 0; d < D; ++d) w[d] = __shfl_up_sync(0xffffffffu, v[d], off);
+                    if (lane >= off) matvec_acc<D>(tab_s + k * DD, w, v);
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const double w = __shfl_up_sync(0xffffffffu, v[d], CG & 31);
+                z[d] = gl == 0 ? 0.0 : w;
+            }
+            if (gl == GW - 1) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) wagg[(warp * CG + cw) * D + d] = v[d];
+            }
+            zp_team_bar(team);
+            double pre[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) pre[d] = 0.0;
+            for (int j = 0; j < warp; ++j) {
+                double w[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) w[d] = wagg[(j * CG + cw) * D + d];
+                matvec_acc<D>(tab_wpow + (warp - 1 - j) * DD, w, pre);
+            }
+            matvec_acc<D>(tab_fix + gl * DD, pre, z);        // z = ex + A^(L gl) pre
+            if (ttid < CG * D) {
+                const int ch = ttid / D, r = ttid - ch * D;
+                double acc = 0.0;
+                for (int w = 0; w < SOS_NW; ++w) {
+                    const double* M = tab_wpow + (SOS_NW - 1 - w) * DD + r * D;
+                    const double* q = wagg + (w * CG + ch) * D;
+                    for (int c = 0; c < D; ++c) acc = fma(M[c], q[c], acc);
+                }
+                aggr[(size_t)team * CG * D + ttid] = acc;
+            }
+            zp_team_bar(team);
+            if (ttid == 0) { __threadfence_block(); la_flag[team] = t; }
+        }
+        if (t < a) continue;                                 // below the run: only its aggregate is needed
+        const bool store = t < b;
+        const bool last = t == P.ntt - 1;
+        // ---- forward state entering the tile: sum_{j=1..JJ} (A^T)^(j-1) agg[t-j], from the teams behind
+        {
+            double sf[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) sf[d] = 0.0;
+            for (int j = 1; j <= JJ; ++j) {
+                const int tj = (team + j) % ZP_NTEAM;
+                zp_wait_le(la_flag + tj, t - j, lane);
+                double q[D], M[DD];
+#pragma unroll
+                for (int d = 0; d < D; ++d) q[d] = aggr[(size_t)tj * CG * D + cw * D + d];
+#pragma unroll
+                for (int e = 0; e < DD; ++e) M[e] = __ldg(Pt + (size_t)(j - 1) * DD + e);
+                matvec_acc<D>(M, q, sf);
+            }
+            double tmp[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) tmp[d] = 0.0;
+            matvec_acc<D>(tab_wpow + warp * DD, sf, tmp);
+            matvec_acc<D>(tab_fix + gl * DD, tmp, z);
+        }
+        zp_df2t<S, false>(K, x, z);                          // x <- y1
+        // ---- backward sweep over the same registers
+        double vb[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) vb[d] = 0.0;
+        int lstar = SOS_L;                                   // last tile: index of the last row in its owner
+        bool owner = false;
+        double sb0[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) sb0[d] = 0.0;
+        if (last) {
+            const int il = (int)(P.N - 1 - t * T);
+            const int gstar = il / SOS_L;
+            lstar = il - gstar * SOS_L;
+            owner = g == gstar;
+            double ylast = 0.0;
+#pragma unroll
+            for (int i = 0; i < SOS_L; ++i) {
+                if (owner && i == lstar) ylast = x[i];
+                if (g > gstar || (owner && i > lstar)) x[i] = 0.0;
+            }
+            if (owner && P.zi_right) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) sb0[d] = P.zi.z[d] * ylast;
+            }
+        }
+        zp_pass_a<S, true>(K, x, vb);
+        if (last && owner) {
+            double h[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) h[d] = sb0[d];
+            for (int k = 0; k <= lstar; ++k) zp_step0<S>(K, h);
+#pragma unroll
+            for (int d = 0; d < D; ++d) vb[d] += h[d];
+        }
+        {
+            int k = 0;
+            for (int off = CG; off < 32; off <<= 1, ++k) {
+                double w[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) w[d] = __shfl_down_sync(0xffffffffu, vb[d], off);
+                if (lane + off < 32) matvec_acc<D>(tab_s + k * DD, w, vb);
+            }
+        }
+        double zb[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const double w = __shfl_down_sync(0xffffffffu, vb[d], CG & 31);
+            zb[d] = gl == GW - 1 ? 0.0 : w;
+        }
+        if (gl == 0) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) waggb[(warp * CG + cw) * D + d] = vb[d];
+        }
+        zp_team_bar(team);
+        // ---- the backward state entering this tile (from the team of tile t + 1)
+        double sv[D];
+        {
+            const int tn = (team + ZP_NTEAM - 1) % ZP_NTEAM;
+            if (t < top) zp_wait_le(sb_flag, t + 1, lane);
+#pragma unroll
+            for (int d = 0; d < D; ++d) sv[d] = (last || t == top) ? 0.0 : sinb_s[(size_t)tn * CG * D + cw * D + d];
+        }
+        zp_team_bar(team);                                   // every warp of the team has read it
+        if (warp == 0) {
+            // hand the state on: sin_b(t) = A^T sin_b(t+1) + sum_w A^(L GW w) wagg[w]
+            for (int e = lane; e < CG * D; e += 32) {
+                const int ch = e / D, r = e - ch * D;
+                double acc = 0.0;
+                for (int w = 0; w < SOS_NW; ++w) {
+                    const double* M = tab_wpow + w * DD + r * D;
+                    const double* q = waggb + (w * CG + ch) * D;
+                    for (int c = 0; c < D; ++c) acc = fma(M[c], q[c], acc);
+                }
+                if (!(last || t == top)) {
+                    const int tn = (team + ZP_NTEAM - 1) % ZP_NTEAM;
+                    const double* M = Pt + DD + r * D;
+                    const double* q = sinb_s + (size_t)tn * CG * D + ch * D;
+                    for (int c = 0; c < D; ++c) acc = fma(__ldg(M + c), q[c], acc);
+                }
+                sinb_s[(size_t)team * CG * D + e] = acc;
+            }
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); *sb_flag = t; }
+        }
+        {
+            double pre[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) pre[d] = 0.0;
+            for (int j = SOS_NW - 1; j > warp; --j) {
+                double w[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) w[d] = waggb[(j * CG + cw) * D + d];
+                matvec_acc<D>(tab_wpow + (j - 1 - warp) * DD, w, pre);
+            }
+            matvec_acc<D>(tab_wpow + (SOS_NW - 1 - warp) * DD, sv, pre);
+            matvec_acc<D>(tab_fix + (GW - 1 - gl) * DD, pre, zb);
+        }
+        if (last) {
+            double tmp[SOS_L];
+#pragma unroll
+            for (int i = 0; i < SOS_L; ++i) tmp[i] = x[i];
+#pragma unroll 1
+            for (int i = SOS_L - 1; i >= 0; --i) {
+                if (owner && i == lstar) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) zb[d] = sb0[d];
+                }
+                double xv = tmp[i];
+#pragma unroll
+                for (int q = 0; q < S; ++q) {
+                    const double y = fma(K.coef[q][0], xv, zb[2 * q]);
+                    zb[2 * q] = fma(K.coef[q][1], xv, zb[2 * q + 1]) - K.coef[q][3] * y;
+                    zb[2 * q + 1] = K.coef[q][2] * xv - K.coef[q][4] * y;
+                    xv = y;
+                }
+                tmp[i] = xv;
+            }
+#pragma unroll
+            for (int i = 0; i < SOS_L; ++i) x[i] = tmp[i];
+        } else {
+            zp_df2t<S, true>(K, x, zb);                      // x <- y2
+        }
+        if (store && chan_ok) {
+            if (P.clamp) {
+#pragma unroll
+                for (int i = 0; i < SOS_L; ++i) x[i] = x[i] < 0.0 ? 0.0 : x[i];
+            }
+            const int64_t e0 = t * T + (int64_t)g * SOS_L;
+            const bool fast = t * T >= P.out_first && (t + 1) * (int64_t)T <= P.out_first + P.n_dst;
+            double* p = P.dst + (e0 - P.out_first) * C + c0 + cw;
+            if (fast && C == 8) {
+#pragma unroll
+                for (int i = 0; i < SOS_L; ++i) __stcs(p + i * 8, x[i]);
+            } else {
+                const int64_t o0 = e0 - P.out_first;
+#pragma unroll
+                for (int i = 0; i < SOS_L; ++i) {
+                    if (fast || (o0 + i >= 0 && o0 + i < P.n_dst)) __stcs(p, x[i]);
+                    p += C;
+                }
+            }
+        }
+        // the team's wagg is rewritten by its next tile only after the team barrier there
+    }
+}
+
+std::atomic<int64_t> g_zp_launches{0};
+
+template <int S, bool RECT>
+int32_t launch_zp(const SosPlan& plan, const ZpArgs& P, size_t smem, unsigned grid, bool pipe, cudaStream_t st) {
+    SosK<S> K;
+    fill_sosk<S>(plan, K);
+    if (pipe) {
+        auto kern = sos_zp_pipe_kernel<S, RECT>;
+        static bool attr_done = false;           // per instantiation
+        if (!attr_done) {
+            ADN_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            attr_done = true;
+        }
+        kern<<<grid, ZP_PNT, smem, st>>>(K, P);
+    } else {
+        auto kern = sos_zp_kernel<S, RECT>;
+        static bool attr_done = false;
+        if (!attr_done) {
+            ADN_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            attr_done = true;
+        }
+        kern<<<grid, SOS_NT, smem, st>>>(K, P);
+    }
+    count_launch();
+    g_zp_launches.fetch_add(1);
+    ADN_CK(cudaGetLastError());
+    return ADN_OK;
+}
+
+template <int S>
+int32_t launch_zp_S(bool rect, const SosPlan& plan, const ZpArgs& P, size_t smem, unsigned grid, bool pipe,
+                    cudaStream_t st) {
+    return rect ? launch_zp<S, true>(plan, P, smem, grid, pipe, st)
+                : launch_zp<S, false>(plan, P, smem, grid, pipe, st);
+}
+
+int zp_env(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
+
+}  // namespace
+
+int64_t zp_launches() { return g_zp_launches.load(); }
+
+int32_t zero_phase_regs_dev(bool rect, const double* sos, int32_t S, const double* src, int64_t n_src,
+                            int32_t C, int32_t edge_left, int32_t edge_right, int64_t out_first,
+                            double* dst, int64_t n_dst, int32_t clamp_negative, bool* handled,
+                            cudaStream_t st) {
+    *handled = false;
+    if (!option(ADN_OPT_ZERO_PHASE_ONEPASS) || S < 1 || S > 4 || n_dst <= 0) return ADN_OK;
+    const int CG = pick_cg(C);
+    std::shared_ptr<SosPlan> plan;
+    int32_t rc = get_sos_plan(sos, S, CG, st, &plan);
+    if (rc) return rc;
+    if (plan->jzp > ZP_MAX_JJ) return ADN_OK;               // forgets too slowly: two sweeps with look-back
+    const int D = 2 * S;
+    ZpArgs P;
+    memset(&P, 0, sizeof P);
+    P.src = src; P.dst = dst; P.tab = plan->dtab;
+    P.off_fix = plan->off_fix; P.off_wpow = plan->off_wpow; P.off_tile = plan->off_tile;
+    P.n_staged = plan->n_staged;
+    P.nx = n_src;
+    P.edgeL = edge_left; P.edgeR = edge_right;
+    P.N = n_src + edge_left + edge_right;
+    P.out_first = out_first; P.n_dst = n_dst;
+    P.C = C; P.CG = CG; P.ngroups = (C + CG - 1) / CG;
+    P.T = (SOS_NT / CG) * SOS_L;
+    P.ntt = (P.N + P.T - 1) / P.T;
+    P.t_out0 = out_first / P.T;
+    P.t_out1 = (out_first + n_dst - 1) / P.T + 1;
+    P.zi_left = edge_left > 0; P.zi_right = edge_right > 0;
+    P.clamp = clamp_negative ? 1 : 0;
+    P.JJ = plan->jzp;
+    P.JO = plan->jzp;
+    P.pf = zp_env("ADN_ZP_PREFETCH", 1);
+    sosfilt_zi_host(sos, S, P.zi.z);
+    const int64_t out_tiles = P.t_out1 - P.t_out0;
+    // the register pipeline (one block of ZP_NTEAM teams per SM) when the look-ahead fits its teams
+    const bool pipe = P.JJ <= ZP_NTEAM - 2 && zp_env("ADN_ZP_PIPE", 1);
+    size_t smem;
+    int64_t resident;
+    if (pipe) {
+        smem = ((size_t)plan->n_staged * D * D + (size_t)ZP_NTEAM * (2 * SOS_NW + 2) * CG * D) * 8 +
+               (ZP_NTEAM + 1) * 8 + 64;
+        resident = ctx().sm_count;
+    } else {
+        smem = ((size_t)plan->n_staged * D * D + (size_t)(SOS_NW + 3) * CG * D +
+                (size_t)(P.JJ + 1) * (CG * D + SOS_NT * D)) * 8;
+        int bps = (int)((220 * 1024) / (smem + 1024));
+        const int bmax = S <= 2 ? ZP_BLOCKS : 3;
+        if (bps > bmax) bps = bmax;
+        resident = (int64_t)ctx().sm_count * bps;
+    }
+    if (smem > 96 * 1024) return ADN_OK;
+    int64_t runs = resident / P.ngroups;
+    if (runs < 1) runs = 1;
+    int64_t run_tiles = (out_tiles + runs - 1) / runs;
+    // the run-out and the look-ahead may cost a third of a run at most
+    const int64_t min_run = 2 * (int64_t)(P.JJ + P.JO);
+    if (run_tiles < min_run) run_tiles = min_run;
+    runs = (out_tiles + run_tiles - 1) / run_tiles;
+    if (out_tiles < 2 * min_run) return ADN_OK;              // short input: the two sweeps
+    if (run_tiles > 0x3fffffff || runs * P.ngroups > 0x7fffffff) return ADN_OK;
+    P.run_tiles = (int32_t)run_tiles;
+    const unsigned grid = (unsigned)(runs * P.ngroups);
+    switch (S) {
+        case 1: rc = launch_zp_S<1>(rect, *plan, P, smem, grid, pipe, st); break;
+        case 2: rc = launch_zp_S<2>(rect, *plan, P, smem, grid, pipe, st); break;
+        case 3: rc = launch_zp_S<3>(rect, *plan, P, smem, grid, pipe, st); break;
+        default: rc = launch_zp_S<4>(rect, *plan, P, smem, grid, pipe, st); break;
+    }
+    if (rc == ADN_OK) *handled = true;
+    return rc;
+}
+
+}  // namespace adn

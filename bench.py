@@ -457,9 +457,9 @@ def run_ours(args):
         tf = BufferedFilter()
         tf.configure_standalone(RATE, C, highpass_cutoff=HIGHPASS, lowpass_cutoff=LOWPASS)
         ts = BufferedSpectrogram(nfft=NFFT, overlap_frac=0.5)
-        ts.configure_standalone(RATE, C)
+        ts.configure_standalone(RATE, C, source=tf)
         te = BufferedEnvelope(envelope_cutoff=ENV_CUTOFF)
-        te.configure_standalone(RATE, C)
+        te.configure_standalone(RATE, C, source=tf)
 
         def host_step(i):
             x = host_x[i % len(host_x)]

@@ -23,11 +23,13 @@
  *
  * Host-pointer entry points copy to and from device memory that the library
  * owns, on the library's own streams (upload, kernels and download overlap
- * chunk by chunk), and block until the result is in `dst`.
+ * chunk by chunk), and block until the result is in `dst`.  They are serialised
+ * by one library mutex: safe to call from several threads, one runs at a time.
  * The *_dev entry points take device pointers and a cudaStream_t (passed as
  * void*; NULL = CUDA's default stream), only enqueue work and do not
- * synchronise.  Scratch memory of the library is shared by all *_dev calls:
- * issue them from one stream at a time.
+ * synchronise.  Their scratch memory is kept per stream, so calls on different
+ * streams are independent; it grows on first use (cudaMalloc), so warm a
+ * stream up before capturing it into a CUDA graph.
  */
 #ifndef AUDIAN_B200_H
 #define AUDIAN_B200_H
@@ -51,28 +53,27 @@ extern "C" {
                                        transforms run in a global-memory work buffer */
 
 /* adn_set_option() */
-#define ADN_OPT_RESIDENT            0  /* keep large results on the device, keyed by the host
-                                          range they were written to; later calls whose source
-                                          lies inside such a range skip the upload (default 0) */
-#define ADN_OPT_VERIFY              1  /* verify a resident copy on sampled values before it
-                                          is used (default 1) */
+#define ADN_OPT_RESIDENT            0  /* 1 (default): mirrors (adn_mirror_create) keep results on the
+                                          device for the calls that name them; 0: mirror arguments
+                                          are ignored, every call uploads its source */
+#define ADN_OPT_VERIFY              1  /* reserved (was: sampled verification of the address-keyed
+                                          cache of version 1.0, which no longer exists) */
 #define ADN_OPT_CHUNK_BYTES         2  /* granularity of the upload/kernel/download pipeline
                                           of the host-pointer entry points (default 32 MiB) */
-#define ADN_OPT_RESIDENT_MIN_BYTES  3  /* smaller results are never kept (default 8 MiB) */
-#define ADN_OPT_RESIDENT_CAP_BYTES  4  /* least recently used copies are dropped beyond this
-                                          total (default 16 GiB) */
-#define ADN_OPT_ENVELOPE_CHUNK_BYTES 5 /* > 0: the two envelope sweeps run chunk by chunk (forward
-                                          over chunk j+1, backward over chunk j) when the cascade
-                                          forgets its state well within a chunk, so that the
-                                          forward result stays in L2.  Default 0 = two full
-                                          sweeps: measured on B200 the scan kernel is not HBM
-                                          bound enough for the saved traffic to pay for the
-                                          extra launches (16 MiB chunks: 0.74 ms vs 0.25 ms) */
+#define ADN_OPT_RESIDENT_MIN_BYTES  3  /* smaller results are never kept in a mirror (default 1 MiB) */
+#define ADN_OPT_RESIDENT_CAP_BYTES  4  /* a result that would take the device memory of all mirrors
+                                          beyond this total is not kept (default 16 GiB) */
+#define ADN_OPT_ENVELOPE_CHUNK_BYTES 5 /* reserved (was: chunked two-sweep schedule of the envelope;
+                                          superseded by the one-pass kernel, option 7) */
 #define ADN_OPT_SCAN_RUNS           6  /* 1 (default): SOS cascades that forget their state within
                                           a few tiles are filtered by the run kernel (a block walks
                                           along time, state handed on in shared memory, run-in from
                                           zero state); 0: always the look-back kernel */
-#define ADN_OPT_COUNT               7
+#define ADN_OPT_ZERO_PHASE_ONEPASS  7  /* 1 (default): envelope / sosfiltfilt of cascades that forget
+                                          their state within a few tiles run as ONE pass with the tile
+                                          held in registers (csrc/zerophase.cu: 16 B per sample);
+                                          0: always a forward and a backward sweep through memory */
+#define ADN_OPT_COUNT               8
 
 #define ADN_WINDOW_HANN      0   /* periodic Hann == scipy get_window('hann', nfft) */
 #define ADN_DETREND_NONE     0
@@ -85,6 +86,7 @@ const char* adn_last_error(void);
 int32_t adn_version(void);
 int64_t adn_launch_count(void);        /* kernels launched by this library so far */
 int64_t adn_scan_run_count(void);      /* of these: launches of the SOS run kernel (ADN_OPT_SCAN_RUNS) */
+int64_t adn_zero_phase_count(void);    /* launches of the one-pass zero-phase kernel (ADN_OPT_ZERO_PHASE_ONEPASS) */
 int32_t adn_synchronize(void);         /* waits for the library's stream */
 /* page-lock a host range so that the host-pointer entry points copy at full
  * PCIe rate (optional; plain pageable memory works too) */
@@ -92,10 +94,23 @@ int32_t adn_host_register(void* ptr, int64_t bytes);
 int32_t adn_host_unregister(void* ptr);
 int32_t adn_set_option(int32_t option, int64_t value);
 int64_t adn_get_option(int32_t option);
-/* The host range changed by other means than a call of this library (a buffer
- * was moved, reloaded, freed): forget device copies that overlap it. */
+/* Mirrors: explicit hand-over of device copies from the call that produces a
+ * buffer to the calls that consume it (the derived traces of a data graph:
+ * reference src/audian/buffereddata.py:149-153 walks filtered -> its dests).
+ * The owner of a host buffer creates a mirror and names it as `dst_mirror` in the
+ * *_m call that fills the buffer (or part of it): the result then also stays on
+ * the device, tagged with the host range it was copied to -- only after the
+ * computation and the download succeeded.  A consumer names the same handle as
+ * `src_mirror`: if its source range lies inside the mirror's valid range the
+ * upload is skipped.  The owner calls adn_mirror_invalidate() whenever the host
+ * buffer changes by other means (moved, reallocated, reloaded, edited in place).
+ * Handle 0 = no mirror: the plain entry points never read device copies. */
+int32_t adn_mirror_create(int64_t* handle);
+int32_t adn_mirror_release(int64_t handle);
+int32_t adn_mirror_invalidate(int64_t handle);
+/* invalidates every mirror whose host range overlaps [host, host + bytes) */
 int32_t adn_invalidate(const void* host, int64_t bytes);
-int64_t adn_resident_hits(void);       /* sources served from a resident copy so far */
+int64_t adn_resident_hits(void);       /* sources served from a mirror so far */
 /* bytes the host-pointer entry points have copied to / from the device so far */
 int32_t adn_transfer_bytes(int64_t* h2d_bytes, int64_t* d2h_bytes);
 
@@ -147,8 +162,8 @@ int32_t adn_decibel_f64(const double* power, int64_t n, double ref_power,
 
 /* Decibel image of one channel, what SpecItem.update_plot hands to setImage()
  * (src/audian/specitem.py:33-39): dst (F, n) = decibel(spec[:, channel, :].T),
- * spec (n, C, F).  If the buffer is resident on the device (it was written by
- * adn_spectrogram_f64 with ADN_OPT_RESIDENT) nothing is uploaded; otherwise only
+ * spec (n, C, F).  With the mirror of the buffer (adn_spec_image_db_f64_m, the
+ * buffer was written by adn_spectrogram_f64_m) nothing is uploaded; otherwise only
  * the rows of that channel are (strided copy). */
 int32_t adn_spec_image_db_f64(const double* spec, int64_t n, int32_t C, int32_t F,
                               int32_t channel, double* dst);
@@ -172,7 +187,65 @@ int32_t adn_sosfiltfilt_f64(const double* sos, int32_t S,
                             const double* src, int64_t n_src, int32_t C,
                             double* dst, int64_t n_dst);
 
+/* ---- the same entry points with mirrors (0 = none) ------------------- */
+int32_t adn_minmax_f64_m(const double* src, int64_t n, int32_t C, int64_t step,
+                         double* dst, int64_t src_mirror);
+int32_t adn_sosfilt_f64_m(const double* sos, int32_t S,
+                          const double* src, int64_t n_src, int32_t C,
+                          int64_t nbefore, double* dst, int64_t n_dst,
+                          double* zi_inout, int64_t src_mirror, int64_t dst_mirror);
+int32_t adn_envelope_f64_m(const double* sos, int32_t S,
+                           const double* src, int64_t n_src, int32_t C,
+                           int64_t nbefore, double* dst, int64_t n_dst,
+                           int32_t clamp_negative, int64_t src_mirror, int64_t dst_mirror);
+int32_t adn_spectrogram_f64_m(const double* src, int64_t n_src, int32_t C,
+                              double rate, int32_t nfft, int32_t hop,
+                              int32_t window_id, int32_t detrend_id,
+                              double* dst, int64_t n_dst, int32_t out_db,
+                              int64_t* n_computed, int64_t src_mirror, int64_t dst_mirror);
+int32_t adn_spec_image_db_f64_m(const double* spec, int64_t n, int32_t C, int32_t F,
+                                int32_t channel, double* dst, int64_t src_mirror);
+int32_t adn_mean_power_db_f64_m(const double* spec, int64_t n, int32_t C, int32_t F,
+                                int32_t channel, int64_t i0, int64_t i1,
+                                double floor_db, double* dst, int64_t src_mirror);
+
+/* One channel of a trace, the reduction TraceItem.update_plot draws
+ * (src/audian/traceitem.py:58-61): dst (2*ceil(n/step)) = interleaved min / max of
+ * src[:, channel].  With the trace's mirror the column is gathered on the device,
+ * otherwise only the column is uploaded (n x 8 bytes, not n x C x 8). */
+int32_t adn_minmax_channel_f64_m(const double* src, int64_t n, int32_t C, int32_t channel,
+                                 int64_t step, double* dst, int64_t src_mirror);
+/* The loader's unwrap option (src/audian/data.py:180 -> audioio unwrap(data, thresh,
+ * clips)), in place on a (n, C) host array: a step between consecutive samples of a
+ * channel below -thresh adds 2 to everything that follows, a step above +thresh takes
+ * 2 away (the file format wrapped the signal around +-1); clips != 0 limits the result to
+ * [-1, 1].  thresh <= 0: nothing is done.  audioio is not vendored with the reference:
+ * this restates its documented behaviour (parity unpinned for this entry). */
+int32_t adn_unwrap_f64(double* data, int64_t n, int32_t C, double thresh, int32_t clips);
+/* The signal DataBrowser.play_region plays (src/audian/databrowser.py:1702-1731):
+ * dst[:, 0] = mean(src[:, left], 1), dst[:, 1] = mean(src[:, right], 1) (nright == 0: one
+ * column); if het_freq > 0 the columns are multiplied by sin(2 pi het_freq k / rate),
+ * zero-phase filtered with `sos` (the caller designs butter(2, 20000, 'low', fs=rate)) and
+ * every nstep-th row is kept.  dst: (ceil(n/nstep), 1 or 2); nstep is ignored (1) without
+ * heterodyne. */
+int32_t adn_play_region_f64_m(const double* src, int64_t n, int32_t C,
+                              const int32_t* left, int32_t nleft,
+                              const int32_t* right, int32_t nright,
+                              double rate, double het_freq,
+                              const double* sos, int32_t S, int64_t nstep,
+                              double* dst, int64_t src_mirror);
+
 /* ---- device-pointer entry points (bench / multi-GPU path) ----------- */
+/* out of place: dst != src */
+int32_t adn_unwrap_f64_dev(const double* src, int64_t n, int32_t C, double thresh,
+                           int32_t clips, double* dst, void* stream);
+/* left / right / sos are HOST pointers */
+int32_t adn_play_region_f64_dev(const double* src, int64_t n, int32_t C,
+                                const int32_t* left, int32_t nleft,
+                                const int32_t* right, int32_t nright,
+                                double rate, double het_freq,
+                                const double* sos, int32_t S, int64_t nstep,
+                                double* dst, void* stream);
 int32_t adn_sosfiltfilt_f64_dev(const double* sos, int32_t S,
                                 const double* src, int64_t n_src, int32_t C,
                                 double* dst, int64_t n_dst, void* stream);

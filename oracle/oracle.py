@@ -371,3 +371,44 @@ def spectrogram_frames_restated(x, rate, nfft, hop):
             P[1:] *= 2
         out[k] = P.T
     return out
+
+
+# ---------------------------------------------------------------- f4: play-back and ingest
+
+def play_region(data, show_channels, rate, use_heterodyne=False, heterodyne_freq=0.0):
+    """DataBrowser.play_region up to the fade (src/audian/databrowser.py:1711-1728), on the
+    rows `data` (frames, channels) of the region: returns (playdata, rate)."""
+    from scipy.signal import butter, sosfiltfilt
+    n2 = (len(show_channels) + 1)//2
+    playdata = np.zeros((len(data), min(2, len(show_channels))))
+    playdata[:, 0] = np.mean(data[:, show_channels[:n2]], 1)
+    if len(show_channels) > 1:
+        playdata[:, 1] = np.mean(data[:, show_channels[n2:]], 1)
+    if use_heterodyne:
+        heterodyne = np.sin(2*np.pi*heterodyne_freq*np.arange(len(playdata))/rate)
+        playdata = (playdata.T * heterodyne).T
+        fcutoff = 20000.0
+        sos = butter(2, 20000, 'low', output='sos', fs=rate)
+        nstep = int(np.round(rate/(2*fcutoff)))
+        if nstep < 1:
+            nstep = 1
+        playdata = sosfiltfilt(sos, playdata, 0)[::nstep]
+        rate /= nstep
+    return playdata, rate
+
+
+def unwrap(data, thresh=-1.0, clips=False):
+    """audioio.unwrap(data, thresh, clips) as the loader applies it when Data.open passes
+    `unwrap` (src/audian/data.py:180).  audioio is not vendored with the reference and not
+    installed here: this restates its documented behaviour [recalled] -- parity unpinned.
+    In place; a step between consecutive samples of a channel below -thresh adds 2 to
+    everything that follows, a step above +thresh takes 2 away; clips limits to [-1, 1]."""
+    if thresh <= 0:
+        return data
+    d = data.reshape(len(data), -1)
+    dd = np.diff(d, axis=0)
+    k = np.cumsum((dd < -thresh).astype(np.int64) - (dd > thresh).astype(np.int64), axis=0)
+    d[1:] += 2.0*k
+    if clips:
+        np.clip(d, -1.0, 1.0, out=d)
+    return data

@@ -70,7 +70,12 @@ def test_product_does_not_import_the_oracle():
 
 
 def test_options_and_invalidate_need_no_gpu():
-    assert _lib.get_option(_lib.ADN_OPT_VERIFY) == 1
+    assert _lib.get_option(_lib.ADN_OPT_RESIDENT) == 1
+    assert _lib.get_option(_lib.ADN_OPT_ZERO_PHASE_ONEPASS) == 1
+    m = _lib.Mirror()                            # mirrors are host-side bookkeeping until used
+    assert m.handle > 0
+    m.invalidate()
+    m.release()
     old = _lib.get_option(_lib.ADN_OPT_CHUNK_BYTES)
     _lib.set_option(_lib.ADN_OPT_CHUNK_BYTES, 12345)
     assert _lib.get_option(_lib.ADN_OPT_CHUNK_BYTES) == 12345

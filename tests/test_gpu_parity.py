@@ -339,7 +339,11 @@ def test_envelope_run_kernel(C, n, order, hp):
         _lib.envelope(sos, x, got, nbefore, hp == 0)
         return got
 
-    a, b, nrun = _both_scan_kernels(call)
+    _lib.set_option(_lib.ADN_OPT_ZERO_PHASE_ONEPASS, 0)     # the two sweeps through memory
+    try:
+        a, b, nrun = _both_scan_kernels(call)
+    finally:
+        _lib.set_option(_lib.ADN_OPT_ZERO_PHASE_ONEPASS, 1)
     if hp == 0:
         assert nrun >= 2, 'both sweeps are meant to take the run kernel'
     assert np.max(np.abs(a - b)) <= 1e-11*max(1.0, np.max(np.abs(b)))
@@ -347,6 +351,80 @@ def test_envelope_run_kernel(C, n, order, hp):
     orc.envelope_process(sos, x, ref, nbefore, hp)
     assert_trace_close(a, ref, f'envelope run kernel C={C} order={order} hp={hp}')
     assert np.max(np.abs(a - ref)) <= 1e-10*max(1.0, np.max(np.abs(ref)))
+
+
+# ---------------------------------------------------------------- one-pass zero-phase kernel
+
+@pytest.mark.parametrize('C,n,order,fc,nbefore', [
+    (8, 1500000, 2, 500., 0), (8, 700001, 2, 500., 11), (64, 300000, 2, 500., 0),
+    (1, 3000001, 2, 500., 5), (2, 2500000, 4, 500., 0), (3, 1200000, 2, 800., 7),
+    (4, 900000, 2, 2000., 0), (13, 400000, 2, 500., 1), (16, 600000, 4, 1000., 100000),
+    (8, 123457, 2, 4000., 0)])
+@pytest.mark.parametrize('pipe', [1, 0])
+def test_envelope_onepass_kernel(C, n, order, fc, nbefore, pipe, monkeypatch):
+    """csrc/zerophase.cu (one pass, tile in registers; pipe = 1: the register pipeline where the
+    cascade allows it, 0: the variant that reads every tile twice) against the two sweeps
+    through memory and against scipy's sosfiltfilt (oracle); bufferedenvelope.py:34-41."""
+    monkeypatch.setenv('ADN_ZP_PIPE', str(pipe))
+    fs = 48000.
+    x = synth(3, n, C, fs, seed=C + 300)
+    sos = orc.envelope_design(fs, fc, 0, order)
+
+    def call():
+        got = np.empty((n - nbefore, C))
+        _lib.envelope(sos, x, got, nbefore, True)
+        return got
+
+    z0 = _lib.zero_phase_count()
+    a = call()
+    assert _lib.zero_phase_count() == z0 + 1, 'the one-pass kernel is meant to take this shape'
+    _lib.set_option(_lib.ADN_OPT_ZERO_PHASE_ONEPASS, 0)
+    try:
+        b = call()
+        assert _lib.zero_phase_count() == z0 + 1
+    finally:
+        _lib.set_option(_lib.ADN_OPT_ZERO_PHASE_ONEPASS, 1)
+    ref = np.empty((n - nbefore, C))
+    orc.envelope_process(sos, x, ref, nbefore, 0)
+    scale = max(1.0, np.max(np.abs(ref)))
+    assert np.max(np.abs(a - b)) <= 1e-11*scale
+    assert np.max(np.abs(a - ref)) <= 1e-10*scale, f'one-pass envelope C={C} n={n} order={order}'
+    assert (a >= 0).all()
+
+
+@pytest.mark.parametrize('C,n,order', [(8, 800000, 2), (2, 1000003, 4), (5, 500000, 6)])
+def test_sosfiltfilt_onepass_kernel(C, n, order):
+    """The same kernel without the rectification == scipy.signal.sosfiltfilt (databrowser.py:1725)."""
+    from scipy.signal import sosfiltfilt
+    fs = 96000.
+    x = synth(1, n, C, fs, seed=C + 400)
+    sos = butter(order, 12000., 'lowpass', fs=fs, output='sos')
+    z0 = _lib.zero_phase_count()
+    got = _lib.sosfiltfilt(sos, x)
+    assert _lib.zero_phase_count() == z0 + 1
+    ref = sosfiltfilt(sos, x, axis=0)
+    assert np.max(np.abs(got - ref)) <= 1e-10*max(1.0, np.max(np.abs(ref)))
+
+
+def test_envelope_onepass_falls_back():
+    """Cascades that forget slowly (band-pass envelope with a 20-Hz high-pass) and short inputs
+    keep the two sweeps."""
+    fs = 48000.
+    x = synth(0, 400000, 4, fs, seed=77)
+    z0 = _lib.zero_phase_count()
+    sos = orc.envelope_design(fs, 500., 20., 2)
+    got = np.empty_like(x)
+    _lib.envelope(sos, x, got, 0, False)
+    ref = np.empty_like(x)
+    orc.envelope_process(sos, x, ref, 0, 20.)
+    assert_trace_close(got, ref, 'slow cascade')
+    sos = orc.envelope_design(fs, 500.)
+    got = np.empty((5000, 4))
+    _lib.envelope(sos, x[:5000], got, 0, True)
+    ref = np.empty((5000, 4))
+    orc.envelope_process(sos, x[:5000], ref, 0, 0)
+    assert_trace_close(got, ref, 'short input')
+    assert _lib.zero_phase_count() == z0
 
 
 # ---------------------------------------------------------------- envelope

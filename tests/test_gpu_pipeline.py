@@ -80,16 +80,17 @@ def test_resident_chain_matches_oracle_and_skips_uploads(resident):
     sos = orc.filter_design(fs, 1000., 15000., 2)
     esos = orc.envelope_design(fs, 500.)
     filt = np.empty((n, C))
+    m = _lib.Mirror()                                    # owned by whoever owns `filt`
     hits0 = _lib.resident_hits()
-    _lib.sosfilt(sos, x, filt, 0)
+    _lib.sosfilt(sos, x, filt, 0, dst_mirror=m)
     rf = np.empty((n, C))
     orc.filter_process(sos, x, rf, 0)
     assert np.max(np.abs(filt - rf)) <= 1e-9
     nfft, hop = 1024, 512
     spec = np.empty((n//hop, C, nfft//2 + 1))
-    ns = _lib.spectrogram(filt, fs, nfft, hop, spec)
+    ns = _lib.spectrogram(filt, fs, nfft, hop, spec, src_mirror=m)
     env = np.empty((n, C))
-    _lib.envelope(esos, filt, env, 0, True)
+    _lib.envelope(esos, filt, env, 0, True, src_mirror=m)
     assert _lib.resident_hits() == hits0 + 2            # both consumers read the device copy
     rs = np.empty_like(spec)
     assert orc.spectrogram_process(filt, rs, fs, nfft, hop) == ns
@@ -99,37 +100,109 @@ def test_resident_chain_matches_oracle_and_skips_uploads(resident):
     assert np.max(np.abs(env - re)) <= 1e-9
     # a slice of the kept range hits too
     part = np.empty((n - 40000, C))
-    _lib.envelope(esos, filt[40000:], part, 0, True)
+    _lib.envelope(esos, filt[40000:], part, 0, True, src_mirror=m)
     assert _lib.resident_hits() == hits0 + 3
     orc.envelope_process(esos, filt[40000:], re[:n - 40000], 0, 0)
     assert np.max(np.abs(part - re[:n - 40000])) <= 1e-9
+    # a range that is not inside the mirror's does not
+    other = filt.copy()
+    _lib.envelope(esos, other, env, 0, True, src_mirror=m)
+    assert _lib.resident_hits() == hits0 + 3
+    m.release()
 
 
-def test_stale_resident_copy_is_not_used(resident):
+def test_stale_device_copy_is_never_used(resident):
+    """Explicit hand-over: calls that name no mirror never see device copies, so an array
+    edited in place -- three samples are enough -- or freed and reallocated at the same
+    address is always read from the host."""
     fs, C, n = 48000., 2, 50000
     x = synth(0, n, C, fs, seed=12)
     sos = orc.filter_design(fs, 1000., 15000., 2)
     filt = np.empty((n, C))
-    _lib.sosfilt(sos, x, filt, 0)
-    # the caller says so
+    m = _lib.Mirror()
+    _lib.sosfilt(sos, x, filt, 0, dst_mirror=m)
+    # three samples change in place; a plain call sees the new values
+    filt[7, 0] = 5.0
+    filt[20001, 1] = -6.0
+    filt[n - 1, 0] = 7.0
+    hits = _lib.resident_hits()
+    got = _lib.minmax(filt, 100)
+    assert _lib.resident_hits() == hits
+    assert np.array_equal(got.view(np.uint64), orc.minmax_rows(filt, 100).view(np.uint64))
+    assert got[1, 0] == 5.0 and got[2*200, 1] == -6.0 and got[-1, 0] == 7.0
+    # the owner says so: the mirror is not used until its buffer is filled again
+    m.invalidate()
+    got = _lib.minmax(filt, 100, src_mirror=m)
+    assert _lib.resident_hits() == hits
+    assert np.array_equal(got.view(np.uint64), orc.minmax_rows(filt, 100).view(np.uint64))
+    _lib.sosfilt(sos, x, filt, 0, dst_mirror=m)
+    got = _lib.minmax(filt, 100, src_mirror=m)
+    assert _lib.resident_hits() == hits + 1
+    assert np.array_equal(got.view(np.uint64), orc.minmax_rows(filt, 100).view(np.uint64))
+    # address-based invalidation still works (adn_invalidate)
     filt *= 0.5
     _lib.invalidate(filt)
-    hits = _lib.resident_hits()
-    got = _lib.minmax(filt, 100)
-    assert _lib.resident_hits() == hits
-    assert np.array_equal(got.view(np.uint64), orc.minmax_rows(filt, 100).view(np.uint64))
-    # the caller forgets to say so: the sampled verification notices
-    _lib.sosfilt(sos, x, filt, 0)
-    filt += 1.0
-    hits = _lib.resident_hits()
-    got = _lib.minmax(filt, 100)
-    assert _lib.resident_hits() == hits
+    got = _lib.minmax(filt, 100, src_mirror=m)
+    assert _lib.resident_hits() == hits + 1
     assert np.array_equal(got.view(np.uint64), orc.minmax_rows(filt, 100).view(np.uint64))
     # results written over a kept range replace it
-    _lib.sosfilt(sos, x, filt, 0)
-    _lib.sosfilt(sos, 2.0*x, filt, 0)
-    got = _lib.minmax(filt, 100)
+    _lib.sosfilt(sos, x, filt, 0, dst_mirror=m)
+    _lib.sosfilt(sos, 2.0*x, filt, 0, dst_mirror=m)
+    got = _lib.minmax(filt, 100, src_mirror=m)
     assert np.array_equal(got.view(np.uint64), orc.minmax_rows(filt, 100).view(np.uint64))
+    # temporaries: a freed array whose address is reused is never served from the device
+    m.release()
+    for k in range(3):
+        tmp = np.empty((n, C))
+        _lib.sosfilt(sos, (k + 1.0)*x, tmp, 0)
+        ref = np.empty((n, C))
+        orc.filter_process(sos, (k + 1.0)*x, ref, 0)
+        got = _lib.minmax(tmp, 50)
+        assert np.array_equal(got.view(np.uint64), orc.minmax_rows(tmp, 50).view(np.uint64))
+        assert np.max(np.abs(tmp - ref)) <= 1e-9
+        del tmp
+
+
+def test_failed_call_leaves_the_mirror_invalid(resident):
+    fs, C = 1000., 2
+    sos = orc.envelope_design(fs, 100.)
+    edge = orc.sosfiltfilt_edge(sos)
+    m = _lib.Mirror()
+    x = synth(0, edge, C, fs)
+    out = np.empty_like(x)
+    with pytest.raises(ValueError):
+        _lib.envelope(sos, x, out, dst_mirror=m)
+    hits = _lib.resident_hits()
+    _lib.minmax(out, 3, src_mirror=m)
+    assert _lib.resident_hits() == hits
+    m.release()
+
+
+def test_host_calls_from_two_threads(resident):
+    """ctypes releases the GIL: the library serialises the host-pointer entry points."""
+    import threading
+    fs, C, n = 48000., 4, 200000
+    sos = orc.filter_design(fs, 1000., 15000., 2)
+    xs = [synth(k, n, C, fs, seed=90 + k) for k in range(4)]
+    outs = [np.empty((n, C)) for _ in xs]
+    errs = []
+
+    def work(k):
+        try:
+            for _ in range(3):
+                _lib.sosfilt(sos, xs[k], outs[k], 0)
+                _lib.minmax(outs[k], 64)
+        except Exception as exc:                      # pragma: no cover
+            errs.append(exc)
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs
+    for k in range(4):
+        ref = np.empty((n, C))
+        orc.filter_process(sos, xs[k], ref, 0)
+        assert np.max(np.abs(outs[k] - ref)) <= 1e-9
 
 
 def test_traces_invalidate_on_buffer_moves(resident):
@@ -145,30 +218,3 @@ def test_traces_invalidate_on_buffer_moves(resident):
     assert np.max(np.abs(env.buffer - g['env_buffer'])) <= 1e-6
     ref = g['spec_buffer']
     assert np.allclose(spect.buffer, ref, rtol=1e-5, atol=1e-20*ref.max())
-
-
-@pytest.mark.parametrize('C,nbefore,cut', [(2, 0, 500.), (8, 4321, 300.), (3, 17, 2000.), (1, 0, 800.)])
-def test_envelope_chunked_schedule_equals_two_full_sweeps(C, nbefore, cut):
-    """The L2-resident chunked schedule of the envelope (forward over chunk j+1, backward over
-    chunk j from a decay-length warm-up) against scipy and against the two-full-sweeps path."""
-    fs, n = 48000., 400000
-    x = synth(3, n, C, fs, seed=50 + C)
-    esos = orc.envelope_design(fs, cut)
-    ref = np.empty((n - nbefore, C))
-    orc.envelope_process(esos, x, ref, nbefore, 0)
-    old = _lib.get_option(_lib.ADN_OPT_ENVELOPE_CHUNK_BYTES)
-    try:
-        _lib.set_option(_lib.ADN_OPT_ENVELOPE_CHUNK_BYTES, 0)
-        full = np.empty_like(ref)
-        _lib.envelope(esos, x, full, nbefore, True)
-        _lib.set_option(_lib.ADN_OPT_ENVELOPE_CHUNK_BYTES, 40000*C*8)      # 10 chunks
-        got = np.full_like(ref, np.nan)
-        _lib.envelope(esos, x, got, nbefore, True)
-        short = np.full((1000, C), np.nan)
-        _lib.envelope(esos, x, short, nbefore, True)                      # n_dst < n_src - nbefore
-    finally:
-        _lib.set_option(_lib.ADN_OPT_ENVELOPE_CHUNK_BYTES, old)
-    assert np.max(np.abs(full - ref)) <= 1e-9
-    assert np.max(np.abs(got - ref)) <= 1e-9
-    assert np.max(np.abs(got - full)) <= 1e-12
-    assert np.array_equal(short, got[:1000])

@@ -34,8 +34,11 @@ def main():
     ap.add_argument('--step', type=int, default=2000)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--onepass', type=int, default=1, help='0: envelope as two sweeps through memory')
+    ap.add_argument('--env-cutoff', type=float, default=500.0)
     a = ap.parse_args()
     _lib.init(0)
+    _lib.set_option(_lib.ADN_OPT_ZERO_PHASE_ONEPASS, a.onepass)
     n = int(a.rate*a.seconds)
     C = a.C
     xs = [device.synth(i*n, n, C, a.rate) for i in range(3)]
@@ -43,7 +46,7 @@ def main():
         sos = butter(a.order, (0.02*a.rate, 0.3*a.rate), 'bandpass', fs=a.rate, output='sos')
     else:
         sos = butter(a.order, 0.1*a.rate, a.kind, fs=a.rate, output='sos')
-    esos = butter(a.order, 500.0*a.rate/48000., 'lowpass', fs=a.rate, output='sos')
+    esos = butter(a.order, a.env_cutoff*a.rate/48000., 'lowpass', fs=a.rate, output='sos')
     out = torch.empty((n, C), dtype=torch.float64, device='cuda')
     nsp = (n - (a.nfft - a.hop))//a.hop
     if a.op == 'spectrogram':
