@@ -86,12 +86,15 @@ SIGNATURES = {
     'adn_pcm_to_f64': (_i32, [_dp, _i64, _i32, _f64, _dp]),
     'adn_spec_image_db_f64_dev': (_i32, [_dp, _i64, _i32, _i32, _i32, _dp, _dp]),
     'adn_mean_power_db_f64_dev': (_i32, [_dp, _i32, _i32, _i32, _i64, _i64, _f64, _dp, _dp]),
+    'adn_colsum_f64_dev': (_i32, [_dp, _i64, _i64, _dp, _dp]),
     'adn_pcm_to_f64_dev': (_i32, [_dp, _i64, _i32, _f64, _dp, _dp]),
     'adn_minmax_f64_dev': (_i32, [_dp, _i64, _i32, _i64, _dp, _dp]),
     'adn_sosfilt_f64_dev': (_i32, [_dp, _i32, _dp, _i64, _i32, _i64, _dp, _i64,
                                    _dp, _dp, _dp]),
     'adn_envelope_f64_dev': (_i32, [_dp, _i32, _dp, _i64, _i32, _i64, _dp, _i64,
                                     _i32, _dp]),
+    'adn_zero_phase_range_f64_dev': (_i32, [_dp, _i32, _dp, _i64, _i32, _i32, _i32, _i32, _i64, _dp, _i64,
+                                            _i32, _dp]),
     'adn_envelope_forward_f64_dev': (_i32, [_dp, _i32, _dp, _i64, _i32, _i32, _i32, _dp, _dp,
                                             _dp, _dp]),
     'adn_envelope_state0_f64_dev': (_i32, [_dp, _i32, _dp, _i32, _i32, _i32, _dp, _dp]),

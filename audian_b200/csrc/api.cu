@@ -884,6 +884,15 @@ int32_t adn_mean_power_db_f64_dev(const double* spec, int32_t C, int32_t F, int3
     return mean_power_dev(spec, C, F, channel, i0, i1, floor_db, dst, pick(stream));
 }
 
+int32_t adn_colsum_f64_dev(const double* spec, int64_t n, int64_t width, double* acc, void* stream) {
+    if (n < 0 || width < 1 || (n > 0 && !spec) || !acc)
+        return fail(ADN_ERR_INVALID, "adn_colsum_f64_dev: bad arguments");
+    if (n == 0) return ADN_OK;
+    int32_t rc = ensure_init();
+    if (rc) return rc;
+    return colsum_dev(spec, n, width, acc, pick(stream));
+}
+
 int32_t adn_pcm_to_f64_dev(const void* pcm, int64_t n, int32_t bits, double gain, double* dst, void* stream) {
     if (n < 0 || (bits != 16 && bits != 24 && bits != 32) || (n > 0 && (!pcm || !dst)))
         return fail(ADN_ERR_INVALID, "adn_pcm_to_f64_dev: bad arguments");
@@ -978,6 +987,22 @@ int32_t adn_sosfiltfilt_f64_dev(const double* sos, int32_t S, const double* src,
     int32_t rc = ensure_init();
     if (rc) return rc;
     return sosfiltfilt_dev(sos, S, src, n_src, C, 0, dst, n_dst, pick(stream));
+}
+
+int32_t adn_zero_phase_range_f64_dev(const double* sos, int32_t S, const double* src, int64_t n_src,
+                                     int32_t C, int32_t rectify, int32_t edge_left, int32_t edge_right,
+                                     int64_t first, double* dst, int64_t n_dst, int32_t clamp_negative,
+                                     void* stream) {
+    if (S < 1 || S > ADN_MAX_SECTIONS || C < 1 || n_src < 1 || first < 0 || n_dst < 0 ||
+        first + n_dst > n_src || !sos || !src || (n_dst > 0 && !dst))
+        return fail(ADN_ERR_INVALID, "adn_zero_phase_range_f64_dev: bad arguments");
+    if (n_src <= adn_sosfiltfilt_edge(sos, S))
+        return fail(ADN_ERR_SHORT, "adn_zero_phase_range_f64_dev: input not longer than the sosfiltfilt pad");
+    if (n_dst == 0) return ADN_OK;
+    int32_t rc = ensure_init();
+    if (rc) return rc;
+    return zero_phase_range_dev(rectify != 0, sos, S, src, n_src, C, edge_left, edge_right, first, dst,
+                                n_dst, clamp_negative, pick(stream));
 }
 
 int32_t adn_envelope_forward_f64_dev(const double* sos, int32_t S, const double* src, int64_t n_src,

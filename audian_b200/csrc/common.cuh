@@ -74,6 +74,9 @@ int32_t sosfilt_reverse_dev(const double* sos, int32_t S, const double* src, int
                             int32_t clamp_negative, double* zf, cudaStream_t st);
 int32_t sosfiltfilt_dev(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
                         int64_t nbefore, double* dst, int64_t n_dst, cudaStream_t st);
+int32_t zero_phase_range_dev(bool rect, const double* sos, int32_t S, const double* src, int64_t n_src,
+                             int32_t C, int32_t edge_left, int32_t edge_right, int64_t first, double* dst,
+                             int64_t n_dst, int32_t clamp_negative, cudaStream_t st);
 int32_t spectrogram_dev(const double* src, int64_t n_src, int32_t C, double rate, int32_t nfft,
                         int32_t hop, int32_t window_id, int32_t detrend_id, double* dst,
                         int64_t n_dst, int32_t out_db, int64_t* n_computed, cudaStream_t st);
@@ -83,6 +86,7 @@ int32_t spec_image_dev(const double* spec, int64_t n, int32_t C, int32_t F, int3
                        cudaStream_t st);
 int32_t mean_power_dev(const double* spec, int32_t C, int32_t F, int32_t channel, int64_t i0, int64_t i1,
                        double floor_db, double* dst, cudaStream_t st);
+int32_t colsum_dev(const double* spec, int64_t n, int64_t W, double* acc, cudaStream_t st);
 int32_t pcm_dev(const void* pcm, int64_t n, int32_t bits, double gain, double* dst, cudaStream_t st);
 int32_t synth_dev(double* dst, int64_t t0, int64_t n, int32_t C, double rate, uint64_t seed,
                   cudaStream_t st);

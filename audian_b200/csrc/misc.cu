@@ -108,6 +108,41 @@ int32_t mean_power_dev(const double* spec, int32_t C, int32_t F, int32_t channel
 
 // PCM samples -> float64 in [-1, 1) times gain, the scaling audio readers apply
 // (int16: / 2^15, packed little-endian int24: / 2^23, int32: / 2^31)
+// acc[j] += sum_i spec[i, j], j < W: column sums of a (n, W) block of frames, accumulated
+// across calls (the mean power spectrum of a whole recording streamed chunk by chunk,
+// spectrogramplot.py:158 over all frames).  One block per 256 columns x a slab of rows.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const double* __restrict__ spec, int64_t n, int64_t W, int64_t rows_per_block,
+              double* __restrict__ acc) {
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j >= W) return;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t r1 = min(n, r0 + rows_per_block);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int64_t r = r0;
+    for (; r + 3 < r1; r += 4) {
+        s0 += __ldcs(spec + r * W + j);
+        s1 += __ldcs(spec + (r + 1) * W + j);
+        s2 += __ldcs(spec + (r + 2) * W + j);
+        s3 += __ldcs(spec + (r + 3) * W + j);
+    }
+    for (; r < r1; ++r) s0 += __ldcs(spec + r * W + j);
+    atomicAdd(acc + j, (s0 + s1) + (s2 + s3));
+}
+
+int32_t colsum_dev(const double* spec, int64_t n, int64_t W, double* acc, cudaStream_t st) {
+    const int64_t bx = (W + 255) / 256;
+    int64_t by = ((int64_t)ctx().sm_count * 8 + bx - 1) / bx;
+    if (by > n) by = n;
+    if (by < 1) by = 1;
+    if (by > 65535) by = 65535;
+    const int64_t rpb = (n + by - 1) / by;
+    colsum_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, st>>>(spec, n, W, rpb, acc);
+    count_launch();
+    ADN_CK(cudaGetLastError());
+    return ADN_OK;
+}
+
 __global__ void __launch_bounds__(256)
 pcm_kernel(const unsigned char* __restrict__ pcm, int64_t n, int32_t bytes, double scale,
            double* __restrict__ dst) {

@@ -1296,6 +1296,52 @@ static int32_t zero_phase_dev(bool rect, const double* sos, int32_t S, const dou
                     clamp_negative ? 1 : 0, d_s0b, nullptr, SCR_SOS_MISC, st);
 }
 
+// sosfiltfilt (rect: of (pi/2)|src|) over a RANGE of a longer recording: scipy's odd extension and
+// sosfilt_zi initial conditions only at the ends that are ends of the recording (edge_left /
+// edge_right != 0); at the other ends the sweeps start from zero state, so the caller passes
+// enough extra rows there for the cascade to forget it (adn_sos_decay_length) and drops them:
+// dst rows = result rows [first, first + n_dst) of the n_src rows.  One pass in registers where
+// the cascade allows it, else the two sweeps through memory.
+int32_t zero_phase_range_dev(bool rect, const double* sos, int32_t S, const double* src, int64_t n_src,
+                             int32_t C, int32_t edge_left, int32_t edge_right, int64_t first, double* dst,
+                             int64_t n_dst, int32_t clamp_negative, cudaStream_t st) {
+    const int D = 2 * S;
+    const int edge = adn_sosfiltfilt_edge(sos, S);
+    const int el = edge_left ? edge : 0, er = edge_right ? edge : 0;
+    {
+        bool handled = false;
+        int32_t rc1 = zero_phase_regs_dev(rect, sos, S, src, n_src, C, el, er, el + first, dst, n_dst,
+                                          clamp_negative, &handled, st);
+        if (rc1 || handled) return rc1;
+    }
+    const int64_t next = n_src + el + er;
+    ZiK zik;
+    sosfilt_zi_host(sos, S, zik.z);
+    DevBuf& fwd = scratch(SCR_ENV_FWD, st);
+    DevBuf& misc = scratch(SCR_ENV_MISC, st);
+    int32_t rc;
+    if ((rc = fwd.reserve((size_t)next * C * 8))) return rc;
+    if ((rc = misc.reserve((size_t)(2 * C * D) * 8))) return rc;
+    double* d_s0f = misc.as<double>();
+    double* d_s0b = d_s0f + (size_t)C * D;
+    const int nb = (C * D + 127) / 128;
+    if (el) {
+        env_s0_kernel<<<nb, 128, 0, st>>>(rect ? 0 : 2, src, C, D, edge, zik, d_s0f);
+        count_launch();
+    }
+    double* y1 = fwd.as<double>();
+    if ((rc = run_scan(rect ? MODE_ENVF : MODE_ZPF, sos, S, src, next, n_src, el, C, y1, 0, next, 0,
+                       el ? d_s0f : nullptr, nullptr, SCR_SOS_TILES, st)))
+        return rc;
+    if (er) {
+        env_s0_kernel<<<nb, 128, 0, st>>>(1, y1 + (next - 1) * C, C, D, 0, zik, d_s0b);
+        count_launch();
+    }
+    ADN_CK(cudaGetLastError());
+    return run_scan(MODE_REV, sos, S, y1, next, next, 0, C, dst, el + first, n_dst,
+                    clamp_negative ? 1 : 0, er ? d_s0b : nullptr, nullptr, SCR_SOS_MISC, st);
+}
+
 // The two sweeps of the envelope as separate steps (time-sharded recordings run them with the
 // boundary states exchanged in between): forward sosfilt of (pi/2)|src| with scipy's odd
 // extension of edge_left / edge_right rows at the respective end (0 = none), from state zi;

@@ -60,6 +60,11 @@ class CudaOps(object):
     def envelope(self, sos, src, nbefore=0, clamp_negative=True):
         return envelope(sos, src, nbefore, clamp_negative)
 
+    def zero_phase_range(self, sos, src, first, n_dst, edge_left=False, edge_right=False,
+                         rectify=True, clamp_negative=True, out=None):
+        return zero_phase_range(sos, src, first, n_dst, edge_left, edge_right, rectify,
+                                clamp_negative, out)
+
     def env_forward(self, sos, src, edge_left=0, edge_right=0, zi=None, state_only=False,
                     zf_out=None):
         return env_forward(sos, src, edge_left, edge_right, zi, state_only, zf_out)
@@ -123,6 +128,23 @@ def envelope(sos, src, nbefore=0, clamp_negative=True, out=None):
     _lib.check(_lib.lib().adn_envelope_f64_dev(
         None if sos is None else sos.ctypes.data, S, _p(src), n, ch, int(nbefore),
         _p(out), out.shape[0], 1 if clamp_negative else 0, _stream()))
+    return out
+
+
+def zero_phase_range(sos, src, first, n_dst, edge_left=False, edge_right=False, rectify=True,
+                     clamp_negative=True, out=None):
+    """sosfiltfilt (rectify: of (pi/2)|src|) over the rows `src` of a longer recording, rows
+    first..first+n_dst of the result; scipy's edge handling only at the ends flagged as ends of
+    the recording, zero state at the others (the caller brings halo rows)."""
+    torch = _torch()
+    _check_trace(src, 'src')
+    sos, S = _lib.sos_array(sos)
+    n, ch = src.shape
+    if out is None:
+        out = torch.empty((n_dst, ch), dtype=src.dtype, device=src.device)
+    _lib.check(_lib.lib().adn_zero_phase_range_f64_dev(
+        sos.ctypes.data, S, _p(src), n, ch, 1 if rectify else 0, 1 if edge_left else 0,
+        1 if edge_right else 0, int(first), _p(out), int(n_dst), 1 if clamp_negative else 0, _stream()))
     return out
 
 
@@ -200,6 +222,13 @@ def spectrogram(src, rate, nfft, hop, n_dst, out_db=False, out=None):
         _lib.ADN_DETREND_CONSTANT, _p(out), out.shape[0], 1 if out_db else 0,
         C.byref(ncomp), _stream()))
     return out, ncomp.value
+
+
+def colsum(spec, acc):
+    """acc (C, F) += sum over the frames of spec (n, C, F); returns acc."""
+    n = spec.shape[0]
+    _lib.check(_lib.lib().adn_colsum_f64_dev(_p(spec), n, spec.numel()//max(n, 1), _p(acc), _stream()))
+    return acc
 
 
 def decibel(power, ref_power=1.0, min_power=1e-20, out=None):

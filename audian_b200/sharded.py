@@ -17,6 +17,13 @@ ranks:
                   shard transition matrices A^len and filters its shard from that
                   incoming state: equal to one sosfilt over the whole recording.
 
+Cascades that forget their state quickly (every cut-off audian offers at audio
+rates: |A^n| < 1e-20 within a few thousand samples) need no exchange at all: a rank
+that holds `decay length` extra raw rows on each side of its shard (it reads or
+generates them itself, like the STFT halo) computes exactly what one pass over the
+whole recording computes, to below the rounding of the states -- `HaloChain`.  The
+boundary-state exchange of `ShardedRecording` remains for cascades with long memory.
+
 The arithmetic is delegated to an `ops` object (default: the sm_100a kernels,
 audian_b200.device.CudaOps); the CPU tests of the exchange logic inject their
 own oracle-backed ops with the gloo backend.
@@ -45,6 +52,95 @@ def shard_bounds(frames, world, align=1):
         bounds.append((lo, hi))
         lo = hi
     return bounds
+
+
+def decay_rows(sos, tol=1e-20):
+    """Rows after which the cascade has forgotten its state to within `tol` (a power of
+    two), 0 for no filter, -1 if it practically never does."""
+    sos_a, S = _lib.sos_array(sos)
+    if S == 0:
+        return 0
+    return _lib.sos_decay_length(sos_a, tol)
+
+
+class HaloChain(object):
+    """data -> filtered -> {spectrogram, envelope} (the dependency walk of the reference,
+    src/audian/buffereddata.py:149-153) for ONE time shard [lo, hi) of a recording, from the
+    shard's raw rows plus halo rows on both sides -- no exchange between ranks:
+
+        raw rows       [r0, r1) = [f0 - keep_f, f1)      (clipped to the recording)
+        filtered rows  [f0, f1) = [lo - keep_e, hi + max(keep_e, nfft - hop))
+        spectrogram    frames lo/hop .. hi/hop (global frame index), halo nfft - hop
+        envelope       rows [lo, hi); scipy's odd padding / sosfilt_zi only at the ends of the
+                       recording, zero state at the ends of the halo
+
+    keep_f / keep_e = decay lengths of the filter and of the envelope low-pass (to `tol`):
+    behind them the zero state a shard starts from is forgotten to below the rounding of the
+    state itself, so every shard equals the corresponding rows of one pass over the recording."""
+
+    def __init__(self, frames, rate, channels, bounds, rank, sos, esos, nfft, hop, ops=None,
+                 tol=1e-20):
+        self.frames, self.rate, self.channels = int(frames), float(rate), int(channels)
+        self.bounds, self.rank = bounds, rank
+        self.lo, self.hi = bounds[rank]
+        self.sos, self.S = _lib.sos_array(sos)
+        self.esos, self.ES = _lib.sos_array(esos)
+        self.nfft, self.hop = int(nfft), int(hop)
+        if ops is None:
+            from .device import CudaOps
+            ops = CudaOps()
+        self.ops = ops
+        self.keep_f = decay_rows(self.sos, tol)
+        self.keep_e = decay_rows(self.esos, tol)
+        if self.keep_f < 0 or self.keep_e < 0:
+            raise ValueError('a cascade never forgets its state: use ShardedRecording')
+        if self.lo % self.hop:
+            raise ValueError('shard boundary is not a multiple of hop')
+        halo = self.nfft - self.hop
+        self.first, self.last = self.lo == 0, self.hi == self.frames
+        self.f0 = max(0, self.lo - self.keep_e)
+        self.f1 = min(self.frames, self.hi + max(self.keep_e, halo))
+        self.r0 = max(0, self.f0 - self.keep_f)
+        self.r1 = self.f1
+        nf_total = (self.frames - halo)//self.hop if self.frames >= self.nfft else 0
+        self.nf_total = nf_total
+        self.k0 = self.lo//self.hop
+        self.k1 = nf_total if self.last else min(nf_total, self.hi//self.hop)
+        self.n_frames = max(0, self.k1 - self.k0)
+
+    @staticmethod
+    def supported(sos, esos, bounds, tol=1e-20, max_fraction=0.25):
+        """True if both cascades forget within a fraction of the shortest shard."""
+        shortest = min(hi - lo for lo, hi in bounds)
+        for q in (sos, esos):
+            k = decay_rows(q, tol)
+            if k < 0 or k > max_fraction*shortest:
+                return False
+        return True
+
+    def raw_range(self):
+        """Rows [r0, r1) of the recording this rank has to hold."""
+        return self.r0, self.r1
+
+    def run(self, raw, filt=None, spec=None, env=None, clamp_negative=True, want_env=True):
+        """raw: rows r0..r1 of the recording.  Returns (filtered rows lo..hi, spectrogram
+        frames k0..k1, envelope rows lo..hi, k0).  filt: optional (f1 - f0, C) buffer."""
+        ops = self.ops
+        if raw.shape[0] != self.r1 - self.r0:
+            raise ValueError('raw rows do not match raw_range()')
+        if self.S > 0:
+            fext = ops.sosfilt(self.sos, raw, self.f0 - self.r0, out=filt)
+        else:
+            fext = raw[self.f0 - self.r0:]
+        a = self.lo - self.f0
+        n = self.hi - self.lo
+        spec, ncomp = ops.spectrogram(fext[a:], self.rate, self.nfft, self.hop, self.n_frames, out=spec)
+        if ncomp != self.n_frames:
+            raise RuntimeError('spectrogram frames: %d computed, %d expected' % (ncomp, self.n_frames))
+        if want_env and self.ES > 0:
+            env = ops.zero_phase_range(self.esos, fext, a, n, self.first, self.last, True,
+                                       clamp_negative, out=env)
+        return fext[a:a + n], spec, env, self.k0
 
 
 class ShardedRecording(object):

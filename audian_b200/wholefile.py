@@ -98,7 +98,8 @@ class WholeFile(object):
             for t0 in range(lo, hi, self.chunk_frames):
                 n = min(self.chunk_frames, hi - t0)
                 z = self.ops.sosfilt(sos_a, self.source(t0, n), 0, z, state_only=True)
-            pack[0].copy_(z.reshape(C, D))
+            if z is not None:                   # an empty range leaves the pack zero
+                pack[0].copy_(z.reshape(C, D))
         g = self._gatherer(pack)
         packs = g._gather(pack)
         mats = g._matrices(sos_a, [h - l for l, h in bounds], pack)

@@ -15,10 +15,18 @@ frames x 8 channels = 30.72 M samples, 246 MB fp64):
          BufferedSpectrogram / BufferedEnvelope.process on pinned numpy
          buffers), host<->device copies inside the timed region.
 N > 1    weak scaling: an N x 80 s recording time-sharded over N GPUs
-         (audian_b200.sharded): IIR boundary states all-gathered (filter: one
-         exchange, envelope: one per sweep), STFT halo exchanged over NCCL.
-One sample = one channel-sample of input.  Successive steps use different
-windows of the recording; every window (246 MB) exceeds the 126 MB L2.
+         (audian_b200.sharded.HaloChain): every rank holds its 80-s shard plus the
+         halo rows the STFT and the two cascades need (decay length to 1e-20), so the
+         step needs no exchange; results equal one pass over the whole recording
+         (checked at every seam, `parity`).
+Every N runs the same code: eager launches, CUDA events around each op inside the
+timed region (op_ms sums to the step).  One sample = one channel-sample of input.
+Successive steps use different windows of the recording; every window (246 MB)
+exceeds the 126 MB L2.
+Besides the line's headline it carries: `minmax` (the fourth op of the path, timed on
+its own), `cpu_baseline` (the oracle on the host: the chain and the full-trace pass with
+the reference's own worker scheme), `parity` at every N, and `wholefile` -- BASELINE
+configs 3 and 4 streamed through audian_b200.wholefile, strong-scaled over the ranks.
 """
 
 import argparse
@@ -42,6 +50,8 @@ HIGHPASS, LOWPASS, ORDER = 1000.0, 15000.0, 2
 NFFT, HOP = 1024, 512
 ENV_CUTOFF = 500.0
 N_WINDOWS = 4                      # distinct windows rotated through the steps
+MAX_PIXEL = 1920                   # full-trace plot of the 1-h recording: step = frames // max_pixel
+RECORDING_S = 3600.0
 WINDOW_STRIDE_S = 450.0            # offsets inside the 1-h recording
 SEED = 0xA0D1A9 + 2
 
@@ -56,8 +66,10 @@ def algorithmic_bytes(op, frames, channels):
         return 16.0*n
     if op == 'spectrogram':
         return (8.0 + 8.0*(NFFT//2 + 1)/HOP)*n
-    if op == 'envelope_sweep':       # one of the two scan launches of sosfiltfilt
+    if op == 'envelope':             # one pass: every row read once, written once
         return 16.0*n
+    if op == 'minmax':
+        return 8.0*n
     raise KeyError(op)
 
 
@@ -268,6 +280,44 @@ def run_reference(args):
 
 # ------------------------------------------------------------------ our arm
 
+def seam_parity(chain, sos, esos, C, filt_rows, spec, env, abs0, where):
+    """Outputs of one rank's shard against the oracle at one end of the shard (`where` =
+    'lo' | 'hi'): the oracle filters a host-generated window that starts 1 s before the rows
+    compared (both cascades forget their state within a few thousand rows, so this equals the
+    rows of one pass over the whole recording to rounding; at the ends of the recording the
+    window starts / ends there and the oracle sees the true edge)."""
+    from audian_b200.synth import synth
+    from oracle import oracle as orc
+    W, M = 48000, 20480
+    lo, hi, frames = chain.lo, chain.hi, chain.frames
+    if where == 'lo':
+        a, b = lo, min(hi, lo + M)
+    else:
+        a, b = max(lo, hi - M), hi
+    w0, w1 = max(0, a - W), min(frames, b + W)
+    x = synth(abs0 + w0, w1 - w0, C, RATE, SEED)
+    rf = np.empty_like(x)
+    orc.filter_process(sos, x, rf, 0)
+    re_ = np.empty_like(x)
+    orc.envelope_process(esos, rf, re_, 0, 0)
+    gf = filt_rows[a - lo:b - lo].cpu().numpy()
+    ge = env[a - lo:b - lo].cpu().numpy()
+    out = {'filter_max_abs_err': float(np.max(np.abs(gf - rf[a - w0:b - w0]))),
+           'envelope_max_abs_err': float(np.max(np.abs(ge - re_[a - w0:b - w0])))}
+    # frames that start in [a, b) and lie inside the window
+    k0 = (a + HOP - 1)//HOP
+    k1 = min(chain.k1, (b + HOP - 1)//HOP, (w1 - NFFT)//HOP + 1)
+    if k1 > k0:
+        seg = rf[k0*HOP - w0:(k1 - 1)*HOP + NFFT - w0]
+        rs = np.empty((k1 - k0, C, NFFT//2 + 1))
+        nn = orc.spectrogram_process(np.ascontiguousarray(seg), rs, RATE, NFFT, HOP)
+        gs = spec[k0 - chain.k0:k0 - chain.k0 + nn].cpu().numpy()
+        out['spectrogram_max_rel_err'] = float(np.max(np.abs(gs - rs[:nn])/np.maximum(rs[:nn], 1e-20*rs.max())))
+    else:
+        out['spectrogram_max_rel_err'] = 0.0
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -291,47 +341,13 @@ def run_ours(args):
     sos, esos = designs()
     C, n = CHANNELS, FRAMES
     stride = int(RATE*WINDOW_STRIDE_S)
-
-    # windows of the synthetic recording, generated on the device; with N ranks the
-    # recording of a step is N x 80 s long and rank r owns [r*80 s, (r+1)*80 s)
-    bounds = [(r*n, (r + 1)*n) for r in range(world)]
-    windows = [device.synth(w*stride + rank*n, n, C, RATE, SEED) for w in range(N_WINDOWS)]
-    nspec = n//HOP
-    filt = torch.empty((n, C), dtype=torch.float64, device='cuda')
-    spec = torch.empty((nspec, C, NFFT//2 + 1), dtype=torch.float64, device='cuda')
-    env = torch.empty((n, C), dtype=torch.float64, device='cuda')
-    ops = device.CudaOps()
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    marks = []
 
-    def step(i, record=False):
-        x = windows[i % N_WINDOWS]
-        e = [ev() for _ in range(4)] if record else None
-        if record:
-            e[0].record()
-        if world == 1:
-            device.sosfilt(sos, x, 0, out=filt)
-            y = filt
-        else:
-            rec = sharded.ShardedRecording(x, n*world, RATE, ops, rank, world, bounds)
-            y = rec.sosfilt(sos, room=NFFT - HOP)
-            frec = sharded.ShardedRecording(y, n*world, RATE, ops, rank, world, bounds,
-                                            buffer=rec.last_buffer)
-        if record:
-            e[1].record()
-        if world == 1:
-            device.spectrogram(y, RATE, NFFT, HOP, nspec, out=spec)
-        else:
-            frec.spectrogram(NFFT, HOP)
-        if record:
-            e[2].record()
-        if world == 1:
-            device.envelope(esos, y, 0, True, out=env)
-        else:
-            frec.envelope(esos, True)
-        if record:
-            e[3].record()
-            marks.append(e)
+    def allmax(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     def sync_all():
         torch.cuda.synchronize()
@@ -339,35 +355,42 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # ---- geometry: the recording of a step is N x 80 s, rank r owns [r*80 s, (r+1)*80 s) and
+    # holds the halo rows around it (none at the ends of the recording); no exchange
+    frames_total = n*world
+    bounds = [(r*n, (r + 1)*n) for r in range(world)]
+    if not sharded.HaloChain.supported(sos, esos, bounds):
+        raise SystemExit('the cascades of the bench forget fast: HaloChain must apply')
+    chain = sharded.HaloChain(frames_total, RATE, C, bounds, rank, sos, esos, NFFT, HOP)
+    r0, r1 = chain.raw_range()
+    windows = [device.synth(w*stride + r0, r1 - r0, C, RATE, SEED) for w in range(N_WINDOWS)]
+    filt_ext = torch.empty((chain.f1 - chain.f0, C), dtype=torch.float64, device='cuda')
+    spec = torch.empty((chain.n_frames, C, NFFT//2 + 1), dtype=torch.float64, device='cuda')
+    env = torch.empty((n, C), dtype=torch.float64, device='cuda')
+    marks = []
+    last = {}
+
+    def step(i, record=False):
+        x = windows[i % N_WINDOWS]
+        e = [ev() for _ in range(4)] if record else None
+        a = chain.lo - chain.f0
+        if record:
+            e[0].record()
+        fext = device.sosfilt(sos, x, chain.f0 - chain.r0, out=filt_ext)
+        if record:
+            e[1].record()
+        device.spectrogram(fext[a:], RATE, NFFT, HOP, chain.n_frames, out=spec)
+        if record:
+            e[2].record()
+        device.zero_phase_range(esos, fext, a, n, chain.first, chain.last, True, True, out=env)
+        if record:
+            e[3].record()
+            marks.append(e)
+        last['filt'] = fext[a:a + n]
+
     for i in range(args.warmup):
         step(i)
     sync_all()
-    # N > 1: one CUDA graph per input window (kernels, NCCL collectives and the small torch ops
-    # of the exchange in one launch); falls back to eager launches if capture is refused
-    graphs = None
-    graph_launches = 0
-    if world > 1 and args.graphs:
-        try:
-            graphs = []
-            l0 = _lib.launch_count()
-            for w in range(N_WINDOWS):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    step(w)
-                graphs.append(g)
-            graph_launches = (_lib.launch_count() - l0)//N_WINDOWS
-            for g in graphs:
-                g.replay()
-            sync_all()
-        except Exception as exc:                      # pragma: no cover
-            sys.stderr.write('CUDA graph capture failed (%s): eager launches\n' % (exc,))
-            graphs = None
-    ok = torch.tensor([1 if graphs is not None else 0], device='cuda')
-    if world > 1:
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok.item()) == 0:
-            graphs = None
-    # per-op times (and, without graphs, the timed region itself) from eager steps
     try:
         uuid = 'GPU-' + str(torch.cuda.get_device_properties(local).uuid)
     except Exception:
@@ -381,56 +404,54 @@ def run_ours(args):
     t_start, t_stop = ev(), ev()
     wall0 = time.perf_counter()
     torch.cuda.nvtx.range_push('timed')          # ncu --nvtx --nvtx-include "timed/"
-    if graphs is None:
-        t_start.record()
-        for i in range(args.steps):
-            step(args.warmup + i, record=True)
-        t_stop.record()
-        sync_all()
-        launches = _lib.launch_count() - launches0
-    else:
-        for i in range(min(args.steps, 5)):
-            step(i, record=True)
-        sync_all()
-        t_start.record()
-        for i in range(args.steps):
-            graphs[(args.warmup + i) % N_WINDOWS].replay()
-        t_stop.record()
-        sync_all()
-        launches = graph_launches*args.steps
+    t_start.record()
+    for i in range(args.steps):
+        step(args.warmup + i, record=True)
+    t_stop.record()
+    sync_all()
+    launches = _lib.launch_count() - launches0
     torch.cuda.nvtx.range_pop()
     wall1 = time.perf_counter()
-    ms_total = t_start.elapsed_time(t_stop)
-    tt = torch.tensor([ms_total], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_step = float(tt.item())/args.steps
+    ms_step = allmax(t_start.elapsed_time(t_stop))/args.steps
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     samples_step = n*C*world
     value = samples_step/(ms_step*1e-3)/1e6
 
-    # per-op shares from the events recorded inside the timed region
+    # per-op times from the events recorded inside the timed region (this rank's)
     t_f = float(np.mean([e[0].elapsed_time(e[1]) for e in marks]))
     t_s = float(np.mean([e[1].elapsed_time(e[2]) for e in marks]))
     t_e = float(np.mean([e[2].elapsed_time(e[3]) for e in marks]))
     peak, peak_kind = measured_peak()
-    edge = _lib.sosfiltfilt_edge(esos)
 
-    def roof(op, ms, frames, launches_per_step=1, kernel=''):
-        # per LAUNCH of the kernel: its algorithmic bytes, its average duration, its share of the step
-        ach = algorithmic_bytes(op, frames, C)/(ms/launches_per_step*1e-3)/1e9
+    # ---- the fourth op of the path, full-trace min/max of the raw window, timed on its own
+    mm_step = max(1, int(RATE*RECORDING_S)//MAX_PIXEL)
+    raw_own = [w[chain.lo - r0:chain.lo - r0 + n] for w in windows]
+    for i in range(3):
+        device.minmax(raw_own[i % N_WINDOWS], mm_step)
+    sync_all()
+    m0, m1 = ev(), ev()
+    m0.record()
+    for i in range(args.steps):
+        mm_rows = device.minmax(raw_own[i % N_WINDOWS], mm_step)
+    m1.record()
+    sync_all()
+    t_m = allmax(m0.elapsed_time(m1))/args.steps
+
+    def roof(op, ms, frames, kernel, share_of=None):
+        ach = algorithmic_bytes(op, frames, C)/(ms*1e-3)/1e9
         return {'kernel': kernel, 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
                 'frac': ach/peak, 'traffic': None, 'peak_kind': peak_kind,
-                'ms_per_launch': ms/launches_per_step, 'launches_per_step': launches_per_step,
-                'share_of_step': ms/launches_per_step/(t_f + t_s + t_e)}
+                'ms_per_launch': ms, 'launches_per_step': 1,
+                'share_of_step': (ms/(t_f + t_s + t_e)) if share_of is None else share_of}
 
-    # which scan kernel ran: the run kernel (cascades that forget fast) or the look-back kernel
     scan_name = 'sos_run_kernel' if _lib.scan_run_count() > 0 else 'sos_scan_kernel'
+    env_name = ('sos_zp_pipe_kernel<S=1,RECT>: one pass, tile in registers' if _lib.zero_phase_count() > 0
+                else scan_name + '<S=1,ENVF> + <S=1,REV>')
     roofs = {
-        'filter': roof('filter', t_f, n, 1, scan_name + '<S=2,FWD>'),
-        'spectrogram': roof('spectrogram', t_s, n, 1, 'spectrogram_ring_kernel<10>'),
-        'envelope': roof('envelope_sweep', t_e, n + 2*edge, 2,
-                         scan_name + '<S=1,ENVF> and <S=1,REV>: the two sweeps of the envelope, each'),
+        'filter': roof('filter', t_f, chain.f1 - chain.f0, scan_name + '<S=2,FWD>'),
+        'spectrogram': roof('spectrogram', t_s, n, 'spectrogram_ring_kernel<10>'),
+        'envelope': roof('envelope', t_e, n, env_name),
+        'minmax': roof('minmax', t_m, n, 'minmax_split_kernel (step %d, not part of the step)' % mm_step, 0.0),
     }
     traffic_file = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.isfile(traffic_file):
@@ -442,84 +463,85 @@ def run_ours(args):
                     roofs[k]['traffic'] = tr[k]
         except Exception:
             pass
-    dominant = max(roofs, key=lambda k: roofs[k]['share_of_step'])
+    dominant = max(('filter', 'spectrogram', 'envelope'), key=lambda k: roofs[k]['share_of_step'])
 
-    # ---- end to end through the plugin path: host buffers, copies inside the timed region
-    e2e = None
+    # ---- parity at every N: both ends of every shard (= every seam) against the oracle
+    step(0)
+    torch.cuda.synchronize()
+    pr = {}
+    for where in ('lo', 'hi'):
+        one = seam_parity(chain, sos, esos, C, last['filt'], spec, env, 0*stride, where)
+        for k, v in one.items():
+            pr[k] = max(pr.get(k, 0.0), v)
+    mm_ref = None
+    from oracle import oracle as orc
+    mm_got = device.minmax(raw_own[0], mm_step).cpu().numpy()
+    mm_ref = orc.minmax_rows(raw_own[0].cpu().numpy(), mm_step)
+    mm_ok = bool(np.array_equal(mm_got.view(np.uint64), mm_ref.view(np.uint64)))
+    parity = {k: allmax(v) for k, v in sorted(pr.items())}
+    parity['minmax_bit_exact'] = allmax(0.0 if mm_ok else 1.0) == 0.0
+    parity['checked'] = ('first and last 20480 rows (and the frames inside them) of every rank\'s shard '
+                         '= every seam and both ends of the %d x 80-s recording; min/max of the whole '
+                         'window of every rank' % world)
+    parity['tolerance'] = 'filter/envelope 1e-6 of full scale, spectrogram rtol 1e-5, min/max bit-exact'
+    parity['ok'] = bool(parity['filter_max_abs_err'] <= 1e-6 and parity['envelope_max_abs_err'] <= 1e-6 and
+                        parity['spectrogram_max_rel_err'] <= 1e-5 and parity['minmax_bit_exact'])
+
+    # ---- end to end through the plugin path: host buffers, copies inside the timed region.
+    # With N ranks: N independent replicas of the single-GPU plugin path (audian's interactive
+    # updates stay on one GPU), each on its own 80-s window.
+    own = slice(chain.lo - r0, chain.lo - r0 + n)
+    host_x = [np.ascontiguousarray(w[own].cpu().numpy()) for w in windows[:2]]
+    nspec = n//HOP
+    h_filt = np.empty((n, C))
+    h_spec = np.empty((nspec, C, NFFT//2 + 1))
+    h_env = np.empty((n, C))
+    for a_ in host_x + [h_filt, h_spec, h_env]:
+        _lib.host_register(a_)
+    tf = BufferedFilter()
+    tf.configure_standalone(RATE, C, highpass_cutoff=HIGHPASS, lowpass_cutoff=LOWPASS)
+    ts = BufferedSpectrogram(nfft=NFFT, overlap_frac=0.5)
+    ts.configure_standalone(RATE, C, source=tf)
+    te = BufferedEnvelope(envelope_cutoff=ENV_CUTOFF)
+    te.configure_standalone(RATE, C, source=tf)
+
+    def host_step(i):
+        x = host_x[i % len(host_x)]
+        tf.process(x, h_filt, 0)
+        ts.process(h_filt, h_spec, 0)
+        te.process(h_filt, h_env, 0)
+
+    ksteps = max(1, min(args.steps, 5))
+    for i in range(2):
+        host_step(i)
+    sync_all()
+    moved0 = _lib.transfer_bytes()
+    t0 = time.perf_counter()
+    for i in range(ksteps):
+        host_step(i)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    moved1 = _lib.transfer_bytes()
+    te2e = allmax(dt/ksteps)
+    e2e = {'value': samples_step/te2e/1e6, 'unit': 'Msamples/s',
+           # counted by the library around every copy it issues
+           'h2d_bytes_per_step': int((moved1[0] - moved0[0])//ksteps),
+           'd2h_bytes_per_step': int((moved1[1] - moved0[1])//ksteps),
+           'steps': ksteps, 'ms_per_step': te2e*1e3,
+           'api': 'BufferedFilter/BufferedSpectrogram/BufferedEnvelope.process on pinned numpy '
+                  'buffers; the filtered buffer is handed to its two consumers through the '
+                  'filter trace\'s device mirror, copies and kernels overlap chunk by chunk'
+                  + ('' if world == 1 else '; %d independent replicas, one per GPU' % world)}
+    for a_ in host_x + [h_filt, h_spec, h_env]:
+        _lib.host_unregister(a_)
+    del tf, ts, te
+
+    # ---- the oracle on the host's cores, bounded samples of the same workload (N = 1 only)
     cpu_baseline = None
-    if world == 1 or True:
-        host_x = [np.ascontiguousarray(w.cpu().numpy()) for w in windows[:2]]
-        h_filt = np.empty((n, C))
-        h_spec = np.empty((nspec, C, NFFT//2 + 1))
-        h_env = np.empty((n, C))
-        for a in host_x + [h_filt, h_spec, h_env]:
-            _lib.host_register(a)
-        tf = BufferedFilter()
-        tf.configure_standalone(RATE, C, highpass_cutoff=HIGHPASS, lowpass_cutoff=LOWPASS)
-        ts = BufferedSpectrogram(nfft=NFFT, overlap_frac=0.5)
-        ts.configure_standalone(RATE, C, source=tf)
-        te = BufferedEnvelope(envelope_cutoff=ENV_CUTOFF)
-        te.configure_standalone(RATE, C, source=tf)
-
-        def host_step(i):
-            x = host_x[i % len(host_x)]
-            tf.process(x, h_filt, 0)
-            ts.process(h_filt, h_spec, 0)
-            te.process(h_filt, h_env, 0)
-
-        ksteps = max(1, min(args.steps, 5))
-        for i in range(2):
-            host_step(i)
-        sync_all()
-        moved0 = _lib.transfer_bytes()
-        t0 = time.perf_counter()
-        for i in range(ksteps):
-            host_step(i)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        moved1 = _lib.transfer_bytes()
-        te2e = torch.tensor([dt/ksteps], dtype=torch.float64, device='cuda')
-        if world > 1:
-            dist.all_reduce(te2e, op=dist.ReduceOp.MAX)
-        e2e = {'value': samples_step/float(te2e.item())/1e6, 'unit': 'Msamples/s',
-               # counted by the library around every copy it issues
-               'h2d_bytes_per_step': int((moved1[0] - moved0[0])//ksteps),
-               'd2h_bytes_per_step': int((moved1[1] - moved0[1])//ksteps),
-               'steps': ksteps, 'ms_per_step': float(te2e.item())*1e3,
-               'api': 'BufferedFilter/BufferedSpectrogram/BufferedEnvelope.process on pinned numpy '
-                      'buffers; the filtered buffer stays resident on the device for its two '
-                      'consumers, copies and kernels overlap chunk by chunk'}
-        for a in host_x + [h_filt, h_spec, h_env]:
-            _lib.host_unregister(a)
-
-    parity = None
     if rank == 0 and world == 1:
-        # outputs of the timed path against the oracle (not timed)
-        from oracle import oracle as orc
-        x0 = windows[0]
-        device.sosfilt(sos, x0, 0, out=filt)
-        device.spectrogram(filt, RATE, NFFT, HOP, nspec, out=spec)
-        device.envelope(esos, filt, 0, True, out=env)
-        torch.cuda.synchronize()
-        m = 400000
-        hx = np.ascontiguousarray(x0[:m].cpu().numpy())
-        hf = filt.cpu().numpy()
-        rf = np.empty((m, C))
-        orc.filter_process(sos, hx, rf, 0)
-        rs = np.empty((m//HOP, C, NFFT//2 + 1))
-        ns_ = orc.spectrogram_process(hf[:m], rs, RATE, NFFT, HOP)
-        gs = spec[:ns_].cpu().numpy()
-        re_ = np.empty((n, C))
-        orc.envelope_process(esos, hf, re_, 0, 0)
-        parity = {'filter_max_abs_err': float(np.max(np.abs(hf[:m] - rf))),
-                  'spectrogram_max_rel_err': float(np.max(np.abs(gs - rs[:ns_])/np.maximum(rs[:ns_], 1e-20*rs.max()))),
-                  'envelope_max_abs_err': float(np.max(np.abs(env.cpu().numpy() - re_))),
-                  'checked': f'filter/spectrogram on the first {m} frames, envelope on the whole window'}
-    if rank == 0 and world == 1:
-        # the oracle on the host's cores, bounded sample of the same workload
         sample_s = 10.0
         m = int(RATE*sample_s)
-        xs = np.ascontiguousarray(windows[0][:m].cpu().numpy())
+        xs = np.ascontiguousarray(host_x[0][:m])
         cpu_chain(xs[:m//4], sos, esos)
         t0 = time.perf_counter()
         reps = 2
@@ -537,6 +559,47 @@ def run_ours(args):
                                   f'{reps} repetitions; value: one worker process per channel, '
                                   f'single_thread_value: one thread as audian runs the path; '
                                   f'host has {os.cpu_count()} cpus'}
+        # full-trace min/max with the reference's own worker scheme (compresseddata.py:104-122):
+        # cpu_count() - 1 processes, block-cyclic 30-s blocks, one shared array under its lock
+        try:
+            # the workers share the recording through /dev/shm: size it to what is free there
+            free = os.statvfs('/dev/shm')
+            room = free.f_bavail*free.f_frsize//3
+            rows_max = int(min(4*n, room//(C*8)))
+            if rows_max < int(RATE*35):
+                raise RuntimeError('/dev/shm has room for %d rows only' % rows_max)
+            data = np.concatenate(host_x + host_x, axis=0)[:rows_max]    # up to 320 s in memory
+            mp_px = max(1, len(data)//mm_step)
+            _, rows, dtm, nw = orc.fulltrace_parallel(data, mp_px, RATE)
+            t0 = time.perf_counter()
+            orc.fulltrace_long(data, mp_px, RATE, 1)
+            dts = time.perf_counter() - t0
+            cpu_baseline['minmax'] = {'value': data.size/dtm/1e6, 'unit': 'Msamples/s', 'cores': nw,
+                                      'single_thread_value': data.size/dts/1e6,
+                                      'sample': f'{len(data)/RATE:g} s x {C} ch in memory, step {len(data)//mp_px}: '
+                                                f'the reference\'s worker scheme (os.cpu_count()-1 processes, '
+                                                f'block-cyclic 30-s blocks, shared array + lock; block loops timed)'}
+            del data
+        except Exception as exc:                       # pragma: no cover
+            sys.stderr.write('min/max cpu baseline failed (%s)\n' % (exc,))
+
+    # ---- BASELINE configs 3 and 4: whole-file passes, strong-scaled over the ranks
+    wholefile = None
+    if args.wholefile:
+        del windows, raw_own, filt_ext, spec, env
+        last.clear()
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, 'tools'))
+        import wholefile_bench
+        wholefile = {}
+        for cfg, key in ((3, 'c3'), (4, 'c4')):
+            try:
+                wholefile[key] = wholefile_bench.run_config(cfg, rank, world, dist if world > 1 else None,
+                                                            None, args.wholefile_budget, None, peak)
+            except Exception as exc:                   # pragma: no cover
+                wholefile[key] = {'error': repr(exc)}
+                if world > 1:
+                    raise
 
     if rank == 0:
         line = {
@@ -550,24 +613,22 @@ def run_ours(args):
                        'envelope_cutoff_hz': ENV_CUTOFF,
                        'l2': 'inputs larger than L2: each step reads a different 246 MB window',
                        'parallelism': 'single GPU' if world == 1 else
-                                      f'time-sharded x{world} (IIR state all-gather + STFT halo over NCCL)',
-                       'launch': 'eager' if graphs is None else 'one CUDA graph per step; op_ms from eager steps'},
+                                      f'time-sharded x{world}: every rank holds its shard plus halo rows '
+                                      f'(filter {chain.keep_f}, envelope {chain.keep_e}, STFT {NFFT - HOP}); '
+                                      f'no exchange in the step',
+                       'launch': 'eager, CUDA events around each op inside the timed region'},
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
             'roofline': roofs[dominant], 'roofline_all': roofs, 'dominant': dominant,
-            'op_ms': {'filter': t_f, 'spectrogram': t_s, 'envelope': t_e},
-            'cpu_baseline': cpu_baseline, 'parity': parity,
+            'op_ms': {'filter': t_f, 'spectrogram': t_s, 'envelope': t_e, 'minmax_separate': t_m},
+            'minmax': {'value': n*C*world/(t_m*1e-3)/1e6, 'unit': 'Msamples/s', 'step': mm_step,
+                       'ms': t_m, 'frac': roofs['minmax']['frac']},
+            'cpu_baseline': cpu_baseline, 'parity': parity, 'wholefile': wholefile,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
-        if graphs is not None:
-            # tearing down CUDA graphs that hold captured NCCL work together with their
-            # communicator can deadlock: everything is done and flushed, leave directly
-            sys.stdout.flush()
-            sys.stderr.flush()
-            os._exit(0)
         dist.destroy_process_group()
 
 
@@ -577,8 +638,12 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--no-graphs', dest='graphs', action='store_false',
-                    help='N > 1: launch every step eagerly instead of replaying CUDA graphs')
+    ap.add_argument('--no-wholefile', dest='wholefile', action='store_false',
+                    help='skip the whole-file passes of BASELINE configs 3 and 4')
+    ap.add_argument('--wholefile-budget', type=float,
+                    default=float(os.environ.get('ADN_BENCH_WHOLEFILE_BUDGET_S', '70')),
+                    help='seconds of run time per whole-file config (the recording is shortened to fit)')
+    ap.add_argument('--no-graphs', dest='graphs', action='store_false', help='(ignored: every N runs eagerly)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

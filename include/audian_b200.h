@@ -254,6 +254,11 @@ int32_t adn_spec_image_db_f64_dev(const double* spec, int64_t n, int32_t C, int3
 int32_t adn_mean_power_db_f64_dev(const double* spec, int32_t C, int32_t F,
                                   int32_t channel, int64_t i0, int64_t i1,
                                   double floor_db, double* dst, void* stream);
+/* acc[j] += sum_i spec[i, j], j < width: column sums of n rows, accumulated across calls --
+ * the mean power spectrum of a streamed recording (src/audian/spectrogramplot.py:158 over all
+ * frames; the caller divides by the frame count).  acc must be zeroed by the caller. */
+int32_t adn_colsum_f64_dev(const double* spec, int64_t n, int64_t width, double* acc,
+                           void* stream);
 int32_t adn_pcm_to_f64_dev(const void* pcm, int64_t n, int32_t bits, double gain,
                            double* dst, void* stream);
 int32_t adn_minmax_f64_dev(const double* src, int64_t n, int32_t C,
@@ -268,6 +273,17 @@ int32_t adn_envelope_f64_dev(const double* sos, int32_t S,
                              const double* src, int64_t n_src, int32_t C,
                              int64_t nbefore, double* dst, int64_t n_dst,
                              int32_t clamp_negative, void* stream);
+/* Zero-phase filtering of a RANGE of a longer recording (time shards with halo rows, chunks of
+ * a streamed file): sosfiltfilt (rectify != 0: of (pi/2)*|src|, the envelope) over the n_src
+ * rows with scipy's odd padding and sosfilt_zi initial conditions only at the ends flagged as
+ * ends of the recording (edge_left / edge_right != 0); the other ends start from zero state:
+ * pass adn_sos_decay_length(sos, S, tol) extra rows there and drop them.  dst rows = result
+ * rows [first, first + n_dst). */
+int32_t adn_zero_phase_range_f64_dev(const double* sos, int32_t S,
+                                     const double* src, int64_t n_src, int32_t C,
+                                     int32_t rectify, int32_t edge_left, int32_t edge_right,
+                                     int64_t first, double* dst, int64_t n_dst,
+                                     int32_t clamp_negative, void* stream);
 /* The two sweeps of the envelope as separate steps, for time-sharded recordings
  * (audian_b200/sharded.py exchanges the boundary states in between):
  * forward sosfilt of (pi/2)*|src| extended by scipy's odd padding of edge_left /

@@ -30,6 +30,8 @@ power <= 1e-20 -> -inf.  Window and detrend stay parameters.
 
 from math import floor, ceil
 
+import os
+
 import numpy as np
 from scipy.signal import butter, sosfilt, sosfiltfilt, sosfilt_zi
 from scipy.signal import spectrogram as _scipy_spectrogram
@@ -412,3 +414,78 @@ def unwrap(data, thresh=-1.0, clips=False):
     if clips:
         np.clip(d, -1.0, 1.0, out=d)
     return data
+
+
+# ---------------------------------------------------------------- full-trace pass with the reference's workers
+
+def _fulltrace_worker(proc_idx, num_proc, nblock, step, data_name, data_shape, out_name, out_shape, lock,
+                      stamps):
+    """down_sample_worker (src/audian/compresseddata.py:25-53) on in-memory data: the block copy
+    into the worker's buffer stands in for `data.load_buffer(index, nblock, buffer)`."""
+    import time
+    from multiprocessing import shared_memory
+    dshm = shared_memory.SharedMemory(name=data_name)
+    oshm = shared_memory.SharedMemory(name=out_name)
+    try:
+        data = np.ndarray(data_shape, dtype=np.float64, buffer=dshm.buf)
+        datas = np.ndarray(out_shape, dtype=np.float64, buffer=oshm.buf)
+        frames = data_shape[0]
+        buffer = np.zeros((nblock, data_shape[1]))
+        segments = np.arange(0, len(buffer), step)
+        stamps[2*proc_idx] = time.perf_counter()      # CLOCK_MONOTONIC: comparable across processes
+        for index in range(proc_idx*nblock, frames, num_proc*nblock):
+            if frames - index < nblock:
+                nblock = frames - index
+                buffer = buffer[:nblock, :]
+                segments = np.arange(0, len(buffer), step)
+            buffer[:] = data[index:index + nblock]
+            i = 2*index//step
+            with lock:
+                np.minimum.reduceat(buffer, segments, out=datas[i + 0:i + 0 + 2*len(segments):2])
+                np.maximum.reduceat(buffer, segments, out=datas[i + 1:i + 1 + 2*len(segments):2])
+        stamps[2*proc_idx + 1] = time.perf_counter()
+    finally:
+        dshm.close()
+        oshm.close()
+
+
+def fulltrace_parallel(data, max_pixel, rate, num_proc=None):
+    """CompressedData.start's long-file path (src/audian/compresseddata.py:104-122) with real
+    worker processes: os.cpu_count() - 1 of them, block-cyclic over 30-s blocks, writing into one
+    shared array under its lock.  `data`: in-memory (frames, C) recording.  Returns
+    (times, datas, seconds, workers); seconds = first worker entering its block loop to
+    the last one leaving it (process start-up and imports are not counted)."""
+    import multiprocessing as mp
+    import time
+    from multiprocessing import shared_memory
+    frames, channels = data.shape
+    step, nblock, times = fulltrace_params(frames, rate, max_pixel)
+    if num_proc is None:
+        num_proc = max(1, (os.cpu_count() or 2) - 1)
+    ctx = mp.get_context('spawn')               # never fork a process that may hold a CUDA context
+    dshm = shared_memory.SharedMemory(create=True, size=max(8, data.nbytes))
+    oshm = shared_memory.SharedMemory(create=True, size=max(8, len(times)*channels*8))
+    try:
+        shared = np.ndarray(data.shape, dtype=np.float64, buffer=dshm.buf)
+        shared[:] = data
+        datas = np.ndarray((len(times), channels), dtype=np.float64, buffer=oshm.buf)
+        datas[:] = 0.0
+        lock = ctx.Lock()
+        stamps = ctx.Array('d', 2*num_proc)
+        procs = [ctx.Process(target=_fulltrace_worker,
+                             args=(i, num_proc, nblock, step, dshm.name, data.shape, oshm.name,
+                                   datas.shape, lock, stamps)) for i in range(num_proc)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join()
+        st = np.array(stamps[:]).reshape(num_proc, 2)
+        st = st[st[:, 1] > 0]
+        dt = float(st[:, 1].max() - st[:, 0].min()) if len(st) else float('nan')
+        result = datas.copy()
+    finally:
+        dshm.close()
+        dshm.unlink()
+        oshm.close()
+        oshm.unlink()
+    return times, result, dt, num_proc

@@ -174,6 +174,76 @@ def test_fake_cluster_matches_single_pass(world):
         assert np.max(np.abs(env - eref)) <= 1e-6
 
 
+@pytest.mark.parametrize('world,C', [(1, 8), (2, 8), (4, 3), (8, 2)])
+def test_halo_chain_matches_single_pass(world, C):
+    """HaloChain: every rank computes its shard of filtered / spectrogram / envelope from its raw
+    rows plus halo rows, no exchange; equal to one pass over the whole recording (oracle)."""
+    import torch
+    from audian_b200 import device
+    fs = 48000.
+    nfft, hop = 1024, 512
+    frames = 1200000//hop*hop + 137
+    x = synth(0, frames, C, fs, seed=31)
+    sos = orc.filter_design(fs, 1000., 15000., 2)
+    esos = orc.envelope_design(fs, 500.)
+    rf = np.empty_like(x)
+    orc.filter_process(sos, x, rf, 0)
+    nf = (frames - (nfft - hop))//hop
+    rs = np.empty((nf, C, nfft//2 + 1))
+    assert orc.spectrogram_process(rf, rs, fs, nfft, hop) == nf
+    re = np.empty_like(x)
+    orc.envelope_process(esos, rf, re, 0, 0)
+    bounds = sharded.shard_bounds(frames, world, hop)
+    assert sharded.HaloChain.supported(sos, esos, bounds)
+    filt, spec, env = [], [], []
+    for r in range(world):
+        hc = sharded.HaloChain(frames, fs, C, bounds, r, sos, esos, nfft, hop)
+        r0, r1 = hc.raw_range()
+        assert r1 - r0 <= bounds[r][1] - bounds[r][0] + 3*4096
+        raw = torch.from_numpy(x[r0:r1]).cuda()
+        f, s, e, k0 = hc.run(raw)
+        assert k0 == bounds[r][0]//hop
+        filt.append(f.cpu().numpy()); spec.append(s.cpu().numpy()); env.append(e.cpu().numpy())
+    f = np.concatenate(filt); s = np.concatenate(spec); e = np.concatenate(env)
+    assert f.shape == rf.shape and s.shape == rs.shape and e.shape == re.shape
+    assert np.max(np.abs(f - rf)) <= 1e-10
+    assert np.max(np.abs(e - re)) <= 1e-10
+    assert np.allclose(s, rs, rtol=1e-5, atol=1e-20*rs.max())
+
+
+@pytest.mark.parametrize('el,er,rect', [(1, 1, 1), (0, 1, 1), (1, 0, 0), (0, 0, 1)])
+def test_zero_phase_range_edges(el, er, rect):
+    """adn_zero_phase_range_f64_dev: scipy's edge handling only at the flagged ends, zero state at
+    the others; both the one-pass kernel (long input) and the two sweeps (short input)."""
+    import torch
+    from scipy.signal import sosfilt, sosfilt_zi
+    from audian_b200 import device
+    fs, C = 48000., 4
+    sos = orc.envelope_design(fs, 500.)
+    edge = orc.sosfiltfilt_edge(sos)
+    for n in (3000, 400000):
+        x = synth(5, n, C, fs, seed=n)
+        r = (np.pi/2)*np.abs(x) if rect else x
+        parts = [2*r[0] - r[edge:0:-1]] if el else []
+        parts.append(r)
+        if er:
+            parts.append(2*r[-1] - r[-2:-edge - 2:-1])
+        ext = np.concatenate(parts)
+        zi = sosfilt_zi(sos)
+        ref = np.empty_like(ext)
+        for c in range(C):
+            y1, _ = sosfilt(sos, ext[:, c], zi=zi*ext[0, c] if el else np.zeros_like(zi))
+            y2, _ = sosfilt(sos, y1[::-1], zi=zi*y1[-1] if er else np.zeros_like(zi))
+            ref[:, c] = y2[::-1]
+        off = edge if el else 0
+        first, n_dst = 100, n - 300
+        z0 = _lib.zero_phase_count()
+        got = device.zero_phase_range(sos, torch.from_numpy(x).cuda(), first, n_dst, bool(el), bool(er),
+                                      bool(rect), False).cpu().numpy()
+        assert (_lib.zero_phase_count() > z0) == (n > 100000)
+        assert np.max(np.abs(got - ref[off + first:off + first + n_dst])) <= 1e-10
+
+
 def test_envelope_sweeps_match_scipy_pieces():
     """The two sweeps exposed for the sharded driver, against scipy on the same pieces."""
     import torch

@@ -106,6 +106,36 @@ class OracleOps(object):
             y[y < 0] = 0
         return torch.from_numpy(y), torch.from_numpy(zf)
 
+    def zero_phase_range(self, sos, src, first, n_dst, edge_left=False, edge_right=False,
+                         rectify=True, clamp_negative=True, out=None):
+        from scipy.signal import sosfilt_zi
+        x = src.numpy()
+        r = (np.pi/2)*np.abs(x) if rectify else x
+        edge = orc.sosfiltfilt_edge(sos)
+        parts = [2*r[0] - r[edge:0:-1]] if edge_left else []
+        parts.append(r)
+        if edge_right:
+            parts.append(2*r[-1] - r[-2:-edge - 2:-1])
+        ext = np.concatenate(parts)
+        zi = sosfilt_zi(sos)
+        S = sos.shape[0]
+        y = np.empty_like(ext)
+        for c in range(ext.shape[1]):
+            z0 = zi*ext[0, c] if edge_left else np.zeros((S, 2))
+            y1, _ = sosfilt(sos, ext[:, c], zi=z0)
+            z1 = zi*y1[-1] if edge_right else np.zeros((S, 2))
+            y2, _ = sosfilt(sos, y1[::-1], zi=z1)
+            y[:, c] = y2[::-1]
+        el = edge if edge_left else 0
+        res = y[el + first:el + first + n_dst].copy()
+        if clamp_negative:
+            res[res < 0] = 0
+        res = torch.from_numpy(res)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+
     def spectrogram(self, src, rate, nfft, hop, n_dst, out_db=False, out=None):
         dst = np.empty((n_dst, src.shape[1], nfft//2 + 1))
         n = orc.spectrogram_process(src.numpy(), dst, rate, nfft, hop)
@@ -159,6 +189,18 @@ def _worker(rank, world, port, frames, C, rate, q):
             dist.all_gather_object(parts, (lo, e.numpy()))
             if rank == 0:
                 out[name] = parts
+        # ---- the same chain from halo rows, no exchange (fast-forgetting cascades)
+        sosf = butter(2, (0.05*rate, 0.3*rate), 'bandpass', fs=rate, output='sos')
+        esosf = butter(2, 0.05*rate, 'lowpass', fs=rate, output='sos')
+        assert sharded.HaloChain.supported(sosf, esosf, b)
+        hc = sharded.HaloChain(frames, rate, C, b, rank, sosf, esosf, nfft, hop, ops)
+        r0, r1 = hc.raw_range()
+        raw = torch.from_numpy(synth(r0, r1 - r0, C, rate, seed=99))
+        fy, fs_, fe, k0 = hc.run(raw)
+        parts = [None]*world
+        dist.all_gather_object(parts, (lo, fy.numpy(), k0, fs_.numpy(), fe.numpy(), (r0, r1)))
+        if rank == 0:
+            out['halo'] = parts
         if rank == 0:
             q.put(out)
     finally:
@@ -209,6 +251,27 @@ def test_sharded_matches_single_pass(world):
         e = np.concatenate([p[1] for p in sorted(out[name], key=lambda p: p[0])])
         assert e.shape == eref.shape
         assert np.max(np.abs(e - eref)) <= 1e-9, name
+
+
+    # the halo chain: every shard equals the rows of one pass over the whole recording
+    sosf = butter(2, (0.05*rate, 0.3*rate), 'bandpass', fs=rate, output='sos')
+    esosf = butter(2, 0.05*rate, 'lowpass', fs=rate, output='sos')
+    yref = np.empty_like(x)
+    orc.filter_process(sosf, x, yref, 0)
+    parts = sorted(out['halo'], key=lambda p: p[0])
+    y = np.concatenate([p[1] for p in parts])
+    assert y.shape == yref.shape and np.max(np.abs(y - yref)) <= 1e-12
+    sref = np.empty((nf, C, nfft//2 + 1))
+    assert orc.spectrogram_process(yref, sref, rate, nfft, hop) == nf
+    spec = np.concatenate([p[3] for p in parts])
+    assert spec.shape == sref.shape and np.allclose(spec, sref, rtol=1e-7, atol=1e-22*sref.max())
+    eref = np.empty_like(x)
+    orc.envelope_process(esosf, yref, eref, 0, 0)
+    e = np.concatenate([p[4] for p in parts])
+    assert e.shape == eref.shape and np.max(np.abs(e - eref)) <= 1e-12
+    # halos are a few hundred rows, not shards
+    for p in parts:
+        assert (p[5][1] - p[5][0]) <= frames//world + 64 + 2*2048
 
 
 def test_shard_bounds():
