@@ -29,6 +29,22 @@ def test_wav_f64_round_trip(tmp_path):
     assert raw[:4] == b'RIFF' and raw[8:12] == b'WAVE' and raw[20:22] == bytes([3, 0])   # IEEE float
 
 
+def test_wav_f64_against_an_independent_implementation(tmp_path):
+    """libsndfile (which audioio uses for encoding='DOUBLE') is not installed here; scipy's
+    WAV reader / writer is an independent implementation of the same IEEE-float WAV layout."""
+    from scipy.io import wavfile
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((777, 4))
+    p = tmp_path / 'ours.wav'
+    write_wav_f64(p, x, 144144)
+    rate, y = wavfile.read(p)
+    assert rate == 144144 and y.dtype == np.float64 and np.array_equal(x, y)
+    q = tmp_path / 'theirs.wav'
+    wavfile.write(q, 48000, x)
+    z, rate = read_wav_f64(q)
+    assert rate == 48000 and np.array_equal(x, z)
+
+
 def make(tmp_path, name='rec.wav'):
     frames, rate, C, step = 4_000_000, 48000., 2, 666
     d = FakeData(tmp_path / name, frames, rate, C)
@@ -78,3 +94,69 @@ def test_user_cache_index_and_lru(tmp_path):
     cd4.load_data()
     assert cd4.datas is None
     assert json.load(open(tmp_path / 'cache' / 'fulltraces.json')) == {}
+
+
+def test_start_is_non_blocking_and_cancellable(monkeypatch):
+    """CompressedData.start returns at once for long recordings (compresseddata.py:104-122): the
+    pass runs in a background thread with its own loader, rows appear under get_lock(), is_busy()
+    is true until the last block, close() stops it (fulltraceplot.py:166-190 polls these).  The
+    kernel is replaced by the oracle's reduceat here -- what is under test is the threading."""
+    import threading
+    import time
+    from audian_b200 import compresseddata
+    from oracle import oracle as orc
+    from audian_b200.synth import synth
+
+    monkeypatch.setattr(compresseddata._lib, 'minmax', lambda buf, step: orc.minmax_rows(buf, step))
+    monkeypatch.setattr(compresseddata._lib, 'host_register', lambda a: None)
+    monkeypatch.setattr(compresseddata._lib, 'host_unregister', lambda a: None)
+    rate, C = 8000., 2
+    frames = int(rate*200)                          # seven 30-s blocks
+    x = synth(0, frames, C, rate, seed=5)
+    gate = threading.Semaphore(0)
+    loads = []
+
+    class Loader(FakeData):
+        def load_buffer(self, index, n, buffer):
+            gate.acquire()                          # the test releases one block at a time
+            loads.append((threading.get_ident(), index))
+            buffer[:] = x[index:index + n]
+
+    d = Loader('rec.wav', frames, rate, C)
+    private = Loader('rec.wav', frames, rate, C)
+    cd = compresseddata.CompressedData(d, loader_factory=lambda: private)
+    t0 = time.perf_counter()
+    cd.start(1000, {})
+    assert time.perf_counter() - t0 < 1.0 and cd.is_busy() and not cd.short_data
+    lock = cd.get_lock()
+    assert lock.acquire(block=False)                # the reference's polling idiom
+    assert not cd.datas.any()
+    lock.release()
+    gate.release(); gate.release(); gate.release()
+    deadline = time.time() + 20
+    step = max(1, frames//1000)
+    nblock = max(step, int(30.0*rate//step)*step)
+    while time.time() < deadline:
+        with cd.get_lock():
+            done = cd.datas[:2*(nblock//step)].any()
+        if done:
+            break
+        time.sleep(0.01)
+    assert done and cd.is_busy()                    # partial rows while the pass is running
+    for _ in range(10):
+        gate.release()
+    cd.wait()
+    assert not cd.is_busy()
+    _, ref = orc.fulltrace_long(x, 1000, rate, 1)
+    assert np.array_equal(cd.datas.view(np.uint64), ref.view(np.uint64))
+    assert all(tid != threading.get_ident() for tid, _ in loads)      # never on the caller's thread
+    # close() cancels a running pass
+    cd2 = compresseddata.CompressedData(d, loader_factory=lambda: private)
+    cd2.start(1000, {})
+    gate.release()
+    cd2.procs[0].terminate()
+    for _ in range(10):
+        gate.release()
+    cd2.close()
+    assert not cd2.is_busy() and cd2.procs == []
+    assert not cd2.datas[-4:].any()                 # it stopped before the end of the recording

@@ -200,6 +200,8 @@ def test_compresseddata_class_matches_reference_fixture():
             data = ArrayLoader(x, a['rate'], 0, 50000)           # buffer shorter than the file
         cd = CompressedData(data)
         cd.start(a['max_pixel'], {})
+        cd.wait()                                  # long recordings are reduced in the background
+        assert not cd.is_busy()
         assert cd.short_data == name.startswith('short')
         assert np.array_equal(cd.times, g[name + '_times'])
         ref = g[name + '_datas']
