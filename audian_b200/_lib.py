@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libaudian_b200.so')
+# ADN_LIB: a differently built copy of the library (kernel experiments), default the in-tree one
+LIB_PATH = os.environ.get('ADN_LIB') or os.path.join(_HERE, 'libaudian_b200.so')
 
 ADN_OK = 0
 ADN_ERR_INVALID = 1
@@ -38,6 +39,16 @@ _dp = C.c_void_p
 _i32 = C.c_int32
 _i64 = C.c_int64
 _f64 = C.c_double
+
+class ChainSpec(C.Structure):
+    """adn_chain_t of include/audian_b200.h."""
+    _fields_ = [('sos', C.c_void_p), ('S', C.c_int32), ('out_db', C.c_int32), ('nbefore', C.c_int64),
+                ('nfft', C.c_int32), ('hop', C.c_int32),
+                ('spec_first', C.c_int64), ('spec_rows', C.c_int64), ('n_spec', C.c_int64),
+                ('esos', C.c_void_p), ('ES', C.c_int32), ('clamp_negative', C.c_int32),
+                ('env_first', C.c_int64), ('env_rows', C.c_int64), ('env_nbefore', C.c_int64),
+                ('n_env', C.c_int64), ('mm_step', C.c_int64)]
+
 
 # name: (restype, argtypes) -- every symbol include/audian_b200.h declares
 SIGNATURES = {
@@ -67,6 +78,10 @@ SIGNATURES = {
     'adn_decibel_f64': (_i32, [_dp, _i64, _f64, _f64, _dp]),
     'adn_sosfiltfilt_f64': (_i32, [_dp, _i32, _dp, _i64, _i32, _dp, _i64]),
     'adn_minmax_f64_m': (_i32, [_dp, _i64, _i32, _i64, _dp, _i64]),
+    'adn_chain_f64': (_i32, [C.POINTER(ChainSpec), _dp, _i64, _i32, _f64, _dp, _i64, _dp, _dp, _dp,
+                             C.POINTER(_i64), _i64, _i64]),
+    'adn_chain_f64_dev': (_i32, [C.POINTER(ChainSpec), _dp, _i64, _i32, _f64, _dp, _i64, _dp, _dp, _dp,
+                                 C.POINTER(_i64), _dp]),
     'adn_sosfilt_f64_m': (_i32, [_dp, _i32, _dp, _i64, _i32, _i64, _dp, _i64, _dp, _i64, _i64]),
     'adn_envelope_f64_m': (_i32, [_dp, _i32, _dp, _i64, _i32, _i64, _dp, _i64, _i32, _i64, _i64]),
     'adn_spectrogram_f64_m': (_i32, [_dp, _i64, _i32, _f64, _i32, _i32, _i32, _i32,
@@ -290,6 +305,52 @@ def play_region(src, left, right, rate, het_freq=0.0, cutoff=20000.0, src_mirror
                                       None if sos is None else sos.ctypes.data, S, nstep,
                                       ptr(out), _h(src_mirror)))
     return out, rate/nstep
+
+
+def chain_spec(sos, nbefore=0, nfft=0, hop=0, spec_first=0, spec_rows=0, n_spec=0, out_db=False,
+               esos=None, env_first=0, env_rows=0, env_nbefore=0, n_env=0, clamp_negative=True,
+               mm_step=0):
+    """(ChainSpec, keep-alive references) for adn_chain_f64[_dev]."""
+    sos, S = sos_array(sos)
+    esos, ES = sos_array(esos)
+    cs = ChainSpec(None if sos is None else sos.ctypes.data, S, 1 if out_db else 0, int(nbefore),
+                   int(nfft), int(hop), int(spec_first), int(spec_rows), int(n_spec),
+                   None if esos is None else esos.ctypes.data, ES, 1 if clamp_negative else 0,
+                   int(env_first), int(env_rows), int(env_nbefore), int(n_env), int(mm_step))
+    return cs, (sos, esos)
+
+
+def chain(sos, src, filtered, rate, nbefore=0, spec=None, nfft=0, hop=0, spec_first=0, spec_rows=None,
+          out_db=False, esos=None, env=None, env_first=0, env_rows=None, env_nbefore=0,
+          clamp_negative=True, mm_step=0, minmax_out=None, src_mirror=None, filt_mirror=None):
+    """data -> filtered -> {spectrogram, envelope} (+ min/max of the raw rows) in one call
+    (bufferedfilter.py:53 / buffereddata.py:149-153: a parameter change recomputes filtered,
+    then its dests).  Each stage equals sosfilt() / spectrogram() / envelope() / minmax() on
+    the same arrays.  Returns the number of spectrogram frames computed."""
+    src = _f64_array(src, 'src')
+    filtered = _f64_array(filtered, 'filtered')
+    n_filt = filtered.shape[0]
+    if spec is not None:
+        spec = _f64_array(spec, 'spec')
+    if env is not None:
+        env = _f64_array(env, 'env')
+    if minmax_out is not None:
+        minmax_out = _f64_array(minmax_out, 'minmax_out')
+    if spec_rows is None:
+        spec_rows = n_filt - spec_first
+    if env_rows is None:
+        env_rows = n_filt - env_first
+    cs, keep = chain_spec(sos, nbefore, nfft, hop, spec_first, spec_rows,
+                          0 if spec is None else spec.shape[0], out_db, esos, env_first, env_rows,
+                          env_nbefore, 0 if env is None else env.shape[0], clamp_negative, mm_step)
+    n = _i64(0)
+    check(lib().adn_chain_f64(C.byref(cs), ptr(src), src.shape[0], src.shape[1], float(rate),
+                              ptr(filtered), n_filt, None if spec is None else ptr(spec),
+                              None if env is None else ptr(env),
+                              None if minmax_out is None else ptr(minmax_out), C.byref(n),
+                              _h(src_mirror), _h(filt_mirror)))
+    del keep
+    return n.value
 
 
 def sosfilt(sos, src, dst, nbefore=0, zi=None, src_mirror=None, dst_mirror=None):

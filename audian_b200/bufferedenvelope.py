@@ -51,7 +51,22 @@ class BufferedEnvelope(BufferedData):
     def _standalone_update(self):
         self.sos = self.design()
 
+    chain_kind = 'envelope'
+
+    def chain_stage(self, start, count, nbefore):
+        """This trace's stage of BufferedFilter's fused recompute (adn_chain_f64)."""
+        return dict(esos=self.sos, env=self.buffer, env_first=start, env_rows=count,
+                    env_nbefore=nbefore, clamp_negative=(self.highpass_cutoff == 0))
+
+    def chain_done(self, n):
+        pass
+
     def process(self, source, dest, nbefore):
         _lib.envelope(self.sos, source, dest, nbefore,
                       clamp_negative=(self.highpass_cutoff == 0),
                       src_mirror=self.source_mirror(), dst_mirror=self.mirror())
+
+
+# the process() the fused recompute of BufferedFilter stands in for: subclasses that override
+# process() are recomputed trace by trace
+BufferedEnvelope.chain_process = BufferedEnvelope.process

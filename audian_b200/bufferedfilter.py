@@ -58,6 +58,65 @@ class BufferedFilter(BufferedData):
     def _standalone_update(self):
         self.sos = self.design()
 
+    def recompute_all(self):
+        """buffereddata.py:149-153 for the filter: recompute filtered, then its dests.  When the
+        dests that need an update are a spectrogram and / or an envelope of this package, the
+        whole walk is ONE library call (adn_chain_f64): the source is uploaded once, the filtered
+        buffer is consumed on the device, all results come down overlapped.  The buffers end up
+        exactly as the walk trace by trace leaves them."""
+        if not self.need_update:
+            return
+        stages = self._chain_stages()
+        if not stages:
+            return super().recompute_all()
+        # what recompute() does for this trace: allocate_buffer() + reload_buffer()
+        if len(self.source.buffer) > 0:
+            self.allocate_buffer()
+        self.invalidate_device()
+        if len(self.buffer) == 0:
+            return super().recompute_all()
+        start, count, nbefore = self.source_slice(self.offset, len(self.buffer))
+        src = self.source.buffer[start:start + count]
+        kw = {}
+        for d in stages:
+            d.allocate_buffer()
+            d.invalidate_device()
+            s0, cnt, nb = d.source_slice(d.offset, len(d.buffer))
+            if len(d.buffer) == 0 or cnt <= 0:
+                return super().recompute_all()
+            kw.update(d.chain_stage(s0, cnt, nb))
+        try:
+            n = _lib.chain(self.sos, src, self.buffer, self.source.rate, nbefore,
+                           src_mirror=self.source_mirror(), filt_mirror=self.mirror(), **kw)
+        except ValueError:
+            # an envelope slice shorter than its pad: the plain walk raises where the reference does
+            return super().recompute_all()
+        self.buffer_changed[:] = True
+        for d in stages:
+            d.buffer_changed[:] = True
+            d.chain_done(n)
+        for d in self.dests:
+            if d in stages:
+                for dd in d.dests:
+                    dd.recompute_all()
+            else:
+                d.recompute_all()
+
+    def _chain_stages(self):
+        """The dests the chain call can fill: at most one spectrogram and one envelope."""
+        kinds = {}
+        if type(self).process is not BufferedFilter.process:
+            return []                   # a subclass computes its own way: keep the plain walk
+        for d in self.dests:
+            kind = getattr(d, 'chain_kind', None)
+            if kind is None or not d.need_update:
+                continue
+            if kind in kinds or (kind == 'envelope' and d.sos is None) or \
+               type(d).process is not getattr(type(d), 'chain_process', None):
+                return []
+            kinds[kind] = d
+        return list(kinds.values())
+
     def process(self, source, dest, nbefore):
         # sos None -> the library copies source[nbefore:] (bufferedfilter.py:32-33)
         _lib.sosfilt(self.sos, source, dest, nbefore, src_mirror=self.source_mirror(),

@@ -77,9 +77,21 @@ class BufferedSpectrogram(BufferedData):
     def _standalone_update(self):
         self.hop = int(self.nfft*(1 - self.overlap_frac))
 
+    chain_kind = 'spectrogram'
+
+    def chain_stage(self, start, count, nbefore):
+        """This trace's stage of BufferedFilter's fused recompute (adn_chain_f64)."""
+        return dict(spec=self.buffer, nfft=self.nfft, hop=self.hop, spec_first=start, spec_rows=count)
+
+    def chain_done(self, n):
+        self._after_process(n)
+
     def process(self, source, dest, nbefore):
         n = _lib.spectrogram(source, self.source.rate, self.nfft, self.hop, dest,
                              src_mirror=self.source_mirror(), dst_mirror=self.mirror())
+        self._after_process(n)
+
+    def _after_process(self, n):
         if n > 0:
             # what scipy returns as `freq` (bufferedspectrogram.py:60)
             self.frequencies = np.fft.rfftfreq(self.nfft, 1/self.source.rate)
@@ -105,3 +117,8 @@ class BufferedSpectrogram(BufferedData):
         if zmax - zmin > 80:
             zmin = zmax - 80
         return zmin, zmax
+
+
+# the process() the fused recompute of BufferedFilter stands in for: subclasses that override
+# process() are recomputed trace by trace
+BufferedSpectrogram.chain_process = BufferedSpectrogram.process

@@ -863,6 +863,182 @@ int32_t adn_play_region_f64_m(const double* src, int64_t n, int32_t C, const int
     return copy_out(dst, c.out.as<double>(), (size_t)no * ncols * 8);
 }
 
+// ---------------------------------------------------------------- the chain
+// data -> filtered -> {spectrogram, envelope} (+ min/max of the raw rows) in one call: what a
+// parameter change walks through in the reference (BufferedFilter.update -> recompute_all ->
+// recompute of filtered, then of its dests: src/audian/bufferedfilter.py:53,
+// buffereddata.py:149-153).  The source goes up once, the filtered trace never leaves the
+// device between its producer and its consumers, every result starts on its way down as soon
+// as its kernel has run, and the host waits once at the end.
+
+static int32_t chain_check(const adn_chain_t* c, int64_t n_src, int32_t C, double rate, int64_t n_filt,
+                           bool want_spec, bool want_env, bool want_mm) {
+    if (!c || C < 1 || n_src < 1 || !(rate > 0) || c->S < 0 || c->S > ADN_MAX_SECTIONS || c->nbefore < 0 ||
+        n_filt < 1 || n_filt > n_src - c->nbefore || (c->S > 0 && !c->sos))
+        return fail(ADN_ERR_INVALID, "adn_chain_f64: filter stage n_src=%lld nbefore=%lld n_filt=%lld",
+                    (long long)n_src, c ? (long long)c->nbefore : -1LL, (long long)n_filt);
+    if (want_spec && (c->nfft < 1 || c->hop < 1 || c->hop > c->nfft || c->spec_first < 0 || c->spec_rows < 0 ||
+                      c->spec_first + c->spec_rows > n_filt || c->n_spec < 0))
+        return fail(ADN_ERR_INVALID, "adn_chain_f64: spectrogram stage");
+    if (want_env && (c->ES < 1 || c->ES > ADN_MAX_SECTIONS || !c->esos || c->env_first < 0 || c->env_rows < 1 ||
+                     c->env_first + c->env_rows > n_filt || c->env_nbefore < 0 || c->n_env < 0 ||
+                     c->n_env > c->env_rows - c->env_nbefore))
+        return fail(ADN_ERR_INVALID, "adn_chain_f64: envelope stage");
+    if (want_env && c->env_rows <= adn_sosfiltfilt_edge(c->esos, c->ES))
+        return fail(ADN_ERR_SHORT, "adn_chain_f64: the length of the envelope's input (%lld) must be greater "
+                    "than the sosfiltfilt pad length %d", (long long)c->env_rows, adn_sosfiltfilt_edge(c->esos, c->ES));
+    if (want_mm && c->mm_step < 1) return fail(ADN_ERR_INVALID, "adn_chain_f64: mm_step");
+    return ADN_OK;
+}
+
+// the stages after the filter, on device buffers; spectrogram frames land in dspec (zero-filled
+// beyond the computed ones), *nf = computed frames
+static int32_t chain_consumers(const adn_chain_t* c, const double* dfilt, int32_t C, double rate,
+                               double* dspec, double* denv, int64_t* nf, cudaStream_t st) {
+    int32_t rc;
+    if (dspec && c->n_spec > 0) {
+        const size_t F = (size_t)c->nfft / 2 + 1;
+        int64_t got = 0;
+        if ((rc = spectrogram_dev(dfilt + c->spec_first * C, c->spec_rows, C, rate, c->nfft, c->hop,
+                                  ADN_WINDOW_HANN, ADN_DETREND_CONSTANT, dspec, c->n_spec, c->out_db, &got, st)))
+            return rc;
+        if (got < c->n_spec)
+            ADN_CK(cudaMemsetAsync(dspec + (size_t)got * C * F, 0, (size_t)(c->n_spec - got) * C * F * 8, st));
+        if (nf) *nf = got;
+    }
+    if (denv && c->n_env > 0) {
+        if ((rc = envelope_dev(c->esos, c->ES, dfilt + c->env_first * C, c->env_rows, C, c->env_nbefore, denv,
+                               c->n_env, c->clamp_negative, st)))
+            return rc;
+    }
+    return ADN_OK;
+}
+
+int32_t adn_chain_f64_dev(const adn_chain_t* c, const double* src, int64_t n_src, int32_t C, double rate,
+                          double* filtered, int64_t n_filt, double* spec, double* env, double* minmax,
+                          int64_t* n_computed, void* stream) {
+    int32_t rc = chain_check(c, n_src, C, rate, n_filt, spec != nullptr, env != nullptr, minmax != nullptr);
+    if (rc) return rc;
+    if (!src || !filtered) return fail(ADN_ERR_INVALID, "adn_chain_f64_dev: NULL pointer");
+    if ((rc = ensure_init())) return rc;
+    cudaStream_t st = pick(stream);
+    if (n_computed) *n_computed = 0;
+    if (minmax && (rc = minmax_dev(src, n_src, C, c->mm_step, minmax, st))) return rc;
+    if ((rc = sosfilt_dev(c->sos, c->S, src, n_src, C, c->nbefore, filtered, n_filt, nullptr, nullptr, st)))
+        return rc;
+    return chain_consumers(c, filtered, C, rate, spec, env, n_computed, st);
+}
+
+int32_t adn_chain_f64(const adn_chain_t* c, const double* src, int64_t n_src, int32_t C, double rate,
+                      double* filtered, int64_t n_filt, double* spec, double* env, double* minmax,
+                      int64_t* n_computed, int64_t src_mirror, int64_t filt_mirror) {
+    int32_t rc = chain_check(c, n_src, C, rate, n_filt, spec != nullptr, env != nullptr, minmax != nullptr);
+    if (rc) return rc;
+    if (!src || !filtered) return fail(ADN_ERR_INVALID, "adn_chain_f64: NULL pointer");
+    ADN_API_LOCK;
+    if ((rc = ensure_init())) return rc;
+    if ((rc = ensure_streams())) return rc;
+    Ctx& cx = ctx();
+    if (n_computed) *n_computed = 0;
+    const size_t in_b = (size_t)n_src * C * 8, filt_b = (size_t)n_filt * C * 8;
+    const size_t F = (size_t)c->nfft / 2 + 1;
+    const size_t spec_b = spec ? (size_t)c->n_spec * C * F * 8 : 0;
+    const size_t env_b = env ? (size_t)c->n_env * C * 8 : 0;
+    const int64_t nseg = minmax ? (n_src + c->mm_step - 1) / c->mm_step : 0;
+    const size_t mm_b = (size_t)nseg * 2 * C * 8;
+    // device buffers: filtered in its mirror (or staging), the other results in the chain's own
+    double* dfilt = nullptr;
+    if ((rc = out_buffer(filt_mirror, filtered, filt_b, &dfilt))) return rc;
+    DevBuf& bs = scratch(SCR_CHAIN_SPEC, cx.stream);
+    DevBuf& be = scratch(SCR_CHAIN_ENV, cx.stream);
+    if ((rc = bs.reserve(spec_b + mm_b + 16))) return rc;
+    if ((rc = be.reserve(env_b + 16))) return rc;
+    double* dspec = spec ? bs.as<double>() : nullptr;
+    double* dmm = minmax ? reinterpret_cast<double*>(static_cast<char*>(bs.p) + ((spec_b + 15) & ~(size_t)15)) : nullptr;
+    double* denv = env ? be.as<double>() : nullptr;
+    // ---- the source: its mirror, or uploaded in chunks while the filter follows behind
+    const double* dsrc = nullptr;
+    if ((rc = in_resident(src_mirror, src, in_b, &dsrc))) return rc;
+    if (c->S == 0) {
+        // reference: sos is None -> filtered = source[nbefore:]
+        if (!dsrc) {
+            if ((rc = cx.in.reserve(in_b))) return rc;
+            ADN_CK(h2d(cx.in.p, src, in_b, cx.stream));
+            dsrc = cx.in.as<double>();
+        }
+        ADN_CK(cudaMemcpyAsync(dfilt, dsrc + c->nbefore * C, filt_b, cudaMemcpyDeviceToDevice, cx.stream));
+        if ((rc = chain(cx.stream, g_d2h))) return rc;
+        ADN_CK(d2h(filtered, dfilt, filt_b, g_d2h));
+    } else if (dsrc) {
+        if ((rc = sosfilt_dev(c->sos, c->S, dsrc, n_src, C, c->nbefore, dfilt, n_filt, nullptr, nullptr, cx.stream)))
+            return rc;
+        if ((rc = chain(cx.stream, g_d2h))) return rc;
+        ADN_CK(d2h(filtered, dfilt, filt_b, g_d2h));
+    } else {
+        if ((rc = cx.in.reserve(in_b))) return rc;
+        double* din = cx.in.as<double>();
+        const size_t z_b = (size_t)C * c->S * 2 * 8;
+        if ((rc = cx.aux.reserve(3 * z_b + 4096))) return rc;
+        double* d_state[2] = {cx.aux.as<double>() + (size_t)C * c->S * 2, cx.aux.as<double>() + (size_t)C * c->S * 4};
+        int64_t R = g_opt[ADN_OPT_CHUNK_BYTES] / ((int64_t)C * 8);
+        if (R < 4096) R = 4096;
+        const int64_t nchunks = (n_src + R - 1) / R;
+        const double* zin = nullptr;
+        for (int64_t k = 0; k < nchunks; ++k) {
+            const int64_t a = k * R, b = a + R < n_src ? a + R : n_src;
+            ADN_CK(h2d(din + a * C, src + a * C, (size_t)(b - a) * C * 8, g_h2d));
+            if ((rc = chain(g_h2d, cx.stream))) return rc;
+            int64_t nb = c->nbefore - a;
+            if (nb < 0) nb = 0;
+            if (nb > b - a) nb = b - a;
+            const int64_t o0 = a + nb - c->nbefore;
+            int64_t no = b - a - nb;
+            if (no > n_filt - o0) no = n_filt - o0;
+            if (no < 0) no = 0;
+            double* zout = k + 1 == nchunks ? nullptr : d_state[k & 1];
+            if (no > 0 || zout) {
+                if ((rc = sosfilt_dev(c->sos, c->S, din + a * C, b - a, C, nb, no > 0 ? dfilt + o0 * C : nullptr, no,
+                                      zin, zout, cx.stream)))
+                    return rc;
+            }
+            zin = zout;
+            if (no > 0) {
+                if ((rc = chain(cx.stream, g_d2h))) return rc;
+                ADN_CK(d2h(filtered + o0 * C, dfilt + o0 * C, (size_t)no * C * 8, g_d2h));
+            }
+        }
+        dsrc = din;
+    }
+    // ---- the consumers read the filtered trace where it is
+    int64_t nf = 0;
+    if (dspec && c->n_spec > 0) {
+        int64_t got = 0;
+        if ((rc = spectrogram_dev(dfilt + c->spec_first * C, c->spec_rows, C, rate, c->nfft, c->hop,
+                                  ADN_WINDOW_HANN, ADN_DETREND_CONSTANT, dspec, c->n_spec, c->out_db, &got, cx.stream)))
+            return rc;
+        nf = got;
+        if ((rc = chain(cx.stream, g_d2h))) return rc;
+        if (got > 0) ADN_CK(d2h(spec, dspec, (size_t)got * C * F * 8, g_d2h));
+    }
+    if (denv && c->n_env > 0) {
+        if ((rc = envelope_dev(c->esos, c->ES, dfilt + c->env_first * C, c->env_rows, C, c->env_nbefore, denv,
+                               c->n_env, c->clamp_negative, cx.stream)))
+            return rc;
+        if ((rc = chain(cx.stream, g_d2h))) return rc;
+        ADN_CK(d2h(env, denv, env_b, g_d2h));
+    }
+    if (dmm) {
+        if ((rc = minmax_dev(dsrc, n_src, C, c->mm_step, dmm, cx.stream))) return rc;
+        if ((rc = chain(cx.stream, g_d2h))) return rc;
+        ADN_CK(d2h(minmax, dmm, mm_b, g_d2h));
+    }
+    if ((rc = sync_pipeline())) return rc;
+    if (spec && c->n_spec > nf) memset(spec + (size_t)nf * C * F, 0, (size_t)(c->n_spec - nf) * C * F * 8);
+    mirror_commit(filt_mirror, filtered, filt_b, dfilt);
+    if (n_computed) *n_computed = nf;
+    return ADN_OK;
+}
+
 // ---------------------------------------------------------------- device entry points
 
 int32_t adn_spec_image_db_f64_dev(const double* spec, int64_t n, int32_t C, int32_t F, int32_t channel,

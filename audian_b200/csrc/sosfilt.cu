@@ -31,32 +31,6 @@ namespace adn {
 
 namespace {
 
-struct SosRun {
-    const double* src;
-    double* dst;                   // may be null: state only
-    const double* tab;
-    double* agg;                   // [tile][CG][D], SOS_EMPTY until published
-    double* incl;                  // [tile][CG][D]
-    int32_t off_fix, off_wpow, off_tile, n_staged;
-    const double* s0;              // [C][D] initial state or null
-    double* zf;                    // [C][D] final state or null
-    int64_t n;                     // logical length (rows the recurrence runs over)
-    int64_t nx;                    // MODE_ENVF: rows of the raw input
-    int64_t out_skip;              // physical rows dropped before dst row 0
-    int64_t n_dst;
-    int64_t ntt;                   // time tiles
-    int32_t C, CG, ngroups, T;
-    int32_t jdecay;                // (A^T)^j ~ 0 for j >= jdecay
-    int32_t edge;                  // MODE_ENVF: odd-extension length
-    int32_t clamp;                 // negative outputs -> 0
-    int32_t vec_in, vec_out;       // 16-byte granules allowed
-    int32_t pf_tiles;              // L2 prefetch distance in time tiles (0 = off)
-    int32_t lc;                    // log2(CG), or -1: no fast path
-    // sos_run_kernel: a block walks over run_tiles consecutive time tiles, after pre_tiles
-    // tiles of run-in from zero state; nbuf tile buffers (nbuf - 1 tiles prefetched)
-    int32_t run_tiles, pre_tiles, nbuf;
-};
-
 __device__ __forceinline__ double ld_relaxed(const double* p) {
     double v;
     asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
@@ -77,23 +51,6 @@ __device__ __forceinline__ bool read_record(const double* p, double (&v)[D]) {
     }
     return ok;
 }
-__device__ __forceinline__ void cp_async16(void* smem, const void* g, int src_bytes) {
-    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(g), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* smem, const void* g, int src_bytes) {
-    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(g), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-
-// input transform of the forward sweeps: (pi/2)|x| for the envelope, identity otherwise
-template <int MODE> __device__ __forceinline__ double pre_x(double x) {
-    return MODE == MODE_ENVF ? HALF_PI * fabs(x) : x;
-}
-
 // results go out with a streaming store, except the forward sweep of the envelope: the reversed
 // sweep starts reading where that one stopped writing, so its tail is left to live in L2
 // (measured on B200: envelope 208.6 against 210.6 us, order 4 262 against 266 us)
@@ -103,125 +60,6 @@ template <int MODE> __device__ __forceinline__ double pre_x(double x) {
 template <int MODE, class T>
 __device__ __forceinline__ void st_out(T* p, T v) {
     if (MODE == MODE_ENVF && ENVF_PLAIN_STORE) *p = v; else __stcs(p, v);
-}
-
-// ---- stage one tile (rows [t0, t0 + T) of channel group c0 .. c0 + Cw) in shared memory with
-// cp.async (the caller commits / waits).  Returns true when the tile holds RAW input that the
-// passes have to rectify on the fly (MODE_ENVF, tile clear of the odd extension).
-template <int MODE>
-__device__ __forceinline__ bool sos_load_tile(const SosRun& R, double* tile_s, int64_t t0, int c0,
-                                              int Cw, int tid) {
-    const int CG = R.CG, C = R.C, T = R.T;
-    const int pad = CG < 16 ? CG : 0;
-    const int GS = SOS_L * Cw + pad;
-    // MODE_ENVF: tiles that do not touch the odd extension are loaded raw and
-    // rectified on the fly; the two edge tiles are built element by element
-    bool xform = false;
-    int64_t shift = 0;
-    if (ADN_EXT(MODE)) {
-        xform = t0 >= R.edge && t0 + T <= R.edge + R.nx;
-        shift = R.edge;
-    }
-    // fast path (block-uniform): a full channel group (CG = 2^k channels), every row of the
-    // tile inside the source: the addresses of the granules a thread copies are shifts and adds
-    const int lc = Cw == CG ? R.lc : -1;                   // log2(CG) when the group is full
-    const int64_t nlim = ADN_EXT(MODE) ? R.edge + R.nx : R.n;
-    const bool fast_in = lc >= 0 && t0 + T <= nlim && !(ADN_EXT(MODE) && !xform);
-    if (fast_in) {
-        const int64_t rowbase = MODE == MODE_REV ? R.n - 1 - t0 : t0 - shift;   // physical row of tile row 0
-        if (R.vec_in) {
-            // granule k of a thread: flat index f = 2 (tid + NT k), row r0 + k DRk (DRk = 2 NT / CG
-            // rows, a multiple of 32 whenever the tile is padded): both addresses advance by
-            // constants
-            const int f0 = 2 * tid, r0 = f0 >> lc;
-            const int DRk = (2 * SOS_NT) >> lc;
-            const int64_t gstr = (MODE == MODE_REV ? -(int64_t)DRk : (int64_t)DRk) * C;
-            const double* gp = R.src + (MODE == MODE_REV ? rowbase - r0 : rowbase + r0) * C + c0 + (f0 & (CG - 1));
-            double* sp = tile_s + f0 + (r0 >> 5) * pad;
-            if (pad) {
-#pragma unroll
-                for (int k = 0; k < SOS_L / 2; ++k) {
-                    cp_async16(sp + k * (2 * SOS_NT + 8), gp, 16);
-                    gp += gstr;
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < SOS_L / 2; ++k) {
-                    cp_async16(sp + k * (2 * SOS_NT), gp, 16);
-                    gp += gstr;
-                }
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < SOS_L; ++k) {
-                const int f = tid + SOS_NT * k;
-                const int r = f >> lc, c = c0 + (f & (CG - 1));
-                const int64_t grow = MODE == MODE_REV ? rowbase - r : rowbase + r;
-                cp_async8(tile_s + f + (r >> 5) * pad, R.src + grow * C + c, 8);
-            }
-        }
-    } else
-    if (ADN_EXT(MODE) && !xform) {
-        // element by element, in batches whose loads are all issued before the first use (a run
-        // whose first tile is an edge tile would otherwise start some 30 load latencies late)
-        const int64_t nx = R.nx, edge = R.edge;
-        const int total = T * Cw;
-        constexpr int UB = 8;
-        for (int q0 = tid; q0 < total; q0 += SOS_NT * UB) {
-            double va[UB], vb[UB];
-            int kind[UB], sidx[UB];          // 0: beyond the end, 1: plain row, 2: reflected, -1: no element
-#pragma unroll
-            for (int u = 0; u < UB; ++u) {
-                const int q = q0 + u * SOS_NT;
-                kind[u] = -1;
-                va[u] = vb[u] = 0.0;
-                sidx[u] = 0;
-                if (q < total) {
-                    const int row = q / Cw, col = q - row * Cw;
-                    const int64_t e = t0 + row;
-                    sidx[u] = (row / SOS_L) * GS + (row % SOS_L) * Cw + col;
-                    const double* xc = R.src + c0 + col;
-                    kind[u] = 0;
-                    if (e < R.n) {
-                        int64_t ra, rb = -1;
-                        if (e < edge) { ra = 0; rb = edge - e; }
-                        else if (e < edge + nx) { ra = e - edge; }
-                        else { ra = nx - 1; rb = nx - 2 - (e - edge - nx); }
-                        va[u] = __ldg(xc + ra * C);
-                        kind[u] = 1;
-                        if (rb >= 0) { vb[u] = __ldg(xc + rb * C); kind[u] = 2; }
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UB; ++u) {
-                if (kind[u] < 0) continue;
-                double val = 0.0;
-                if (kind[u] == 1) val = pre_x<MODE>(va[u]);
-                else if (kind[u] == 2) val = 2.0 * pre_x<MODE>(va[u]) - pre_x<MODE>(vb[u]);
-                tile_s[sidx[u]] = val;
-            }
-        }
-    } else {
-        const int gw = R.vec_in ? 2 : 1;                 // doubles per granule
-        const int gpr = Cw / gw;                         // granules per row
-        const int total = T * gpr;
-        int row = tid / gpr, col = tid - row * gpr;
-        const int drow = SOS_NT / gpr, dcol = SOS_NT - drow * gpr;
-        for (int q = tid; q < total; q += SOS_NT) {
-            int64_t tau = t0 + row;
-            bool ok = tau < nlim;
-            int64_t phys = MODE == MODE_REV ? R.n - 1 - tau : tau - shift;
-            const double* gp = ok ? R.src + phys * C + c0 + col * gw : R.src;
-            double* sp = tile_s + (row / SOS_L) * GS + (row % SOS_L) * Cw + col * gw;
-            if (gw == 2) cp_async16(sp, gp, ok ? 16 : 0);
-            else cp_async8(sp, gp, ok ? 8 : 0);
-            row += drow;
-            col += dcol;
-            if (col >= gpr) { col -= gpr; ++row; }
-        }
-    }
-    return xform;
 }
 
 // ---- write the finished tile back (clamp fused), coalesced

@@ -49,6 +49,7 @@ struct ZpArgs {
     int32_t JJ, JO;                    // look-ahead tiles of the forward state; run-out tiles
     int32_t run_tiles;
     int32_t pf;                        // bulk L2 prefetch of the next look-ahead tile
+    int32_t bulk_ok;                   // tiles of full, contiguous channel groups through the TMA unit
     ZiK zi;
 };
 
@@ -439,20 +440,22 @@ sos_zp_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ ZpArgs 
 }
 
 // ======================================================================================
-// Pipelined variant for cascades that forget within JJ <= ZP_NTEAM - 2 tiles: nothing is read
-// twice, not even from L2.  A block is ZP_NTEAM teams of four warps and owns ONE run; team k
-// takes the tiles top - k, top - k - NTEAM, ...  A team loads its tile into registers, computes
-// the zero-state forward aggregates (pass A) and publishes the tile aggregate; the tile then
-// STAYS in the team's registers until the teams of the JJ tiles before it have published
-// theirs (they load later: the walk goes backward), which gives the forward state entering
-// the tile; forward recurrence, backward pass A and scan follow in the same registers.  The
-// backward state is handed from tile to tile as  sin_b(T) = A^T sin_b(T+1) + agg_b(T)  by one
-// warp as soon as agg_b(T) is known, so the teams work concurrently and only that small
-// matrix-vector product is serial along the run.  The register files of the waiting teams are
-// the look-ahead window: 4 teams x 32 KB of samples per SM, more than shared memory could hold
-// next to anything else.
-constexpr int ZP_NTEAM = 4;
-constexpr int ZP_PNT = SOS_NT * ZP_NTEAM;
+// Pipelined variant for cascades that forget within a few tiles: nothing is read twice, not even
+// from L2, and every warp works all the time.  A block is NTEAM teams of four warps and owns ONE
+// run; tiles are staged in a ring of NTEAM + JJ shared-memory slots by cp.async (the loader of
+// sosfilt.cu: coalesced 16-byte granules, the odd extension built on the fly) one team
+// iteration ahead of their use.  Iteration of a team for walk position w (tile t = top - w):
+//   L(t)       tile slot -> registers, zero-state forward aggregates (pass A + scans), the tile
+//              aggregate and every thread's prefix are published in shared memory; the samples
+//              stay PARKED in their slot
+//   M(t + JJ)  tile slot -> registers again (parked JJ positions ago by another team), the
+//              slot is handed to the prefetch of the team's next tile; forward state from the JJ
+//              aggregates behind it, forward recurrence, backward pass A + scan and backward
+//              recurrence in the same registers, clamp, store from the registers.
+// The backward state is handed from tile to tile as  sin_b(T) = A^T sin_b(T+1) + agg_b(T)  by one
+// warp as soon as agg_b(T) is known, so only that small matrix-vector product is serial along
+// the run and the teams overlap freely.
+constexpr int ZP_NTEAM_MAX = 4;
 
 __device__ __forceinline__ void zp_team_bar(int team) {
     asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(SOS_NT) : "memory");
@@ -466,15 +469,42 @@ __device__ __forceinline__ void zp_wait_le(const volatile long long* f, long lon
     __syncwarp();
 }
 
-template <int S, bool RECT>
-__global__ void __launch_bounds__(ZP_PNT, 1)
-sos_zp_pipe_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ ZpArgs P) {
+// ---- TMA unit: 1-D bulk copies global -> shared memory, completion counted in bytes on an mbarrier
+__device__ __forceinline__ uint32_t zp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void zp_mbar_init(uint64_t* mbar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(zp_smem_u32(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void zp_mbar_arrive(uint64_t* mbar) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(zp_smem_u32(mbar)) : "memory");
+}
+__device__ __forceinline__ void zp_mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}"
+                 ::"r"(zp_smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void zp_mbar_wait(uint64_t* mbar, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
+        ::"r"(zp_smem_u32(mbar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void zp_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(zp_smem_u32(dst)), "l"(src), "r"(bytes), "r"(zp_smem_u32(mbar)) : "memory");
+}
+
+template <int S, int MODE, int NTC>
+__global__ void __launch_bounds__(SOS_NT * NTC, 1)
+sos_zp_park_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ ZpArgs P,
+                   const __grid_constant__ SosRun R) {
     constexpr int D = 2 * S;
     constexpr int DD = D * D;
+    constexpr bool RECT = MODE == MODE_ENVF;
     extern __shared__ __align__(16) double smem[];
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int team = tid >> 7, ttid = tid & (SOS_NT - 1), warp = ttid >> 5;   // warp inside the team
+    constexpr int NTEAM = NTC;
     const int grp = (int)(blockIdx.x % P.ngroups);
     const int64_t run = blockIdx.x / P.ngroups;
     const int CG = P.CG, C = P.C;
@@ -485,157 +515,212 @@ sos_zp_pipe_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ Zp
     const int g = warp * GW + gl;
     const bool chan_ok = cw < Cw;
     const int T = P.T;
-    const int JJ = P.JJ;
+    const int JJ = P.JJ, NSLOT = NTEAM + JJ;
+    const int pad = CG < 16 ? CG : 0;
+    const int GS = SOS_L * Cw + pad;
+    const size_t TS = (size_t)(SOS_NT / CG) * (SOS_L * CG + pad);   // doubles per tile slot
 
     double* tab_s = smem;                                   // n_staged * DD
-    double* wagg_all = tab_s + (size_t)P.n_staged * DD;     // [NTEAM][2][NW][CG][D]: forward / backward phase
-    double* wagg = wagg_all + (size_t)team * 2 * SOS_NW * CG * D;
+    double* wagg = tab_s + (size_t)P.n_staged * DD + (size_t)team * 2 * SOS_NW * CG * D;   // [NTEAM][2][NW][CG][D]
     double* waggb = wagg + (size_t)SOS_NW * CG * D;
-    double* aggr = wagg_all + (size_t)ZP_NTEAM * 2 * SOS_NW * CG * D;   // [NTEAM][CG][D]  forward tile aggregates
-    double* sinb_s = aggr + (size_t)ZP_NTEAM * CG * D;      // [NTEAM][CG][D]  backward state leaving a team's tile
-    volatile long long* la_flag = reinterpret_cast<volatile long long*>(sinb_s + (size_t)ZP_NTEAM * CG * D);  // [NTEAM]
-    volatile long long* sb_flag = la_flag + ZP_NTEAM;       // tile whose outgoing backward state is published
+    double* aggr = tab_s + (size_t)P.n_staged * DD + (size_t)NTEAM * 2 * SOS_NW * CG * D;   // [NSLOT][CG][D]
+    double* sinb_s = aggr + (size_t)NSLOT * CG * D;         // [NTEAM][CG][D]
+    double* etot = sinb_s + (size_t)NTEAM * CG * D;         // [NSLOT][D][NT]
+    volatile long long* la_flag = reinterpret_cast<volatile long long*>(etot + (size_t)NSLOT * D * SOS_NT);  // [NSLOT]
+    volatile long long* sb_flag = la_flag + NSLOT;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(const_cast<long long*>(la_flag) + NSLOT + 1);         // [NSLOT]
+    double* pt_s = reinterpret_cast<double*>(mbar + NSLOT + ((NSLOT + 1 + NSLOT) & 1));   // [(JJ + 2)][DD], 16-byte aligned
+    double* tiles = pt_s + (size_t)(JJ + 2) * DD;           // [NSLOT][TS]
     const double* tab_fix = tab_s + P.off_fix * DD;
     const double* tab_wpow = tab_s + P.off_wpow * DD;
-    const double* Pt = P.tab + (size_t)P.off_tile * DD;     // (A^T)^j, global
+    const double* Pt = pt_s;                                // (A^T)^j, j <= JJ + 1
+    const int G = SOS_NT / CG;
+    // whole tiles come in through the TMA unit when the rows of the group are contiguous
+    const bool bulk_group = P.bulk_ok && Cw == CG;
 
     const int64_t a = P.t_out0 + run * P.run_tiles;         // output tiles [a, b)
     const int64_t b = min(a + (int64_t)P.run_tiles, P.t_out1);
     if (a >= b) return;
     const int64_t top = min(b + (int64_t)P.JO, P.ntt) - 1;  // first tile of the walk
 
-    for (int q = tid; q < P.n_staged * DD; q += ZP_PNT) tab_s[q] = __ldg(P.tab + q);
-    for (int q = tid; q < ZP_NTEAM * CG * D; q += ZP_PNT) sinb_s[q] = 0.0;
-    if (tid < ZP_NTEAM) la_flag[tid] = (long long)1 << 60;
+    for (int q = tid; q < P.n_staged * DD; q += blockDim.x) tab_s[q] = __ldg(P.tab + q);
+    for (int q = tid; q < (JJ + 2) * DD; q += blockDim.x) pt_s[q] = __ldg(P.tab + (size_t)P.off_tile * DD + q);
+    for (int q = tid; q < NTEAM * CG * D; q += blockDim.x) sinb_s[q] = 0.0;
+    if (tid < NSLOT) {
+        la_flag[tid] = (long long)1 << 60;
+        zp_mbar_init(mbar + tid, 1);
+    }
     if (tid == 0) *sb_flag = top + 1;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
+    auto slot_of = [&](int64_t t) { return (int)((t + 64 * (int64_t)NSLOT) % NSLOT); };
+    // how tile t reaches its slot: 0 nothing to load, 1 TMA bulk copies, 2 cp.async granules
+    auto load_kind = [&](int64_t t) {
+        if (t < 0 || t < a - JJ) return 0;
+        if (!bulk_group || t * T < P.edgeL || (t + 1) * (int64_t)T > P.edgeL + P.nx) return 2;
+        const uintptr_t g0 = reinterpret_cast<uintptr_t>(P.src + (t * T - P.edgeL) * C + c0);
+        return (g0 & 15) == 0 ? 1 : 2;
+    };
+    // every use of a slot completes exactly one phase of its mbarrier (count 1): the bulk copies'
+    // bytes + the arrival that announced them, or a plain arrival for the other two kinds
+    auto issue_load = [&](int64_t t, int slot) {
+        const int kind = load_kind(t);
+        if (kind == 1) {
+            if (warp == 0) {
+                // the slot was read through the generic proxy until the barrier before this call
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (lane == 0) zp_mbar_expect_tx(mbar + slot, (uint32_t)(T * C * 8));
+                __syncwarp();
+                const double* gsrc = P.src + (t * T - P.edgeL) * C + c0;
+                double* sdst = tiles + (size_t)slot * TS;
+                for (int q = lane; q < G; q += 32)
+                    zp_bulk_g2s(sdst + (size_t)q * GS, gsrc + (size_t)q * SOS_L * C, (uint32_t)(SOS_L * C * 8), mbar + slot);
+            }
+        } else if (kind == 2) {
+            sos_load_tile<MODE>(R, tiles + (size_t)slot * TS, t * T, c0, Cw, ttid);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // the tile has landed in its slot (all threads of the loading team call this)
+    auto wait_load = [&](int64_t t, int slot) {
+        const int kind = load_kind(t);
+        const uint32_t parity = (uint32_t)(((top - t) / NSLOT) & 1);
+        if (kind == 1) {
+            zp_mbar_wait(mbar + slot, parity);
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            zp_team_bar(team);
+            if (ttid == 0) zp_mbar_arrive(mbar + slot);
+        }
+    };
+    // the team's first tile is on its way
+    issue_load(top - team, slot_of(top - team));
 
-    const double* xc = P.src + c0 + (chan_ok ? cw : 0);
+    // tile slot -> this thread's SOS_L samples
+    auto read_tile = [&](int64_t t, double (&x)[SOS_L]) {
+        const double* xp = tiles + (size_t)slot_of(t) * TS + g * GS + cw;
+        const bool xform = RECT && t * T >= P.edgeL && (t + 1) * (int64_t)T <= P.edgeL + P.nx;
+        if (!chan_ok) {
+#pragma unroll
+            for (int i = 0; i < SOS_L; ++i) x[i] = 0.0;
+        } else if (Cw == 8) {
+#pragma unroll
+            for (int i = 0; i < SOS_L; ++i) x[i] = xp[i * 8];
+        } else {
+#pragma unroll
+            for (int i = 0; i < SOS_L; ++i) x[i] = xp[i * Cw];
+        }
+        if (xform) {
+#pragma unroll
+            for (int i = 0; i < SOS_L; ++i) x[i] = HALF_PI * fabs(x[i]);
+        }
+    };
 
-    for (int64_t t = top - team; t >= a - JJ; t -= ZP_NTEAM) {
-        // L2 prefetch of the tile this team takes next but one (contiguous rows)
-        if (P.pf && ttid == 0 && grp == 0) {
-            const int64_t tp = t - (int64_t)P.pf * ZP_NTEAM;
-            if (tp >= 0 && tp >= a - JJ) {
-                int64_t p0 = tp * T - P.edgeL, p1 = p0 + T;
-                if (p0 < 0) p0 = 0;
-                if (p1 > P.nx) p1 = P.nx;
-                if (p1 > p0) {
-                    const char* adr = reinterpret_cast<const char*>(P.src + p0 * C);
-                    int64_t bytes = (p1 - p0) * (int64_t)C * 8;
-                    const int64_t mis = reinterpret_cast<uintptr_t>(adr) & 15;
-                    adr -= mis;
-                    bytes = (bytes + mis + 15) & ~(int64_t)15;
-                    if (adr >= reinterpret_cast<const char*>(P.src))
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(adr), "r"((uint32_t)bytes) : "memory");
+    for (int64_t w = team; ; w += NTEAM) {
+        const int64_t tl = top - w;                          // look-ahead tile of this iteration
+        const int64_t tm = tl + JJ;                          // main tile of this iteration
+        if (tm < a) break;
+        const bool do_l = tl >= a - JJ;
+        const bool do_m = tm <= top;
+        // ---------------------------------------------------------------- L(tl)
+        if (do_l || tl >= 0) wait_load(tl, slot_of(tl));     // the team's tile tl has landed
+        if (do_l) {
+            const int slot = slot_of(tl);
+            if (tl < 0) {
+                // before the sequence: the virtual tile -1 carries the initial state of the sweep
+                if (ttid < CG * D) {
+                    const int ch = ttid / D, d = ttid - ch * D;
+                    double v = 0.0;
+                    if (tl == -1 && P.zi_left && c0 + ch < C)
+                        v = P.zi.z[d] * zp_ext_value<RECT>(P, P.src + c0 + ch, 0);
+                    aggr[(size_t)slot * CG * D + ttid] = v;
                 }
+                zp_team_bar(team);
+                if (ttid == 0) { __threadfence_block(); la_flag[slot] = tl; }
+            } else {
+                double x[SOS_L];
+                read_tile(tl, x);
+                double v[D], ex[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) v[d] = 0.0;
+                zp_pass_a<S, false>(K, x, v);
+                {
+                    int k = 0;
+                    for (int off = CG; off < 32; off <<= 1, ++k) {
+                        double u[D];
+#pragma unroll
+                        for (int d = 0; d < D; ++d) u[d] = __shfl_up_sync(0xffffffffu, v[d], off);
+                        if (lane >= off) matvec_acc<D>(tab_s + k * DD, u, v);
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const double u = __shfl_up_sync(0xffffffffu, v[d], CG & 31);
+                    ex[d] = gl == 0 ? 0.0 : u;
+                }
+                if (gl == GW - 1) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) wagg[(warp * CG + cw) * D + d] = v[d];
+                }
+                zp_team_bar(team);
+                double pre[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) pre[d] = 0.0;
+                for (int j = 0; j < warp; ++j) {
+                    double u[D];
+#pragma unroll
+                    for (int d = 0; d < D; ++d) u[d] = wagg[(j * CG + cw) * D + d];
+                    matvec_acc<D>(tab_wpow + (warp - 1 - j) * DD, u, pre);
+                }
+                matvec_acc<D>(tab_fix + gl * DD, pre, ex);   // ex + A^(L gl) pre
+#pragma unroll
+                for (int d = 0; d < D; ++d) etot[((size_t)slot * D + d) * SOS_NT + ttid] = ex[d];
+                if (ttid < CG * D) {
+                    const int ch = ttid / D, r = ttid - ch * D;
+                    double acc = 0.0;
+                    for (int q = 0; q < SOS_NW; ++q) {
+                        const double* M = tab_wpow + (SOS_NW - 1 - q) * DD + r * D;
+                        const double* u = wagg + (q * CG + ch) * D;
+                        for (int c = 0; c < D; ++c) acc = fma(M[c], u[c], acc);
+                    }
+                    aggr[(size_t)slot * CG * D + ttid] = acc;
+                }
+                zp_team_bar(team);
+                if (ttid == 0) { __threadfence_block(); la_flag[slot] = tl; }
             }
         }
-        if (t < 0) {
-            // before the sequence: the virtual tile -1 carries the initial state of the sweep
-            if (ttid < CG * D) {
-                const int ch = ttid / D, d = ttid - ch * D;
-                double v = 0.0;
-                if (t == -1 && P.zi_left && c0 + ch < C)
-                    v = P.zi.z[d] * zp_ext_value<RECT>(P, P.src + c0 + ch, 0);
-                aggr[(size_t)team * CG * D + ttid] = v;
-            }
-            zp_team_bar(team);
-            if (ttid == 0) { __threadfence_block(); la_flag[team] = t; }
+        // the team's next look-ahead tile: into the slot the main visit below frees
+        const int64_t tn = tl - NTEAM;
+        if (!do_m) {
+            issue_load(tn, slot_of(tn));
             continue;
         }
-        // ---- rows of tile t of this thread's channel -> registers
-        double x[SOS_L];
-        {
-            const int64_t e0 = t * T + (int64_t)g * SOS_L;  // sequence row of x[0]
-            const bool fast = t * T >= P.edgeL && (t + 1) * (int64_t)T <= P.edgeL + P.nx;
-            if (!chan_ok) {
-#pragma unroll
-                for (int i = 0; i < SOS_L; ++i) x[i] = 0.0;
-            } else if (fast) {
-                const double* p = xc + (e0 - P.edgeL) * C;
-                if (C == 8) {
-#pragma unroll
-                    for (int i = 0; i < SOS_L; ++i) x[i] = __ldg(p + i * 8);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < SOS_L; ++i) { x[i] = __ldg(p); p += C; }
-                }
-#pragma unroll
-                for (int i = 0; i < SOS_L; ++i) x[i] = zp_pre<RECT>(x[i]);
-            } else {
-                double tmp[SOS_L];
-#pragma unroll 1
-                for (int i = 0; i < SOS_L; ++i) tmp[i] = zp_ext_value<RECT>(P, xc, e0 + i);
-#pragma unroll
-                for (int i = 0; i < SOS_L; ++i) x[i] = tmp[i];
-            }
-        }
-        // ---- zero-state forward aggregates of the tile
-        double z[D];                                        // this thread's zero-state prefix, then its state
-        {
-            double v[D];
-#pragma unroll
-            for (int d = 0; d < D; ++d) v[d] = 0.0;
-            zp_pass_a<S, false>(K, x, v);
-            {
-                int k = 0;
-                for (int off = CG; off < 32; off <<= 1, ++k) {
-                    double w[D];
-#pragma unroll
-                    for (int d = 0; d < D; ++d) w[d] = __shfl_up_sync(0xffffffffu, v[d], off);
-                    if (lane >= off) matvec_acc<D>(tab_s + k * DD, w, v);
-                }
-            }
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-                const double w = __shfl_up_sync(0xffffffffu, v[d], CG & 31);
-                z[d] = gl == 0 ? 0.0 : w;
-            }
-            if (gl == GW - 1) {
-#pragma unroll
-                for (int d = 0; d < D; ++d) wagg[(warp * CG + cw) * D + d] = v[d];
-            }
-            zp_team_bar(team);
-            double pre[D];
-#pragma unroll
-            for (int d = 0; d < D; ++d) pre[d] = 0.0;
-            for (int j = 0; j < warp; ++j) {
-                double w[D];
-#pragma unroll
-                for (int d = 0; d < D; ++d) w[d] = wagg[(j * CG + cw) * D + d];
-                matvec_acc<D>(tab_wpow + (warp - 1 - j) * DD, w, pre);
-            }
-            matvec_acc<D>(tab_fix + gl * DD, pre, z);        // z = ex + A^(L gl) pre
-            if (ttid < CG * D) {
-                const int ch = ttid / D, r = ttid - ch * D;
-                double acc = 0.0;
-                for (int w = 0; w < SOS_NW; ++w) {
-                    const double* M = tab_wpow + (SOS_NW - 1 - w) * DD + r * D;
-                    const double* q = wagg + (w * CG + ch) * D;
-                    for (int c = 0; c < D; ++c) acc = fma(M[c], q[c], acc);
-                }
-                aggr[(size_t)team * CG * D + ttid] = acc;
-            }
-            zp_team_bar(team);
-            if (ttid == 0) { __threadfence_block(); la_flag[team] = t; }
-        }
-        if (t < a) continue;                                 // below the run: only its aggregate is needed
+        // ---------------------------------------------------------------- M(tm)
+        const int64_t t = tm;
+        const int slot = slot_of(t);
         const bool store = t < b;
         const bool last = t == P.ntt - 1;
-        // ---- forward state entering the tile: sum_{j=1..JJ} (A^T)^(j-1) agg[t-j], from the teams behind
+        zp_wait_le(la_flag + slot, t, lane);                 // parked by its look-ahead visit
+        double x[SOS_L];
+        read_tile(t, x);
+        double z[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) z[d] = etot[((size_t)slot * D + d) * SOS_NT + ttid];
+        zp_team_bar(team);                                   // every thread of the team has its samples
+        issue_load(tn, slot);
+        // ---- forward state entering the tile: sum_{j=1..JJ} (A^T)^(j-1) agg[t-j]
         {
             double sf[D];
 #pragma unroll
             for (int d = 0; d < D; ++d) sf[d] = 0.0;
             for (int j = 1; j <= JJ; ++j) {
-                const int tj = (team + j) % ZP_NTEAM;
-                zp_wait_le(la_flag + tj, t - j, lane);
+                const int sj = slot_of(t - j);
+                zp_wait_le(la_flag + sj, t - j, lane);
                 double q[D], M[DD];
 #pragma unroll
-                for (int d = 0; d < D; ++d) q[d] = aggr[(size_t)tj * CG * D + cw * D + d];
+                for (int d = 0; d < D; ++d) q[d] = aggr[(size_t)sj * CG * D + cw * D + d];
 #pragma unroll
-                for (int e = 0; e < DD; ++e) M[e] = __ldg(Pt + (size_t)(j - 1) * DD + e);
+                for (int e = 0; e < DD; ++e) M[e] = Pt[(size_t)(j - 1) * DD + e];
                 matvec_acc<D>(M, q, sf);
             }
             double tmp[D];
@@ -682,17 +767,17 @@ sos_zp_pipe_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ Zp
         {
             int k = 0;
             for (int off = CG; off < 32; off <<= 1, ++k) {
-                double w[D];
+                double u[D];
 #pragma unroll
-                for (int d = 0; d < D; ++d) w[d] = __shfl_down_sync(0xffffffffu, vb[d], off);
-                if (lane + off < 32) matvec_acc<D>(tab_s + k * DD, w, vb);
+                for (int d = 0; d < D; ++d) u[d] = __shfl_down_sync(0xffffffffu, vb[d], off);
+                if (lane + off < 32) matvec_acc<D>(tab_s + k * DD, u, vb);
             }
         }
         double zb[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            const double w = __shfl_down_sync(0xffffffffu, vb[d], CG & 31);
-            zb[d] = gl == GW - 1 ? 0.0 : w;
+            const double u = __shfl_down_sync(0xffffffffu, vb[d], CG & 31);
+            zb[d] = gl == GW - 1 ? 0.0 : u;
         }
         if (gl == 0) {
 #pragma unroll
@@ -701,11 +786,11 @@ sos_zp_pipe_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ Zp
         zp_team_bar(team);
         // ---- the backward state entering this tile (from the team of tile t + 1)
         double sv[D];
+        const int tprev = (team + NTEAM - 1) % NTEAM;         // team of the main visit of tile t + 1
         {
-            const int tn = (team + ZP_NTEAM - 1) % ZP_NTEAM;
             if (t < top) zp_wait_le(sb_flag, t + 1, lane);
 #pragma unroll
-            for (int d = 0; d < D; ++d) sv[d] = (last || t == top) ? 0.0 : sinb_s[(size_t)tn * CG * D + cw * D + d];
+            for (int d = 0; d < D; ++d) sv[d] = (last || t == top) ? 0.0 : sinb_s[(size_t)tprev * CG * D + cw * D + d];
         }
         zp_team_bar(team);                                   // every warp of the team has read it
         if (warp == 0) {
@@ -713,16 +798,15 @@ sos_zp_pipe_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ Zp
             for (int e = lane; e < CG * D; e += 32) {
                 const int ch = e / D, r = e - ch * D;
                 double acc = 0.0;
-                for (int w = 0; w < SOS_NW; ++w) {
-                    const double* M = tab_wpow + w * DD + r * D;
-                    const double* q = waggb + (w * CG + ch) * D;
-                    for (int c = 0; c < D; ++c) acc = fma(M[c], q[c], acc);
+                for (int q = 0; q < SOS_NW; ++q) {
+                    const double* M = tab_wpow + q * DD + r * D;
+                    const double* u = waggb + (q * CG + ch) * D;
+                    for (int c = 0; c < D; ++c) acc = fma(M[c], u[c], acc);
                 }
                 if (!(last || t == top)) {
-                    const int tn = (team + ZP_NTEAM - 1) % ZP_NTEAM;
                     const double* M = Pt + DD + r * D;
-                    const double* q = sinb_s + (size_t)tn * CG * D + ch * D;
-                    for (int c = 0; c < D; ++c) acc = fma(__ldg(M + c), q[c], acc);
+                    const double* u = sinb_s + (size_t)tprev * CG * D + ch * D;
+                    for (int c = 0; c < D; ++c) acc = fma(M[c], u[c], acc);
                 }
                 sinb_s[(size_t)team * CG * D + e] = acc;
             }
@@ -734,10 +818,10 @@ sos_zp_pipe_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ Zp
 #pragma unroll
             for (int d = 0; d < D; ++d) pre[d] = 0.0;
             for (int j = SOS_NW - 1; j > warp; --j) {
-                double w[D];
+                double u[D];
 #pragma unroll
-                for (int d = 0; d < D; ++d) w[d] = waggb[(j * CG + cw) * D + d];
-                matvec_acc<D>(tab_wpow + (j - 1 - warp) * DD, w, pre);
+                for (int d = 0; d < D; ++d) u[d] = waggb[(j * CG + cw) * D + d];
+                matvec_acc<D>(tab_wpow + (j - 1 - warp) * DD, u, pre);
             }
             matvec_acc<D>(tab_wpow + (SOS_NW - 1 - warp) * DD, sv, pre);
             matvec_acc<D>(tab_fix + (GW - 1 - gl) * DD, pre, zb);
@@ -787,24 +871,33 @@ sos_zp_pipe_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ Zp
                 }
             }
         }
-        // the team's wagg is rewritten by its next tile only after the team barrier there
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 std::atomic<int64_t> g_zp_launches{0};
 
 template <int S, bool RECT>
-int32_t launch_zp(const SosPlan& plan, const ZpArgs& P, size_t smem, unsigned grid, bool pipe, cudaStream_t st) {
+int32_t launch_zp(const SosPlan& plan, const ZpArgs& P, const SosRun& R, size_t smem, unsigned grid, int nteam,
+                  cudaStream_t st) {
     SosK<S> K;
     fill_sosk<S>(plan, K);
-    if (pipe) {
-        auto kern = sos_zp_pipe_kernel<S, RECT>;
+    if (nteam == 4) {
+        auto kern = sos_zp_park_kernel<S, RECT ? MODE_ENVF : MODE_ZPF, 4>;
         static bool attr_done = false;           // per instantiation
         if (!attr_done) {
-            ADN_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            ADN_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             attr_done = true;
         }
-        kern<<<grid, ZP_PNT, smem, st>>>(K, P);
+        kern<<<grid, SOS_NT * 4, smem, st>>>(K, P, R);
+    } else if (nteam == 3) {
+        auto kern = sos_zp_park_kernel<S, RECT ? MODE_ENVF : MODE_ZPF, 3>;
+        static bool attr_done = false;
+        if (!attr_done) {
+            ADN_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_done = true;
+        }
+        kern<<<grid, SOS_NT * 3, smem, st>>>(K, P, R);
     } else {
         auto kern = sos_zp_kernel<S, RECT>;
         static bool attr_done = false;
@@ -821,10 +914,10 @@ int32_t launch_zp(const SosPlan& plan, const ZpArgs& P, size_t smem, unsigned gr
 }
 
 template <int S>
-int32_t launch_zp_S(bool rect, const SosPlan& plan, const ZpArgs& P, size_t smem, unsigned grid, bool pipe,
-                    cudaStream_t st) {
-    return rect ? launch_zp<S, true>(plan, P, smem, grid, pipe, st)
-                : launch_zp<S, false>(plan, P, smem, grid, pipe, st);
+int32_t launch_zp_S(bool rect, const SosPlan& plan, const ZpArgs& P, const SosRun& R, size_t smem,
+                    unsigned grid, int nteam, cudaStream_t st) {
+    return rect ? launch_zp<S, true>(plan, P, R, smem, grid, nteam, st)
+                : launch_zp<S, false>(plan, P, R, smem, grid, nteam, st);
 }
 
 int zp_env(const char* name, int dflt) {
@@ -869,23 +962,50 @@ int32_t zero_phase_regs_dev(bool rect, const double* sos, int32_t S, const doubl
     P.pf = zp_env("ADN_ZP_PREFETCH", 1);
     sosfilt_zi_host(sos, S, P.zi.z);
     const int64_t out_tiles = P.t_out1 - P.t_out0;
-    // the register pipeline (one block of ZP_NTEAM teams per SM) when the look-ahead fits its teams
-    const bool pipe = P.JJ <= ZP_NTEAM - 2 && zp_env("ADN_ZP_PIPE", 1);
-    size_t smem;
+    // the pipelined kernel (one block of NTEAM teams per SM, tiles parked in shared memory) when
+    // NTEAM + JJ tile slots fit; else every tile is read twice (the second time from L2)
+    SosRun R;
+    memset(&R, 0, sizeof R);
+    R.src = src; R.tab = plan->dtab;
+    R.n = P.N; R.nx = n_src; R.edge = edge_left;
+    R.C = C; R.CG = CG; R.ngroups = P.ngroups; R.T = P.T; R.ntt = P.ntt;
+    {
+        const bool even = (C % 2 == 0) && (CG % 2 == 0);
+        R.vec_in = even && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+        R.lc = 0;
+        while ((1 << R.lc) < CG) ++R.lc;
+        if (C % 2 && CG > 1) R.lc = -1;
+    }
+    // rows of a full group are contiguous (C == CG) and the padded sub-chunks 16-byte aligned
+    // (measured on B200: pays for 64-byte rows, 152 against 164 us; not for narrower groups)
+    P.bulk_ok = (C == CG && CG >= 8 && zp_env("ADN_ZP_TMA", 1)) ? 1 : 0;
+    int nteam = 0;
+    size_t smem = 0;
     int64_t resident;
-    if (pipe) {
-        smem = ((size_t)plan->n_staged * D * D + (size_t)ZP_NTEAM * (2 * SOS_NW + 2) * CG * D) * 8 +
-               (ZP_NTEAM + 1) * 8 + 64;
+    if (zp_env("ADN_ZP_PIPE", 1)) {
+        const size_t TS = (size_t)(SOS_NT / CG) * (SOS_L * CG + (CG < 16 ? CG : 0));
+        // measured on B200 (8 ch x 48 kHz, 80 s): three teams at 168 registers 141 us, four at 128
+        // registers (some spills) 149 us for one section; two sections are even (204 / 200 us)
+        const int want = zp_env("ADN_ZP_NTEAM", S == 1 ? 3 : ZP_NTEAM_MAX);
+        for (int nt = want < ZP_NTEAM_MAX ? want : ZP_NTEAM_MAX; nt >= 3; --nt) {
+            const int ns = nt + P.JJ;
+            const size_t need = ((size_t)plan->n_staged * D * D + (size_t)nt * 2 * SOS_NW * CG * D +
+                                 (size_t)ns * CG * D + (size_t)nt * CG * D + (size_t)ns * D * SOS_NT +
+                                 (size_t)(2 * ns + 2) + (size_t)(P.JJ + 2) * D * D + (size_t)ns * TS) * 8;
+            if (need <= 227 * 1024) { nteam = nt; smem = need; break; }
+        }
+    }
+    if (nteam > 0) {
         resident = ctx().sm_count;
     } else {
         smem = ((size_t)plan->n_staged * D * D + (size_t)(SOS_NW + 3) * CG * D +
                 (size_t)(P.JJ + 1) * (CG * D + SOS_NT * D)) * 8;
+        if (smem > 96 * 1024) return ADN_OK;
         int bps = (int)((220 * 1024) / (smem + 1024));
         const int bmax = S <= 2 ? ZP_BLOCKS : 3;
         if (bps > bmax) bps = bmax;
         resident = (int64_t)ctx().sm_count * bps;
     }
-    if (smem > 96 * 1024) return ADN_OK;
     int64_t runs = resident / P.ngroups;
     if (runs < 1) runs = 1;
     int64_t run_tiles = (out_tiles + runs - 1) / runs;
@@ -898,10 +1018,10 @@ int32_t zero_phase_regs_dev(bool rect, const double* sos, int32_t S, const doubl
     P.run_tiles = (int32_t)run_tiles;
     const unsigned grid = (unsigned)(runs * P.ngroups);
     switch (S) {
-        case 1: rc = launch_zp_S<1>(rect, *plan, P, smem, grid, pipe, st); break;
-        case 2: rc = launch_zp_S<2>(rect, *plan, P, smem, grid, pipe, st); break;
-        case 3: rc = launch_zp_S<3>(rect, *plan, P, smem, grid, pipe, st); break;
-        default: rc = launch_zp_S<4>(rect, *plan, P, smem, grid, pipe, st); break;
+        case 1: rc = launch_zp_S<1>(rect, *plan, P, R, smem, grid, nteam, st); break;
+        case 2: rc = launch_zp_S<2>(rect, *plan, P, R, smem, grid, nteam, st); break;
+        case 3: rc = launch_zp_S<3>(rect, *plan, P, R, smem, grid, nteam, st); break;
+        default: rc = launch_zp_S<4>(rect, *plan, P, R, smem, grid, nteam, st); break;
     }
     if (rc == ADN_OK) *handled = true;
     return rc;

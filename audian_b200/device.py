@@ -148,6 +148,29 @@ def zero_phase_range(sos, src, first, n_dst, edge_left=False, edge_right=False, 
     return out
 
 
+def chain(sos, src, filtered, rate, nbefore=0, spec=None, nfft=0, hop=0, spec_first=0, spec_rows=None,
+          esos=None, env=None, env_first=0, env_rows=None, env_nbefore=0, clamp_negative=True,
+          mm_step=0, minmax_out=None, out_db=False):
+    """adn_chain_f64_dev on torch tensors: filtered (and spec / env / minmax_out if given) are
+    filled; returns the number of spectrogram frames computed."""
+    _check_trace(src, 'src')
+    _check_trace(filtered, 'filtered')
+    n_filt = filtered.shape[0]
+    if spec_rows is None:
+        spec_rows = n_filt - spec_first
+    if env_rows is None:
+        env_rows = n_filt - env_first
+    cs, keep = _lib.chain_spec(sos, nbefore, nfft, hop, spec_first, spec_rows,
+                               0 if spec is None else spec.shape[0], out_db, esos, env_first, env_rows,
+                               env_nbefore, 0 if env is None else env.shape[0], clamp_negative, mm_step)
+    n = _lib._i64(0)
+    _lib.check(_lib.lib().adn_chain_f64_dev(C.byref(cs), _p(src), src.shape[0], src.shape[1], float(rate),
+                                            _p(filtered), n_filt, _p(spec), _p(env), _p(minmax_out),
+                                            C.byref(n), _stream()))
+    del keep
+    return n.value
+
+
 def env_forward(sos, src, edge_left=0, edge_right=0, zi=None, state_only=False, zf_out=None):
     """Forward sweep of the envelope over one time shard: sosfilt of (pi/2)|src|
     with scipy's odd extension at the ends that are ends of the recording.

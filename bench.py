@@ -437,6 +437,22 @@ def run_ours(args):
     sync_all()
     t_m = allmax(m0.elapsed_time(m1))/args.steps
 
+    # ---- the same step as ONE device call (adn_chain_f64_dev), single-GPU geometry
+    t_chain = None
+    if world == 1:
+        for i in range(3):
+            device.chain(sos, windows[i % N_WINDOWS], filt_ext, RATE, 0, spec=spec, nfft=NFFT, hop=HOP,
+                         esos=esos, env=env)
+        sync_all()
+        c0_, c1_ = ev(), ev()
+        c0_.record()
+        for i in range(args.steps):
+            device.chain(sos, windows[i % N_WINDOWS], filt_ext, RATE, 0, spec=spec, nfft=NFFT, hop=HOP,
+                         esos=esos, env=env)
+        c1_.record()
+        sync_all()
+        t_chain = c0_.elapsed_time(c1_)/args.steps
+
     def roof(op, ms, frames, kernel, share_of=None):
         ach = algorithmic_bytes(op, frames, C)/(ms*1e-3)/1e9
         return {'kernel': kernel, 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
@@ -505,33 +521,53 @@ def run_ours(args):
     te = BufferedEnvelope(envelope_cutoff=ENV_CUTOFF)
     te.configure_standalone(RATE, C, source=tf)
 
-    def host_step(i):
+    def host_step_traces(i):
         x = host_x[i % len(host_x)]
         tf.process(x, h_filt, 0)
         ts.process(h_filt, h_spec, 0)
         te.process(h_filt, h_env, 0)
 
-    ksteps = max(1, min(args.steps, 5))
-    for i in range(2):
-        host_step(i)
-    sync_all()
-    moved0 = _lib.transfer_bytes()
-    t0 = time.perf_counter()
-    for i in range(ksteps):
-        host_step(i)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    moved1 = _lib.transfer_bytes()
-    te2e = allmax(dt/ksteps)
-    e2e = {'value': samples_step/te2e/1e6, 'unit': 'Msamples/s',
-           # counted by the library around every copy it issues
-           'h2d_bytes_per_step': int((moved1[0] - moved0[0])//ksteps),
-           'd2h_bytes_per_step': int((moved1[1] - moved0[1])//ksteps),
-           'steps': ksteps, 'ms_per_step': te2e*1e3,
-           'api': 'BufferedFilter/BufferedSpectrogram/BufferedEnvelope.process on pinned numpy '
-                  'buffers; the filtered buffer is handed to its two consumers through the '
-                  'filter trace\'s device mirror, copies and kernels overlap chunk by chunk'
-                  + ('' if world == 1 else '; %d independent replicas, one per GPU' % world)}
+    def host_step_chain(i):
+        # the same three results through ONE call: what BufferedFilter.recompute_all() issues when
+        # its dests are a spectrogram and an envelope (audian_b200/bufferedfilter.py)
+        _lib.chain(sos, host_x[i % len(host_x)], h_filt, RATE, 0, spec=h_spec, nfft=NFFT, hop=HOP,
+                   esos=esos, env=h_env, clamp_negative=True)
+
+    def time_host(fn):
+        ksteps = max(1, min(args.steps, 5))
+        for i in range(2):
+            fn(i)
+        sync_all()
+        moved0 = _lib.transfer_bytes()
+        t0 = time.perf_counter()
+        for i in range(ksteps):
+            fn(i)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        moved1 = _lib.transfer_bytes()
+        t = allmax(dt/ksteps)
+        return {'value': samples_step/t/1e6, 'unit': 'Msamples/s',
+                # counted by the library around every copy it issues
+                'h2d_bytes_per_step': int((moved1[0] - moved0[0])//ksteps),
+                'd2h_bytes_per_step': int((moved1[1] - moved0[1])//ksteps),
+                'steps': ksteps, 'ms_per_step': t*1e3}
+
+    e2e_traces = time_host(host_step_traces)
+    e2e = time_host(host_step_chain)
+    chk = np.empty_like(h_env)
+    host_step_traces(0)
+    chk[:] = h_env
+    f_chk = h_filt.copy()
+    host_step_chain(0)
+    e2e['equals_separate_calls'] = bool(np.array_equal(f_chk, h_filt) and np.max(np.abs(chk - h_env)) <= 1e-12)
+    e2e['api'] = ('adn_chain_f64 (audian_b200._lib.chain) on pinned numpy buffers: the call '
+                  'BufferedFilter.recompute_all() makes for filtered -> spectrogram + envelope; the source '
+                  'goes up once, results come down while the next kernel runs'
+                  + ('' if world == 1 else '; %d independent replicas, one per GPU' % world))
+    e2e['separate_process_calls'] = dict(e2e_traces, api='BufferedFilter / BufferedSpectrogram / '
+                                         'BufferedEnvelope.process one after the other, the filtered buffer '
+                                         'handed over through the filter trace\'s device mirror')
+    del chk, f_chk
     for a_ in host_x + [h_filt, h_spec, h_env]:
         _lib.host_unregister(a_)
     del tf, ts, te
@@ -619,7 +655,8 @@ def run_ours(args):
                        'launch': 'eager, CUDA events around each op inside the timed region'},
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
             'roofline': roofs[dominant], 'roofline_all': roofs, 'dominant': dominant,
-            'op_ms': {'filter': t_f, 'spectrogram': t_s, 'envelope': t_e, 'minmax_separate': t_m},
+            'op_ms': {'filter': t_f, 'spectrogram': t_s, 'envelope': t_e, 'minmax_separate': t_m,
+                      'chain_one_call': t_chain},
             'minmax': {'value': n*C*world/(t_m*1e-3)/1e6, 'unit': 'Msamples/s', 'step': mm_step,
                        'ms': t_m, 'frac': roofs['minmax']['frac']},
             'cpu_baseline': cpu_baseline, 'parity': parity, 'wholefile': wholefile,

@@ -235,7 +235,41 @@ int32_t adn_play_region_f64_m(const double* src, int64_t n, int32_t C,
                               const double* sos, int32_t S, int64_t nstep,
                               double* dst, int64_t src_mirror);
 
+/* ---- the chain: data -> filtered -> {spectrogram, envelope} in one call ---------
+ * What a parameter change recomputes in the reference: BufferedFilter.update() ->
+ * recompute_all() -> filtered, then its dests (src/audian/bufferedfilter.py:53,
+ * buffereddata.py:149-153).  One call: the source goes up once, the filtered trace stays on
+ * the device between its producer and its consumers, results travel down while the next
+ * kernel runs, one wait at the end.  Every stage computes exactly what its own entry point
+ * computes (adn_sosfilt_f64, adn_spectrogram_f64, adn_envelope_f64, adn_minmax_f64). */
+typedef struct adn_chain {
+    /* filtered = sosfilt(sos, src)[nbefore:][:n_filt]; S == 0: copy */
+    const double* sos;          /* host, S x 6 */
+    int32_t S;
+    int32_t out_db;             /* spectrogram in decibel */
+    int64_t nbefore;
+    /* spectrogram of filtered[spec_first : spec_first + spec_rows], n_spec destination frames */
+    int32_t nfft, hop;
+    int64_t spec_first, spec_rows, n_spec;
+    /* envelope of filtered[env_first : env_first + env_rows], rows [env_nbefore:][:n_env] */
+    const double* esos;         /* host, ES x 6 */
+    int32_t ES;
+    int32_t clamp_negative;
+    int64_t env_first, env_rows, env_nbefore, n_env;
+    /* min/max rows of the raw source (2*ceil(n_src/mm_step), C) */
+    int64_t mm_step;
+} adn_chain_t;
+/* spec / env / minmax may be NULL: that stage is skipped.  n_computed: spectrogram frames.
+ * src_mirror / filt_mirror: see adn_mirror_create (0 = none). */
+int32_t adn_chain_f64(const adn_chain_t* chain, const double* src, int64_t n_src, int32_t C,
+                      double rate, double* filtered, int64_t n_filt, double* spec, double* env,
+                      double* minmax, int64_t* n_computed, int64_t src_mirror, int64_t filt_mirror);
+
 /* ---- device-pointer entry points (bench / multi-GPU path) ----------- */
+/* the chain on device buffers (sos / esos stay host pointers); only enqueues */
+int32_t adn_chain_f64_dev(const adn_chain_t* chain, const double* src, int64_t n_src, int32_t C,
+                          double rate, double* filtered, int64_t n_filt, double* spec, double* env,
+                          double* minmax, int64_t* n_computed, void* stream);
 /* out of place: dst != src */
 int32_t adn_unwrap_f64_dev(const double* src, int64_t n, int32_t C, double thresh,
                            int32_t clips, double* dst, void* stream);

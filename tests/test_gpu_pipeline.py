@@ -218,3 +218,85 @@ def test_traces_invalidate_on_buffer_moves(resident):
     assert np.max(np.abs(env.buffer - g['env_buffer'])) <= 1e-6
     ref = g['spec_buffer']
     assert np.allclose(spect.buffer, ref, rtol=1e-5, atol=1e-20*ref.max())
+
+
+@pytest.mark.parametrize('C,nbefore,mm', [(8, 0, 0), (2, 321, 1000), (5, 7, 0)])
+def test_chain_equals_separate_calls(C, nbefore, mm):
+    """adn_chain_f64: data -> filtered -> {spectrogram, envelope} (+ min/max of the raw rows) in one
+    call (bufferedfilter.py:53, buffereddata.py:149-153) == the four entry points one after the
+    other, bit for bit."""
+    fs, n = 48000., 300000
+    x = synth(1, n, C, fs, seed=70 + C)
+    sos = orc.filter_design(fs, 1000., 15000., 2)
+    esos = orc.envelope_design(fs, 500.)
+    nfft, hop = 512, 128
+    nf = n - nbefore
+    filt = np.empty((nf, C))
+    _lib.sosfilt(sos, x, filt, nbefore)
+    s0, srows = 1024, nf - 1024 - 777
+    nspec = srows//hop + 3                              # more frames than the slice can fill: zeros
+    spec = np.full((nspec, C, nfft//2 + 1), np.nan)
+    ncomp = _lib.spectrogram(filt[s0:s0 + srows], fs, nfft, hop, spec)
+    e0, erows, enb = 5000, nf - 5000, 11
+    env = np.empty((erows - enb, C))
+    _lib.envelope(esos, filt[e0:e0 + erows], env, enb, True)
+    f2 = np.full_like(filt, np.nan)
+    s2 = np.full_like(spec, np.nan)
+    e2 = np.full_like(env, np.nan)
+    m2 = np.full((2*((n + mm - 1)//mm), C), np.nan) if mm else None
+    got = _lib.chain(sos, x, f2, fs, nbefore, spec=s2, nfft=nfft, hop=hop, spec_first=s0, spec_rows=srows,
+                     esos=esos, env=e2, env_first=e0, env_rows=erows, env_nbefore=enb,
+                     clamp_negative=True, mm_step=mm, minmax_out=m2)
+    assert got == ncomp
+    assert np.array_equal(f2, filt)
+    assert np.array_equal(s2, spec)
+    assert np.max(np.abs(e2 - env)) <= 1e-13            # one launch over the slice vs the same launch
+    if mm:
+        assert np.array_equal(m2.view(np.uint64), orc.minmax_rows(x, mm).view(np.uint64))
+    # stages can be left out; no filter = copy
+    f3 = np.empty_like(filt)
+    assert _lib.chain(None, x, f3, fs, nbefore) == 0
+    assert np.array_equal(f3, x[nbefore:])
+    with pytest.raises(ValueError):
+        _lib.chain(sos, x, f2, fs, nbefore, esos=esos, env=np.empty((5, C)), env_first=0, env_rows=5)
+
+
+def test_fused_recompute_equals_the_walk(monkeypatch):
+    """BufferedFilter.recompute_all with a spectrogram and an envelope as dests: one chain call
+    leaves every buffer exactly as the reference's walk trace by trace does."""
+    import audian_b200 as ab
+    from oracle.ref_harness import ArrayLoader
+    fs, C = 48000., 2
+    x = synth(0, 2500000, C, fs, seed=91)
+
+    def graph():
+        data = ArrayLoader(x, fs, 600000, 1500000)       # 31 s buffered: 10-s margin + 21 s of filtered
+        filt, spect, env = ab.BufferedFilter(), ab.BufferedSpectrogram(nfft=1024, overlap_frac=0.75), \
+            ab.BufferedEnvelope(envelope_cutoff=400.)
+        filt.open(data)
+        spect.open(filt)
+        env.open(filt)
+        for t in (filt, spect, env):
+            t.need_update = True
+        for t in (filt, spect, env):
+            t.align_buffer()                             # Data.update_times(): buffers follow the loader's
+        filt.highpass_cutoff, filt.lowpass_cutoff = 800., 12000.
+        return data, filt, spect, env
+
+    calls = []
+    real = _lib.chain
+    monkeypatch.setattr(_lib, 'chain', lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    d1, f1, s1, e1 = graph()
+    f1.update()                                          # fused: one chain call
+    assert len(calls) == 1
+    d2, f2, s2, e2 = graph()
+    monkeypatch.setattr(ab.BufferedFilter, '_chain_stages', lambda self: [])
+    f2.update()                                          # the plain walk
+    assert len(calls) == 1
+    for a, b in ((f1, f2), (s1, s2), (e1, e2)):
+        assert a.offset == b.offset and a.buffer.shape == b.buffer.shape and a.buffer.size > 0
+        assert a.buffer_changed.all()
+    assert np.array_equal(f1.buffer, f2.buffer)
+    assert np.array_equal(s1.buffer, s2.buffer)
+    assert np.max(np.abs(e1.buffer - e2.buffer)) <= 1e-13
+    assert s1.spec_rect == s2.spec_rect and np.array_equal(s1.frequencies, s2.frequencies)
