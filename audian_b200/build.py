@@ -12,7 +12,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-SOURCES = ['api.cu', 'misc.cu', 'minmax.cu', 'sosfilt.cu', 'zerophase.cu', 'ingest.cu', 'spectrogram.cu']
+SOURCES = ['api.cu', 'misc.cu', 'minmax.cu', 'sosfilt.cu', 'zerophase.cu', 'sosfwd.cu', 'ingest.cu', 'spectrogram.cu']
 HEADERS = [os.path.join(CSRC, 'common.cuh'), os.path.join(CSRC, 'sos_common.cuh'),
            os.path.join(os.path.dirname(HERE), 'include', 'audian_b200.h')]
 LIB = os.path.join(HERE, 'libaudian_b200.so')

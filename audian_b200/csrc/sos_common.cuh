@@ -213,6 +213,97 @@ __device__ __forceinline__ bool sos_load_tile(const SosRun& R, double* tile_s, i
     return xform;
 }
 
+// ---- register-resident tiles: the recurrences on SOS_L samples held by a thread, and the
+// synchronisation of the pipelined kernels (teams of four warps, TMA bulk copies)
+// exact DF2T recurrence over the SOS_L register-resident samples (in time order, or reversed),
+// outputs in place; the sections run skewed by one sample each so that the S recurrences of
+// a step are independent (as in sosfilt.cu)
+template <int S, bool REVERSE>
+__device__ __forceinline__ void zp_df2t(const SosK<S>& K, double (&x)[SOS_L], double (&z)[2 * S]) {
+    double xin[S + 1];
+#pragma unroll
+    for (int j = 0; j < SOS_L + S - 1; ++j) {
+#pragma unroll
+        for (int s = S - 1; s >= 0; --s) {
+            const int k = j - s;
+            if (k < 0 || k >= SOS_L) continue;
+            const int i = REVERSE ? SOS_L - 1 - k : k;
+            const double xv = s == 0 ? x[i] : xin[s];
+            const double y = fma(K.coef[s][0], xv, z[2 * s]);
+            z[2 * s] = fma(K.coef[s][1], xv, z[2 * s + 1]) - K.coef[s][3] * y;
+            z[2 * s + 1] = K.coef[s][2] * xv - K.coef[s][4] * y;
+            if (s == S - 1) x[i] = y; else xin[s + 1] = y;
+        }
+    }
+}
+
+// zero-state end state of the register-resident samples, processed forward or reversed
+template <int S, bool REVERSE>
+__device__ __forceinline__ void zp_pass_a(const SosK<S>& K, const double (&x)[SOS_L], double (&v)[2 * S]) {
+#pragma unroll
+    for (int i = 0; i < SOS_L; ++i) {
+#pragma unroll
+        for (int d = 0; d < 2 * S; ++d) v[d] = fma(K.W[d][REVERSE ? SOS_L - 1 - i : i], x[i], v[d]);
+    }
+}
+
+// one homogeneous step of the cascade (input 0)
+template <int S>
+__device__ __forceinline__ void zp_step0(const SosK<S>& K, double (&z)[2 * S]) {
+    double xv = 0.0;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const double y = fma(K.coef[s][0], xv, z[2 * s]);
+        z[2 * s] = fma(K.coef[s][1], xv, z[2 * s + 1]) - K.coef[s][3] * y;
+        z[2 * s + 1] = K.coef[s][2] * xv - K.coef[s][4] * y;
+        xv = y;
+    }
+}
+
+__device__ __forceinline__ void zp_team_bar(int team) {
+    asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(SOS_NT) : "memory");
+}
+// lane 0 polls a shared-memory tile counter that counts up along the walk until it is >= v
+__device__ __forceinline__ void zp_wait_ge(const volatile long long* f, long long v, int lane) {
+    if (lane == 0) {
+        while (*f < v) __nanosleep(20);
+        __threadfence_block();
+    }
+    __syncwarp();
+}
+// lane 0 polls a shared-memory tile counter (counts down along the walk) until it is <= v
+__device__ __forceinline__ void zp_wait_le(const volatile long long* f, long long v, int lane) {
+    if (lane == 0) {
+        while (*f > v) __nanosleep(20);
+        __threadfence_block();
+    }
+    __syncwarp();
+}
+
+// ---- TMA unit: 1-D bulk copies global -> shared memory, completion counted in bytes on an mbarrier
+__device__ __forceinline__ uint32_t zp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void zp_mbar_init(uint64_t* mbar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(zp_smem_u32(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void zp_mbar_arrive(uint64_t* mbar) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(zp_smem_u32(mbar)) : "memory");
+}
+__device__ __forceinline__ void zp_mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}"
+                 ::"r"(zp_smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void zp_mbar_wait(uint64_t* mbar, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
+        ::"r"(zp_smem_u32(mbar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void zp_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(zp_smem_u32(dst)), "l"(src), "r"(bytes), "r"(zp_smem_u32(mbar)) : "memory");
+}
+
 // ---- host side plan of a cascade (tables on the device), cached by (sos, CG)
 struct SosPlan {
     std::vector<double> sos;      // key
@@ -254,5 +345,10 @@ int32_t zero_phase_regs_dev(bool rect, const double* sos, int32_t S, const doubl
                             double* dst, int64_t n_dst, int32_t clamp_negative, bool* handled,
                             cudaStream_t st);
 int64_t zp_launches();
+// sosfwd.cu: forward sosfilt of long traces on the pipelined skeleton (tiles in registers)
+int32_t sosfilt_park_dev(const double* sos, int32_t S, const double* src, int64_t n, int32_t C,
+                         int64_t out_skip, double* dst, int64_t n_dst, const double* s0, double* zf,
+                         bool* handled, cudaStream_t st);
+int64_t fwd_park_launches();
 
 }  // namespace adn

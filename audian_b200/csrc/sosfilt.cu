@@ -935,6 +935,12 @@ bool plan_runs(const SosPlan& plan, SosRun& R, int S, size_t* smem_out, unsigned
 int32_t run_scan(int mode, const double* sos, int S, const double* src, int64_t n, int64_t nx,
                  int edge, int32_t C, double* dst, int64_t out_skip, int64_t n_dst, int clamp,
                  const double* s0, double* zf, int tile_slot, cudaStream_t st) {
+    if (mode == MODE_FWD && option(ADN_OPT_SCAN_RUNS)) {
+        // long traces of cascades that forget fast: the pipelined kernel with the tile in registers
+        bool handled = false;
+        int32_t rc1 = sosfilt_park_dev(sos, S, src, n, C, out_skip, dst, n_dst, s0, zf, &handled, st);
+        if (rc1 || handled) return rc1;
+    }
     const int CG = pick_cg(C);
     const int D = 2 * S;
     std::shared_ptr<SosPlan> plan;
@@ -1003,7 +1009,7 @@ int32_t run_scan(int mode, const double* sos, int S, const double* src, int64_t 
 
 }  // namespace
 
-int64_t scan_run_launches() { return g_run_launches.load(); }
+int64_t scan_run_launches() { return g_run_launches.load() + fwd_park_launches(); }
 
 int32_t sosfilt_dev(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
                     int64_t nbefore, double* dst, int64_t n_dst, const double* zi, double* zf,

@@ -1,0 +1,367 @@
+// Forward SOS filtering (scipy sosfilt: BufferedFilter.process, src/audian/bufferedfilter.py:31-36)
+// of long traces on the pipelined skeleton of zerophase.cu: a block is NTEAM teams of four warps
+// and owns one run of consecutive tiles, walking forward along time; team k takes the tiles
+// t0 + k, t0 + k + NTEAM, ...  A tile is staged in the team's shared-memory slot (TMA bulk copies
+// for 64-byte rows, cp.async granules otherwise) one iteration ahead, read into registers (one
+// thread = SOS_L consecutive samples of one channel), and the slot is handed to the next
+// prefetch at once.  In registers: pass A (zero-state end state of the thread's samples), the
+// scans inside the tile, and the exact DF2T recurrence from the true incoming state; the
+// results are stored from the registers (a warp store covers GW rows x CG channels = whole
+// 32-byte sectors for CG >= 4).  The state entering a tile is handed from tile to tile as
+//     s(t + 1) = A^T s(t) + agg(t)
+// by one warp as soon as the tile aggregate agg(t) is known: only that small matrix-vector
+// product is serial along the run, the teams overlap freely.  A run that does not start at row 0
+// runs over `pre` tiles before it from zero state without storing (the cascade has forgotten
+// its state by then: the criterion of sosfilt.cu's run kernel, which this kernel replaces).
+#include "sos_common.cuh"
+#include <cstring>
+#include <cstdlib>
+#include <atomic>
+
+namespace adn {
+
+namespace {
+
+struct FwdArgs {
+    const double* src;
+    double* dst;
+    const double* tab;
+    int32_t off_fix, off_wpow, off_tile, n_staged;
+    const double* s0;                  // [C][D] initial state or null
+    double* zf;                        // [C][D] final state or null
+    int64_t n;                         // rows of the source
+    int64_t out_skip, n_dst;           // source rows [out_skip, out_skip + n_dst) -> dst rows
+    int64_t ntt;                       // tiles of the source
+    int64_t t_out0, t_out1;            // tiles that hold output rows
+    int32_t C, CG, ngroups, T;
+    int32_t pre;                       // run-in tiles
+    int32_t run_tiles;
+    int32_t bulk_ok;
+};
+
+template <int S, int NTC>
+__global__ void __launch_bounds__(SOS_NT * NTC, 1)
+sos_fwd_park_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ FwdArgs P,
+                    const __grid_constant__ SosRun R) {
+    constexpr int D = 2 * S;
+    constexpr int DD = D * D;
+    constexpr int NTEAM = NTC;
+    extern __shared__ __align__(16) double smem[];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int team = tid >> 7, ttid = tid & (SOS_NT - 1), warp = ttid >> 5;
+    const int grp = (int)(blockIdx.x % P.ngroups);
+    const int64_t run = blockIdx.x / P.ngroups;
+    const int CG = P.CG, C = P.C;
+    const int c0 = grp * CG;
+    const int Cw = min(CG, C - c0);
+    const int GW = 32 / CG;
+    const int gl = lane / CG, cw = lane % CG;
+    const int g = warp * GW + gl;
+    const bool chan_ok = cw < Cw;
+    const int T = P.T;
+    const int pad = CG < 16 ? CG : 0;
+    const int GS = SOS_L * Cw + pad;
+    const int G = SOS_NT / CG;
+    const size_t TS = (size_t)G * (SOS_L * CG + pad);
+
+    double* tab_s = smem;                                   // n_staged * DD
+    double* pt_s = tab_s + (size_t)P.n_staged * DD;         // A^T (one tile)
+    double* wagg = pt_s + DD + (size_t)team * SOS_NW * CG * D;          // [NTEAM][NW][CG][D]
+    double* sin_s = pt_s + DD + (size_t)NTEAM * SOS_NW * CG * D;        // [NTEAM][CG][D]: state entering a team's tile
+    volatile long long* sf_flag = reinterpret_cast<volatile long long*>(sin_s + (size_t)NTEAM * CG * D);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(const_cast<long long*>(sf_flag) + 1);      // [NTEAM]
+    double* tiles = reinterpret_cast<double*>(mbar + NTEAM + ((NTEAM + 1) & 1));            // [NTEAM][TS]
+    const double* tab_fix = tab_s + P.off_fix * DD;
+    const double* tab_wpow = tab_s + P.off_wpow * DD;
+    double* slot_s = tiles + (size_t)team * TS;
+
+    const int64_t a = P.t_out0 + run * P.run_tiles;         // output tiles [a, b)
+    const int64_t b = min(a + (int64_t)P.run_tiles, P.t_out1);
+    if (a >= b) return;
+    const int64_t t_first = max((int64_t)0, a - P.pre);     // first tile of the walk
+
+    for (int q = tid; q < P.n_staged * DD; q += blockDim.x) tab_s[q] = __ldg(P.tab + q);
+    for (int q = tid; q < DD; q += blockDim.x) pt_s[q] = __ldg(P.tab + (size_t)(P.off_tile + 1) * DD + q);
+    // state entering the first tile of the walk: the initial state at row 0, else zero (run-in)
+    for (int q = tid; q < CG * D; q += blockDim.x) {
+        const int ch = q / D;
+        double v = 0.0;
+        if (t_first == 0 && P.s0 && c0 + ch < C) v = __ldg(P.s0 + (size_t)c0 * D + q);
+        sin_s[(size_t)0 * CG * D + q] = v;                  // team 0 takes the first tile
+    }
+    if (tid < NTEAM) zp_mbar_init(mbar + tid, 1);
+    if (tid == 0) *sf_flag = t_first;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const bool bulk_group = P.bulk_ok && Cw == CG;
+    auto load_kind = [&](int64_t t) {
+        if (t >= b) return 0;
+        if (!bulk_group || (t + 1) * (int64_t)T > P.n) return 2;
+        const uintptr_t g0 = reinterpret_cast<uintptr_t>(P.src + t * T * C + c0);
+        return (g0 & 15) == 0 ? 1 : 2;
+    };
+    auto issue_load = [&](int64_t t) {
+        const int kind = load_kind(t);
+        if (kind == 1) {
+            if (warp == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (lane == 0) zp_mbar_expect_tx(mbar + team, (uint32_t)(T * C * 8));
+                __syncwarp();
+                const double* gsrc = P.src + t * T * C + c0;
+                for (int q = lane; q < G; q += 32)
+                    zp_bulk_g2s(slot_s + (size_t)q * GS, gsrc + (size_t)q * SOS_L * C, (uint32_t)(SOS_L * C * 8), mbar + team);
+            }
+        } else if (kind == 2) {
+            sos_load_tile<MODE_FWD>(R, slot_s, t * T, c0, Cw, ttid);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    issue_load(t_first + team);
+    int64_t use = 0;                                        // uses of this team's slot so far
+    for (int64_t t = t_first + team; t < b; t += NTEAM, ++use) {
+        // ---- the tile has landed in the team's slot
+        if (load_kind(t) == 1) {
+            zp_mbar_wait(mbar + team, (uint32_t)(use & 1));
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            zp_team_bar(team);
+            if (ttid == 0) zp_mbar_arrive(mbar + team);
+        }
+        double x[SOS_L];
+        {
+            const double* xp = slot_s + g * GS + cw;
+            if (!chan_ok) {
+#pragma unroll
+                for (int i = 0; i < SOS_L; ++i) x[i] = 0.0;
+            } else if (Cw == 8) {
+#pragma unroll
+                for (int i = 0; i < SOS_L; ++i) x[i] = xp[i * 8];
+            } else {
+#pragma unroll
+                for (int i = 0; i < SOS_L; ++i) x[i] = xp[i * Cw];
+            }
+        }
+        zp_team_bar(team);                                   // every thread of the team has its samples
+        issue_load(t + NTEAM);                               // the slot goes to the team's next tile
+        // ---- zero-state aggregates: per thread, per warp, per tile
+        double z[D];
+        {
+            double v[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) v[d] = 0.0;
+            zp_pass_a<S, false>(K, x, v);
+            {
+                int k = 0;
+                for (int off = CG; off < 32; off <<= 1, ++k) {
+                    double u[D];
+#pragma unroll
+                    for (int d = 0; d < D; ++d) u[d] = __shfl_up_sync(0xffffffffu, v[d], off);
+                    if (lane >= off) matvec_acc<D>(tab_s + k * DD, u, v);
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const double u = __shfl_up_sync(0xffffffffu, v[d], CG & 31);
+                z[d] = gl == 0 ? 0.0 : u;
+            }
+            if (gl == GW - 1) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) wagg[(warp * CG + cw) * D + d] = v[d];
+            }
+            zp_team_bar(team);
+            double pre[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) pre[d] = 0.0;
+            for (int j = 0; j < warp; ++j) {
+                double u[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) u[d] = wagg[(j * CG + cw) * D + d];
+                matvec_acc<D>(tab_wpow + (warp - 1 - j) * DD, u, pre);
+            }
+            matvec_acc<D>(tab_fix + gl * DD, pre, z);        // z = ex + A^(L gl) pre
+        }
+        // ---- the state entering this tile (from the team of tile t - 1), and on to tile t + 1
+        double sv[D];
+        zp_wait_ge(sf_flag, t, lane);
+#pragma unroll
+        for (int d = 0; d < D; ++d) sv[d] = sin_s[(size_t)team * CG * D + cw * D + d];
+        zp_team_bar(team);                                   // every warp of the team has read it
+        if (warp == 0) {
+            const int tnext = (team + 1) % NTEAM;
+            for (int e = lane; e < CG * D; e += 32) {
+                const int ch = e / D, r = e - ch * D;
+                double acc = 0.0;
+                for (int q = 0; q < SOS_NW; ++q) {
+                    const double* M = tab_wpow + (SOS_NW - 1 - q) * DD + r * D;
+                    const double* u = wagg + (q * CG + ch) * D;
+                    for (int c = 0; c < D; ++c) acc = fma(M[c], u[c], acc);
+                }
+                const double* M = pt_s + r * D;
+                const double* u = sin_s + (size_t)team * CG * D + ch * D;
+                for (int c = 0; c < D; ++c) acc = fma(M[c], u[c], acc);
+                sin_s[(size_t)tnext * CG * D + e] = acc;
+            }
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); *sf_flag = t + 1; }
+        }
+        {
+            double tmp[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) tmp[d] = 0.0;
+            matvec_acc<D>(tab_wpow + warp * DD, sv, tmp);
+            matvec_acc<D>(tab_fix + gl * DD, tmp, z);
+        }
+        // ---- the exact recurrence from the true incoming state, in registers
+        const int64_t e0 = t * T + (int64_t)g * SOS_L;       // source row of x[0]
+        const int64_t lastrow = P.n - 1;
+        if (P.zf != nullptr && lastrow >= e0 && lastrow < e0 + SOS_L && t >= a) {
+            // the sub-chunk that holds the last row: rolled loop, state captured right after it
+            double tmp[SOS_L];
+#pragma unroll
+            for (int i = 0; i < SOS_L; ++i) tmp[i] = x[i];
+            const int ilast = (int)(lastrow - e0);
+#pragma unroll 1
+            for (int i = 0; i < SOS_L; ++i) {
+                double xv = tmp[i];
+#pragma unroll
+                for (int q = 0; q < S; ++q) {
+                    const double y = fma(K.coef[q][0], xv, z[2 * q]);
+                    z[2 * q] = fma(K.coef[q][1], xv, z[2 * q + 1]) - K.coef[q][3] * y;
+                    z[2 * q + 1] = K.coef[q][2] * xv - K.coef[q][4] * y;
+                    xv = y;
+                }
+                tmp[i] = xv;
+                if (i == ilast && chan_ok) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) P.zf[(size_t)(c0 + cw) * D + d] = z[d];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < SOS_L; ++i) x[i] = tmp[i];
+        } else {
+            zp_df2t<S, false>(K, x, z);
+        }
+        if (t >= a && chan_ok && P.dst != nullptr) {
+            const bool fast = t * T >= P.out_skip && (t + 1) * (int64_t)T <= P.out_skip + P.n_dst;
+            double* p = P.dst + (e0 - P.out_skip) * C + c0 + cw;
+            if (fast && C == 8) {
+#pragma unroll
+                for (int i = 0; i < SOS_L; ++i) __stcs(p + i * 8, x[i]);
+            } else {
+                const int64_t o0 = e0 - P.out_skip;
+#pragma unroll
+                for (int i = 0; i < SOS_L; ++i) {
+                    if (fast || (o0 + i >= 0 && o0 + i < P.n_dst)) __stcs(p, x[i]);
+                    p += C;
+                }
+            }
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+std::atomic<int64_t> g_fwd_launches{0};
+
+template <int S, int NTC>
+int32_t launch_fwd(const SosPlan& plan, const FwdArgs& P, const SosRun& R, size_t smem, unsigned grid,
+                   cudaStream_t st) {
+    SosK<S> K;
+    fill_sosk<S>(plan, K);
+    auto kern = sos_fwd_park_kernel<S, NTC>;
+    static bool attr_done = false;               // per instantiation
+    if (!attr_done) {
+        ADN_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    kern<<<grid, SOS_NT * NTC, smem, st>>>(K, P, R);
+    count_launch();
+    g_fwd_launches.fetch_add(1);
+    ADN_CK(cudaGetLastError());
+    return ADN_OK;
+}
+
+int fwd_env(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
+
+}  // namespace
+
+int64_t fwd_park_launches() { return g_fwd_launches.load(); }
+
+// dst = sosfilt(sos, src)[out_skip:][:n_dst] from state s0 (or zero); zf = state after the last row.
+// *handled = false (nothing launched): the cascade forgets too slowly or the trace is too short.
+int32_t sosfilt_park_dev(const double* sos, int32_t S, const double* src, int64_t n, int32_t C,
+                         int64_t out_skip, double* dst, int64_t n_dst, const double* s0, double* zf,
+                         bool* handled, cudaStream_t st) {
+    *handled = false;
+    // measured on B200 (80 s of 8 ch x 48 kHz): one or two sections 96 / 90 us against 97 / 103 us of
+    // the run kernel (64 ch: 739 against 779 us); four sections 187 against 178 us (register bound)
+    const int smax = fwd_env("ADN_SOS_PARK_SMAX", 2);
+    if (!fwd_env("ADN_SOS_PARK", 1) || S < 1 || S > 4 || S > smax || dst == nullptr || n_dst <= 0) return ADN_OK;
+    const int CG = pick_cg(C);
+    std::shared_ptr<SosPlan> plan;
+    int32_t rc = get_sos_plan(sos, S, CG, st, &plan);
+    if (rc) return rc;
+    if (plan->jpre > SOS_LOOK) return ADN_OK;
+    const int D = 2 * S;
+    FwdArgs P;
+    memset(&P, 0, sizeof P);
+    P.src = src; P.dst = dst; P.tab = plan->dtab; P.s0 = s0; P.zf = zf;
+    P.off_fix = plan->off_fix; P.off_wpow = plan->off_wpow; P.off_tile = plan->off_tile;
+    P.n_staged = plan->n_staged;
+    P.n = n; P.out_skip = out_skip; P.n_dst = n_dst;
+    P.C = C; P.CG = CG; P.ngroups = (C + CG - 1) / CG;
+    P.T = (SOS_NT / CG) * SOS_L;
+    P.ntt = (n + P.T - 1) / P.T;
+    P.t_out0 = out_skip / P.T;
+    // the tile of the last source row always belongs to the walk when the final state is wanted
+    P.t_out1 = zf ? P.ntt : (out_skip + n_dst - 1) / P.T + 1;
+    P.pre = plan->jpre;
+    P.bulk_ok = (C == CG && CG >= 8 && fwd_env("ADN_ZP_TMA", 1)) ? 1 : 0;
+    SosRun R;
+    memset(&R, 0, sizeof R);
+    R.src = src; R.tab = plan->dtab;
+    R.n = n; R.nx = n; R.edge = 0;
+    R.C = C; R.CG = CG; R.ngroups = P.ngroups; R.T = P.T; R.ntt = P.ntt;
+    {
+        const bool even = (C % 2 == 0) && (CG % 2 == 0);
+        R.vec_in = even && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+        R.lc = 0;
+        while ((1 << R.lc) < CG) ++R.lc;
+        if (C % 2 && CG > 1) R.lc = -1;
+    }
+    const int nteam = fwd_env("ADN_SOS_NTEAM", S <= 2 ? 3 : 4) >= 4 ? 4 : 3;
+    const size_t TS = (size_t)(SOS_NT / CG) * (SOS_L * CG + (CG < 16 ? CG : 0));
+    const size_t smem = ((size_t)plan->n_staged * D * D + (size_t)D * D + (size_t)nteam * SOS_NW * CG * D +
+                         (size_t)nteam * CG * D + 1 + (size_t)nteam + (size_t)((nteam + 1) & 1) +
+                         (size_t)nteam * TS) * 8;
+    if (smem > 227 * 1024) return ADN_OK;
+    const int64_t out_tiles = P.t_out1 - P.t_out0;
+    int64_t runs = (int64_t)ctx().sm_count / P.ngroups;
+    if (runs < 1) runs = 1;
+    int64_t run_tiles = (out_tiles + runs - 1) / runs;
+    const int64_t min_run = 4 * (int64_t)P.pre > 8 ? 4 * (int64_t)P.pre : 8;   // run-in: a quarter of a run at most
+    if (run_tiles < min_run) run_tiles = min_run;
+    runs = (out_tiles + run_tiles - 1) / run_tiles;
+    if (runs * P.ngroups * 2 < ctx().sm_count) return ADN_OK;     // too short to fill the device this way
+    if (run_tiles > 0x3fffffff || runs * P.ngroups > 0x7fffffff) return ADN_OK;
+    P.run_tiles = (int32_t)run_tiles;
+    const unsigned grid = (unsigned)(runs * P.ngroups);
+#define ADN_FWD_CASE(SS)                                                                         \
+    case SS: rc = nteam == 4 ? launch_fwd<SS, 4>(*plan, P, R, smem, grid, st)                   \
+                             : launch_fwd<SS, 3>(*plan, P, R, smem, grid, st); break;
+    switch (S) {
+        ADN_FWD_CASE(1) ADN_FWD_CASE(2) ADN_FWD_CASE(3)
+        default: rc = nteam == 4 ? launch_fwd<4, 4>(*plan, P, R, smem, grid, st)
+                                 : launch_fwd<4, 3>(*plan, P, R, smem, grid, st); break;
+    }
+#undef ADN_FWD_CASE
+    if (rc == ADN_OK) *handled = true;
+    return rc;
+}
+
+}  // namespace adn

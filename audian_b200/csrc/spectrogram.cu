@@ -707,6 +707,9 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
     // frames start at multiples of 64 rows in a ring of exactly one frame: the 16 loads of a
     // lane are a rotation of 16 fixed 64-row slices (immediate offsets, picked by a switch)
     const bool rot_ok = T == 32 && RM == N - 1 && (hop & 63) == 0;
+    // the chunk of a step is exactly the SR_PF vectors of every thread and never wraps
+    const bool fastfill = !SR_ASYNC && W == 4 && NT == 128 && allv && CH == SR_PF * 64 && ((RM + 1) % CH) == 0 &&
+                          (span0 % CH) == 0;
     int ws = 0;                 // ring position of the first row of this step
     int npos = span0;           // ring position / row of the chunk the next step adds
     int nrow = span0;
@@ -977,10 +980,22 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
         if (more) {
             if (!loaded) issue_loads();     // warps without an item in the last iteration
             __syncthreads();            // every warp is done with the rows the chunk replaces
+            if (fastfill) {
+                // groups of four channels, 128 threads, chunks that never wrap around the ring:
+                // the SR_PF vectors of a thread land 64 rows apart, two stores each at literal offsets
+                double* sp = sp0 + (npos & RM) + r0;
+                double* sq = sp + RS;
 #pragma unroll
-            for (int j = 0; j < SR_PF; ++j)
-                if (allv || r0 + j * DR < CH) put(pf[j], npos + r0 + j * DR);
-            if (r0 + SR_PF * DR < CH) stage_direct(nrow, npos, CH, SR_PF);
+                for (int j = 0; j < SR_PF; ++j) {
+                    sp[j * 64] = pf[j].x;
+                    sq[j * 64] = pf[j].y;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < SR_PF; ++j)
+                    if (allv || r0 + j * DR < CH) put(pf[j], npos + r0 + j * DR);
+                if (r0 + SR_PF * DR < CH) stage_direct(nrow, npos, CH, SR_PF);
+            }
             __syncthreads();
         }
         ws = (ws + CH) & RM;

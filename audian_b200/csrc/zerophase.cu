@@ -70,51 +70,6 @@ __device__ __forceinline__ double zp_ext_value(const ZpArgs& P, const double* __
     return 2.0 * zp_pre<RECT>(__ldg(xc + (P.nx - 1) * C)) - zp_pre<RECT>(__ldg(xc + (P.nx - 2 - e) * C));
 }
 
-// exact DF2T recurrence over the SOS_L register-resident samples (in time order, or reversed),
-// outputs in place; the sections run skewed by one sample each so that the S recurrences of
-// a step are independent (as in sosfilt.cu)
-template <int S, bool REVERSE>
-__device__ __forceinline__ void zp_df2t(const SosK<S>& K, double (&x)[SOS_L], double (&z)[2 * S]) {
-    double xin[S + 1];
-#pragma unroll
-    for (int j = 0; j < SOS_L + S - 1; ++j) {
-#pragma unroll
-        for (int s = S - 1; s >= 0; --s) {
-            const int k = j - s;
-            if (k < 0 || k >= SOS_L) continue;
-            const int i = REVERSE ? SOS_L - 1 - k : k;
-            const double xv = s == 0 ? x[i] : xin[s];
-            const double y = fma(K.coef[s][0], xv, z[2 * s]);
-            z[2 * s] = fma(K.coef[s][1], xv, z[2 * s + 1]) - K.coef[s][3] * y;
-            z[2 * s + 1] = K.coef[s][2] * xv - K.coef[s][4] * y;
-            if (s == S - 1) x[i] = y; else xin[s + 1] = y;
-        }
-    }
-}
-
-// zero-state end state of the register-resident samples, processed forward or reversed
-template <int S, bool REVERSE>
-__device__ __forceinline__ void zp_pass_a(const SosK<S>& K, const double (&x)[SOS_L], double (&v)[2 * S]) {
-#pragma unroll
-    for (int i = 0; i < SOS_L; ++i) {
-#pragma unroll
-        for (int d = 0; d < 2 * S; ++d) v[d] = fma(K.W[d][REVERSE ? SOS_L - 1 - i : i], x[i], v[d]);
-    }
-}
-
-// one homogeneous step of the cascade (input 0)
-template <int S>
-__device__ __forceinline__ void zp_step0(const SosK<S>& K, double (&z)[2 * S]) {
-    double xv = 0.0;
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-        const double y = fma(K.coef[s][0], xv, z[2 * s]);
-        z[2 * s] = fma(K.coef[s][1], xv, z[2 * s + 1]) - K.coef[s][3] * y;
-        z[2 * s + 1] = K.coef[s][2] * xv - K.coef[s][4] * y;
-        xv = y;
-    }
-}
-
 #ifndef ZP_BLOCKS
 #define ZP_BLOCKS 4
 #endif
@@ -418,7 +373,7 @@ sos_zp_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ ZpArgs 
         if (store && chan_ok) {
             if (P.clamp) {
 #pragma unroll
-                for (int i = 0; i < SOS_L; ++i) x[i] = x[i] < 0.0 ? 0.0 : x[i];
+                for (int i = 0; i < SOS_L; ++i) x[i] = 0.5 * (x[i] + fabs(x[i]));   // max(x, 0), two fp64 ops
             }
             const int64_t e0 = t * T + (int64_t)g * SOS_L;
             const bool fast = t * T >= P.out_first && (t + 1) * (int64_t)T <= P.out_first + P.n_dst;
@@ -456,42 +411,6 @@ sos_zp_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ ZpArgs 
 // warp as soon as agg_b(T) is known, so only that small matrix-vector product is serial along
 // the run and the teams overlap freely.
 constexpr int ZP_NTEAM_MAX = 4;
-
-__device__ __forceinline__ void zp_team_bar(int team) {
-    asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(SOS_NT) : "memory");
-}
-// lane 0 polls a shared-memory tile counter (counts down along the walk) until it is <= v
-__device__ __forceinline__ void zp_wait_le(const volatile long long* f, long long v, int lane) {
-    if (lane == 0) {
-        while (*f > v) __nanosleep(20);
-        __threadfence_block();
-    }
-    __syncwarp();
-}
-
-// ---- TMA unit: 1-D bulk copies global -> shared memory, completion counted in bytes on an mbarrier
-__device__ __forceinline__ uint32_t zp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void zp_mbar_init(uint64_t* mbar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(zp_smem_u32(mbar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void zp_mbar_arrive(uint64_t* mbar) {
-    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(zp_smem_u32(mbar)) : "memory");
-}
-__device__ __forceinline__ void zp_mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
-    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}"
-                 ::"r"(zp_smem_u32(mbar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void zp_mbar_wait(uint64_t* mbar, uint32_t parity) {
-    asm volatile(
-        "{\n.reg .pred p;\nWAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
-        ::"r"(zp_smem_u32(mbar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void zp_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* mbar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(zp_smem_u32(dst)), "l"(src), "r"(bytes), "r"(zp_smem_u32(mbar)) : "memory");
-}
 
 template <int S, int MODE, int NTC>
 __global__ void __launch_bounds__(SOS_NT * NTC, 1)
@@ -600,12 +519,12 @@ sos_zp_park_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ Zp
     auto read_tile = [&](int64_t t, double (&x)[SOS_L]) {
         const double* xp = tiles + (size_t)slot_of(t) * TS + g * GS + cw;
         const bool xform = RECT && t * T >= P.edgeL && (t + 1) * (int64_t)T <= P.edgeL + P.nx;
-        if (!chan_ok) {
-#pragma unroll
-            for (int i = 0; i < SOS_L; ++i) x[i] = 0.0;
-        } else if (Cw == 8) {
+        if (Cw == 8) {                                       // full group (block-uniform): no predicates
 #pragma unroll
             for (int i = 0; i < SOS_L; ++i) x[i] = xp[i * 8];
+        } else if (!chan_ok) {
+#pragma unroll
+            for (int i = 0; i < SOS_L; ++i) x[i] = 0.0;
         } else {
 #pragma unroll
             for (int i = 0; i < SOS_L; ++i) x[i] = xp[i * Cw];
@@ -745,10 +664,17 @@ sos_zp_park_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ Zp
             lstar = il - gstar * SOS_L;
             owner = g == gstar;
             double ylast = 0.0;
+            {
+                double tmp[SOS_L];
 #pragma unroll
-            for (int i = 0; i < SOS_L; ++i) {
-                if (owner && i == lstar) ylast = x[i];
-                if (g > gstar || (owner && i > lstar)) x[i] = 0.0;
+                for (int i = 0; i < SOS_L; ++i) tmp[i] = x[i];
+#pragma unroll 1
+                for (int i = 0; i < SOS_L; ++i) {
+                    if (owner && i == lstar) ylast = tmp[i];
+                    if (g > gstar || (owner && i > lstar)) tmp[i] = 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < SOS_L; ++i) x[i] = tmp[i];
             }
             if (owner && P.zi_right) {
 #pragma unroll
@@ -854,7 +780,7 @@ sos_zp_park_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ Zp
         if (store && chan_ok) {
             if (P.clamp) {
 #pragma unroll
-                for (int i = 0; i < SOS_L; ++i) x[i] = x[i] < 0.0 ? 0.0 : x[i];
+                for (int i = 0; i < SOS_L; ++i) x[i] = 0.5 * (x[i] + fabs(x[i]));   // max(x, 0), two fp64 ops
             }
             const int64_t e0 = t * T + (int64_t)g * SOS_L;
             const bool fast = t * T >= P.out_first && (t + 1) * (int64_t)T <= P.out_first + P.n_dst;
