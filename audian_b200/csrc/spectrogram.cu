@@ -577,8 +577,17 @@ constexpr int SR_MAXNT = 128;
 #ifndef SR_BLOCKS
 #define SR_BLOCKS 3
 #endif
+// SR_WIN_CALC: the Hann window computed where it is used, w[j] = 1/2 - 1/2 cos(2 pi j / N) with
+// j = 2 (T p + t) + s: cos(theta_p + phi) from the sixteen compile-time (cos, sin)(2 pi p / 16) and
+// two per-lane (cos, sin) pairs -- two DFMA per value instead of half a 128-bit shared-memory load
+// (and 8 KB less shared memory: four blocks per SM fit with SR_ASYNC).  Measured on B200 (8 ch,
+// nfft 1024 / hop 512): 175 us against 167 us with the table in shared memory (the eight extra
+// live registers spill); with SR_ASYNC and four blocks per SM 176 us.  Off.
+#ifndef SR_WIN_CALC
+#define SR_WIN_CALC 0
+#endif
 #ifndef SR_WIN_SMEM
-#define SR_WIN_SMEM 1
+#define SR_WIN_SMEM (SR_WIN_CALC ? 0 : 1)
 #endif
 constexpr int SR_PF = 8;            // 16-byte vectors in flight per thread and step
 // SR_ASYNC: the rows of the next step go straight into the ring with 8-byte cp.async, issued as
@@ -610,7 +619,9 @@ template <int LOGN> struct SRCfg {
     static constexpr int T = SWCfg<LOGN>::T;
     // per-frame stride of the exchange buffer (complex): T = 32 rows of 33 (16 k1 rows read
     // by 16 lane pairs: 16-byte offsets, two wavefronts per 128-bit load)
-    static constexpr int FS = T == 32 ? 16 * 33 / 2 + 4 : SWCfg<LOGN>::FS;   // T == 32: 16 x 33 doubles
+    // T == 32: 16 rows of SR_XS doubles; the stride is even, so that a lane pair reads its row as
+    // 16-byte vectors (two wavefronts per 128-bit load of 16 rows: the minimum for 256 bytes)
+    static constexpr int FS = T == 32 ? 16 * 34 / 2 + 4 : SWCfg<LOGN>::FS;
     static constexpr int WB = FS * SWCfg<LOGN>::FPW;
 };
 
@@ -698,6 +709,11 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
     const double2 tw1 = __ldg(P.twA + 1 * T + t), tw2 = __ldg(P.twA + 2 * T + t);
     const double2 tw4 = __ldg(P.twA + 4 * T + t), tw8 = __ldg(P.twA + 8 * T + t);
     const double2 twl = __ldg(P.twS + lane);             // T == 32: W_N^lane of the split step
+    // SR_WIN_CALC: (cos, sin)(2 pi j / N) of this lane's two window positions j = 2 t, 2 t + 1
+    // (from the table of W_N^k = exp(-2 pi i k / N) of the split step: k = 2 t + 1 < M / 8)
+    double2 wcs0 = __ldg(P.twS + 2 * t), wcs1 = __ldg(P.twS + 2 * t + 1);
+    wcs0.y = -wcs0.y;
+    wcs1.y = -wcs1.y;
     const int nitems = FSTEP * W;
     const int niter = (nitems + NW * FPW - 1) / (NW * FPW);
     const double corr = P.detrend ? 0.5 : 0.0;           // (sum x / N) * N/2
@@ -803,10 +819,24 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
                 }
                 sm = (s0 + s1) + (s2 + s3);
             }
+            if (SR_WIN_CALC) {
+                // keeps the compiler from hoisting the 32 window values of a lane out of the frame
+                // loop (they are the same for every frame: 64 registers)
+                asm volatile("" : "+d"(wcs0.x), "+d"(wcs0.y), "+d"(wcs1.x), "+d"(wcs1.y));
+            }
 #pragma unroll
             for (int p = 0; p < 16; ++p) {
-                double2 w = SR_WIN_SMEM ? *reinterpret_cast<const double2*>(wins + 2 * (T * p + t))
-                                        : __ldg(reinterpret_cast<const double2*>(P.win) + (T * p + t));
+                double2 w;
+                if (SR_WIN_CALC) {
+                    // 1/2 cos / sin (2 pi p / 16): W32^(2p) for p < 8, its negative beyond
+                    const double hc = (p < 8 ? 0.5 : -0.5) * w32c(2 * (p & 7), 0);    // folded: p is unrolled
+                    const double hs = (p < 8 ? -0.5 : 0.5) * w32c(2 * (p & 7), 1);
+                    w.x = fma(-hc, wcs0.x, fma(hs, wcs0.y, 0.5));
+                    w.y = fma(-hc, wcs1.x, fma(hs, wcs1.y, 0.5));
+                } else {
+                    w = SR_WIN_SMEM ? *reinterpret_cast<const double2*>(wins + 2 * (T * p + t))
+                                    : __ldg(reinterpret_cast<const double2*>(P.win) + (T * p + t));
+                }
                 a[p].x *= w.x;
                 a[p].y *= w.y;
             }
@@ -828,7 +858,7 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
                         // buffer of doubles (half the shared memory; the 64-bit reads of the 16
                         // lane pairs are one 128-byte wavefront each)
                         b[k1] = v;
-                        reinterpret_cast<double*>(wbf)[k1 * 33 + t] = v.x;
+                        reinterpret_cast<double*>(wbf)[k1 * 34 + t] = v.x;
                     } else {
                         const int f = k1 * T + t;
                         wbf[f + (f >> 4)] = v;
@@ -848,15 +878,23 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
                 const int k1 = lane & 15, tp = lane >> 4;
                 const double sgn = tp ? -1.0 : 1.0;
                 double* wre = reinterpret_cast<double*>(wbf);
-                const double* row = wre + k1 * 33;
+                const double2* row = reinterpret_cast<const double2*>(wre + k1 * 34);
 #pragma unroll
-                for (int n = 0; n < 16; ++n) a[n].x = fma(sgn, row[n + 16], row[n]);
+                for (int m = 0; m < 8; ++m) {
+                    const double2 lo = row[m], hi = row[m + 8];
+                    a[2 * m].x = fma(sgn, hi.x, lo.x);
+                    a[2 * m + 1].x = fma(sgn, hi.y, lo.y);
+                }
                 __syncwarp();
 #pragma unroll
-                for (int kq = 0; kq < 16; ++kq) wre[kq * 33 + t] = b[kq].y;
+                for (int kq = 0; kq < 16; ++kq) wre[kq * 34 + t] = b[kq].y;
                 __syncwarp();
 #pragma unroll
-                for (int n = 0; n < 16; ++n) a[n].y = fma(sgn, row[n + 16], row[n]);
+                for (int m = 0; m < 8; ++m) {
+                    const double2 lo = row[m], hi = row[m + 8];
+                    a[2 * m].y = fma(sgn, hi.x, lo.x);
+                    a[2 * m + 1].y = fma(sgn, hi.y, lo.y);
+                }
                 if (tp) {
 #pragma unroll
                     for (int n = 1; n < 16; ++n) a[n] = cmul(a[n], make_double2(w32c(n, 0), w32c(n, 1)));

@@ -501,9 +501,8 @@ sos_zp_park_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ Zp
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     // the tile has landed in its slot (all threads of the loading team call this)
-    auto wait_load = [&](int64_t t, int slot) {
+    auto wait_load = [&](int64_t t, int slot, uint32_t parity) {
         const int kind = load_kind(t);
-        const uint32_t parity = (uint32_t)(((top - t) / NSLOT) & 1);
         if (kind == 1) {
             zp_mbar_wait(mbar + slot, parity);
         } else {
@@ -516,8 +515,8 @@ sos_zp_park_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ Zp
     issue_load(top - team, slot_of(top - team));
 
     // tile slot -> this thread's SOS_L samples
-    auto read_tile = [&](int64_t t, double (&x)[SOS_L]) {
-        const double* xp = tiles + (size_t)slot_of(t) * TS + g * GS + cw;
+    auto read_tile = [&](int64_t t, int slot, double (&x)[SOS_L]) {
+        const double* xp = tiles + (size_t)slot * TS + g * GS + cw;
         const bool xform = RECT && t * T >= P.edgeL && (t + 1) * (int64_t)T <= P.edgeL + P.nx;
         if (Cw == 8) {                                       // full group (block-uniform): no predicates
 #pragma unroll
@@ -535,16 +534,28 @@ sos_zp_park_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ Zp
         }
     };
 
-    for (int64_t w = team; ; w += NTEAM) {
+    // slots and mbarrier parities advance with the walk (no divisions in the loop): sl = slot of
+    // the look-ahead tile, wr / wpar = walk position modulo NSLOT and the parity of its quotient
+    int sl = slot_of(top - team), wr = team;
+    uint32_t wpar = 0;
+    auto advance = [&]() {
+        sl -= NTEAM;
+        if (sl < 0) sl += NSLOT;
+        wr += NTEAM;
+        if (wr >= NSLOT) { wr -= NSLOT; wpar ^= 1u; }
+    };
+    for (int64_t w = team; ; w += NTEAM, advance()) {
         const int64_t tl = top - w;                          // look-ahead tile of this iteration
         const int64_t tm = tl + JJ;                          // main tile of this iteration
         if (tm < a) break;
         const bool do_l = tl >= a - JJ;
         const bool do_m = tm <= top;
+        int sm = sl + JJ;                                    // slot of the main tile (and of tile tl - NTEAM)
+        if (sm >= NSLOT) sm -= NSLOT;
         // ---------------------------------------------------------------- L(tl)
-        if (do_l || tl >= 0) wait_load(tl, slot_of(tl));     // the team's tile tl has landed
+        if (do_l || tl >= 0) wait_load(tl, sl, wpar);        // the team's tile tl has landed
         if (do_l) {
-            const int slot = slot_of(tl);
+            const int slot = sl;
             if (tl < 0) {
                 // before the sequence: the virtual tile -1 carries the initial state of the sweep
                 if (ttid < CG * D) {
@@ -558,7 +569,7 @@ sos_zp_park_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ Zp
                 if (ttid == 0) { __threadfence_block(); la_flag[slot] = tl; }
             } else {
                 double x[SOS_L];
-                read_tile(tl, x);
+                read_tile(tl, slot, x);
                 double v[D], ex[D];
 #pragma unroll
                 for (int d = 0; d < D; ++d) v[d] = 0.0;
@@ -611,17 +622,17 @@ sos_zp_park_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ Zp
         // the team's next look-ahead tile: into the slot the main visit below frees
         const int64_t tn = tl - NTEAM;
         if (!do_m) {
-            issue_load(tn, slot_of(tn));
+            issue_load(tn, sm);
             continue;
         }
         // ---------------------------------------------------------------- M(tm)
         const int64_t t = tm;
-        const int slot = slot_of(t);
+        const int slot = sm;
         const bool store = t < b;
         const bool last = t == P.ntt - 1;
         zp_wait_le(la_flag + slot, t, lane);                 // parked by its look-ahead visit
         double x[SOS_L];
-        read_tile(t, x);
+        read_tile(t, slot, x);
         double z[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) z[d] = etot[((size_t)slot * D + d) * SOS_NT + ttid];
@@ -633,7 +644,8 @@ sos_zp_park_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ Zp
 #pragma unroll
             for (int d = 0; d < D; ++d) sf[d] = 0.0;
             for (int j = 1; j <= JJ; ++j) {
-                const int sj = slot_of(t - j);
+                int sj = slot - j;
+                if (sj < 0) sj += NSLOT;
                 zp_wait_le(la_flag + sj, t - j, lane);
                 double q[D], M[DD];
 #pragma unroll

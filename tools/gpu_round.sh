@@ -11,7 +11,7 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_
 # the launch list is restricted to the timed region of the bench (NVTX range "timed")
 timeout 900 ncu --nvtx --nvtx-include "timed/" --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-wholefile > $out/${tag}_ncu_launch.log 2>&1
-timeout 1200 ncu --nvtx --nvtx-include "timed/" --set full --clock-control none --import-source on -k regex:'spectrogram_ring|sos_scan|sos_run|sos_zp' -c 3 \
+timeout 1200 ncu --nvtx --nvtx-include "timed/" --set full --clock-control none --import-source on -k regex:'spectrogram_ring|sos_scan|sos_run|sos_zp|sos_fwd' -c 3 \
     -o $out/${tag}_full -f python bench.py --steps 2 --warmup 3 --no-wholefile > $out/${tag}_ncu_full.log 2>&1
 ncu -i $out/${tag}_full.ncu-rep --page raw --csv > $out/${tag}_full_raw.csv 2>/dev/null
 echo done
