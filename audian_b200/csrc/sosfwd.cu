@@ -25,9 +25,10 @@ namespace {
 struct FwdArgs {
     const double* src;
     double* dst;
-    const double* tab;
+    const double* tab;                 // tables of the first sub-cascade
+    const double* tab2;                // ... of the second one (3 and 4 sections: 2 + 1, 2 + 2)
     int32_t off_fix, off_wpow, off_tile, n_staged;
-    const double* s0;                  // [C][D] initial state or null
+    const double* s0;                  // [C][D] initial state or null (D = 2 x all sections)
     double* zf;                        // [C][D] final state or null
     int64_t n;                         // rows of the source
     int64_t out_skip, n_dst;           // source rows [out_skip, out_skip + n_dst) -> dst rows
@@ -39,12 +40,136 @@ struct FwdArgs {
     int32_t bulk_ok;
 };
 
-template <int S, int NTC>
-__global__ void __launch_bounds__(SOS_NT * NTC, 1)
-sos_fwd_park_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ FwdArgs P,
-                    const __grid_constant__ SosRun R) {
+// shared-memory state of one sub-cascade (stage) of the kernel
+template <int S>
+struct FwdStage {
+    const double* tab_s;               // staged scan / fix / wpow tables
+    const double* tab_fix;
+    const double* tab_wpow;
+    const double* pt_s;                // A^T (one tile)
+    double* wagg;                      // this team's [NW][CG][D]
+    double* sin_s;                     // [NTEAM][CG][D]: state entering a team's tile
+    volatile long long* flag;          // tile whose incoming state is published
+};
+
+struct FwdLane {                       // where a thread sits
+    int lane, warp, team, nteam, CG, GW, gl, cw;
+    bool chan_ok;
+};
+
+// One sub-cascade over the SOS_L samples a thread holds (in place): pass A, the scans inside the
+// tile, the hand-over of the state along the run, the exact recurrence.  zf_out (or null): where
+// the state right after sample `ilast` goes (the sub-chunk that holds the last row).
+template <int S>
+__device__ __forceinline__ void fwd_stage(const SosK<S>& K, const FwdStage<S>& st, const FwdLane& L,
+                                          double (&x)[SOS_L], int64_t t, double* zf_out, int ilast) {
     constexpr int D = 2 * S;
     constexpr int DD = D * D;
+    const int lane = L.lane, warp = L.warp, team = L.team, CG = L.CG, GW = L.GW, gl = L.gl, cw = L.cw;
+    double z[D];
+    {
+        double v[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) v[d] = 0.0;
+        zp_pass_a<S, false>(K, x, v);
+        {
+            int k = 0;
+            for (int off = CG; off < 32; off <<= 1, ++k) {
+                double u[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) u[d] = __shfl_up_sync(0xffffffffu, v[d], off);
+                if (lane >= off) matvec_acc<D>(st.tab_s + k * DD, u, v);
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const double u = __shfl_up_sync(0xffffffffu, v[d], CG & 31);
+            z[d] = gl == 0 ? 0.0 : u;
+        }
+        if (gl == GW - 1) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) st.wagg[(warp * CG + cw) * D + d] = v[d];
+        }
+        zp_team_bar(team);
+        double pre[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) pre[d] = 0.0;
+        for (int j = 0; j < warp; ++j) {
+            double u[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) u[d] = st.wagg[(j * CG + cw) * D + d];
+            matvec_acc<D>(st.tab_wpow + (warp - 1 - j) * DD, u, pre);
+        }
+        matvec_acc<D>(st.tab_fix + gl * DD, pre, z);         // z = ex + A^(L gl) pre
+    }
+    // ---- the state entering this tile (from the team of tile t - 1), and on to tile t + 1
+    double sv[D];
+    zp_wait_ge(st.flag, t, lane);
+#pragma unroll
+    for (int d = 0; d < D; ++d) sv[d] = st.sin_s[(size_t)team * CG * D + cw * D + d];
+    zp_team_bar(team);                                       // every warp of the team has read it
+    if (warp == 0) {
+        const int tnext = (team + 1) % L.nteam;
+        for (int e = lane; e < CG * D; e += 32) {
+            const int ch = e / D, r = e - ch * D;
+            double acc = 0.0;
+            for (int q = 0; q < SOS_NW; ++q) {
+                const double* M = st.tab_wpow + (SOS_NW - 1 - q) * DD + r * D;
+                const double* u = st.wagg + (q * CG + ch) * D;
+                for (int c = 0; c < D; ++c) acc = fma(M[c], u[c], acc);
+            }
+            const double* M = st.pt_s + r * D;
+            const double* u = st.sin_s + (size_t)team * CG * D + ch * D;
+            for (int c = 0; c < D; ++c) acc = fma(M[c], u[c], acc);
+            st.sin_s[(size_t)tnext * CG * D + e] = acc;
+        }
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); *st.flag = t + 1; }
+    }
+    {
+        double tmp[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) tmp[d] = 0.0;
+        matvec_acc<D>(st.tab_wpow + warp * DD, sv, tmp);
+        matvec_acc<D>(st.tab_fix + gl * DD, tmp, z);
+    }
+    // ---- the exact recurrence from the true incoming state, in registers
+    if (zf_out != nullptr) {
+        // the sub-chunk that holds the last row: rolled loop, state captured right after it
+        double tmp[SOS_L];
+#pragma unroll
+        for (int i = 0; i < SOS_L; ++i) tmp[i] = x[i];
+#pragma unroll 1
+        for (int i = 0; i < SOS_L; ++i) {
+            double xv = tmp[i];
+#pragma unroll
+            for (int q = 0; q < S; ++q) {
+                const double y = fma(K.coef[q][0], xv, z[2 * q]);
+                z[2 * q] = fma(K.coef[q][1], xv, z[2 * q + 1]) - K.coef[q][3] * y;
+                z[2 * q + 1] = K.coef[q][2] * xv - K.coef[q][4] * y;
+                xv = y;
+            }
+            tmp[i] = xv;
+            if (i == ilast && L.chan_ok) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) zf_out[d] = z[d];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < SOS_L; ++i) x[i] = tmp[i];
+    } else {
+        zp_df2t<S, false>(K, x, z);
+    }
+}
+
+// S1 sections, then S2 more (S2 == 0: one stage): the cascade of S1 + S2 sections is the second
+// sub-cascade applied to the output of the first, sample by sample the same arithmetic
+template <int S1, int S2, int NTC>
+__global__ void __launch_bounds__(SOS_NT * NTC, 1)
+sos_fwd_park_kernel(const __grid_constant__ SosK<S1> K1, const __grid_constant__ SosK<(S2 > 0 ? S2 : 1)> K2,
+                    const __grid_constant__ FwdArgs P, const __grid_constant__ SosRun R) {
+    constexpr int D1 = 2 * S1, D2 = 2 * S2, DT = D1 + D2;
+    constexpr int DD1 = D1 * D1, DD2 = D2 * D2;
     constexpr int NTEAM = NTC;
     extern __shared__ __align__(16) double smem[];
 
@@ -65,15 +190,19 @@ sos_fwd_park_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ F
     const int G = SOS_NT / CG;
     const size_t TS = (size_t)G * (SOS_L * CG + pad);
 
-    double* tab_s = smem;                                   // n_staged * DD
-    double* pt_s = tab_s + (size_t)P.n_staged * DD;         // A^T (one tile)
-    double* wagg = pt_s + DD + (size_t)team * SOS_NW * CG * D;          // [NTEAM][NW][CG][D]
-    double* sin_s = pt_s + DD + (size_t)NTEAM * SOS_NW * CG * D;        // [NTEAM][CG][D]: state entering a team's tile
-    volatile long long* sf_flag = reinterpret_cast<volatile long long*>(sin_s + (size_t)NTEAM * CG * D);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(const_cast<long long*>(sf_flag) + 1);      // [NTEAM]
-    double* tiles = reinterpret_cast<double*>(mbar + NTEAM + ((NTEAM + 1) & 1));            // [NTEAM][TS]
-    const double* tab_fix = tab_s + P.off_fix * DD;
-    const double* tab_wpow = tab_s + P.off_wpow * DD;
+    // shared memory: per stage [tables | A^T | wagg | sin_s], then flags, mbarriers, tile slots
+    double* p = smem;
+    double* tab1_s = p;  p += (size_t)P.n_staged * DD1;
+    double* pt1_s = p;   p += DD1;
+    double* wagg1 = p + (size_t)team * SOS_NW * CG * D1;  p += (size_t)NTEAM * SOS_NW * CG * D1;
+    double* sin1_s = p;  p += (size_t)NTEAM * CG * D1;
+    double* tab2_s = p;  p += (size_t)P.n_staged * DD2;
+    double* pt2_s = p;   p += DD2;
+    double* wagg2 = p + (size_t)team * SOS_NW * CG * D2;  p += (size_t)NTEAM * SOS_NW * CG * D2;
+    double* sin2_s = p;  p += (size_t)NTEAM * CG * D2;
+    volatile long long* sf_flag = reinterpret_cast<volatile long long*>(p);        // [2]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(const_cast<long long*>(sf_flag) + 2);      // [NTEAM]
+    double* tiles = reinterpret_cast<double*>(mbar + NTEAM + (NTEAM & 1));          // [NTEAM][TS]
     double* slot_s = tiles + (size_t)team * TS;
 
     const int64_t a = P.t_out0 + run * P.run_tiles;         // output tiles [a, b)
@@ -81,19 +210,35 @@ sos_fwd_park_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ F
     if (a >= b) return;
     const int64_t t_first = max((int64_t)0, a - P.pre);     // first tile of the walk
 
-    for (int q = tid; q < P.n_staged * DD; q += blockDim.x) tab_s[q] = __ldg(P.tab + q);
-    for (int q = tid; q < DD; q += blockDim.x) pt_s[q] = __ldg(P.tab + (size_t)(P.off_tile + 1) * DD + q);
-    // state entering the first tile of the walk: the initial state at row 0, else zero (run-in)
-    for (int q = tid; q < CG * D; q += blockDim.x) {
-        const int ch = q / D;
+    for (int q = tid; q < P.n_staged * DD1; q += blockDim.x) tab1_s[q] = __ldg(P.tab + q);
+    for (int q = tid; q < DD1; q += blockDim.x) pt1_s[q] = __ldg(P.tab + (size_t)(P.off_tile + 1) * DD1 + q);
+    if (S2 > 0) {
+        for (int q = tid; q < P.n_staged * DD2; q += blockDim.x) tab2_s[q] = __ldg(P.tab2 + q);
+        for (int q = tid; q < DD2; q += blockDim.x) pt2_s[q] = __ldg(P.tab2 + (size_t)(P.off_tile + 1) * DD2 + q);
+    }
+    // state entering the first tile of the walk: the initial state at row 0, else zero (run-in);
+    // team 0 takes the first tile
+    for (int q = tid; q < CG * DT; q += blockDim.x) {
+        const int ch = q / DT, d = q - ch * DT;
         double v = 0.0;
-        if (t_first == 0 && P.s0 && c0 + ch < C) v = __ldg(P.s0 + (size_t)c0 * D + q);
-        sin_s[(size_t)0 * CG * D + q] = v;                  // team 0 takes the first tile
+        if (t_first == 0 && P.s0 && c0 + ch < C) v = __ldg(P.s0 + (size_t)(c0 + ch) * DT + d);
+        if (d < D1) sin1_s[ch * D1 + d] = v;
+        else sin2_s[ch * D2 + (d - D1)] = v;
     }
     if (tid < NTEAM) zp_mbar_init(mbar + tid, 1);
-    if (tid == 0) *sf_flag = t_first;
+    if (tid < 2) sf_flag[tid] = t_first;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
+
+    FwdLane L;
+    L.lane = lane; L.warp = warp; L.team = team; L.nteam = NTEAM; L.CG = CG; L.GW = GW; L.gl = gl; L.cw = cw;
+    L.chan_ok = chan_ok;
+    FwdStage<S1> st1;
+    st1.tab_s = tab1_s; st1.tab_fix = tab1_s + P.off_fix * DD1; st1.tab_wpow = tab1_s + P.off_wpow * DD1;
+    st1.pt_s = pt1_s; st1.wagg = wagg1; st1.sin_s = sin1_s; st1.flag = sf_flag;
+    FwdStage<(S2 > 0 ? S2 : 1)> st2;
+    st2.tab_s = tab2_s; st2.tab_fix = tab2_s + P.off_fix * DD2; st2.tab_wpow = tab2_s + P.off_wpow * DD2;
+    st2.pt_s = pt2_s; st2.wagg = wagg2; st2.sin_s = sin2_s; st2.flag = sf_flag + 1;
 
     const bool bulk_group = P.bulk_ok && Cw == CG;
     auto load_kind = [&](int64_t t) {
@@ -133,12 +278,12 @@ sos_fwd_park_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ F
         double x[SOS_L];
         {
             const double* xp = slot_s + g * GS + cw;
-            if (!chan_ok) {
-#pragma unroll
-                for (int i = 0; i < SOS_L; ++i) x[i] = 0.0;
-            } else if (Cw == 8) {
+            if (Cw == 8) {                                   // full group (block-uniform): no predicates
 #pragma unroll
                 for (int i = 0; i < SOS_L; ++i) x[i] = xp[i * 8];
+            } else if (!chan_ok) {
+#pragma unroll
+                for (int i = 0; i < SOS_L; ++i) x[i] = 0.0;
             } else {
 #pragma unroll
                 for (int i = 0; i < SOS_L; ++i) x[i] = xp[i * Cw];
@@ -146,116 +291,25 @@ sos_fwd_park_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ F
         }
         zp_team_bar(team);                                   // every thread of the team has its samples
         issue_load(t + NTEAM);                               // the slot goes to the team's next tile
-        // ---- zero-state aggregates: per thread, per warp, per tile
-        double z[D];
-        {
-            double v[D];
-#pragma unroll
-            for (int d = 0; d < D; ++d) v[d] = 0.0;
-            zp_pass_a<S, false>(K, x, v);
-            {
-                int k = 0;
-                for (int off = CG; off < 32; off <<= 1, ++k) {
-                    double u[D];
-#pragma unroll
-                    for (int d = 0; d < D; ++d) u[d] = __shfl_up_sync(0xffffffffu, v[d], off);
-                    if (lane >= off) matvec_acc<D>(tab_s + k * DD, u, v);
-                }
-            }
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-                const double u = __shfl_up_sync(0xffffffffu, v[d], CG & 31);
-                z[d] = gl == 0 ? 0.0 : u;
-            }
-            if (gl == GW - 1) {
-#pragma unroll
-                for (int d = 0; d < D; ++d) wagg[(warp * CG + cw) * D + d] = v[d];
-            }
-            zp_team_bar(team);
-            double pre[D];
-#pragma unroll
-            for (int d = 0; d < D; ++d) pre[d] = 0.0;
-            for (int j = 0; j < warp; ++j) {
-                double u[D];
-#pragma unroll
-                for (int d = 0; d < D; ++d) u[d] = wagg[(j * CG + cw) * D + d];
-                matvec_acc<D>(tab_wpow + (warp - 1 - j) * DD, u, pre);
-            }
-            matvec_acc<D>(tab_fix + gl * DD, pre, z);        // z = ex + A^(L gl) pre
-        }
-        // ---- the state entering this tile (from the team of tile t - 1), and on to tile t + 1
-        double sv[D];
-        zp_wait_ge(sf_flag, t, lane);
-#pragma unroll
-        for (int d = 0; d < D; ++d) sv[d] = sin_s[(size_t)team * CG * D + cw * D + d];
-        zp_team_bar(team);                                   // every warp of the team has read it
-        if (warp == 0) {
-            const int tnext = (team + 1) % NTEAM;
-            for (int e = lane; e < CG * D; e += 32) {
-                const int ch = e / D, r = e - ch * D;
-                double acc = 0.0;
-                for (int q = 0; q < SOS_NW; ++q) {
-                    const double* M = tab_wpow + (SOS_NW - 1 - q) * DD + r * D;
-                    const double* u = wagg + (q * CG + ch) * D;
-                    for (int c = 0; c < D; ++c) acc = fma(M[c], u[c], acc);
-                }
-                const double* M = pt_s + r * D;
-                const double* u = sin_s + (size_t)team * CG * D + ch * D;
-                for (int c = 0; c < D; ++c) acc = fma(M[c], u[c], acc);
-                sin_s[(size_t)tnext * CG * D + e] = acc;
-            }
-            __syncwarp();
-            if (lane == 0) { __threadfence_block(); *sf_flag = t + 1; }
-        }
-        {
-            double tmp[D];
-#pragma unroll
-            for (int d = 0; d < D; ++d) tmp[d] = 0.0;
-            matvec_acc<D>(tab_wpow + warp * DD, sv, tmp);
-            matvec_acc<D>(tab_fix + gl * DD, tmp, z);
-        }
-        // ---- the exact recurrence from the true incoming state, in registers
         const int64_t e0 = t * T + (int64_t)g * SOS_L;       // source row of x[0]
         const int64_t lastrow = P.n - 1;
-        if (P.zf != nullptr && lastrow >= e0 && lastrow < e0 + SOS_L && t >= a) {
-            // the sub-chunk that holds the last row: rolled loop, state captured right after it
-            double tmp[SOS_L];
-#pragma unroll
-            for (int i = 0; i < SOS_L; ++i) tmp[i] = x[i];
-            const int ilast = (int)(lastrow - e0);
-#pragma unroll 1
-            for (int i = 0; i < SOS_L; ++i) {
-                double xv = tmp[i];
-#pragma unroll
-                for (int q = 0; q < S; ++q) {
-                    const double y = fma(K.coef[q][0], xv, z[2 * q]);
-                    z[2 * q] = fma(K.coef[q][1], xv, z[2 * q + 1]) - K.coef[q][3] * y;
-                    z[2 * q + 1] = K.coef[q][2] * xv - K.coef[q][4] * y;
-                    xv = y;
-                }
-                tmp[i] = xv;
-                if (i == ilast && chan_ok) {
-#pragma unroll
-                    for (int d = 0; d < D; ++d) P.zf[(size_t)(c0 + cw) * D + d] = z[d];
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < SOS_L; ++i) x[i] = tmp[i];
-        } else {
-            zp_df2t<S, false>(K, x, z);
-        }
+        const bool capture = P.zf != nullptr && lastrow >= e0 && lastrow < e0 + SOS_L && t >= a;
+        double* zf_c = capture ? P.zf + (size_t)(c0 + (chan_ok ? cw : 0)) * DT : nullptr;
+        fwd_stage<S1>(K1, st1, L, x, t, zf_c, (int)(lastrow - e0));
+        if (S2 > 0)
+            fwd_stage<(S2 > 0 ? S2 : 1)>(K2, st2, L, x, t, capture ? zf_c + D1 : nullptr, (int)(lastrow - e0));
         if (t >= a && chan_ok && P.dst != nullptr) {
             const bool fast = t * T >= P.out_skip && (t + 1) * (int64_t)T <= P.out_skip + P.n_dst;
-            double* p = P.dst + (e0 - P.out_skip) * C + c0 + cw;
+            double* q = P.dst + (e0 - P.out_skip) * C + c0 + cw;
             if (fast && C == 8) {
 #pragma unroll
-                for (int i = 0; i < SOS_L; ++i) __stcs(p + i * 8, x[i]);
+                for (int i = 0; i < SOS_L; ++i) __stcs(q + i * 8, x[i]);
             } else {
                 const int64_t o0 = e0 - P.out_skip;
 #pragma unroll
                 for (int i = 0; i < SOS_L; ++i) {
-                    if (fast || (o0 + i >= 0 && o0 + i < P.n_dst)) __stcs(p, x[i]);
-                    p += C;
+                    if (fast || (o0 + i >= 0 && o0 + i < P.n_dst)) __stcs(q, x[i]);
+                    q += C;
                 }
             }
         }
@@ -265,18 +319,21 @@ sos_fwd_park_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ F
 
 std::atomic<int64_t> g_fwd_launches{0};
 
-template <int S, int NTC>
-int32_t launch_fwd(const SosPlan& plan, const FwdArgs& P, const SosRun& R, size_t smem, unsigned grid,
-                   cudaStream_t st) {
-    SosK<S> K;
-    fill_sosk<S>(plan, K);
-    auto kern = sos_fwd_park_kernel<S, NTC>;
+template <int S1, int S2, int NTC>
+int32_t launch_fwd(const SosPlan& plan1, const SosPlan* plan2, const FwdArgs& P, const SosRun& R, size_t smem,
+                   unsigned grid, cudaStream_t st) {
+    SosK<S1> K1;
+    fill_sosk<S1>(plan1, K1);
+    SosK<(S2 > 0 ? S2 : 1)> K2;
+    memset(&K2, 0, sizeof K2);
+    if (S2 > 0) fill_sosk<(S2 > 0 ? S2 : 1)>(*plan2, K2);
+    auto kern = sos_fwd_park_kernel<S1, S2, NTC>;
     static bool attr_done = false;               // per instantiation
     if (!attr_done) {
         ADN_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
-    kern<<<grid, SOS_NT * NTC, smem, st>>>(K, P, R);
+    kern<<<grid, SOS_NT * NTC, smem, st>>>(K1, K2, P, R);
     count_launch();
     g_fwd_launches.fetch_add(1);
     ADN_CK(cudaGetLastError());
@@ -299,18 +356,21 @@ int32_t sosfilt_park_dev(const double* sos, int32_t S, const double* src, int64_
                          bool* handled, cudaStream_t st) {
     *handled = false;
     // measured on B200 (80 s of 8 ch x 48 kHz): one or two sections 96 / 90 us against 97 / 103 us of
-    // the run kernel (64 ch: 739 against 779 us); four sections 187 against 178 us (register bound)
-    const int smax = fwd_env("ADN_SOS_PARK_SMAX", 2);
+    // the run kernel (64 ch: 739 against 779 us); three and four sections run as two chained
+    // sub-cascades of at most two sections (all eight states at once are register bound: 187 us)
+    const int smax = fwd_env("ADN_SOS_PARK_SMAX", 4);
     if (!fwd_env("ADN_SOS_PARK", 1) || S < 1 || S > 4 || S > smax || dst == nullptr || n_dst <= 0) return ADN_OK;
     const int CG = pick_cg(C);
-    std::shared_ptr<SosPlan> plan;
-    int32_t rc = get_sos_plan(sos, S, CG, st, &plan);
+    const int S1 = S <= 2 ? S : 2, S2 = S - S1;
+    std::shared_ptr<SosPlan> plan, plan2;
+    int32_t rc = get_sos_plan(sos, S1, CG, st, &plan);
     if (rc) return rc;
-    if (plan->jpre > SOS_LOOK) return ADN_OK;
-    const int D = 2 * S;
+    if (S2 > 0 && (rc = get_sos_plan(sos + 6 * S1, S2, CG, st, &plan2))) return rc;
+    if (plan->jpre > SOS_LOOK || (S2 > 0 && plan2->jpre > SOS_LOOK)) return ADN_OK;
+    const int D1 = 2 * S1, D2 = 2 * S2;
     FwdArgs P;
     memset(&P, 0, sizeof P);
-    P.src = src; P.dst = dst; P.tab = plan->dtab; P.s0 = s0; P.zf = zf;
+    P.src = src; P.dst = dst; P.tab = plan->dtab; P.tab2 = S2 > 0 ? plan2->dtab : nullptr; P.s0 = s0; P.zf = zf;
     P.off_fix = plan->off_fix; P.off_wpow = plan->off_wpow; P.off_tile = plan->off_tile;
     P.n_staged = plan->n_staged;
     P.n = n; P.out_skip = out_skip; P.n_dst = n_dst;
@@ -320,7 +380,8 @@ int32_t sosfilt_park_dev(const double* sos, int32_t S, const double* src, int64_
     P.t_out0 = out_skip / P.T;
     // the tile of the last source row always belongs to the walk when the final state is wanted
     P.t_out1 = zf ? P.ntt : (out_skip + n_dst - 1) / P.T + 1;
-    P.pre = plan->jpre;
+    // the second sub-cascade forgets what the first one feeds it while that one still converges
+    P.pre = plan->jpre + (S2 > 0 ? plan2->jpre : 0);
     P.bulk_ok = (C == CG && CG >= 8 && fwd_env("ADN_ZP_TMA", 1)) ? 1 : 0;
     SosRun R;
     memset(&R, 0, sizeof R);
@@ -334,10 +395,12 @@ int32_t sosfilt_park_dev(const double* sos, int32_t S, const double* src, int64_
         while ((1 << R.lc) < CG) ++R.lc;
         if (C % 2 && CG > 1) R.lc = -1;
     }
-    const int nteam = fwd_env("ADN_SOS_NTEAM", S <= 2 ? 3 : 4) >= 4 ? 4 : 3;
+    const int nteam = fwd_env("ADN_SOS_NTEAM", 3) >= 4 ? 4 : 3;
     const size_t TS = (size_t)(SOS_NT / CG) * (SOS_L * CG + (CG < 16 ? CG : 0));
-    const size_t smem = ((size_t)plan->n_staged * D * D + (size_t)D * D + (size_t)nteam * SOS_NW * CG * D +
-                         (size_t)nteam * CG * D + 1 + (size_t)nteam + (size_t)((nteam + 1) & 1) +
+    auto stage_doubles = [&](int D) {
+        return (size_t)plan->n_staged * D * D + (size_t)D * D + (size_t)nteam * SOS_NW * CG * D + (size_t)nteam * CG * D;
+    };
+    const size_t smem = (stage_doubles(D1) + stage_doubles(D2) + 2 + (size_t)nteam + (size_t)(nteam & 1) +
                          (size_t)nteam * TS) * 8;
     if (smem > 227 * 1024) return ADN_OK;
     const int64_t out_tiles = P.t_out1 - P.t_out0;
@@ -351,13 +414,14 @@ int32_t sosfilt_park_dev(const double* sos, int32_t S, const double* src, int64_
     if (run_tiles > 0x3fffffff || runs * P.ngroups > 0x7fffffff) return ADN_OK;
     P.run_tiles = (int32_t)run_tiles;
     const unsigned grid = (unsigned)(runs * P.ngroups);
-#define ADN_FWD_CASE(SS)                                                                         \
-    case SS: rc = nteam == 4 ? launch_fwd<SS, 4>(*plan, P, R, smem, grid, st)                   \
-                             : launch_fwd<SS, 3>(*plan, P, R, smem, grid, st); break;
+#define ADN_FWD_CASE(A, B)                                                                            \
+    rc = nteam == 4 ? launch_fwd<A, B, 4>(*plan, plan2.get(), P, R, smem, grid, st)                  \
+                    : launch_fwd<A, B, 3>(*plan, plan2.get(), P, R, smem, grid, st)
     switch (S) {
-        ADN_FWD_CASE(1) ADN_FWD_CASE(2) ADN_FWD_CASE(3)
-        default: rc = nteam == 4 ? launch_fwd<4, 4>(*plan, P, R, smem, grid, st)
-                                 : launch_fwd<4, 3>(*plan, P, R, smem, grid, st); break;
+        case 1: ADN_FWD_CASE(1, 0); break;
+        case 2: ADN_FWD_CASE(2, 0); break;
+        case 3: ADN_FWD_CASE(2, 1); break;
+        default: ADN_FWD_CASE(2, 2); break;
     }
 #undef ADN_FWD_CASE
     if (rc == ADN_OK) *handled = true;
