@@ -106,6 +106,8 @@ SIGNATURES = {
     'adn_minmax_f64_dev': (_i32, [_dp, _i64, _i32, _i64, _dp, _dp]),
     'adn_sosfilt_f64_dev': (_i32, [_dp, _i32, _dp, _i64, _i32, _i64, _dp, _i64,
                                    _dp, _dp, _dp]),
+    'adn_sosfilt_minmax_f64_dev': (_i32, [_dp, _i32, _dp, _i64, _i32, _i64, _dp, _i64, _dp, _dp, _i64, _dp, _dp,
+                                          _dp]),
     'adn_envelope_f64_dev': (_i32, [_dp, _i32, _dp, _i64, _i32, _i64, _dp, _i64,
                                     _i32, _dp]),
     'adn_zero_phase_range_f64_dev': (_i32, [_dp, _i32, _dp, _i64, _i32, _i32, _i32, _i32, _i64, _dp, _i64,

@@ -871,6 +871,10 @@ int32_t adn_play_region_f64_m(const double* src, int64_t n, int32_t C, const int
 // device between its producer and its consumers, every result starts on its way down as soon
 // as its kernel has run, and the host waits once at the end.
 
+static int32_t sosfilt_minmax_any_dev(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
+                                      int64_t nbefore, double* dst, int64_t n_dst, const double* zi, double* zf,
+                                      int64_t mm_step, double* mm_raw, double* mm_filt, cudaStream_t st);
+
 static int32_t chain_check(const adn_chain_t* c, int64_t n_src, int32_t C, double rate, int64_t n_filt,
                            bool want_spec, bool want_env, bool want_mm) {
     if (!c || C < 1 || n_src < 1 || !(rate > 0) || c->S < 0 || c->S > ADN_MAX_SECTIONS || c->nbefore < 0 ||
@@ -923,9 +927,14 @@ int32_t adn_chain_f64_dev(const adn_chain_t* c, const double* src, int64_t n_src
     if ((rc = ensure_init())) return rc;
     cudaStream_t st = pick(stream);
     if (n_computed) *n_computed = 0;
-    if (minmax && (rc = minmax_dev(src, n_src, C, c->mm_step, minmax, st))) return rc;
-    if ((rc = sosfilt_dev(c->sos, c->S, src, n_src, C, c->nbefore, filtered, n_filt, nullptr, nullptr, st)))
+    if (minmax) {
+        // the raw rows' min/max in the filter's own pass over them where the kernel allows it
+        if ((rc = sosfilt_minmax_any_dev(c->sos, c->S, src, n_src, C, c->nbefore, filtered, n_filt, nullptr, nullptr,
+                                         c->mm_step, minmax, nullptr, st)))
+            return rc;
+    } else if ((rc = sosfilt_dev(c->sos, c->S, src, n_src, C, c->nbefore, filtered, n_filt, nullptr, nullptr, st))) {
         return rc;
+    }
     return chain_consumers(c, filtered, C, rate, spec, env, n_computed, st);
 }
 
@@ -1130,6 +1139,37 @@ int32_t adn_sosfilt_f64_dev(const double* sos, int32_t S, const double* src, int
     int32_t rc = ensure_init();
     if (rc) return rc;
     return sosfilt_dev(sos, S, src, n_src, C, nbefore, dst, dst ? n_dst : 0, zi, zf, pick(stream));
+}
+
+// filter + the full-trace min/max rows of the raw source rows and / or of the filtered rows, in one
+// pass over the data where the pipelined kernel applies (csrc/sosfwd.cu), else three launches
+static int32_t sosfilt_minmax_any_dev(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
+                                      int64_t nbefore, double* dst, int64_t n_dst, const double* zi, double* zf,
+                                      int64_t mm_step, double* mm_raw, double* mm_filt, cudaStream_t st) {
+    int32_t rc;
+    if (S > 0 && option(ADN_OPT_SCAN_RUNS)) {
+        bool handled = false;
+        if ((rc = sosfilt_minmax_park_dev(sos, S, src, n_src, C, nbefore, dst, n_dst, zi, zf, mm_step, mm_raw,
+                                          mm_filt, &handled, st)))
+            return rc;
+        if (handled) return ADN_OK;
+    }
+    if (mm_raw && (rc = minmax_dev(src, n_src, C, mm_step, mm_raw, st))) return rc;
+    if ((rc = sosfilt_dev(sos, S, src, n_src, C, nbefore, dst, n_dst, zi, zf, st))) return rc;
+    if (mm_filt && (rc = minmax_dev(dst, n_dst, C, mm_step, mm_filt, st))) return rc;
+    return ADN_OK;
+}
+
+int32_t adn_sosfilt_minmax_f64_dev(const double* sos, int32_t S, const double* src, int64_t n_src, int32_t C,
+                                   int64_t nbefore, double* dst, int64_t n_dst, const double* zi, double* zf,
+                                   int64_t mm_step, double* mm_raw, double* mm_filt, void* stream) {
+    if (S < 0 || S > ADN_MAX_SECTIONS || C < 1 || n_src < 1 || nbefore < 0 || n_dst < 1 ||
+        n_dst > n_src - nbefore || mm_step < 1 || (S > 0 && !sos) || !src || !dst)
+        return fail(ADN_ERR_INVALID, "adn_sosfilt_minmax_f64_dev: bad arguments");
+    int32_t rc = ensure_init();
+    if (rc) return rc;
+    return sosfilt_minmax_any_dev(sos, S, src, n_src, C, nbefore, dst, n_dst, zi, zf, mm_step, mm_raw, mm_filt,
+                                  pick(stream));
 }
 
 int32_t adn_envelope_f64_dev(const double* sos, int32_t S, const double* src, int64_t n_src,

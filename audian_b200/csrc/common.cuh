@@ -51,7 +51,7 @@ inline void count_launch(int n = 1) { ctx().launches += n; }
 // stream are ordered by the stream.
 DevBuf& scratch(int slot, cudaStream_t st);
 enum { SCR_SOS_TILES = 0, SCR_SOS_TABLES, SCR_SOS_MISC, SCR_ENV_FWD, SCR_ENV_MISC,
-       SCR_MINMAX_PART, SCR_SPEC_TABLES, SCR_SPEC_WORK, SCR_UNWRAP, SCR_PLAY, SCR_CHAIN_SPEC, SCR_CHAIN_ENV, SCR_COUNT };
+       SCR_MINMAX_PART, SCR_SPEC_TABLES, SCR_SPEC_WORK, SCR_UNWRAP, SCR_PLAY, SCR_CHAIN_SPEC, SCR_CHAIN_ENV, SCR_MM_TILES, SCR_COUNT };
 
 // ---- kernels' host launchers (device pointers, asynchronous) ----
 int32_t minmax_dev(const double* src, int64_t n, int32_t C, int64_t step, double* dst,

@@ -181,22 +181,36 @@ struct SynthInc { uint32_t inc[64]; };
 
 __global__ void __launch_bounds__(256)
 synth_kernel(double* __restrict__ dst, int64_t t0, int64_t n, int32_t C, uint64_t seed,
-             uint32_t period, uint32_t on, const __grid_constant__ SynthInc incs) {
-    int64_t total = n * C;
+             uint32_t period, uint32_t on, int64_t threads, const __grid_constant__ SynthInc incs) {
+    // `threads` (a multiple of C) threads stride over the samples: a thread keeps its channel and
+    // advances by threads / C rows per round, so the row-dependent quantities (noise counter,
+    // carrier phase, position in the gate period) advance by constants -- no division in the loop
+    const int64_t total = n * C;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < total; i += stride) {
-        uint64_t t = (uint64_t)(t0 + i / C);
-        uint32_t c = (uint32_t)(i % C);
-        uint64_t r = splitmix64(seed ^ (t * (uint64_t)C + c));
-        int64_t noise = (int64_t)(int16_t)(uint16_t)(r >> 48);
-        uint32_t phase = (uint32_t)(t * (uint64_t)incs.inc[c & 63]);
-        int64_t q = (int64_t)(phase >> 16);
-        int64_t tri = q < 32768 ? 2 * q - 32767 : 98303 - 2 * q;
-        int64_t g = (t % period) < on ? 1 : 0;
-        int64_t v = ((13107 * tri * g) >> 15) + (noise >> 5);
+    if (i >= threads) return;
+    const int64_t row0 = i / C;
+    const uint32_t c = (uint32_t)(i - row0 * C);
+    const int64_t drow = threads / C;
+    const uint32_t inc = incs.inc[c & 63];
+    uint64_t t = (uint64_t)(t0 + row0);
+    uint64_t counter = t * (uint64_t)C + c;                  // argument of the noise hash
+    uint32_t phase = (uint32_t)(t * (uint64_t)inc);
+    uint32_t tmod = (uint32_t)(t % period);
+    const uint32_t dphase = (uint32_t)((uint64_t)drow * (uint64_t)inc);
+    const uint32_t dmod = (uint32_t)((uint64_t)drow % period);
+    for (; i < total; i += threads) {
+        const uint64_t r = splitmix64(seed ^ counter);
+        const int32_t noise = (int32_t)(int16_t)(uint16_t)(r >> 48);
+        const int32_t q = (int32_t)(phase >> 16);
+        const int32_t tri = q < 32768 ? 2 * q - 32767 : 98303 - 2 * q;
+        int32_t v = tmod < on ? (int32_t)(((int64_t)13107 * tri) >> 15) : 0;
+        v += noise >> 5;
         v = v < -32768 ? -32768 : (v > 32767 ? 32767 : v);
         dst[i] = (double)v * (1.0 / 32768.0);
+        counter += (uint64_t)threads;
+        phase += dphase;
+        tmod += dmod;
+        if (tmod >= period) tmod -= period;
     }
 }
 
@@ -213,8 +227,10 @@ int32_t synth_dev(double* dst, int64_t t0, int64_t n, int32_t C, double rate, ui
     int64_t blocks = (total + 255) / 256;
     int64_t cap = (int64_t)ctx().sm_count * 16;
     if (blocks > cap) blocks = cap;
+    int64_t threads = blocks * 256 / C * C;                  // a multiple of C
+    if (threads < C) { threads = C; blocks = (C + 255) / 256; }
     synth_kernel<<<(unsigned)blocks, 256, 0, st>>>(dst, t0, n, C, seed, (uint32_t)period,
-                                                   (uint32_t)on, incs);
+                                                   (uint32_t)on, threads, incs);
     count_launch();
     ADN_CK(cudaGetLastError());
     return ADN_OK;

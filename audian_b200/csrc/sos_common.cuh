@@ -349,6 +349,10 @@ int64_t zp_launches();
 int32_t sosfilt_park_dev(const double* sos, int32_t S, const double* src, int64_t n, int32_t C,
                          int64_t out_skip, double* dst, int64_t n_dst, const double* s0, double* zf,
                          bool* handled, cudaStream_t st);
+int32_t sosfilt_minmax_park_dev(const double* sos, int32_t S, const double* src, int64_t n, int32_t C,
+                                int64_t out_skip, double* dst, int64_t n_dst, const double* s0, double* zf,
+                                int64_t mm_step, double* mm_raw, double* mm_filt, bool* handled,
+                                cudaStream_t st);
 int64_t fwd_park_launches();
 
 }  // namespace adn

@@ -38,7 +38,121 @@ struct FwdArgs {
     int32_t pre;                       // run-in tiles
     int32_t run_tiles;
     int32_t bulk_ok;
+    // full-trace min/max of the same pass (compresseddata.py:49-52): per-tile partial (min, max)
+    // of the raw rows / of the filtered rows, [tile][C][2]; folded per segment by mm_fold_kernel
+    double* mm_raw;
+    double* mm_filt;
 };
+
+// ---- min / max with numpy's ordered rule (axis 0 of a 2-D array): a NaN wins and stays (the
+// latest one), equal values resolve to the later row (signed zeros).  `a` comes before `b`.
+__device__ __forceinline__ double mm_min2(double a, double b) {
+    if (b != b) return b;
+    if (a != a) return a;
+    return a < b ? a : b;
+}
+__device__ __forceinline__ double mm_max2(double a, double b) {
+    if (b != b) return b;
+    if (a != a) return a;
+    return a > b ? a : b;
+}
+
+// (min, max) of the nv <= SOS_L samples a thread holds, in time order
+__device__ __forceinline__ void mm_thread(const double (&x)[SOS_L], int nv, double& mn, double& mx) {
+    if (nv == SOS_L) {
+        // plain compare-and-select (later wins ties); NaNs and infinities are spotted on the
+        // exponent bits and sent through the exact rule
+        double m = x[0], M = x[0];
+        int top = __double2hiint(x[0]) & 0x7fffffff;
+#pragma unroll
+        for (int i = 1; i < SOS_L; ++i) {
+            m = m < x[i] ? m : x[i];
+            M = M > x[i] ? M : x[i];
+            top = max(top, __double2hiint(x[i]) & 0x7fffffff);
+        }
+        if (top < 0x7ff00000) { mn = m; mx = M; return; }
+    }
+    double tmp[SOS_L];
+#pragma unroll
+    for (int i = 0; i < SOS_L; ++i) tmp[i] = x[i];
+    double m = tmp[0], M = tmp[0];
+#pragma unroll 1
+    for (int i = 1; i < nv; ++i) { m = mm_min2(m, tmp[i]); M = mm_max2(M, tmp[i]); }
+    mn = m; mx = M;
+}
+
+struct FwdLane;
+// fold the threads of a team over time (sub-chunks in order) and write the tile's partial
+__device__ __forceinline__ void mm_tile(double mn, double mx, bool valid, int lane, int warp, int gl, int cw,
+                                        int CG, int GW, int team, bool chan_ok, double* wmm, double* out) {
+    // inside the warp: ordered tree over gl (lanes CG apart); a lane without valid rows passes
+    // its later neighbour's value on unchanged
+    for (int off = CG; off < 32; off <<= 1) {
+        const double bn = __shfl_down_sync(0xffffffffu, mn, off);
+        const double bx = __shfl_down_sync(0xffffffffu, mx, off);
+        const int bv = __shfl_down_sync(0xffffffffu, (int)valid, off);
+        if (lane + off < 32 && bv) {
+            mn = valid ? mm_min2(mn, bn) : bn;
+            mx = valid ? mm_max2(mx, bx) : bx;
+            valid = true;
+        }
+    }
+    if (gl == 0) {
+        wmm[(warp * CG + cw) * 3 + 0] = mn;
+        wmm[(warp * CG + cw) * 3 + 1] = mx;
+        wmm[(warp * CG + cw) * 3 + 2] = valid ? 1.0 : 0.0;
+    }
+    zp_team_bar(team);
+    if (warp == 0 && gl == 0 && chan_ok) {
+        double m = 0.0, M = 0.0;
+        bool v = false;
+        for (int q = 0; q < SOS_NW; ++q) {
+            if (wmm[(q * CG + cw) * 3 + 2] != 0.0) {
+                const double bn = wmm[(q * CG + cw) * 3 + 0], bx = wmm[(q * CG + cw) * 3 + 1];
+                m = v ? mm_min2(m, bn) : bn;
+                M = v ? mm_max2(M, bx) : bx;
+                v = true;
+            }
+        }
+        out[0] = m;
+        out[1] = M;
+    }
+    zp_team_bar(team);                                       // wmm is free again
+}
+
+// rows 2 j / 2 j + 1 of dst = fold of the partials of the tiles of segment j, in time order
+__global__ void __launch_bounds__(32)
+mm_fold_kernel(const double* __restrict__ part, int64_t ntiles, int32_t C, int64_t tiles_per_seg,
+               double* __restrict__ dst) {
+    const int64_t seg = blockIdx.x / C;
+    const int c = (int)(blockIdx.x % C);
+    const int lane = threadIdx.x;
+    const int64_t t0 = seg * tiles_per_seg, t1 = min(ntiles, t0 + tiles_per_seg);
+    const int64_t per = (t1 - t0 + 31) / 32;
+    const int64_t a = t0 + lane * per, b = min(t1, a + per);
+    double m = 0.0, M = 0.0;
+    bool v = false;
+    for (int64_t t = a; t < b; ++t) {
+        const double bn = part[(t * C + c) * 2], bx = part[(t * C + c) * 2 + 1];
+        m = v ? mm_min2(m, bn) : bn;
+        M = v ? mm_max2(M, bx) : bx;
+        v = true;
+    }
+    for (int off = 1; off < 32; off <<= 1) {
+        const double bn = __shfl_down_sync(0xffffffffu, m, off);
+        const double bx = __shfl_down_sync(0xffffffffu, M, off);
+        const int bv = __shfl_down_sync(0xffffffffu, (int)v, off);
+        if (lane + off < 32 && bv) {
+            m = v ? mm_min2(m, bn) : bn;
+            M = v ? mm_max2(M, bx) : bx;
+            v = true;
+        }
+    }
+    if (lane == 0) {
+        dst[(2 * seg) * C + c] = m;
+        dst[(2 * seg + 1) * C + c] = M;
+    }
+}
 
 // shared-memory state of one sub-cascade (stage) of the kernel
 template <int S>
@@ -200,6 +314,7 @@ sos_fwd_park_kernel(const __grid_constant__ SosK<S1> K1, const __grid_constant__
     double* pt2_s = p;   p += DD2;
     double* wagg2 = p + (size_t)team * SOS_NW * CG * D2;  p += (size_t)NTEAM * SOS_NW * CG * D2;
     double* sin2_s = p;  p += (size_t)NTEAM * CG * D2;
+    double* wmm = p + (size_t)team * SOS_NW * CG * 3;  p += (size_t)NTEAM * SOS_NW * CG * 3 + ((NTEAM * SOS_NW * CG * 3) & 1);
     volatile long long* sf_flag = reinterpret_cast<volatile long long*>(p);        // [2]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(const_cast<long long*>(sf_flag) + 2);      // [NTEAM]
     double* tiles = reinterpret_cast<double*>(mbar + NTEAM + (NTEAM & 1));          // [NTEAM][TS]
@@ -295,9 +410,23 @@ sos_fwd_park_kernel(const __grid_constant__ SosK<S1> K1, const __grid_constant__
         const int64_t lastrow = P.n - 1;
         const bool capture = P.zf != nullptr && lastrow >= e0 && lastrow < e0 + SOS_L && t >= a;
         double* zf_c = capture ? P.zf + (size_t)(c0 + (chan_ok ? cw : 0)) * DT : nullptr;
+        // rows of this thread that exist (the last tile is zero-filled behind the recording)
+        const int nv = (int)max((int64_t)0, min((int64_t)SOS_L, P.n - e0));
+        if (P.mm_raw != nullptr && t >= a) {
+            double mn = 0.0, mx = 0.0;
+            if (nv > 0) mm_thread(x, nv, mn, mx);
+            mm_tile(mn, mx, nv > 0, lane, warp, gl, cw, CG, GW, team, chan_ok, wmm,
+                    P.mm_raw + ((size_t)t * C + c0 + (chan_ok ? cw : 0)) * 2);
+        }
         fwd_stage<S1>(K1, st1, L, x, t, zf_c, (int)(lastrow - e0));
         if (S2 > 0)
             fwd_stage<(S2 > 0 ? S2 : 1)>(K2, st2, L, x, t, capture ? zf_c + D1 : nullptr, (int)(lastrow - e0));
+        if (P.mm_filt != nullptr && t >= a) {
+            double mn = 0.0, mx = 0.0;
+            if (nv > 0) mm_thread(x, nv, mn, mx);
+            mm_tile(mn, mx, nv > 0, lane, warp, gl, cw, CG, GW, team, chan_ok, wmm,
+                    P.mm_filt + ((size_t)t * C + c0 + (chan_ok ? cw : 0)) * 2);
+        }
         if (t >= a && chan_ok && P.dst != nullptr) {
             const bool fast = t * T >= P.out_skip && (t + 1) * (int64_t)T <= P.out_skip + P.n_dst;
             double* q = P.dst + (e0 - P.out_skip) * C + c0 + cw;
@@ -354,7 +483,19 @@ int64_t fwd_park_launches() { return g_fwd_launches.load(); }
 int32_t sosfilt_park_dev(const double* sos, int32_t S, const double* src, int64_t n, int32_t C,
                          int64_t out_skip, double* dst, int64_t n_dst, const double* s0, double* zf,
                          bool* handled, cudaStream_t st) {
+    return sosfilt_minmax_park_dev(sos, S, src, n, C, out_skip, dst, n_dst, s0, zf, 0, nullptr, nullptr,
+                                   handled, st);
+}
+
+// the same with the full-trace min/max rows of the raw source rows (mm_raw, 2 ceil(n / step) x C)
+// and / or of the filtered rows (mm_filt) computed in the same pass: needs out_skip == 0,
+// n_dst == n, whole tiles per segment (step a multiple of the tile's rows) and C >= 2
+int32_t sosfilt_minmax_park_dev(const double* sos, int32_t S, const double* src, int64_t n, int32_t C,
+                                int64_t out_skip, double* dst, int64_t n_dst, const double* s0, double* zf,
+                                int64_t mm_step, double* mm_raw, double* mm_filt, bool* handled,
+                                cudaStream_t st) {
     *handled = false;
+    const bool want_mm = mm_step > 0 && (mm_raw || mm_filt);
     // measured on B200 (80 s of 8 ch x 48 kHz): one or two sections 96 / 90 us against 97 / 103 us of
     // the run kernel (64 ch: 739 against 779 us); three and four sections run as two chained
     // sub-cascades of at most two sections (all eight states at once are register bound: 187 us)
@@ -378,6 +519,14 @@ int32_t sosfilt_park_dev(const double* sos, int32_t S, const double* src, int64_
     P.T = (SOS_NT / CG) * SOS_L;
     P.ntt = (n + P.T - 1) / P.T;
     P.t_out0 = out_skip / P.T;
+    if (want_mm) {
+        if (out_skip != 0 || n_dst != n || mm_step % P.T != 0 || C < 2) return ADN_OK;
+        DevBuf& pb = scratch(SCR_MM_TILES, st);
+        const size_t one = (size_t)P.ntt * C * 2 * 8;
+        if ((rc = pb.reserve(2 * one))) return rc;
+        P.mm_raw = mm_raw ? pb.as<double>() : nullptr;
+        P.mm_filt = mm_filt ? pb.as<double>() + (size_t)P.ntt * C * 2 : nullptr;
+    }
     // the tile of the last source row always belongs to the walk when the final state is wanted
     P.t_out1 = zf ? P.ntt : (out_skip + n_dst - 1) / P.T + 1;
     // the second sub-cascade forgets what the first one feeds it while that one still converges
@@ -400,8 +549,9 @@ int32_t sosfilt_park_dev(const double* sos, int32_t S, const double* src, int64_
     auto stage_doubles = [&](int D) {
         return (size_t)plan->n_staged * D * D + (size_t)D * D + (size_t)nteam * SOS_NW * CG * D + (size_t)nteam * CG * D;
     };
-    const size_t smem = (stage_doubles(D1) + stage_doubles(D2) + 2 + (size_t)nteam + (size_t)(nteam & 1) +
-                         (size_t)nteam * TS) * 8;
+    const size_t wmm_d = (size_t)nteam * SOS_NW * CG * 3;
+    const size_t smem = (stage_doubles(D1) + stage_doubles(D2) + wmm_d + (wmm_d & 1) + 2 + (size_t)nteam +
+                         (size_t)(nteam & 1) + (size_t)nteam * TS) * 8;
     if (smem > 227 * 1024) return ADN_OK;
     const int64_t out_tiles = P.t_out1 - P.t_out0;
     int64_t runs = (int64_t)ctx().sm_count / P.ngroups;
@@ -424,8 +574,17 @@ int32_t sosfilt_park_dev(const double* sos, int32_t S, const double* src, int64_
         default: ADN_FWD_CASE(2, 2); break;
     }
 #undef ADN_FWD_CASE
-    if (rc == ADN_OK) *handled = true;
-    return rc;
+    if (rc) return rc;
+    if (want_mm) {
+        const int64_t nseg = (n + mm_step - 1) / mm_step;
+        const int64_t tps = mm_step / P.T;
+        if (P.mm_raw) mm_fold_kernel<<<(unsigned)(nseg * C), 32, 0, st>>>(P.mm_raw, P.ntt, C, tps, mm_raw);
+        if (P.mm_filt) mm_fold_kernel<<<(unsigned)(nseg * C), 32, 0, st>>>(P.mm_filt, P.ntt, C, tps, mm_filt);
+        count_launch((P.mm_raw ? 1 : 0) + (P.mm_filt ? 1 : 0));
+        ADN_CK(cudaGetLastError());
+    }
+    *handled = true;
+    return ADN_OK;
 }
 
 }  // namespace adn

@@ -57,6 +57,9 @@ class CudaOps(object):
     def spectrogram(self, src, rate, nfft, hop, n_dst, out_db=False, out=None):
         return spectrogram(src, rate, nfft, hop, n_dst, out_db, out)
 
+    def sosfilt_minmax(self, sos, src, step, zi=None, want_raw=True, want_filt=True, out=None):
+        return sosfilt_minmax(sos, src, step, zi, want_raw, want_filt, out)
+
     def envelope(self, sos, src, nbefore=0, clamp_negative=True):
         return envelope(sos, src, nbefore, clamp_negative)
 
@@ -116,6 +119,28 @@ def sosfilt(sos, src, nbefore=0, zi=None, want_zf=False, out=None, state_only=Fa
     if state_only:
         return zf
     return (out, zf) if want_zf else out
+
+
+def sosfilt_minmax(sos, src, step, zi=None, want_raw=True, want_filt=True, out=None):
+    """sosfilt of src (state zi carried) plus the full-trace min/max rows of the raw and of the
+    filtered rows in the same pass (compresseddata.py:49-52; BASELINE config 4).
+    Returns (filtered, zf, rows_raw or None, rows_filt or None)."""
+    torch = _torch()
+    _check_trace(src, 'src')
+    sos, S = _lib.sos_array(sos)
+    n, ch = src.shape
+    nseg = (n + step - 1)//step
+    if out is None:
+        out = torch.empty((n, ch), dtype=src.dtype, device=src.device)
+    zf = torch.empty((ch, S, 2), dtype=src.dtype, device=src.device) if S > 0 else None
+    rr = torch.empty((2*nseg, ch), dtype=src.dtype, device=src.device) if want_raw else None
+    rf = torch.empty((2*nseg, ch), dtype=src.dtype, device=src.device) if want_filt else None
+    if zi is not None:
+        _check_trace(zi, 'zi')
+    _lib.check(_lib.lib().adn_sosfilt_minmax_f64_dev(
+        None if sos is None else sos.ctypes.data, S, _p(src), n, ch, 0, _p(out), n, _p(zi), _p(zf),
+        int(step), _p(rr), _p(rf), _stream()))
+    return out, zf, rr, rf
 
 
 def envelope(sos, src, nbefore=0, clamp_negative=True, out=None):

@@ -123,6 +123,43 @@ class WholeFile(object):
             y, z = self.ops.sosfilt(sos_a, x, 0, z, want_zf=True)
             sink(t0, y)
 
+    def fulltrace_filter_minmax(self, sos, step, sink=None):
+        """BASELINE config 4 with the reductions fused into the filter's pass over the data
+        (adn_sosfilt_minmax_f64_dev): returns (rows of the raw recording, rows of the filtered
+        recording), each (2*ceil(frames/step), C) gathered to rank 0 (None elsewhere);
+        sink(t0, y), if given, also sees every filtered chunk."""
+        import torch
+        bounds, (lo, hi) = self._shard(step)
+        chunk = max(step, self.chunk_frames//step*step)
+        sos_a, S = _lib.sos_array(sos)
+        saved = self.chunk_frames
+        self.chunk_frames = chunk
+        try:
+            z = self._incoming_state(sos_a, S, bounds) if S > 0 else None
+            raw, filt = [], []
+            for t0 in range(lo, hi, chunk):
+                n = min(chunk, hi - t0)
+                x = self.source(t0, n)
+                y, z, rr, rf = self.ops.sosfilt_minmax(sos_a, x, step, z)
+                raw.append(rr)
+                filt.append(rf)
+                if sink is not None:
+                    sink(t0, y)
+        finally:
+            self.chunk_frames = saved
+        counts = [2*((h - l + step - 1)//step) for l, h in bounds]
+        out = []
+        for rows in (raw, filt):
+            local = torch.cat(rows, dim=0) if rows else self.ops.empty((0, self.channels))
+            if self.world == 1:
+                out.append(local)
+                continue
+            padded = self.ops.zeros((max(counts), self.channels))
+            padded[:local.shape[0]] = local
+            g = self._gatherer(local)._gather(padded)
+            out.append(torch.cat([g[i, :c] for i, c in enumerate(counts)], dim=0) if self.rank == 0 else None)
+        return out[0], out[1]
+
     def fulltrace_and_filter(self, sos, step, sink):
         """BASELINE config 4 in one pass over the data: the full-trace min/max rows of
         the raw recording (gathered to rank 0) and the filtered recording (to `sink`)."""

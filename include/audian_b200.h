@@ -303,6 +303,18 @@ int32_t adn_sosfilt_f64_dev(const double* sos, int32_t S,
                             const double* src, int64_t n_src, int32_t C,
                             int64_t nbefore, double* dst, int64_t n_dst,
                             const double* zi, double* zf, void* stream);
+/* adn_sosfilt_f64_dev plus the full-trace min/max rows (compresseddata.py:49-52) of the raw
+ * source rows (mm_raw, 2*ceil(n_src/mm_step) x C, or NULL) and / or of the filtered rows
+ * (mm_filt, 2*ceil(n_dst/mm_step) x C, or NULL): BASELINE config 4 in ONE pass over the data.
+ * Fused into the filter kernel when nbefore == 0, n_dst == n_src, C >= 2 and mm_step is a
+ * multiple of the kernel's tile (4096 / min(8, C') rows, C' = C rounded up to a power of two);
+ * otherwise the separate kernels run.  Results are those of adn_minmax_f64 either way. */
+int32_t adn_sosfilt_minmax_f64_dev(const double* sos, int32_t S,
+                                   const double* src, int64_t n_src, int32_t C,
+                                   int64_t nbefore, double* dst, int64_t n_dst,
+                                   const double* zi, double* zf,
+                                   int64_t mm_step, double* mm_raw, double* mm_filt,
+                                   void* stream);
 int32_t adn_envelope_f64_dev(const double* sos, int32_t S,
                              const double* src, int64_t n_src, int32_t C,
                              int64_t nbefore, double* dst, int64_t n_dst,

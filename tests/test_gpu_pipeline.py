@@ -300,3 +300,51 @@ def test_fused_recompute_equals_the_walk(monkeypatch):
     assert np.array_equal(s1.buffer, s2.buffer)
     assert np.max(np.abs(e1.buffer - e2.buffer)) <= 1e-13
     assert s1.spec_rect == s2.spec_rect and np.array_equal(s1.frequencies, s2.frequencies)
+
+
+@pytest.mark.parametrize('C,order,step_tiles,n', [(4, 4, 3, 3000000), (8, 2, 5, 1000003), (2, 2, 1, 2500000),
+                                                  (3, 2, 2, 1500000), (16, 4, 4, 1200000)])
+def test_filter_with_fused_minmax(C, order, step_tiles, n):
+    """adn_sosfilt_minmax_f64_dev: the filter and the full-trace min/max rows of the raw and of the
+    filtered rows in one pass (BASELINE config 4; compresseddata.py:49-52) == the separate entry
+    points, bit for bit, including NaN / inf / signed-zero rows and carried filter state."""
+    import torch
+    from scipy.signal import butter
+    from audian_b200 import device
+    fs = 96000.
+    x = synth(2, n, C, fs, seed=5 + C)
+    x[1000, 0] = np.nan
+    x[1001, 0] = np.inf
+    x[70000:70010, 1] = 0.0
+    x[70003, 1] = -0.0
+    x[n - 1, C - 1] = -np.inf
+    sos = butter(order, (1000., 15000.), 'bandpass', fs=fs, output='sos')
+    cg = 1
+    while cg < C and cg < 8:
+        cg *= 2
+    T = (128//cg)*32
+    step = step_tiles*T
+    xd = torch.from_numpy(x).cuda()
+    zi = torch.from_numpy(np.random.default_rng(1).standard_normal((C, sos.shape[0], 2))*1e-3).cuda()
+    launches = _lib.launch_count()
+    y, zf, rr, rf = device.sosfilt_minmax(sos, xd, step, zi)
+    fused = _lib.launch_count() - launches
+    assert fused <= 3, 'one filter launch plus the two folds (recordings long enough to fill the device)'
+    yr, zfr = device.sosfilt(sos, xd, 0, zi, want_zf=True)
+    ok = ~np.isnan(yr.cpu().numpy())
+    assert np.array_equal(y.cpu().numpy()[ok], yr.cpu().numpy()[ok])
+    assert np.array_equal(zf.cpu().numpy(), zfr.cpu().numpy(), equal_nan=True)
+    ref_raw = orc.minmax_rows(x, step)
+    got = rr.cpu().numpy()
+    rn = np.isnan(ref_raw)
+    assert np.array_equal(np.isnan(got), rn) and np.array_equal(got.view(np.uint64)[~rn], ref_raw.view(np.uint64)[~rn])
+    ref_f = device.minmax(yr, step).cpu().numpy()
+    gf = rf.cpu().numpy()
+    fn = np.isnan(ref_f)
+    assert np.array_equal(np.isnan(gf), fn) and np.array_equal(gf.view(np.uint64)[~fn], ref_f.view(np.uint64)[~fn])
+    # a step that is no multiple of the tile: the separate kernels, same answers
+    y2, zf2, rr2, rf2 = device.sosfilt_minmax(sos, xd, step + 7, zi)
+    ref2 = orc.minmax_rows(x, step + 7)
+    g2 = rr2.cpu().numpy()
+    r2n = np.isnan(ref2)
+    assert np.array_equal(g2.view(np.uint64)[~r2n], ref2.view(np.uint64)[~r2n])

@@ -92,16 +92,16 @@ def run_config(config, rank=0, world=1, dist=None, seconds=None, budget_s=None, 
                 dist.all_reduce(acc)
             return acc/max(nf, 1)
         step = max(1, frames//cfg['max_pixel'])
-        frows = []
         first = {}
 
         def sink(t0, y):
-            frows.append(device.minmax(y, step) if t0 % step == 0 else None)
             if 't0' not in first:
                 first['t0'] = t0
                 keep['filtered'] = (t0, y[:200000].clone())
-        rows = wf.fulltrace_and_filter(sos, step, sink)
+        # min/max of the raw rows and of the filtered rows in the filter's own pass over the chunk
+        rows, frows = wf.fulltrace_filter_minmax(sos, step, sink)
         keep['step'] = step
+        keep['filtered_rows'] = frows
         return rows
 
     # ---- probe: two chunks per rank (plans, scratch, allocator pools) -> rate estimate
@@ -182,9 +182,17 @@ def run_config(config, rank=0, world=1, dist=None, seconds=None, budget_s=None, 
                 ok_rows = ok_rows and bool(np.array_equal(got[2*j:2*j + 2].view(np.uint64),
                                                           ref.view(np.uint64)))
             check['fulltrace_rows_checked'] = len(segs)
+            # the rows of the filtered recording against the oracle's filter of the first segment
+            frows = keep['filtered_rows'].cpu().numpy()
+            m1 = min(frames, step)
+            yr = np.empty((m1, C))
+            orc.filter_process(sos, synth(0, m1, C, rate, seed), yr, 0)
+            rref = orc.minmax_rows(yr, step)
+            check['filtered_rows_max_abs_err'] = float(np.max(np.abs(frows[:2] - rref[:2])))
         check['fulltrace_rows_bit_exact'] = allmax(0.0 if ok_rows else 1.0) == 0.0
         check['tolerance'] = 'min/max bit-exact; filter max abs err 1e-6 of full scale'
-        check['ok'] = check['fulltrace_rows_bit_exact'] and check['seam_filter_max_abs_err'] <= 1e-6
+        check['ok'] = bool(check['fulltrace_rows_bit_exact'] and check['seam_filter_max_abs_err'] <= 1e-6 and
+                           check.get('filtered_rows_max_abs_err', 0.0) <= 1e-6)
     samples = frames*C
     bps = cfg['bytes_per_sample']
     out = {'config': config, 'workload': cfg['what'], 'channels': C, 'rate_hz': rate,
