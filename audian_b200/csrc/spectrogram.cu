@@ -589,6 +589,20 @@ constexpr int SR_MAXNT = 128;
 #ifndef SR_WIN_SMEM
 #define SR_WIN_SMEM (SR_WIN_CALC ? 0 : 1)
 #endif
+// SR_WIN_HALF: only the first half of the window is kept in shared memory: the periodic Hann
+// window has w[j + N/2] = 1 - w[j], so the second half of a frame is x - x w[j] (one DFMA in the
+// place of the DMUL).  Half the window loads of a frame and 4 KB less shared memory per block; the
+// two forms of w[j + N/2] differ by less than 2^-53 absolute.
+#ifndef SR_WIN_HALF
+#define SR_WIN_HALF 1
+#endif
+// SR_PAIRMAP: second pass with the two lanes of a row next to each other (T == 32): their identical
+// 128-bit reads of the exchange buffer are served as one access.  Measured on B200 (8 ch, nfft
+// 1024 / hop 512; ncu): shared-memory load wavefronts per frame 231 -> 164 (with SR_WIN_HALF: 263
+// -> 164), 164.9 -> 163.8 us -- the kernel is not bound by the shared-memory pipe.
+#ifndef SR_PAIRMAP
+#define SR_PAIRMAP 1
+#endif
 constexpr int SR_PF = 8;            // 16-byte vectors in flight per thread and step
 // SR_ASYNC: the rows of the next step go straight into the ring with 8-byte cp.async, issued as
 // soon as every warp holds its frame of this step in registers (one barrier after the frame
@@ -654,7 +668,7 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
 
     double* xs = sbuf;                                               // [W][RS]
     double* wins = sbuf + (size_t)W * RS;                            // [N] (if SR_WIN_SMEM)
-    constexpr int NWIN = SR_WIN_SMEM ? N : 0;
+    constexpr int NWIN = SR_WIN_SMEM ? (SR_WIN_HALF ? N / 2 : N) : 0;
     constexpr int NTWS = T == 32 ? 0 : M / 2 + 2;                    // T == 32 builds them in registers
     double2* tws = reinterpret_cast<double2*>(wins + NWIN);          // [NTWS]
     double2* wb = tws + NTWS + (size_t)warp * SRCfg<LOGN>::WB;
@@ -698,7 +712,7 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
 
     stage_direct(0, 0, span0, 0);
     if (SR_WIN_SMEM)
-        for (int i = tid; i < N; i += NT) wins[i] = __ldg(P.win + i);
+        for (int i = tid; i < NWIN; i += NT) wins[i] = __ldg(P.win + i);
     if (NTWS > 0)
         for (int i = tid; i <= M / 2; i += NT) tws[i] = __ldg(P.twS + i);
     __syncthreads();
@@ -708,7 +722,11 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
     // W_M^(t k1), k1 = 1, 2, 4, 8 from the table; the other powers are products of two of them
     const double2 tw1 = __ldg(P.twA + 1 * T + t), tw2 = __ldg(P.twA + 2 * T + t);
     const double2 tw4 = __ldg(P.twA + 4 * T + t), tw8 = __ldg(P.twA + 8 * T + t);
+#if SR_PAIRMAP
+    const double2 twl = __ldg(P.twS + ((lane >> 1) + 16 * (lane & 1)));
+#else
     const double2 twl = __ldg(P.twS + lane);             // T == 32: W_N^lane of the split step
+#endif
     // SR_WIN_CALC: (cos, sin)(2 pi j / N) of this lane's two window positions j = 2 t, 2 t + 1
     // (from the table of W_N^k = exp(-2 pi i k / N) of the split step: k = 2 t + 1 < M / 8)
     double2 wcs0 = __ldg(P.twS + 2 * t), wcs1 = __ldg(P.twS + 2 * t + 1);
@@ -833,6 +851,12 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
                     const double hs = (p < 8 ? -0.5 : 0.5) * w32c(2 * (p & 7), 1);
                     w.x = fma(-hc, wcs0.x, fma(hs, wcs0.y, 0.5));
                     w.y = fma(-hc, wcs1.x, fma(hs, wcs1.y, 0.5));
+                } else if (SR_WIN_SMEM && SR_WIN_HALF) {
+                    // 2 (T p + t) < N / 2 for p < 8; the second half from w[j + N/2] = 1 - w[j]
+                    if (p >= 8) continue;
+                    w = *reinterpret_cast<const double2*>(wins + 2 * (T * p + t));
+                    a[p + 8].x = fma(-a[p + 8].x, w.x, a[p + 8].x);
+                    a[p + 8].y = fma(-a[p + 8].y, w.y, a[p + 8].y);
                 } else {
                     w = SR_WIN_SMEM ? *reinterpret_cast<const double2*>(wins + 2 * (T * p + t))
                                     : __ldg(reinterpret_cast<const double2*>(P.win) + (T * p + t));
@@ -875,7 +899,15 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
             if constexpr (T == 32) {
                 // lane (k1, tp): outputs k2 = 2 kk + tp of the 32-point DFT of row k1, i.e.
                 // Z[lane + 32 kk], kk < 16 (first radix-2 step done here, decimation in frequency)
+#if SR_PAIRMAP
+                // the two lanes of a row are neighbours (same quarter warp: their identical 16-byte
+                // reads are one access); kl = the lane's place in frequency order
+                const int k1 = lane >> 1, tp = lane & 1;
+                const int kl = k1 + 16 * tp;
+#else
                 const int k1 = lane & 15, tp = lane >> 4;
+                const int kl = lane;
+#endif
                 const double sgn = tp ? -1.0 : 1.0;
                 double* wre = reinterpret_cast<double*>(wbf);
                 const double2* row = reinterpret_cast<const double2*>(wre + k1 * 34);
@@ -904,24 +936,29 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
                 // split step in registers: Z[M - k] of k = lane + 32 kk sits in lane 32 - lane,
                 // register 15 - kk (lane 0: its own register 16 - kk), so a lane handles the
                 // pairs of its registers kk < 8 and fetches the partner by shuffle
+#if SR_PAIRMAP
+                const int kp = (32 - kl) & 31;
+                const int partner = 2 * (kp & 15) + (kp >> 4);
+#else
                 const int partner = (32 - lane) & 31;
-                double* outk = out + lane;
-                double* outm = out + M - lane;
+#endif
+                double* outk = out + kl;
+                double* outm = out + M - kl;
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
                     double2 zk = b[kk], zm;
                     zm.x = __shfl_sync(0xffffffffu, b[15 - kk].x, partner);
                     zm.y = __shfl_sync(0xffffffffu, b[15 - kk].y, partner);
-                    if (kk > 0 && lane == 0) zm = b[16 - kk];
+                    if (kk > 0 && kl == 0) zm = b[16 - kk];
                     double2 tw = kk == 0 ? twl : cmul(twl, make_double2(w32c(kk, 0), w32c(kk, 1)));
                     double e_r = zk.x + zm.x, e_i = zk.y - zm.y;          // Zk + conj(Zm)
                     double o_r = zk.y + zm.y, o_i = zm.x - zk.x;          // -i (Zk - conj(Zm))
                     double t_r = o_r * tw.x - o_i * tw.y, t_i = o_r * tw.y + o_i * tw.x;
                     double pr = e_r + t_r, pi = e_i + t_i, qr = e_r - t_r, qi = e_i - t_i;
                     // p = 2 X[k]; the window's spectrum at bin 1 is -N/4
-                    if (kk == 0) pr += lane == 1 ? mN2 : 0.0;
+                    if (kk == 0) pr += kl == 1 ? mN2 : 0.0;
                     double pk = (pr * pr + pi * pi) * sc, pm = (qr * qr + qi * qi) * sc;
-                    if (kk == 0 && lane == 0) {                           // bins 0 and M from Z[0]
+                    if (kk == 0 && kl == 0) {                             // bins 0 and M from Z[0]
                         double x0 = zk.x + zk.y - mN2, xM = zk.x - zk.y;
                         pk = x0 * x0 * P.scale;
                         pm = xM * xM * P.scale;
@@ -932,7 +969,7 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
                         __stcs(outm - 32 * kk, pm);
                     }
                 }
-                if (lane == 0 && live) {                                  // k = M/2 pairs with itself
+                if (kl == 0 && live) {                                    // k = M/2 pairs with itself
                     double2 zk = b[8];
                     double2 tw = make_double2(w32c(8, 0), w32c(8, 1));    // W_N^(M/2) = -i
                     double e_r = zk.x + zk.x, o_r = zk.y + zk.y;
@@ -1072,7 +1109,7 @@ int32_t launch_ring_kernel(SpecRArgs& P, int64_t nf, cudaStream_t st) {
         P.RC = Cf::N;
         while (P.RC < span0) P.RC <<= 1;                   // power of two >= the rows of a step
         P.RS = P.RC + 4;                                   // == 4 mod 8
-        smem = ((size_t)P.CB * P.RS + (SR_WIN_SMEM ? Cf::N : 0)) * 8 +
+        smem = ((size_t)P.CB * P.RS + (SR_WIN_SMEM ? (SR_WIN_HALF ? Cf::N / 2 : Cf::N) : 0)) * 8 +
                ((Cf::T == 32 ? 0 : (size_t)Cf::M / 2 + 2) + (size_t)NW * SRCfg<LOGN>::WB) * 16;
         if (smem <= limit || P.FSTEP == 1) break;
     }

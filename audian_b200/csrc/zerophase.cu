@@ -48,6 +48,7 @@ struct ZpArgs {
     int32_t clamp;
     int32_t JJ, JO;                    // look-ahead tiles of the forward state; run-out tiles
     int32_t run_tiles;
+    int32_t short0;                    // the first run of the pipelined kernel is this many tiles shorter
     int32_t pf;                        // bulk L2 prefetch of the next look-ahead tile
     int32_t bulk_ok;                   // tiles of full, contiguous channel groups through the TMA unit
     ZiK zi;
@@ -116,7 +117,7 @@ sos_zp_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ ZpArgs 
     auto slot_of = [&](int64_t t) { return (int)((t + 64 * (int64_t)NS) % NS); };
 
     auto prefetch = [&](int64_t t) {
-        if (!P.pf || tid != 0 || grp != 0 || t < 0 || t >= P.ntt) return;
+        if (!(P.pf & 1) || tid != 0 || grp != 0 || t < 0 || t >= P.ntt) return;
         int64_t p0 = t * T - P.edgeL, p1 = p0 + T;
         if (p0 < 0) p0 = 0;
         if (p1 > P.nx) p1 = P.nx;
@@ -412,6 +413,19 @@ sos_zp_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ ZpArgs 
 // the run and the teams overlap freely.
 constexpr int ZP_NTEAM_MAX = 4;
 
+#ifdef ADN_ZP_TIMING
+// development builds only (tools/build_alt.sh ... -DADN_ZP_TIMING): per block start, end of every
+// team and the SM it ran on, read back by adn_debug_zp_times
+__device__ unsigned long long zp_times[2 * 1024 * 8];     // [launch parity][block][8]
+__device__ unsigned int zp_count;
+__device__ unsigned long long zp_tile_times[4 * 64];      // runs 0..3: end of the main visit of tile a + i
+__device__ __forceinline__ unsigned long long zp_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
 template <int S, int MODE, int NTC>
 __global__ void __launch_bounds__(SOS_NT * NTC, 1)
 sos_zp_park_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ ZpArgs P,
@@ -425,7 +439,13 @@ sos_zp_park_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ Zp
     const int team = tid >> 7, ttid = tid & (SOS_NT - 1), warp = ttid >> 5;   // warp inside the team
     constexpr int NTEAM = NTC;
     const int grp = (int)(blockIdx.x % P.ngroups);
+#ifdef ADN_ZP_TIMING
+    // development: runs rotated over the blocks (is a slow block slow because of its run or its SM?)
+    const int64_t nruns_dbg = (P.t_out1 - P.t_out0 + P.run_tiles - 1) / P.run_tiles;
+    const int64_t run = (blockIdx.x / P.ngroups + (P.pf >> 8)) % nruns_dbg;
+#else
     const int64_t run = blockIdx.x / P.ngroups;
+#endif
     const int CG = P.CG, C = P.C;
     const int c0 = grp * CG;
     const int Cw = min(CG, C - c0);
@@ -457,10 +477,22 @@ sos_zp_park_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ Zp
     // whole tiles come in through the TMA unit when the rows of the group are contiguous
     const bool bulk_group = P.bulk_ok && Cw == CG;
 
-    const int64_t a = P.t_out0 + run * P.run_tiles;         // output tiles [a, b)
-    const int64_t b = min(a + (int64_t)P.run_tiles, P.t_out1);
+    // output tiles [a, b); the run that builds the left extension tile is shorter by what that costs
+    const int64_t a = run == 0 ? P.t_out0 : P.t_out0 + run * P.run_tiles - P.short0;
+    const int64_t b = min(P.t_out0 + (run + 1) * P.run_tiles - P.short0, P.t_out1);
     if (a >= b) return;
     const int64_t top = min(b + (int64_t)P.JO, P.ntt) - 1;  // first tile of the walk
+#ifdef ADN_ZP_TIMING
+    __shared__ unsigned zp_slot_s;
+    if (tid == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const unsigned long long now = zp_now();
+        zp_slot_s = ((atomicAdd(&zp_count, 1u) / gridDim.x) & 1u) * 1024u + blockIdx.x;
+        zp_times[zp_slot_s * 8] = now;
+        zp_times[zp_slot_s * 8 + 6] = smid;
+    }
+#endif
 
     for (int q = tid; q < P.n_staged * DD; q += blockDim.x) tab_s[q] = __ldg(P.tab + q);
     for (int q = tid; q < (JJ + 2) * DD; q += blockDim.x) pt_s[q] = __ldg(P.tab + (size_t)P.off_tile * DD + q);
@@ -472,6 +504,9 @@ sos_zp_park_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ Zp
     if (tid == 0) *sb_flag = top + 1;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
+#ifdef ADN_ZP_TIMING
+    if (tid == 0) zp_times[zp_slot_s * 8 + 1] = zp_now();
+#endif
     auto slot_of = [&](int64_t t) { return (int)((t + 64 * (int64_t)NSLOT) % NSLOT); };
     // how tile t reaches its slot: 0 nothing to load, 1 TMA bulk copies, 2 cp.async granules
     auto load_kind = [&](int64_t t) {
@@ -809,11 +844,22 @@ sos_zp_park_kernel(const __grid_constant__ SosK<S> K, const __grid_constant__ Zp
                 }
             }
         }
+#ifdef ADN_ZP_TIMING
+        if (ttid == 0 && run < 4 && t - a < 64 && t >= a) zp_tile_times[run * 64 + (t - a)] = zp_now();
+#endif
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+#ifdef ADN_ZP_TIMING
+    if (ttid == 0) zp_times[zp_slot_s * 8 + 2 + team] = zp_now();
+#endif
 }
 
 std::atomic<int64_t> g_zp_launches{0};
+#ifdef ADN_ZP_TIMING
+constexpr int ZP_SMEM_MAX = 226 * 1024;     // the timing build keeps a word of static shared memory
+#else
+constexpr int ZP_SMEM_MAX = 227 * 1024;
+#endif
 
 template <int S, bool RECT>
 int32_t launch_zp(const SosPlan& plan, const ZpArgs& P, const SosRun& R, size_t smem, unsigned grid, int nteam,
@@ -824,7 +870,7 @@ int32_t launch_zp(const SosPlan& plan, const ZpArgs& P, const SosRun& R, size_t 
         auto kern = sos_zp_park_kernel<S, RECT ? MODE_ENVF : MODE_ZPF, 4>;
         static bool attr_done = false;           // per instantiation
         if (!attr_done) {
-            ADN_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            ADN_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ZP_SMEM_MAX));
             attr_done = true;
         }
         kern<<<grid, SOS_NT * 4, smem, st>>>(K, P, R);
@@ -832,7 +878,7 @@ int32_t launch_zp(const SosPlan& plan, const ZpArgs& P, const SosRun& R, size_t 
         auto kern = sos_zp_park_kernel<S, RECT ? MODE_ENVF : MODE_ZPF, 3>;
         static bool attr_done = false;
         if (!attr_done) {
-            ADN_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            ADN_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ZP_SMEM_MAX));
             attr_done = true;
         }
         kern<<<grid, SOS_NT * 3, smem, st>>>(K, P, R);
@@ -867,6 +913,17 @@ int zp_env(const char* name, int dflt) {
 
 int64_t zp_launches() { return g_zp_launches.load(); }
 
+#ifdef ADN_ZP_TIMING
+extern "C" int adn_debug_zp_times(unsigned long long* out, int n) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, zp_times, sizeof(unsigned long long) * (size_t)n);
+}
+extern "C" int adn_debug_zp_tile_times(unsigned long long* out) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, zp_tile_times, sizeof(unsigned long long) * 4 * 64);
+}
+#endif
+
 int32_t zero_phase_regs_dev(bool rect, const double* sos, int32_t S, const double* src, int64_t n_src,
                             int32_t C, int32_t edge_left, int32_t edge_right, int64_t out_first,
                             double* dst, int64_t n_dst, int32_t clamp_negative, bool* handled,
@@ -898,6 +955,9 @@ int32_t zero_phase_regs_dev(bool rect, const double* sos, int32_t S, const doubl
     P.JJ = plan->jzp;
     P.JO = plan->jzp;
     P.pf = zp_env("ADN_ZP_PREFETCH", 1);
+#ifdef ADN_ZP_TIMING
+    P.pf = (P.pf & 1) | (zp_env("ADN_ZP_ROT", 0) << 8);
+#endif
     sosfilt_zi_host(sos, S, P.zi.z);
     const int64_t out_tiles = P.t_out1 - P.t_out0;
     // the pipelined kernel (one block of NTEAM teams per SM, tiles parked in shared memory) when
@@ -946,11 +1006,22 @@ int32_t zero_phase_regs_dev(bool rect, const double* sos, int32_t S, const doubl
     }
     int64_t runs = resident / P.ngroups;
     if (runs < 1) runs = 1;
-    int64_t run_tiles = (out_tiles + runs - 1) / runs;
+    // the runs at the two ends of the sequence build their extension tile element by element with
+    // blocking loads (measured on B200: some 10 us, five tiles' worth, at the end of the first
+    // run's walk): those two runs are that much shorter, so that all blocks end together
+    int64_t short0 = 0, short1 = 0;
+    if (nteam > 0 && zp_env("ADN_ZP_SHORT_EDGE", 1)) {
+        if (edge_left > 0 && P.t_out0 == 0) short0 = 5;
+        if (edge_right > 0 && P.t_out1 == P.ntt) short1 = 5;
+    }
+    int64_t run_tiles = (out_tiles + short0 + short1 + runs - 1) / runs;
     // the run-out and the look-ahead may cost a third of a run at most
     const int64_t min_run = 2 * (int64_t)(P.JJ + P.JO);
     if (run_tiles < min_run) run_tiles = min_run;
-    runs = (out_tiles + run_tiles - 1) / run_tiles;
+    if (run_tiles < 4 * (short0 + short1)) short0 = short1 = 0;
+    if (short0 + short1 == 0) run_tiles = (out_tiles + runs - 1) / runs < min_run ? min_run : (out_tiles + runs - 1) / runs;
+    P.short0 = (int32_t)short0;
+    runs = (out_tiles + short0 + run_tiles - 1) / run_tiles;
     if (out_tiles < 2 * min_run) return ADN_OK;              // short input: the two sweeps
     if (run_tiles > 0x3fffffff || runs * P.ngroups > 0x7fffffff) return ADN_OK;
     P.run_tiles = (int32_t)run_tiles;
