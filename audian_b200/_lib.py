@@ -58,6 +58,7 @@ SIGNATURES = {
     'adn_version': (_i32, []),
     'adn_launch_count': (_i64, []),
     'adn_scan_run_count': (_i64, []),
+    'adn_fwd_park_count': (_i64, []),
     'adn_zero_phase_count': (_i64, []),
     'adn_synchronize': (_i32, []),
     'adn_host_register': (_i32, [_dp, _i64]),
@@ -235,6 +236,11 @@ def launch_count():
 def scan_run_count():
     """Launches of the SOS run kernel so far (the look-back kernel is the other scan kernel)."""
     return int(lib().adn_scan_run_count())
+
+
+def fwd_park_count():
+    """Launches of the pipelined forward kernel so far (csrc/sosfwd.cu)."""
+    return int(lib().adn_fwd_park_count())
 
 
 def zero_phase_count():

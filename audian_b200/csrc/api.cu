@@ -307,6 +307,7 @@ const char* adn_last_error(void) { return g_err.c_str(); }
 int32_t adn_version(void) { return 100; }
 int64_t adn_launch_count(void) { return g_ctx.launches.load(); }
 int64_t adn_scan_run_count(void) { return adn::scan_run_launches(); }
+int64_t adn_fwd_park_count(void) { return adn::fwd_park_launches(); }
 int64_t adn_zero_phase_count(void) { return adn::zp_launches(); }
 
 int32_t adn_synchronize(void) {

@@ -8,6 +8,20 @@
 #include <atomic>
 #include "../../include/audian_b200.h"
 
+// Output stores of the streaming kernels.  ADN_STORE_CS=1: evict-first (st.global.cs).  Measured on
+// B200 (8 ch x 48 kHz x 80 s): the spectrogram's rows of 513 doubles start at odd offsets, the
+// partial sectors at the ends of every warp store merge in L1 only with the default policy
+// (163.1 -> 157.7 us); the forward filter gains 1.6 % (87.2 -> 85.8 us), the zero-phase kernel loses
+// 2.5 % and keeps evict-first stores (zerophase.cu).
+#ifndef ADN_STORE_CS
+#define ADN_STORE_CS 0
+#endif
+#if ADN_STORE_CS
+#define ADN_STORE(p, v) __stcs((p), (v))
+#else
+#define ADN_STORE(p, v) (*(p) = (v))
+#endif
+
 namespace adn {
 
 int32_t fail(int32_t code, const char* fmt, ...);

@@ -59,7 +59,7 @@ __device__ __forceinline__ bool read_record(const double* p, double (&v)[D]) {
 #endif
 template <int MODE, class T>
 __device__ __forceinline__ void st_out(T* p, T v) {
-    if (MODE == MODE_ENVF && ENVF_PLAIN_STORE) *p = v; else __stcs(p, v);
+    if (MODE == MODE_ENVF && ENVF_PLAIN_STORE) *p = v; else ADN_STORE(p, v);
 }
 
 // ---- write the finished tile back (clamp fused), coalesced

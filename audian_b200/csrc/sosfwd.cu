@@ -432,12 +432,12 @@ sos_fwd_park_kernel(const __grid_constant__ SosK<S1> K1, const __grid_constant__
             double* q = P.dst + (e0 - P.out_skip) * C + c0 + cw;
             if (fast && C == 8) {
 #pragma unroll
-                for (int i = 0; i < SOS_L; ++i) __stcs(q + i * 8, x[i]);
+                for (int i = 0; i < SOS_L; ++i) ADN_STORE(q + i * 8, x[i]);
             } else {
                 const int64_t o0 = e0 - P.out_skip;
 #pragma unroll
                 for (int i = 0; i < SOS_L; ++i) {
-                    if (fast || (o0 + i >= 0 && o0 + i < P.n_dst)) __stcs(q, x[i]);
+                    if (fast || (o0 + i >= 0 && o0 + i < P.n_dst)) ADN_STORE(q, x[i]);
                     q += C;
                 }
             }

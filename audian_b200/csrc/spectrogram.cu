@@ -603,6 +603,13 @@ constexpr int SR_MAXNT = 128;
 #ifndef SR_PAIRMAP
 #define SR_PAIRMAP 1
 #endif
+// SR_LDCS: the rows of the next chunk come in with evict-first loads (they are used once by this
+// block).  Measured on B200: nothing gained next to the default store policy (157.7 us both ways) and
+// DRAM reads grow from 253 to 286 MB (the other channel group's block finds the line evicted).  Off.
+#ifndef SR_LDCS
+#define SR_LDCS 0
+#endif
+
 constexpr int SR_PF = 8;            // 16-byte vectors in flight per thread and step
 // SR_ASYNC: the rows of the next step go straight into the ring with 8-byte cp.async, issued as
 // soon as every warp holds its frame of this step in registers (one barrier after the frame
@@ -769,7 +776,11 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
                 const double* gp = gnext;
 #pragma unroll
                 for (int j = 0; j < SR_PF; ++j) {
+#if SR_LDCS
+                    pf[j] = __ldcs(reinterpret_cast<const double2*>(gp));
+#else
                     pf[j] = __ldg(reinterpret_cast<const double2*>(gp));
+#endif
                     gp += gstep;
                 }
             } else {
@@ -965,8 +976,8 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
                     }
                     if (DB) { pk = to_db(pk); pm = to_db(pm); }
                     if (live) {
-                        __stcs(outk + 32 * kk, pk);
-                        __stcs(outm - 32 * kk, pm);
+                        ADN_STORE(outk + 32 * kk, pk);
+                        ADN_STORE(outm - 32 * kk, pm);
                     }
                 }
                 if (kl == 0 && live) {                                    // k = M/2 pairs with itself
@@ -1029,8 +1040,8 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
                             if (h == 0 && j == 0) pr += t == 0 ? mN2 : 0.0;
                             double pk = (pr * pr + pi * pi) * sc, pm = (qr * qr + qi * qi) * sc;
                             if (DB) { pk = to_db(pk); pm = to_db(pm); }
-                            __stcs(out + k, pk);
-                            if (km != k) __stcs(out + km, pm);
+                            ADN_STORE(out + k, pk);
+                            if (km != k) ADN_STORE(out + km, pm);
                         }
                     }
                     if (t == 0) {
@@ -1343,8 +1354,8 @@ __device__ __forceinline__ void mp_channel(double2 (&za)[R], double2* S, const d
         if (k == 1) pr += mN2;                                // the window's spectrum at bin 1 is -N/4
         double pk = (pr * pr + pi * pi) * sc, pm = (qr * qr + qi * qi) * sc;
         if (DB) { pk = to_db(pk); pm = to_db(pm); }
-        __stcs(out + k, pk);
-        if (km != k) __stcs(out + km, pm);
+        ADN_STORE(out + k, pk);
+        if (km != k) ADN_STORE(out + km, pm);
     }
     if (t == 0) {
         double2 z0 = S[0];

@@ -146,12 +146,13 @@ class ClockSampler(threading.Thread):
                     bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
                 except Exception:
                     bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-                try:
-                    self.power.append(nv.nvmlDeviceGetPowerUsage(h)/1000.0)
-                except Exception:
-                    pass
+                if len(self.rows) % 8 == 0:             # every NVML query takes about a millisecond
+                    try:
+                        self.power.append(nv.nvmlDeviceGetPowerUsage(h)/1000.0)
+                    except Exception:
+                        pass
                 self.rows.append((time.perf_counter(), sm, [k for k, m in masks.items() if bits & m]))
-                time.sleep(0.001)
+                time.sleep(float(os.environ.get('BENCH_CLOCK_SLEEP', '0.0002')))
             return
         except Exception:
             pass
@@ -461,10 +462,12 @@ def run_ours(args):
                 'share_of_step': (ms/(t_f + t_s + t_e)) if share_of is None else share_of}
 
     scan_name = 'sos_run_kernel' if _lib.scan_run_count() > 0 else 'sos_scan_kernel'
-    env_name = ('sos_zp_pipe_kernel<S=1,RECT>: one pass, tile in registers' if _lib.zero_phase_count() > 0
+    filt_name = ('sos_fwd_park_kernel<2,0,3>: pipelined, tile in registers' if _lib.fwd_park_count() > 0
+                 else scan_name + '<S=2,FWD>')
+    env_name = ('sos_zp_park_kernel<1,ENVF,3>: one pass, tile in registers' if _lib.zero_phase_count() > 0
                 else scan_name + '<S=1,ENVF> + <S=1,REV>')
     roofs = {
-        'filter': roof('filter', t_f, chain.f1 - chain.f0, scan_name + '<S=2,FWD>'),
+        'filter': roof('filter', t_f, chain.f1 - chain.f0, filt_name),
         'spectrogram': roof('spectrogram', t_s, n, 'spectrogram_ring_kernel<10>'),
         'envelope': roof('envelope', t_e, n, env_name),
         'minmax': roof('minmax', t_m, n, 'minmax_split_kernel (step %d, not part of the step)' % mm_step, 0.0),

@@ -85,7 +85,8 @@ int32_t adn_shutdown(void);
 const char* adn_last_error(void);
 int32_t adn_version(void);
 int64_t adn_launch_count(void);        /* kernels launched by this library so far */
-int64_t adn_scan_run_count(void);      /* of these: launches of the SOS run kernel (ADN_OPT_SCAN_RUNS) */
+int64_t adn_scan_run_count(void);      /* of these: launches of the SOS run kernels (ADN_OPT_SCAN_RUNS) */
+int64_t adn_fwd_park_count(void);      /* of those: launches of the pipelined forward kernel (csrc/sosfwd.cu) */
 int64_t adn_zero_phase_count(void);    /* launches of the one-pass zero-phase kernel (ADN_OPT_ZERO_PHASE_ONEPASS) */
 int32_t adn_synchronize(void);         /* waits for the library's stream */
 /* page-lock a host range so that the host-pointer entry points copy at full

@@ -63,9 +63,19 @@ def main():
             ms = timed(lambda: device.spectrogram(nxt(), rate, nfft, hop, nf, out=out), 3)
             del out
             bps = 8.0 + 8.0*F/hop
+            # second floor: the fp64 pipe.  Flops of a frame by the usual count for a real
+            # transform (2.5 N log2 N) + window, mean and power (2 N + 3 F), at the B200's nominal
+            # 64 DFMA / clock / SM x 148 SMs x 1.965 GHz x 2 flops (every operation counted as
+            # half an FMA: optimistic for the kernel, i.e. a floor)
+            flops = nf*C*(2.5*nfft*np.log2(nfft) + 2*nfft + 3*F)
+            fp64_ms = flops/(64*148*1.965e9*2)*1e3
+            hbm_ms = n*C*bps/peak/1e6
             rows.append({'op': 'spectrogram', 'nfft': nfft, 'overlap': 1 - 1/div, 'ms': ms,
                          'gsamples_s': n*C/ms/1e6, 'alg_gbs': n*C*bps/ms/1e6,
-                         'frac': n*C*bps/ms/1e6/peak})
+                         'frac': n*C*bps/ms/1e6/peak,
+                         'hbm_floor_ms': hbm_ms, 'fp64_floor_ms': fp64_ms,
+                         'bound': 'fp64' if fp64_ms > hbm_ms else 'hbm',
+                         'frac_of_binding_floor': max(hbm_ms, fp64_ms)/ms})
             print(json.dumps(rows[-1]), flush=True)
     out = torch.empty((n, C), dtype=torch.float64, device='cuda')
     for hp, lp, order in ((0, 20000., 2), (1000., 60000., 2), (5000., rate/2, 2), (1000., 60000., 4)):
