@@ -935,12 +935,34 @@ int32_t zero_phase_regs_dev(bool rect, const double* sos, int32_t S, const doubl
                             cudaStream_t st) {
     *handled = false;
     if (!option(ADN_OPT_ZERO_PHASE_ONEPASS) || S < 1 || S > 4 || n_dst <= 0) return ADN_OK;
-    const int CG = pick_cg(C);
+    const int D = 2 * S;
+    // Channels per group.  A tile is 4096 / CG rows long, and the pipelined kernel holds NTEAM + JJ
+    // tiles in shared memory, JJ = the tiles the cascade needs to forget: a slow cascade (500 Hz at
+    // 250 kHz: 4400 rows) gets narrower groups = longer tiles until that fits (16-byte row segments
+    // at least, as long as the channel count is even).  Measured on B200, 500-Hz envelope at 250 kHz:
+    // 8 ch (groups of 2) 0.236 against 0.441 ms for 32 M samples; 64 ch 0.552 against 0.506 ms -- the
+    // 16-byte segments of 512-byte rows are scattered over too many lines, so only rows of at most
+    // one 128-byte line take narrower groups.
+    int CG = pick_cg(C);
     std::shared_ptr<SosPlan> plan;
     int32_t rc = get_sos_plan(sos, S, CG, st, &plan);
     if (rc) return rc;
+    auto pipe_need = [&](const SosPlan& pl, int cg, int nt) {
+        const size_t TS = (size_t)(SOS_NT / cg) * (SOS_L * cg + (cg < 16 ? cg : 0));
+        const int ns = nt + pl.jzp;
+        return ((size_t)pl.n_staged * D * D + (size_t)nt * 2 * SOS_NW * cg * D + (size_t)ns * cg * D +
+                (size_t)nt * cg * D + (size_t)ns * D * SOS_NT + (size_t)(2 * ns + 2) +
+                (size_t)(pl.jzp + 2) * D * D + (size_t)ns * TS) * 8;
+    };
+    if (zp_env("ADN_ZP_PIPE", 1) && zp_env("ADN_ZP_NARROW", 1) && C <= 16 && pipe_need(*plan, CG, 3) > 227 * 1024) {
+        const int cg_min = C % 2 == 0 ? 2 : 1;
+        for (int cg = CG / 2; cg >= cg_min; cg /= 2) {
+            std::shared_ptr<SosPlan> pl;
+            if ((rc = get_sos_plan(sos, S, cg, st, &pl))) return rc;
+            if (pipe_need(*pl, cg, 3) <= 227 * 1024) { CG = cg; plan = pl; break; }
+        }
+    }
     if (plan->jzp > ZP_MAX_JJ) return ADN_OK;               // forgets too slowly: two sweeps with look-back
-    const int D = 2 * S;
     ZpArgs P;
     memset(&P, 0, sizeof P);
     P.src = src; P.dst = dst; P.tab = plan->dtab;
@@ -986,15 +1008,11 @@ int32_t zero_phase_regs_dev(bool rect, const double* sos, int32_t S, const doubl
     size_t smem = 0;
     int64_t resident;
     if (zp_env("ADN_ZP_PIPE", 1)) {
-        const size_t TS = (size_t)(SOS_NT / CG) * (SOS_L * CG + (CG < 16 ? CG : 0));
         // measured on B200 (8 ch x 48 kHz, 80 s): three teams at 168 registers 141 us, four at 128
         // registers (some spills) 149 us for one section; two sections are even (204 / 200 us)
         const int want = zp_env("ADN_ZP_NTEAM", S == 1 ? 3 : ZP_NTEAM_MAX);
         for (int nt = want < ZP_NTEAM_MAX ? want : ZP_NTEAM_MAX; nt >= 3; --nt) {
-            const int ns = nt + P.JJ;
-            const size_t need = ((size_t)plan->n_staged * D * D + (size_t)nt * 2 * SOS_NW * CG * D +
-                                 (size_t)ns * CG * D + (size_t)nt * CG * D + (size_t)ns * D * SOS_NT +
-                                 (size_t)(2 * ns + 2) + (size_t)(P.JJ + 2) * D * D + (size_t)ns * TS) * 8;
+            const size_t need = pipe_need(*plan, CG, nt);
             if (need <= 227 * 1024) { nteam = nt; smem = need; break; }
         }
     }

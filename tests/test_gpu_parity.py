@@ -392,6 +392,37 @@ def test_envelope_onepass_kernel(C, n, order, fc, nbefore, pipe, monkeypatch):
     assert (a >= 0).all()
 
 
+@pytest.mark.parametrize('C,n,fs,fc', [(16, 900000, 250000., 500.), (8, 1500000, 250000., 500.),
+                                       (16, 900000, 500000., 1000.), (6, 800001, 250000., 300.),
+                                       (64, 600000, 250000., 500.)])
+def test_envelope_onepass_narrow_groups(C, n, fs, fc):
+    """Slow cascades (the 500-Hz envelope of ultrasound recordings): the pipelined kernel takes
+    narrower channel groups = longer tiles, so that the tiles it has to park still fit
+    (zerophase.cu: zero_phase_regs_dev); same answers as the two sweeps and scipy."""
+    x = synth(3, n, C, fs, seed=C + 700)
+    sos = orc.envelope_design(fs, fc, 0, 2)
+
+    def call():
+        got = np.empty((n, C))
+        _lib.envelope(sos, x, got, 0, True)
+        return got
+
+    z0 = _lib.zero_phase_count()
+    a = call()
+    assert _lib.zero_phase_count() == z0 + 1
+    _lib.set_option(_lib.ADN_OPT_ZERO_PHASE_ONEPASS, 0)
+    try:
+        b = call()
+    finally:
+        _lib.set_option(_lib.ADN_OPT_ZERO_PHASE_ONEPASS, 1)
+    ref = np.empty((n, C))
+    orc.envelope_process(sos, x, ref, 0, 0)
+    scale = max(1.0, np.max(np.abs(ref)))
+    assert np.max(np.abs(a - b)) <= 1e-11*scale
+    assert np.max(np.abs(a - ref)) <= 1e-10*scale
+    assert (a >= 0).all()
+
+
 @pytest.mark.parametrize('C,n,order', [(8, 800000, 2), (2, 1000003, 4), (5, 500000, 6)])
 def test_sosfiltfilt_onepass_kernel(C, n, order):
     """The same kernel without the rectification == scipy.signal.sosfiltfilt (databrowser.py:1725)."""
