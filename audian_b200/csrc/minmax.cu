@@ -461,14 +461,30 @@ int32_t minmax_dev(const double* src, int64_t n, int32_t C, int64_t step, double
     // threads whose per-iteration flat stride is a multiple of C
     int32_t q = C / (C % VEC == 0 ? VEC : 1);
     int32_t active = (MM_THREADS / q) * q;
-    // rows per block: ~32K samples, but enough blocks to fill the chip a few times over
-    int64_t rows = 32768 / C;
-    if (rows < 1) rows = 1;
-    int64_t want_blocks = (int64_t)ctx().sm_count * 8;
+    // rows per block: between ~4K and ~32K samples, chosen so that the blocks come in whole waves
+    // of the resident slots (sm_count x 8 blocks of 256 threads): a last wave that fills a fraction
+    // of the chip costs as much as a full one.  Measured on B200, 3.84 M rows x 8 ch in segments of
+    // 90 000 rows: 938 blocks of 4096 rows 62.6 us, 1161 blocks of 3334 rows (one wave) see profiles/
     int64_t seg_rows = step < n ? step : n;
-    while (rows > 4096 / C + 1 && nseg * ((seg_rows + rows - 1) / rows) < want_blocks) rows /= 2;
+    const int64_t rows_hi = 32768 / C > 1 ? 32768 / C : 1;
+    const int64_t rows_lo = 4096 / C + 1 < rows_hi ? 4096 / C + 1 : rows_hi;
+    const int64_t slots = (int64_t)ctx().sm_count * (2048 / MM_THREADS);
+    int64_t rows = rows_hi;
+    {
+        const int64_t k0 = (seg_rows + rows_hi - 1) / rows_hi, k1 = (seg_rows + rows_lo - 1) / rows_lo;
+        const int64_t kstep = (k1 - k0) / 4096 + 1;
+        double best = 0.0;
+        for (int64_t k = k0; k <= k1; k += kstep) {
+            int64_t r = (seg_rows + k - 1) / k;
+            if (C == 1 && vec2 && (r & 1)) ++r;
+            const int64_t nb = nseg * ((seg_rows + r - 1) / r);
+            const double cost = (double)((nb + slots - 1) / slots) * ((double)r * C + 2048.0);
+            if (k == k0 || cost < best) { best = cost; rows = r; }
+        }
+    }
     if (C == 1 && vec2 && rows > 1) rows &= ~(int64_t)1;
     if (rows > seg_rows) rows = seg_rows;
+    if (rows < 1) rows = 1;
     if (rows >= (int64_t)1 << 30) rows = ((int64_t)1 << 30) - 1;          // row index is int32
     int64_t nsplit64 = (seg_rows + rows - 1) / rows;
     if (nsplit64 > 0x7fffffff || nseg * nsplit64 > 0x7fffffff)

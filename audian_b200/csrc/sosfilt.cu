@@ -14,7 +14,8 @@
 //   scan     Kogge-Stone over the sub-chunks of a channel inside a warp with
 //            precomputed A^(L 2^k), then a short serial scan over the warps
 //   carry    decoupled look-back over preceding tiles (aggregate / inclusive
-//            state records + flags in global memory, tickets give the order);
+//            state records in global memory; a tile's index is blockIdx.x, which relies on
+//            blocks being dispatched in index order, as CUB's look-back does);
 //            contributions are weighted with (A^T)^j tables and the look-back stops
 //            where the filter has decayed below 1e-30
 //   pass B   the exact DF2T recurrence from the true incoming state, outputs

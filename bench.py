@@ -281,6 +281,44 @@ def run_reference(args):
 
 # ------------------------------------------------------------------ our arm
 
+class gpu_near_cpus:
+    """Binds this process to the CPUs NVML names as nearest to the GPU (the NUMA node its PCIe
+    root hangs on) until restore(); a no-op when NVML gives no mask or the mask is every CPU."""
+
+    def __init__(self, index):
+        self.old = None
+        self.cpus = None
+        if os.environ.get('ADN_BENCH_NUMA', '1') == '0' or not hasattr(os, 'sched_getaffinity'):
+            return
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+            idx = int(vis.split(',')[index]) if vis else index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            ncpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63)//64)
+            cpus = {64*w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+            old = os.sched_getaffinity(0)
+            cpus &= old
+            if cpus and cpus != old:
+                os.sched_setaffinity(0, cpus)
+                self.old, self.cpus = old, cpus
+        except Exception as exc:                       # pragma: no cover
+            sys.stderr.write('gpu_near_cpus: %s\n' % (exc,))
+
+    def describe(self):
+        if self.cpus is None:
+            return 'unbound (no NVML mask, or the mask is every CPU)'
+        c = sorted(self.cpus)
+        return '%d cpus near the GPU: %d..%d' % (len(c), c[0], c[-1])
+
+    def restore(self):
+        if self.old is not None:
+            os.sched_setaffinity(0, self.old)
+            self.old = None
+
+
 def seam_parity(chain, sos, esos, C, filt_rows, spec, env, abs0, where):
     """Outputs of one rank's shard against the oracle at one end of the shard (`where` =
     'lo' | 'hi'): the oracle filters a host-generated window that starts 1 s before the rows
@@ -510,6 +548,9 @@ def run_ours(args):
     # With N ranks: N independent replicas of the single-GPU plugin path (audian's interactive
     # updates stay on one GPU), each on its own 80-s window.
     own = slice(chain.lo - r0, chain.lo - r0 + n)
+    # the host buffers of the plugin path are first touched (and page-locked) by threads on the CPUs
+    # next to this rank's GPU, as a NUMA-aware host application would place them; restored below
+    near = gpu_near_cpus(local)
     host_x = [np.ascontiguousarray(w[own].cpu().numpy()) for w in windows[:2]]
     nspec = n//HOP
     h_filt = np.empty((n, C))
@@ -574,6 +615,8 @@ def run_ours(args):
     for a_ in host_x + [h_filt, h_spec, h_env]:
         _lib.host_unregister(a_)
     del tf, ts, te
+    e2e['host_cpus'] = near.describe()
+    near.restore()
 
     # ---- the oracle on the host's cores, bounded samples of the same workload (N = 1 only)
     cpu_baseline = None
