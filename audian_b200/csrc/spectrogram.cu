@@ -642,7 +642,8 @@ template <int LOGN> struct SRCfg {
     // by 16 lane pairs: 16-byte offsets, two wavefronts per 128-bit load)
     // T == 32: 16 rows of SR_XS doubles; the stride is even, so that a lane pair reads its row as
     // 16-byte vectors (two wavefronts per 128-bit load of 16 rows: the minimum for 256 bytes)
-    static constexpr int FS = T == 32 ? 16 * 34 / 2 + 4 : SWCfg<LOGN>::FS;
+    // T == 8: rows of 8 padded to 9 (lane t owns rows t and t + 8 in the second pass), 16 rows
+    static constexpr int FS = T == 32 ? 16 * 34 / 2 + 4 : (T == 8 ? 148 : SWCfg<LOGN>::FS);
     static constexpr int WB = FS * SWCfg<LOGN>::FPW;
 };
 
@@ -894,6 +895,10 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
                         // lane pairs are one 128-byte wavefront each)
                         b[k1] = v;
                         reinterpret_cast<double*>(wbf)[k1 * 34 + t] = v.x;
+                    } else if (T == 8) {
+                        wbf[k1 * 9 + t] = v;
+                    } else if (T == 4) {
+                        wbf[k1 * 4 + ((t + k1) & 3)] = v;       // rows of 4, rotated by the row index
                     } else {
                         const int f = k1 * T + t;
                         wbf[f + (f >> 4)] = v;
@@ -994,8 +999,16 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
                 double2 zout[16];
                 int kout[16];
                 constexpr int Q = 16 / (T == 32 ? 16 : T);
+                // T == 8: lane t transforms rows t and t + 8 (rows of 9: the lanes of a frame read and,
+                // below, write eight different 16-byte bank groups; with rows 2 t, 2 t + 1 the
+                // natural-order stores were two-way conflicts: 8 instead of 4 wavefronts each).
+                // T == 4: rows t + 4 r, rows of 4 rotated by the row index (no padding: the two frames
+                // of a quarter warp sit FS == 4 mod 8 apart); with rows 4 t + r the natural-order
+                // stores were four-way conflicts
 #pragma unroll
-                for (int i = 0; i < 16; ++i) a[i] = wbf[t * 17 + i];
+                for (int i = 0; i < 16; ++i)
+                    a[i] = T == 8 ? wbf[(t + 8 * (i >> 3)) * 9 + (i & 7)]
+                         : T == 4 ? wbf[(t + 4 * (i >> 2)) * 4 + ((t + i) & 3)] : wbf[t * 17 + i];
                 if (T == 16) {
                     dft16(a, b);
                 } else if (T == 8) {
@@ -1011,7 +1024,7 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
                 for (int i = 0; i < 16; ++i) {
                     const int r = i / (16 / Q), k2 = i % (16 / Q);
                     zout[i] = b[i];
-                    kout[i] = (t * Q + r) + 16 * k2;
+                    kout[i] = (T <= 8 ? t + T * r : t * Q + r) + 16 * k2;
                 }
                 if (last_iter) { issue_loads(); loaded = true; }
                 __syncwarp();
