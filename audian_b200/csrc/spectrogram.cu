@@ -633,6 +633,7 @@ struct SpecRArgs {
     int32_t FSTEP, FRUN;        // frames per step / per block (FRUN % FSTEP == 0)
     int32_t RC, RS;             // ring length in rows; per-channel stride in doubles
     int32_t detrend;
+    int32_t pfsplit;            // L2 prefetch of the next chunk: every group's block its share of the rows
     double scale;               // 1 / (rate * sum(w^2))
 };
 
@@ -759,10 +760,16 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
         // pull the rows of the next step into L2 while this step computes
         const bool more = s + 1 < nsteps;
         const bool inside = nrow + CH <= rows_run;       // the whole next chunk exists
-        if (more && tid == 0) {                  // whole rows (every group's block: measured faster)
-            const int64_t nr = inside ? CH : rows_run - nrow;
+        if (more && tid == 0 && P.pfsplit != 2) {    // whole rows (every group's block: measured faster)
+            int64_t nr = inside ? CH : rows_run - nrow;
+            int64_t rlo = 0;
+            if (P.pfsplit == 1) {
+                const int64_t per = (nr + P.ngrp - 1) / P.ngrp;
+                rlo = grp * per;
+                nr = nr - rlo < per ? nr - rlo : per;
+            }
             if (nr > 0) {
-                const double* a0 = P.src + (f0 * hop + nrow) * (int64_t)C;
+                const double* a0 = P.src + (f0 * hop + nrow + rlo) * (int64_t)C;
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0),
                              "r"((uint32_t)(nr * C * 8)) : "memory");
             }
@@ -1928,6 +1935,10 @@ int32_t spectrogram_dev(const double* src, int64_t n_src, int32_t C, double rate
         R.src = src; R.dst = dst; R.win = plan.win; R.twA = plan.twA; R.twS = plan.tw;
         R.nframes = nf; R.C = C; R.hop = hop;
         R.detrend = detrend_id == ADN_DETREND_CONSTANT;
+        // wide arrays: every group's block pulls its share of the next rows into L2 instead of all of
+        // them (measured on B200, 64 ch x 250 kHz: nfft 1024 / hop 512 293 -> 276 us, 256 / 128 334 ->
+        // 327 us; 512 / 128 508 -> 517 us, 16 and 8 channels +-1 %); 2 = no prefetch (3 - 12 % slower)
+        R.pfsplit = env_int("ADN_SPEC_PFSPLIT", C >= 32 && 2 * hop >= nfft ? 1 : 0);
         R.scale = 1.0 / (rate * plan.sumw2);
         int32_t rr = ADN_ERR_UNSUPPORTED;
         switch (nfft) {
