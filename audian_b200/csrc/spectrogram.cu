@@ -678,7 +678,7 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
     double* xs = sbuf;                                               // [W][RS]
     double* wins = sbuf + (size_t)W * RS;                            // [N] (if SR_WIN_SMEM)
     constexpr int NWIN = SR_WIN_SMEM ? (SR_WIN_HALF ? N / 2 : N) : 0;
-    constexpr int NTWS = T == 32 ? 0 : M / 2 + 2;                    // T == 32 builds them in registers
+    constexpr int NTWS = 0;                                          // split-step twiddles are built in registers
     double2* tws = reinterpret_cast<double2*>(wins + NWIN);          // [NTWS]
     double2* wb = tws + NTWS + (size_t)warp * SRCfg<LOGN>::WB;
 
@@ -722,8 +722,6 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
     stage_direct(0, 0, span0, 0);
     if (SR_WIN_SMEM)
         for (int i = tid; i < NWIN; i += NT) wins[i] = __ldg(P.win + i);
-    if (NTWS > 0)
-        for (int i = tid; i <= M / 2; i += NT) tws[i] = __ldg(P.twS + i);
     __syncthreads();
 
     const int sub = lane / T, t = lane % T;
@@ -732,9 +730,9 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
     const double2 tw1 = __ldg(P.twA + 1 * T + t), tw2 = __ldg(P.twA + 2 * T + t);
     const double2 tw4 = __ldg(P.twA + 4 * T + t), tw8 = __ldg(P.twA + 8 * T + t);
 #if SR_PAIRMAP
-    const double2 twl = __ldg(P.twS + ((lane >> 1) + 16 * (lane & 1)));
+    const double2 twl = __ldg(P.twS + (T == 32 ? (lane >> 1) + 16 * (lane & 1) : lane % T));
 #else
-    const double2 twl = __ldg(P.twS + lane);             // T == 32: W_N^lane of the split step
+    const double2 twl = __ldg(P.twS + lane % T);         // W_N^t of the split step
 #endif
     // SR_WIN_CALC: (cos, sin)(2 pi j / N) of this lane's two window positions j = 2 t, 2 t + 1
     // (from the table of W_N^k = exp(-2 pi i k / N) of the split step: k = 2 t + 1 < M / 8)
@@ -1003,15 +1001,9 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
                     out[M / 2] = pk;
                 }
             } else {
-                double2 zout[16];
-                int kout[16];
-                constexpr int Q = 16 / (T == 32 ? 16 : T);
-                // T == 8: lane t transforms rows t and t + 8 (rows of 9: the lanes of a frame read and,
-                // below, write eight different 16-byte bank groups; with rows 2 t, 2 t + 1 the
-                // natural-order stores were two-way conflicts: 8 instead of 4 wavefronts each).
-                // T == 4: rows t + 4 r, rows of 4 rotated by the row index (no padding: the two frames
-                // of a quarter warp sit FS == 4 mod 8 apart); with rows 4 t + r the natural-order
-                // stores were four-way conflicts
+                // T == 8: lane t transforms rows t and t + 8 (rows of 9: the lanes of a frame read eight
+                // different 16-byte bank groups).  T == 4: rows t + 4 r, rows of 4 rotated by the row
+                // index (no padding: the two frames of a quarter warp sit FS == 4 mod 8 apart)
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
                     a[i] = T == 8 ? wbf[(t + 8 * (i >> 3)) * 9 + (i & 7)]
@@ -1027,54 +1019,55 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
                         dft4(a[4 * r], a[4 * r + 1], a[4 * r + 2], a[4 * r + 3],
                              b[4 * r], b[4 * r + 1], b[4 * r + 2], b[4 * r + 3]);
                 }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int r = i / (16 / Q), k2 = i % (16 / Q);
-                    zout[i] = b[i];
-                    kout[i] = (T <= 8 ? t + T * r : t * Q + r) + 16 * k2;
-                }
                 if (last_iter) { issue_loads(); loaded = true; }
-                __syncwarp();
-                // ---- Z in natural order
+                // split step in registers, as for T == 32: lane t of a frame holds Z[t + T m], m < 16
+                // (row t + T r, output k2 of its DFT: m = r + (16 / T) k2), so Z[M - k] of k = t + T m
+                // sits in lane (T - t) % T of the frame, at m' = 15 - m (lane 0: its own m' = 16 - m);
+                // a lane handles the pairs of m < 8 and fetches the partner by shuffle.  The twiddle
+                // W_N^(t + T m) is W_N^t W_32^m.  (Until round 2 this path wrote Z back to the exchange
+                // buffer in natural order and read pairs and twiddles from shared memory: 40 of the
+                // 104 shared-memory wavefronts of a 256-point frame.)
+#define ADN_RG(m) (T == 16 ? (m) : (T == 8 ? 8 * ((m) & 1) + ((m) >> 1) : 4 * ((m) & 3) + ((m) >> 2)))
+                const int partner = (lane & ~(T - 1)) | ((T - t) & (T - 1));
+                double* outk = out + t;
+                double* outm = out + M - t;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) wbf[kout[i]] = zout[i];
-                __syncwarp();
-                if (live) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        double2 zk[4], zm[4], tw[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {              // k = 1 + t + T i  in [1, M/2]
-                            const int k = 1 + t + T * (4 * h + j), km = M - k;
-                            zk[j] = wbf[k];
-                            zm[j] = wbf[km];
-                            tw[j] = tws[k];
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int k = 1 + t + T * (4 * h + j), km = M - k;
-                            double e_r = zk[j].x + zm[j].x, e_i = zk[j].y - zm[j].y;
-                            double o_r = zk[j].y + zm[j].y, o_i = zm[j].x - zk[j].x;
-                            double t_r = o_r * tw[j].x - o_i * tw[j].y, t_i = o_r * tw[j].y + o_i * tw[j].x;
-                            double pr = e_r + t_r, pi = e_i + t_i, qr = e_r - t_r, qi = e_i - t_i;
-                            if (h == 0 && j == 0) pr += t == 0 ? mN2 : 0.0;
-                            double pk = (pr * pr + pi * pi) * sc, pm = (qr * qr + qi * qi) * sc;
-                            if (DB) { pk = to_db(pk); pm = to_db(pm); }
-                            // evict-first here: measured on B200 (64 ch x 250 kHz, nfft 128 .. 512, overlap
-                            // <= 50 %) the default policy is 8 - 13 % slower on this path
-                            __stcs(out + k, pk);
-                            if (km != k) __stcs(out + km, pm);
-                        }
+                for (int kk = 0; kk < 8; ++kk) {
+                    double2 zk = b[ADN_RG(kk)], zm;
+                    zm.x = __shfl_sync(0xffffffffu, b[ADN_RG(15 - kk)].x, partner);
+                    zm.y = __shfl_sync(0xffffffffu, b[ADN_RG(15 - kk)].y, partner);
+                    if (kk > 0 && t == 0) zm = b[ADN_RG(16 - kk)];
+                    double2 tw = kk == 0 ? twl : cmul(twl, make_double2(w32c(kk, 0), w32c(kk, 1)));
+                    double e_r = zk.x + zm.x, e_i = zk.y - zm.y;          // Zk + conj(Zm)
+                    double o_r = zk.y + zm.y, o_i = zm.x - zk.x;          // -i (Zk - conj(Zm))
+                    double t_r = o_r * tw.x - o_i * tw.y, t_i = o_r * tw.y + o_i * tw.x;
+                    double pr = e_r + t_r, pi = e_i + t_i, qr = e_r - t_r, qi = e_i - t_i;
+                    if (kk == 0) pr += t == 1 ? mN2 : 0.0;                // the window's spectrum at bin 1 is -N/4
+                    double pk = (pr * pr + pi * pi) * sc, pm = (qr * qr + qi * qi) * sc;
+                    if (kk == 0 && t == 0) {                              // bins 0 and M from Z[0]
+                        double x0 = zk.x + zk.y - mN2, xM = zk.x - zk.y;
+                        pk = x0 * x0 * P.scale;
+                        pm = xM * xM * P.scale;
                     }
-                    if (t == 0) {
-                        double2 z0 = wbf[0];
-                        double x0 = z0.x + z0.y - mN2, xM = z0.x - z0.y;
-                        double p0 = x0 * x0 * P.scale, pM = xM * xM * P.scale;
-                        if (DB) { p0 = to_db(p0); pM = to_db(pM); }
-                        out[0] = p0;
-                        out[M] = pM;
+                    if (DB) { pk = to_db(pk); pm = to_db(pm); }
+                    if (live) {
+                        // evict-first here: measured on B200 (64 ch x 250 kHz, nfft 128 .. 512, overlap
+                        // <= 50 %) the default policy is 8 - 13 % slower on this path
+                        __stcs(outk + T * kk, pk);
+                        __stcs(outm - T * kk, pm);
                     }
                 }
+                if (t == 0 && live) {                                     // k = M/2 pairs with itself
+                    double2 zk = b[ADN_RG(8)];
+                    double2 tw = make_double2(w32c(8, 0), w32c(8, 1));    // W_N^(M/2) = -i
+                    double e_r = zk.x + zk.x, o_r = zk.y + zk.y;
+                    double t_r = o_r * tw.x, t_i = o_r * tw.y;
+                    double pr = e_r + t_r, pi = t_i;
+                    double pk = (pr * pr + pi * pi) * sc;
+                    if (DB) pk = to_db(pk);
+                    out[M / 2] = pk;
+                }
+#undef ADN_RG
             }
             __syncwarp();
         }
