@@ -610,6 +610,13 @@ constexpr int SR_MAXNT = 128;
 #define SR_LDCS 0
 #endif
 
+// Timing ablations (wrong results, build flags of tools/build_alt.sh only): SR_ABL & 1: no output
+// stores (the arithmetic stays live), & 2: no loads of the next chunk and no ring fill, & 4: no
+// block barriers around the fill
+#ifndef SR_ABL
+#define SR_ABL 0
+#endif
+#define SR_ST_OK(v) (!(SR_ABL & 1) || (v) == 1.2345e300)
 constexpr int SR_PF = 8;            // 16-byte vectors in flight per thread and step
 // SR_ASYNC: the rows of the next step go straight into the ring with 8-byte cp.async, issued as
 // soon as every warp holds its frame of this step in registers (one barrier after the frame
@@ -778,6 +785,7 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
         // the loads of the next chunk are issued late in the last item of the step, when the
         // registers of the first pass are free again (they come from L2 by then)
         auto issue_loads = [&]() {
+            if (SR_ABL & 2) return;
             if (inside && allv) {                   // every vector of every thread exists
                 const double* gp = gnext;
 #pragma unroll
@@ -985,7 +993,7 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
                         pm = xM * xM * P.scale;
                     }
                     if (DB) { pk = to_db(pk); pm = to_db(pm); }
-                    if (live) {
+                    if (live && SR_ST_OK(pk)) {
                         ADN_STORE(outk + 32 * kk, pk);
                         ADN_STORE(outm - 32 * kk, pm);
                     }
@@ -1080,7 +1088,9 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
         } else
         if (more) {
             if (!loaded) issue_loads();     // warps without an item in the last iteration
-            __syncthreads();            // every warp is done with the rows the chunk replaces
+            if (!(SR_ABL & 4)) __syncthreads();            // every warp is done with the rows the chunk replaces
+            if (SR_ABL & 2) {
+            } else
             if (fastfill) {
                 // groups of four channels, 128 threads, chunks that never wrap around the ring:
                 // the SR_PF vectors of a thread land 64 rows apart, two stores each at literal offsets
@@ -1097,7 +1107,7 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
                     if (allv || r0 + j * DR < CH) put(pf[j], npos + r0 + j * DR);
                 if (r0 + SR_PF * DR < CH) stage_direct(nrow, npos, CH, SR_PF);
             }
-            __syncthreads();
+            if (!(SR_ABL & 4)) __syncthreads();
         }
         ws = (ws + CH) & RM;
         npos = (npos + CH) & RM;
