@@ -623,7 +623,11 @@ constexpr int SR_PF = 8;            // 16-byte vectors in flight per thread and 
 // loads): the copies land while the transforms run and no register stages them.  Needs one
 // item per warp and step (the launcher sees to it).  Measured on B200 (nfft 1024, hop 512):
 // 8 ch 178 us against 172 us with register staging, 1 ch 155 / 145 us, 64 ch 396 / 407 us: the
-// barrier in the middle of the step costs what the hidden load latency gains, so off.
+// barrier in the middle of the step costs what the hidden load latency gains.  With shorter steps
+// (hop < 512) it wins 3 - 9 % (measured after the round-2 changes of the small transforms: 64 ch
+// 256 / 128 316 -> 289 us, 512 / 128 482 -> 454 us, 1024 / 128 951 -> 899 us; 8 ch 1024 / 128 597 ->
+// 560 us, 256 / 32 521 -> 491 us), so it is a template parameter chosen by shape in launch_ring();
+// SR_ASYNC = 1 forces it for every launch.
 #ifndef SR_ASYNC
 #define SR_ASYNC 0
 #endif
@@ -659,9 +663,10 @@ __device__ __forceinline__ double to_db(double p) {
     return p > 1e-20 ? 10.0 * log10(p) : (p <= 1e-20 ? -INFINITY : p);
 }
 
-template <int LOGN, bool DB>
+template <int LOGN, bool DB, bool ASYNC_FILL>
 __global__ void __launch_bounds__(SR_MAXNT, SR_BLOCKS)
 spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
+    constexpr bool ASYNC = ASYNC_FILL || SR_ASYNC;
     using Cf = SWCfg<LOGN>;
     constexpr int N = Cf::N, M = Cf::M, T = Cf::T, FPW = Cf::FPW;
     constexpr int FS = SRCfg<LOGN>::FS;
@@ -756,7 +761,7 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
     // lane are a rotation of 16 fixed 64-row slices (immediate offsets, picked by a switch)
     const bool rot_ok = T == 32 && RM == N - 1 && (hop & 63) == 0;
     // the chunk of a step is exactly the SR_PF vectors of every thread and never wraps
-    const bool fastfill = !SR_ASYNC && W == 4 && NT == 128 && allv && CH == SR_PF * 64 && ((RM + 1) % CH) == 0 &&
+    const bool fastfill = !ASYNC && W == 4 && NT == 128 && allv && CH == SR_PF * 64 && ((RM + 1) % CH) == 0 &&
                           (span0 % CH) == 0;
     int ws = 0;                 // ring position of the first row of this step
     int npos = span0;           // ring position / row of the chunk the next step adds
@@ -810,15 +815,15 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
             int fi = it >> LW, ci = it & (W - 1);
             const bool live = it < nitems && s * FSTEP + fi < FRa;
             const bool any_live = __any_sync(0xffffffffu, live);
-            if (!SR_ASYNC && !any_live) continue;
-            const bool last_iter = !SR_ASYNC && more && iter == niter - 1;
+            if (!ASYNC && !any_live) continue;
+            const bool last_iter = !ASYNC && more && iter == niter - 1;
             if (!live) { fi = 0; ci = 0; }
             const int start = ws + fi * hop + 2 * t;
             const double* xr = xs + ci * RS;
 
             // ---- load, window; the frame sum for the mean goes on in the background
             double2 a[16];
-            if (SR_ASYNC && !any_live) {
+            if (ASYNC && !any_live) {
                 // no frame for this warp: it only takes part in the hand-over of the ring
 #pragma unroll
                 for (int p = 0; p < 16; ++p) a[p] = make_double2(0.0, 0.0);
@@ -837,7 +842,7 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
                 for (int p = 0; p < 16; ++p)
                     a[p] = *reinterpret_cast<const double2*>(xr + ((start + 2 * T * p) & RM));
             }
-            if (SR_ASYNC) {
+            if (ASYNC) {
                 // every warp holds its frame: the oldest rows of the ring are free for the chunk
                 // of the next step
                 __syncthreads();
@@ -1080,7 +1085,7 @@ spectrogram_ring_kernel(const __grid_constant__ SpecRArgs P) {
             __syncwarp();
         }
 
-        if (SR_ASYNC) {
+        if (ASYNC) {
             if (more) {
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
                 __syncthreads();
@@ -1122,7 +1127,7 @@ int env_int(const char* name, int dflt) {
 }
 
 // returns ADN_ERR_UNSUPPORTED (without an error message) when the shape does not fit
-template <int LOGN, bool DB>
+template <int LOGN, bool DB, bool ASYNC>
 int32_t launch_ring_kernel(SpecRArgs& P, int64_t nf, cudaStream_t st) {
     using Cf = SWCfg<LOGN>;
     const int C = P.C, hop = P.hop;
@@ -1150,8 +1155,8 @@ int32_t launch_ring_kernel(SpecRArgs& P, int64_t nf, cudaStream_t st) {
         if (smem <= limit || P.FSTEP == 1) break;
     }
     if (smem > limit) return ADN_ERR_UNSUPPORTED;
-    if (SR_ASYNC && P.FSTEP * P.CB > items) return ADN_ERR_UNSUPPORTED;    // one item per warp and step
-    auto kern = spectrogram_ring_kernel<LOGN, DB>;
+    if ((ASYNC || SR_ASYNC) && P.FSTEP * P.CB > items) return ADN_ERR_UNSUPPORTED;    // one item per warp and step
+    auto kern = spectrogram_ring_kernel<LOGN, DB, ASYNC>;
     static bool attr_done = false;
     if (!attr_done) {
         ADN_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1178,7 +1183,18 @@ int32_t launch_ring_kernel(SpecRArgs& P, int64_t nf, cudaStream_t st) {
 
 template <int LOGN>
 int32_t launch_ring(SpecRArgs& P, int64_t nf, int out_db, cudaStream_t st) {
-    return out_db ? launch_ring_kernel<LOGN, true>(P, nf, st) : launch_ring_kernel<LOGN, false>(P, nf, st);
+    if (out_db) return launch_ring_kernel<LOGN, true, false>(P, nf, st);
+    // ring fill by cp.async (the copies land while the transforms run) or through registers (8
+    // vectors per thread, loaded late in the step): the choice is by shape, see SR_ASYNC above
+    int async = env_int("ADN_SPEC_ASYNC", -1);
+    // measured on B200 (tools/kbench.py, 8 and 64 channels): async wins 1 - 9 % for every shape but
+    // nfft 1024 with hop >= 512 (-3 %) and one or two channels (-3 %)
+    if (async < 0) async = P.C >= 4 && (LOGN < 10 || P.hop < 512) ? 1 : 0;
+    if (async) {
+        int32_t rc = launch_ring_kernel<LOGN, false, true>(P, nf, st);
+        if (rc != ADN_ERR_UNSUPPORTED) return rc;
+    }
+    return launch_ring_kernel<LOGN, false, false>(P, nf, st);
 }
 
 template <int LOGN>

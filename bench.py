@@ -375,9 +375,8 @@ def run_ours(args):
     _lib.init(local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        # NCCL's version banner goes to stdout, which carries the one JSON line
-        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'
+        # NCCL's version banner and warnings go to stdout by default, which carries the one JSON line
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', rank=rank, world_size=world,
                                 device_id=torch.device('cuda', local))
     sos, esos = designs()
