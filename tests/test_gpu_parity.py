@@ -542,6 +542,26 @@ def test_spectrogram_channels(C):
     assert_spec_close(got, ref, f'C={C}')
 
 
+@pytest.mark.parametrize('fill', ['0', '1'])
+@pytest.mark.parametrize('C,nfft,hop', [(8, 1024, 512), (8, 256, 128), (4, 128, 32), (16, 512, 512),
+                                        (64, 256, 128), (6, 1024, 128), (2, 512, 64)])
+def test_spectrogram_ring_fill_variants(C, nfft, hop, fill, monkeypatch):
+    """The ring kernel fills its ring through registers or by cp.async (a template parameter the
+    launcher picks by shape, spectrogram.cu: launch_ring) and prefetches the next rows into L2 whole
+    or in shares: every variant on long runs (several steps per block), against the oracle."""
+    monkeypatch.setenv('ADN_SPEC_ASYNC', fill)
+    monkeypatch.setenv('ADN_SPEC_PFSPLIT', fill)
+    fs = 96000.
+    n_src = 300000 + 7
+    x = synth(11, n_src, C, fs, seed=nfft + C + hop) + 0.25
+    n_dst = (n_src - (nfft - hop))//hop
+    ref = np.empty((n_dst, C, nfft//2 + 1))
+    nref = orc.spectrogram_process(x, ref, fs, nfft, hop)
+    got = np.full_like(ref, np.nan)
+    assert _lib.spectrogram(x, fs, nfft, hop, got) == nref
+    assert_spec_close(got, ref, f'C={C} nfft={nfft} hop={hop} fill={fill}')
+
+
 @pytest.mark.parametrize('nfft,C', [(2048, 1), (2048, 3), (4096, 8), (8192, 5), (16384, 2), (4096, 64)])
 def test_spectrogram_midsize_channels(nfft, C):
     fs = 250000.
