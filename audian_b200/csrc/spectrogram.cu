@@ -12,6 +12,7 @@
 // fp64 pocketfft, which an fp32 FFT cannot give for tonal frames).
 // No cuFFT, no tensor cores.
 #include "common.cuh"
+#include <cuda.h>               // CUtensorMap: types only, the encoder comes through cudaGetDriverEntryPoint
 #include <cmath>
 #include <cstdlib>
 #include <mutex>
@@ -1537,6 +1538,275 @@ spectrogram_mpr_kernel(const __grid_constant__ SpecMArgs P, int32_t frun) {
     }
 }
 
+// Frame-per-block kernel with the rows of the channel pair gathered by the TMA unit (nfft 2048, 4096).
+// The frame-per-block kernel above is bound by the L1 data pipe (ncu, 64 ch x 250 kHz: 85 %): a block
+// needs 16 bytes of every row, so each of its 128-bit global loads touches 32 lines = 32 wavefronts,
+// as many as the shared-memory passes of the transform.  Here one thread issues N / 256 tensor
+// copies (a 2-D tensor map over the source: box = 2 channels x 256 rows, 4 KB each) that complete on
+// an mbarrier; the rows arrive in shared memory as [row][2] without passing through the L1 data
+// pipe, the threads read them as 128-bit vectors, and the exchange buffer of the transform reuses
+// the space.
+constexpr int MPT_ROWS = 256;
+
+__device__ __forceinline__ uint32_t sp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int LOGN, bool DB>
+__global__ void __launch_bounds__((1 << (LOGN - 1)) / 8, LOGN == 11 ? 3 : 2)
+spectrogram_mpt_kernel(const __grid_constant__ SpecMArgs P, const __grid_constant__ CUtensorMap tmap) {
+    constexpr int R = 8;
+    constexpr int N = 1 << LOGN, M = N / 2, T = M / R, F = M + 1;
+    extern __shared__ __align__(16) double sbuf[];
+    double* sb = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sbuf) + 127) & ~(uintptr_t)127);
+    double2* S = reinterpret_cast<double2*>(sb);                   // M + M/8 complex, after the rows are read
+    const double2* raw = reinterpret_cast<const double2*>(sb);     // [N]: (channel c0, c0 + 1) of a row
+    __shared__ double red[2][32];
+    __shared__ __align__(8) uint64_t mbar;
+    const int t = threadIdx.x;
+    const int64_t frame = blockIdx.x / P.npair;
+    const int pair = blockIdx.x % P.npair;
+    const int C = P.C;
+    const int c0 = pair * 2;
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sp_smem_u32(&mbar)), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (t == 0) {
+        asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}"
+                     ::"r"(sp_smem_u32(&mbar)), "r"((uint32_t)(N * 16)) : "memory");
+        const int row0 = (int)(frame * P.hop);
+#pragma unroll 1
+        for (int j = 0; j < N / MPT_ROWS; ++j)
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+                         "[%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(sp_smem_u32(sb + (size_t)j * MPT_ROWS * 2)), "l"(reinterpret_cast<uint64_t>(&tmap)),
+                           "r"(c0), "r"(row0 + j * MPT_ROWS), "r"(sp_smem_u32(&mbar)) : "memory");
+    }
+    double2 wb[5];
+    mp_twiddles<LOGN, R>(wb, P.tw, t);
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
+        ::"r"(sp_smem_u32(&mbar)), "r"(0) : "memory");
+
+    double2 za[R], zb[R];
+    double sa = 0.0, sbsum = 0.0;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        const int row = 2 * (t + k * T);
+        const double2 v0 = raw[row], v1 = raw[row + 1];
+        za[k] = make_double2(v0.x, v1.x);
+        zb[k] = make_double2(v0.y, v1.y);
+        sa += v0.x + v1.x;
+        sbsum += v0.y + v1.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+        sbsum += __shfl_xor_sync(0xffffffffu, sbsum, o);
+    }
+    if ((t & 31) == 0) { red[0][t >> 5] = sa; red[1][t >> 5] = sbsum; }
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        double2 w = __ldg(reinterpret_cast<const double2*>(P.win) + (t + k * T));
+        za[k].x *= w.x; za[k].y *= w.y;
+        zb[k].x *= w.x; zb[k].y *= w.y;
+    }
+    __syncthreads();                                  // every row has been read: S takes the place
+    for (int ch = 0; ch < 2; ++ch) {
+        if (ch == 1) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) za[k] = zb[k];
+        }
+        mp_channel<LOGN, R, DB>(za, S, wb, t, red[ch], P.detrend, P.scale, P.tw,
+                                P.dst + ((frame * C + c0 + ch) * (int64_t)F));
+        __syncthreads();                              // S is reused by the second channel
+    }
+}
+
+// Overlapping frames with the TMA unit: a block owns a run of consecutive frames of a channel pair
+// (as spectrogram_mpr_kernel) and keeps one frame of rows in a shared-memory ring, here as [row][2]
+// exactly as the tensor copies deliver them.  Every step waits for the rows of its frame (mbarrier,
+// one phase per step), reads both channels into registers, and -- one barrier later, when the
+// oldest `hop` rows are free -- one thread issues the tensor copies of the next step's rows, which
+// land while the two transforms run.  No thread loads a row, no register stages one.
+template <int LOGN, bool DB>
+__global__ void __launch_bounds__((1 << (LOGN - 1)) / 8, LOGN == 11 ? 3 : 2)
+spectrogram_mprt_kernel(const __grid_constant__ SpecMArgs P, const __grid_constant__ CUtensorMap tmap, int32_t frun) {
+    constexpr int R = 8;
+    constexpr int N = 1 << LOGN, M = N / 2, T = M / R, F = M + 1;
+    extern __shared__ __align__(16) double sbuf[];
+    double* sb = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sbuf) + 127) & ~(uintptr_t)127);
+    const double2* ring = reinterpret_cast<const double2*>(sb);    // [N]: (channel c0, c0 + 1) of a row
+    double2* S = reinterpret_cast<double2*>(sb + 2 * N);           // M + M/8 (+8) complex
+    __shared__ double red[2][32];
+    __shared__ __align__(8) uint64_t mbar;
+    const int t = threadIdx.x;
+    const int pair = blockIdx.x % P.npair;
+    const int64_t f0 = (int64_t)(blockIdx.x / P.npair) * frun;
+    const int nfr = (int)min((int64_t)frun, P.nframes - f0);
+    const int C = P.C, hop = P.hop;
+    const int c0 = 2 * pair;
+    const int row_run = (int)(f0 * hop);                           // first source row of the run
+    auto copy_rows = [&](int row_first, int nrows) {               // source rows -> ring at row_first mod N
+        asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}"
+                     ::"r"(sp_smem_u32(&mbar)), "r"((uint32_t)(nrows * 16)) : "memory");
+#pragma unroll 1
+        for (int j = 0; j < nrows; j += MPT_ROWS)
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+                         "[%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(sp_smem_u32(sb + (size_t)((row_first + j) & (N - 1)) * 2)),
+                           "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(c0), "r"(row_run + row_first + j),
+                           "r"(sp_smem_u32(&mbar)) : "memory");
+    };
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sp_smem_u32(&mbar)), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (t == 0) copy_rows(0, N);
+    double2 wb[5];
+    mp_twiddles<LOGN, R>(wb, P.tw, t);
+
+    for (int s = 0; s < nfr; ++s) {
+        asm volatile(
+            "{\n.reg .pred p;\nWAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
+            ::"r"(sp_smem_u32(&mbar)), "r"(s & 1) : "memory");
+        const int start = (s * hop) & (N - 1);
+        double2 za[R], zb[R];
+        double sa = 0.0, sbsum = 0.0;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int row = (start + 2 * (t + k * T)) & (N - 1);   // even: row + 1 does not wrap
+            const double2 v0 = ring[row], v1 = ring[row + 1];
+            za[k] = make_double2(v0.x, v1.x);
+            zb[k] = make_double2(v0.y, v1.y);
+            sa += v0.x + v1.x;
+            sbsum += v0.y + v1.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
+            sbsum += __shfl_xor_sync(0xffffffffu, sbsum, o);
+        }
+        if ((t & 31) == 0) { red[0][t >> 5] = sa; red[1][t >> 5] = sbsum; }
+        __syncthreads();                              // every thread holds its rows: the oldest are free
+        if (t == 0 && s + 1 < nfr) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            copy_rows(s * hop + N, hop);                  // replaces rows [s hop, (s + 1) hop) of the ring
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            double2 w = __ldg(reinterpret_cast<const double2*>(P.win) + (t + k * T));
+            za[k].x *= w.x; za[k].y *= w.y;
+            zb[k].x *= w.x; zb[k].y *= w.y;
+        }
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ++ch) {
+            if (ch == 1) {
+#pragma unroll
+                for (int k = 0; k < R; ++k) za[k] = zb[k];
+            }
+            mp_channel<LOGN, R, DB>(za, S, wb, t, red[ch], P.detrend, P.scale, P.tw,
+                                    P.dst + (((f0 + s) * C + c0 + ch) * (int64_t)F));
+            __syncthreads();                          // S (and, after the second channel, red) free again
+        }
+    }
+}
+
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+TmapEncodeFn tmap_encoder() {
+    static TmapEncodeFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        (void)cudaGetLastError();
+        return reinterpret_cast<TmapEncodeFn>(p);
+    }();
+    return fn;
+}
+
+int32_t make_pair_tmap(const double* src, int32_t C, int64_t rows, CUtensorMap* tm) {
+    TmapEncodeFn enc = tmap_encoder();
+    if (!enc || C % 2 != 0 || (reinterpret_cast<uintptr_t>(src) & 15) != 0 || rows >= 0x7fffffff)
+        return ADN_ERR_UNSUPPORTED;
+    const cuuint64_t gdim[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)C * 8};
+    const cuuint32_t box[2] = {2, MPT_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(src), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return ADN_ERR_UNSUPPORTED;
+    return ADN_OK;
+}
+
+// ADN_ERR_UNSUPPORTED (no message) when the shape or the driver does not allow it: the caller falls back
+template <int LOGN>
+int32_t launch_mpt(SpecMArgs& P, const double* src, int64_t nf, int out_db, cudaStream_t st) {
+    constexpr int M = 1 << (LOGN - 1), T = M / 8, N = 2 * M;
+    CUtensorMap tm;
+    if (make_pair_tmap(src, P.C, (nf - 1) * (int64_t)P.hop + N, &tm) != ADN_OK) return ADN_ERR_UNSUPPORTED;
+    P.npair = P.C / 2;
+    const size_t smem = (size_t)N * 16 + 128;
+    const int64_t grid = nf * P.npair;
+    if (grid > 0x7fffffff) return ADN_ERR_UNSUPPORTED;
+    auto k0 = spectrogram_mpt_kernel<LOGN, false>;
+    auto k1 = spectrogram_mpt_kernel<LOGN, true>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        ADN_CK(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ADN_CK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done = true;
+    }
+    if (out_db) k1<<<(unsigned)grid, T, smem, st>>>(P, tm);
+    else k0<<<(unsigned)grid, T, smem, st>>>(P, tm);
+    count_launch();
+    ADN_CK(cudaGetLastError());
+    return ADN_OK;
+}
+
+template <int LOGN>
+int32_t launch_mprt(SpecMArgs& P, const double* src, int64_t nf, int out_db, cudaStream_t st) {
+    constexpr int M = 1 << (LOGN - 1), T = M / 8, N = 2 * M;
+    if (P.hop % MPT_ROWS != 0 || P.hop > N) return ADN_ERR_UNSUPPORTED;
+    CUtensorMap tm;
+    if (make_pair_tmap(src, P.C, (nf - 1) * (int64_t)P.hop + N, &tm) != ADN_OK) return ADN_ERR_UNSUPPORTED;
+    P.npair = P.C / 2;
+    const size_t smem = (size_t)N * 16 + 128 + (size_t)(M + M / 8 + 8) * 16;
+    auto k0 = spectrogram_mprt_kernel<LOGN, false>;
+    auto k1 = spectrogram_mprt_kernel<LOGN, true>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        ADN_CK(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ADN_CK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done = true;
+    }
+    int bps = 1;
+    ADN_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k0, T, smem));
+    if (bps < 1) return ADN_ERR_UNSUPPORTED;
+    // about two resident waves of blocks, runs of at least 8 frames
+    int64_t nruns = (int64_t)ctx().sm_count * bps * 2 / P.npair;
+    if (nruns < 1) nruns = 1;
+    int64_t frun = (nf + nruns - 1) / nruns;
+    if (frun < 8) frun = nf < 8 ? nf : 8;
+    const int64_t grid = ((nf + frun - 1) / frun) * P.npair;
+    if (grid > 0x7fffffff) return ADN_ERR_UNSUPPORTED;
+    if (out_db) k1<<<(unsigned)grid, T, smem, st>>>(P, tm, (int32_t)frun);
+    else k0<<<(unsigned)grid, T, smem, st>>>(P, tm, (int32_t)frun);
+    count_launch();
+    ADN_CK(cudaGetLastError());
+    return ADN_OK;
+}
+
 template <int LOGN, int R>
 int32_t launch_mpr(SpecMArgs& P, int64_t nf, int out_db, cudaStream_t st) {
     constexpr int M = 1 << (LOGN - 1), T = M / R, N = 2 * M;
@@ -1992,8 +2262,27 @@ int32_t spectrogram_dev(const double* src, int64_t n_src, int32_t C, double rate
         Q.scale = 1.0 / (rate * plan.sumw2);
         // channel pairs need 16-byte aligned rows: even C and an aligned base
         const bool pairs = C % 2 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
-        // overlapping frames of channel pairs: the staging ring (nfft 2048, 4096)
-        // (measured: pays from 75 % overlap on; at 50 % only for few channels, where runs are long)
+        const bool tma_ok = pairs && C >= 4 && env_int("ADN_SPEC_TMA", 1) != 0;
+        // overlapping frames of channel pairs: a ring of one frame of rows per block (nfft 2048, 4096).
+        // Filled by the TMA unit while the transforms run (mprt) up to 75 % overlap -- measured on B200
+        // against the thread-staged ring (mpr): 64 ch 2048 / 75 % 815 -> 714 us, 4096 / 75 % 928 -> 796 us,
+        // 16 ch 4096 / 50 % 532 -> 405 us, 8 ch 2048 / 50 % 268 -> 237 us; at 87.5 % mpr's 16 points per
+        // thread win (64 ch 2048: 1349 against 1393 us, 8 ch: 797 against 884 us), and at 75 % on 8
+        // channels too (4096: 491 against 513 us)
+        if (pairs && hop % 2 == 0 && nf >= 4 && 2 * hop <= nfft && (nfft == 2048 || nfft == 4096)) {
+            int mprt = env_int("ADN_SPEC_MPRT", -1);
+            // 50 %: always (64 ch 2048: 375 against 397 us of the frame-per-block TMA kernel, 4096 even);
+            // 75 %: from 16 channels on; 87.5 %: never
+            if (mprt < 0) mprt = 4 * hop > nfft ? 1 : (8 * hop > nfft ? (C >= 16) : 0);
+            if (mprt && tma_ok) {
+                int32_t rt = ADN_ERR_UNSUPPORTED;
+                if (nfft == 2048) rt = launch_mprt<11>(Q, src, nf, out_db, st);
+                if (nfft == 4096) rt = launch_mprt<12>(Q, src, nf, out_db, st);
+                if (rt != ADN_ERR_UNSUPPORTED) return rt;
+            }
+        }
+        // (measured: the thread-staged ring pays from 75 % overlap on; at 50 % only for few channels, where
+        // runs are long)
         if (pairs && hop % 2 == 0 && nf >= 4 && (4 * hop <= nfft || (2 * hop <= nfft && C <= 16)) &&
             env_int("ADN_SPEC_MPR", 1) != 0) {
             // 16 points per thread (three passes instead of four, half the threads): measured on B200
@@ -2002,6 +2291,15 @@ int32_t spectrogram_dev(const double* src, int64_t n_src, int32_t C, double rate
             int32_t rr = ADN_ERR_UNSUPPORTED;
             if (nfft == 2048) rr = launch_mpr<11, 16>(Q, nf, out_db, st);
             if (nfft == 4096) rr = launch_mpr<12, 16>(Q, nf, out_db, st);
+            if (rr != ADN_ERR_UNSUPPORTED) return rr;
+        }
+        // rows gathered by the TMA unit (measured on B200: 64 ch 2048 / 0 % 270 -> 210 us, 4096 / 50 %
+        // 516 -> 421 us, 8 ch 2048 168 -> 141 us; two channels = contiguous rows: 120 -> 142 us, so not there)
+        // (8192 points the same way, 128 KB of rows per block: 342 against 335 us -- not taken)
+        if (tma_ok) {
+            int32_t rr = ADN_ERR_UNSUPPORTED;
+            if (nfft == 2048) rr = launch_mpt<11>(Q, src, nf, out_db, st);
+            if (nfft == 4096) rr = launch_mpt<12>(Q, src, nf, out_db, st);
             if (rr != ADN_ERR_UNSUPPORTED) return rr;
         }
         switch (nfft) {

@@ -562,6 +562,27 @@ def test_spectrogram_ring_fill_variants(C, nfft, hop, fill, monkeypatch):
     assert_spec_close(got, ref, f'C={C} nfft={nfft} hop={hop} fill={fill}')
 
 
+@pytest.mark.parametrize('tma', ['0', '1'])
+@pytest.mark.parametrize('C,nfft,hop', [(8, 2048, 2048), (8, 2048, 1024), (16, 2048, 512), (4, 4096, 2048),
+                                        (64, 4096, 1024), (6, 4096, 4096), (8, 2048, 256), (8, 4096, 768)])
+def test_spectrogram_tma_gather(C, nfft, hop, tma, monkeypatch):
+    """nfft 2048 / 4096: the rows of a channel pair come in through the TMA unit (2-D tensor map over the
+    source, frame-per-block kernel and ring-staged kernel for overlapping frames) or through the
+    threads' own loads (ADN_SPEC_TMA=0): both against the oracle, runs of many frames per block,
+    hops the tensor boxes do not divide fall back."""
+    monkeypatch.setenv('ADN_SPEC_TMA', tma)
+    monkeypatch.setenv('ADN_SPEC_MPRT', '1' if tma == '1' else '-1')
+    fs = 250000.
+    n_src = 150 * hop + nfft + 5
+    x = synth(3, n_src, C, fs, seed=nfft + C + hop) - 0.5
+    n_dst = (n_src - (nfft - hop))//hop
+    ref = np.empty((n_dst, C, nfft//2 + 1))
+    nref = orc.spectrogram_process(x, ref, fs, nfft, hop)
+    got = np.full_like(ref, np.nan)
+    assert _lib.spectrogram(x, fs, nfft, hop, got) == nref
+    assert_spec_close(got, ref, f'C={C} nfft={nfft} hop={hop} tma={tma}')
+
+
 @pytest.mark.parametrize('nfft,C', [(2048, 1), (2048, 3), (4096, 8), (8192, 5), (16384, 2), (4096, 64)])
 def test_spectrogram_midsize_channels(nfft, C):
     fs = 250000.
