@@ -11,7 +11,7 @@ import re
 import subprocess
 import sys
 
-KEYS = ['UBLKCP', 'UBLKPF', 'SYNCS', 'LDGSTS', 'BAR', 'DFMA', 'DADD', 'DMUL', 'LDS', 'STS', 'SHFL', 'LDG', 'STG',
+KEYS = ['UTMALDG', 'UBLKCP', 'UBLKPF', 'SYNCS', 'LDGSTS', 'BAR', 'DFMA', 'DADD', 'DMUL', 'LDS', 'STS', 'SHFL', 'LDG', 'STG',
         'LDL', 'STL']
 
 
