@@ -276,7 +276,7 @@ def run_reference(args):
         'e2e': {'value': value, 'unit': 'Msamples/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------ our arm
@@ -375,8 +375,6 @@ def run_ours(args):
     _lib.init(local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        # NCCL's version banner and warnings go to stdout by default, which carries the one JSON line
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', rank=rank, world_size=world,
                                 device_id=torch.device('cuda', local))
     sos, esos = designs()
@@ -709,7 +707,7 @@ def run_ours(args):
                        'ms': t_m, 'frac': roofs['minmax']['frac']},
             'cpu_baseline': cpu_baseline, 'parity': parity, 'wholefile': wholefile,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         torch.cuda.synchronize()
         dist.barrier()
@@ -730,12 +728,29 @@ def main():
                     help='seconds of run time per whole-file config (the recording is shortened to fit)')
     ap.add_argument('--no-graphs', dest='graphs', action='store_false', help='(ignored: every N runs eagerly)')
     args = ap.parse_args()
+    # stdout carries the one JSON line and nothing else: whatever libraries print on file descriptor 1
+    # while the bench runs (NCCL's version banner, for one) goes to stderr instead
+    sys.stdout.flush()
+    global _STDOUT_FD
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == 'reference':
         run_reference(args)
     else:
         if args.warmup < 3:
             args.warmup = 3
         run_ours(args)
+
+
+_STDOUT_FD = None
+
+
+def emit(line):
+    """Prints the JSON line on the real stdout."""
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.dup2(_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == '__main__':
