@@ -63,6 +63,8 @@ SIGNATURES = {
     'adn_synchronize': (_i32, []),
     'adn_host_register': (_i32, [_dp, _i64]),
     'adn_host_unregister': (_i32, [_dp]),
+    'adn_host_alloc': (_i32, [_i64, C.POINTER(C.c_void_p)]),
+    'adn_host_free': (_i32, [C.c_void_p]),
     'adn_set_option': (_i32, [_i32, _i64]),
     'adn_get_option': (_i64, [_i32]),
     'adn_mirror_create': (_i32, [C.POINTER(_i64)]),
@@ -530,3 +532,88 @@ def host_register(a):
 
 def host_unregister(a):
     check(lib().adn_host_unregister(a.ctypes.data))
+
+
+_PINNED_POOL = {}                   # nbytes -> [pointers]: blocks of released arrays, reused by size
+_PINNED_POOL_LIMIT = 4 << 30        # bytes kept for reuse (page-locking a few hundred MB takes ~0.1 s)
+_pinned_pooled = [0]
+
+
+class _PinnedBlock(object):
+    """Owner of one adn_host_alloc() allocation; released with the last array that views it
+    (back into a small pool keyed by size: a scrolling trace asks for the same size again)."""
+
+    def __init__(self, nbytes):
+        self.nbytes = nbytes
+        free = _PINNED_POOL.get(nbytes)
+        if free:
+            self.ptr = free.pop()
+            _pinned_pooled[0] -= nbytes
+            return
+        p = C.c_void_p()
+        check(lib().adn_host_alloc(nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                if _pinned_pooled[0] + self.nbytes <= _PINNED_POOL_LIMIT:
+                    _PINNED_POOL.setdefault(self.nbytes, []).append(self.ptr)
+                    _pinned_pooled[0] += self.nbytes
+                else:
+                    lib().adn_host_free(C.c_void_p(self.ptr))
+        except Exception:                               # interpreter shutdown
+            pass
+        self.ptr = None
+
+
+def pinned_pool_clear():
+    """Gives the pooled page-locked blocks back to the driver."""
+    for free in _PINNED_POOL.values():
+        while free:
+            lib().adn_host_free(C.c_void_p(free.pop()))
+    _pinned_pooled[0] = 0
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """np.empty(shape, dtype) in page-locked memory from the driver's allocator (adn_host_alloc):
+    copies to and from such arrays run at full PCIe rate and overlap with the kernels.  Raises
+    RuntimeError without a CUDA device (callers that may run without one catch it and use np.empty)."""
+    shape = (shape,) if np.isscalar(shape) else tuple(int(v) for v in shape)
+    dt = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64))*dt.itemsize
+    if nbytes == 0:
+        return np.empty(shape, dt)
+    blk = _PinnedBlock(nbytes)
+    buf = (C.c_char*nbytes).from_address(blk.ptr)
+    buf._adn_block = blk                                # the array's base keeps the block alive
+    return np.frombuffer(buf, dtype=dt).reshape(shape)
+
+
+def buffer_empty(shape, dtype=np.float64):
+    """The allocation behind a trace's `buffer`: page-locked when a CUDA device is there, plain
+    np.empty otherwise (host-only tests of the index algebra; computing needs the device anyway)."""
+    global _pinned_ok
+    if _pinned_ok is not False:
+        try:
+            a = pinned_empty(shape, dtype)
+            _pinned_ok = True
+            return a
+        except (RuntimeError, OSError):
+            if _pinned_ok:                              # worked before: a real failure (out of memory)
+                raise
+            _pinned_ok = False
+    return np.empty(shape, dtype)
+
+
+_pinned_ok = None
+
+
+def is_pinned_array(a):
+    """True for arrays made by pinned_empty() (and views of them)."""
+    b = a
+    while isinstance(b, np.ndarray) and b.base is not None:
+        b = b.base
+    while b is not None and not hasattr(b, '_adn_block'):
+        b = getattr(b, 'obj', None) if isinstance(b, memoryview) else None
+    return b is not None

@@ -332,6 +332,24 @@ int32_t adn_host_unregister(void* ptr) {
     return ADN_OK;
 }
 
+int32_t adn_host_alloc(int64_t bytes, void** ptr) {
+    if (!ptr) return fail(ADN_ERR_INVALID, "adn_host_alloc: NULL pointer");
+    *ptr = nullptr;
+    if (bytes <= 0) return fail(ADN_ERR_INVALID, "adn_host_alloc: %lld bytes", (long long)bytes);
+    int32_t rc = ensure_init();
+    if (rc) return rc;
+    void* p = nullptr;
+    ADN_CK(cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocPortable));
+    *ptr = p;
+    return ADN_OK;
+}
+
+int32_t adn_host_free(void* ptr) {
+    if (!ptr) return ADN_OK;
+    ADN_CK(cudaFreeHost(ptr));
+    return ADN_OK;
+}
+
 // ---------------------------------------------------------------- host entry points
 
 int32_t adn_set_option(int32_t option, int64_t value) {

@@ -551,13 +551,16 @@ def run_ours(args):
     # the host buffers of the plugin path are first touched (and page-locked) by threads on the CPUs
     # next to this rank's GPU, as a NUMA-aware host application would place them; restored below
     near = gpu_near_cpus(local)
-    host_x = [np.ascontiguousarray(w[own].cpu().numpy()) for w in windows[:2]]
+    # page-locked arrays from the library's allocator, as the traces' allocate_buffer() makes them
+    host_x = []
+    for w in windows[:2]:
+        a_ = _lib.pinned_empty((n, C))
+        a_[:] = w[own].cpu().numpy()
+        host_x.append(a_)
     nspec = n//HOP
-    h_filt = np.empty((n, C))
-    h_spec = np.empty((nspec, C, NFFT//2 + 1))
-    h_env = np.empty((n, C))
-    for a_ in host_x + [h_filt, h_spec, h_env]:
-        _lib.host_register(a_)
+    h_filt = _lib.pinned_empty((n, C))
+    h_spec = _lib.pinned_empty((nspec, C, NFFT//2 + 1))
+    h_env = _lib.pinned_empty((n, C))
     tf = BufferedFilter()
     tf.configure_standalone(RATE, C, highpass_cutoff=HIGHPASS, lowpass_cutoff=LOWPASS)
     ts = BufferedSpectrogram(nfft=NFFT, overlap_frac=0.5)
@@ -604,7 +607,7 @@ def run_ours(args):
     f_chk = h_filt.copy()
     host_step_chain(0)
     e2e['equals_separate_calls'] = bool(np.array_equal(f_chk, h_filt) and np.max(np.abs(chk - h_env)) <= 1e-12)
-    e2e['api'] = ('adn_chain_f64 (audian_b200._lib.chain) on pinned numpy buffers: the call '
+    e2e['api'] = ('adn_chain_f64 (audian_b200._lib.chain) on page-locked numpy buffers (adn_host_alloc, what the traces\' allocate_buffer() uses): the call '
                   'BufferedFilter.recompute_all() makes for filtered -> spectrogram + envelope; the source '
                   'goes up once, results come down while the next kernel runs'
                   + ('' if world == 1 else '; %d independent replicas, one per GPU' % world))
@@ -612,8 +615,6 @@ def run_ours(args):
                                          'BufferedEnvelope.process one after the other, the filtered buffer '
                                          'handed over through the filter trace\'s device mirror')
     del chk, f_chk
-    for a_ in host_x + [h_filt, h_spec, h_env]:
-        _lib.host_unregister(a_)
     del tf, ts, te
     e2e['host_cpus'] = near.describe()
     near.restore()

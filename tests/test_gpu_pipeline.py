@@ -220,6 +220,35 @@ def test_traces_invalidate_on_buffer_moves(resident):
     assert np.allclose(spect.buffer, ref, rtol=1e-5, atol=1e-20*ref.max())
 
 
+def test_trace_buffers_are_page_locked():
+    """adn_host_alloc / _lib.pinned_empty: numpy arrays in page-locked memory, blocks reused by size;
+    the traces' allocate_buffer() puts `buffer` there (the scroll replay keeps its answers)."""
+    import gc
+    a = _lib.pinned_empty((1000, 8))
+    a[:] = 1.5
+    assert a.shape == (1000, 8) and a.dtype == np.float64 and a.flags.c_contiguous
+    assert _lib.is_pinned_array(a) and _lib.is_pinned_array(a[10:20])
+    assert not _lib.is_pinned_array(np.empty((10, 8)))
+    ptr = a.ctypes.data
+    del a
+    gc.collect()
+    b = _lib.pinned_empty((1000, 8))
+    assert b.ctypes.data == ptr                          # the released block came back from the pool
+    x = synth(0, 1000, 8, 48000.)
+    b[:] = x
+    sos = orc.filter_design(48000., 1000., 15000., 2)
+    got = _lib.pinned_empty((1000, 8))
+    _lib.sosfilt(sos, b, got, 0)
+    ref = np.empty((1000, 8))
+    orc.filter_process(sos, x, ref, 0)
+    assert np.max(np.abs(got - ref)) <= 1e-9
+    from test_host_traces import replay
+    g, log, states, filt, spect, env = replay(use_gpu=True)
+    for tr in (filt, spect, env):
+        assert _lib.is_pinned_array(tr.buffer), type(tr).__name__
+    assert _lib.pinned_empty((0, 8)).shape == (0, 8)
+
+
 @pytest.mark.parametrize('C,nbefore,mm', [(8, 0, 0), (2, 321, 1000), (5, 7, 0)])
 def test_chain_equals_separate_calls(C, nbefore, mm):
     """adn_chain_f64: data -> filtered -> {spectrogram, envelope} (+ min/max of the raw rows) in one
