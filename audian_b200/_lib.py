@@ -600,9 +600,9 @@ def buffer_empty(shape, dtype=np.float64):
             _pinned_ok = True
             return a
         except (RuntimeError, OSError):
-            if _pinned_ok:                              # worked before: a real failure (out of memory)
-                raise
-            _pinned_ok = False
+            if not _pinned_ok:                          # never worked: no device, stop trying
+                _pinned_ok = False
+            # worked before: this size cannot be page-locked right now; pageable memory works too
     return np.empty(shape, dtype)
 
 
