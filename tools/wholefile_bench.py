@@ -31,10 +31,15 @@ import numpy as np
 CONFIGS = {
     3: dict(channels=16, rate=500000., seconds=1800., seed=0xA0D1A9 + 3, nfft=1024, hop=512,
             what='full-file spectrogram nfft1024/hop512 -> mean power spectrum',
-            bytes_per_sample=8.0 + 8.0*513/512),
+            bytes_per_sample=8.0 + 8.0*513/512,
+            # what the chunk loop really moves through HBM: the generated chunk is written (8), read by the
+            # spectrogram kernel (8), the PSD chunk written (8 x 513/512) and read again by the column sums
+            moved_bytes_per_sample=16.0 + 16.0*513/512),
     4: dict(channels=4, rate=96000., seconds=86400., seed=0xA0D1A9 + 4, max_pixel=6000,
             what='full-trace min/max (6000 px) + band-pass 1-15 kHz order 4 + min/max of the result',
-            bytes_per_sample=8.0 + 16.0),
+            bytes_per_sample=8.0 + 16.0,
+            # generated chunk written (8), read once by the fused filter + min/max pass (8), filtered written (8)
+            moved_bytes_per_sample=24.0),
 }
 
 
@@ -205,6 +210,9 @@ def run_config(config, rank=0, world=1, dist=None, seconds=None, budget_s=None, 
            'parity': check}
     if peak_gbs:
         out['roofline_frac'] = out['alg_gbs']/world/peak_gbs
+        # the same time against the bytes the chunk loop moves, generation of the input included
+        out['moved_bytes_per_sample'] = cfg['moved_bytes_per_sample']
+        out['moved_frac'] = samples*cfg['moved_bytes_per_sample']/ms/1e6/world/peak_gbs
     return out
 
 
