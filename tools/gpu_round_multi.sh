@@ -1,4 +1,6 @@
 #!/bin/bash
+# Multi-GPU pass (run through gpurun --gpus N): bench.py under torchrun at N ranks + the NCCL test.
+#   bash tools/gpu_round_multi.sh <N>   -> gpurun_out/b2_bench_n<N>.json
 out=gpurun_out
 N=${1:-2}
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > $out/b2_bench_n$N.json 2> $out/b2_bench_n$N.err; echo "bench rc=$?"
