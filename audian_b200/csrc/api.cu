@@ -502,10 +502,14 @@ int32_t adn_sosfilt_f64_m(const double* sos, int32_t S, const double* src, int64
     double* din = c.in.as<double>();
     int64_t R = g_opt[ADN_OPT_CHUNK_BYTES] / ((int64_t)C * 8);
     if (R < 4096) R = 4096;
-    const int64_t nchunks = (n_src + R - 1) / R;
     const double* zin = zi_inout ? d_zi : nullptr;
-    for (int64_t k = 0; k < nchunks; ++k) {
-        const int64_t a = k * R, b = a + R < n_src ? a + R : n_src;
+    // short first chunks (R/8, R/4, R/2, then R rows), the same schedule as in adn_chain_f64: the
+    // first results start their way down early, and both calls cut the trace at the same rows
+    int64_t Rk = R / 8 < 4096 ? 4096 : R / 8;
+    int64_t a = 0;
+    for (int64_t k = 0; a < n_src; ++k) {
+        const int64_t b = a + Rk < n_src ? a + Rk : n_src;
+        if (Rk < R) Rk = 2 * Rk < R ? 2 * Rk : R;
         ADN_CK(h2d(din + a * C, src + a * C, (size_t)(b - a) * C * 8, g_h2d));
         if ((rc = chain(g_h2d, c.stream))) return rc;
         int64_t nb = nbefore - a;
@@ -515,7 +519,7 @@ int32_t adn_sosfilt_f64_m(const double* sos, int32_t S, const double* src, int64
         int64_t no = b - a - nb;
         if (no > n_dst - o0) no = n_dst - o0;
         if (no < 0) no = 0;
-        const bool last = k + 1 == nchunks;
+        const bool last = b == n_src;
         double* zout = (last && !zi_inout) ? nullptr : d_state[k & 1];
         if (no > 0 || zout) {
             if ((rc = sosfilt_dev(sos, S, din + a * C, b - a, C, nb, no > 0 ? dout + o0 * C : nullptr, no,
@@ -529,6 +533,7 @@ int32_t adn_sosfilt_f64_m(const double* sos, int32_t S, const double* src, int64
         }
         if (last && zi_inout)
             ADN_CK(d2h(zi_inout, zout, z_b, c.stream));
+        a = b;
     }
     if ((rc = sync_pipeline())) return rc;
     mirror_commit(dst_mirror, dst, out_b, dout);
@@ -1010,10 +1015,14 @@ int32_t adn_chain_f64(const adn_chain_t* c, const double* src, int64_t n_src, in
         double* d_state[2] = {cx.aux.as<double>() + (size_t)C * c->S * 2, cx.aux.as<double>() + (size_t)C * c->S * 4};
         int64_t R = g_opt[ADN_OPT_CHUNK_BYTES] / ((int64_t)C * 8);
         if (R < 4096) R = 4096;
-        const int64_t nchunks = (n_src + R - 1) / R;
         const double* zin = nullptr;
-        for (int64_t k = 0; k < nchunks; ++k) {
-            const int64_t a = k * R, b = a + R < n_src ? a + R : n_src;
+        // the first chunks are short (R/8, R/4, R/2, then R rows): the first results start their way
+        // down after an eighth of a chunk's upload instead of a whole one
+        int64_t Rk = R / 8 < 4096 ? 4096 : R / 8;
+        int64_t a = 0;
+        for (int64_t k = 0; a < n_src; ++k) {
+            const int64_t b = a + Rk < n_src ? a + Rk : n_src;
+            if (Rk < R) Rk = 2 * Rk < R ? 2 * Rk : R;
             ADN_CK(h2d(din + a * C, src + a * C, (size_t)(b - a) * C * 8, g_h2d));
             if ((rc = chain(g_h2d, cx.stream))) return rc;
             int64_t nb = c->nbefore - a;
@@ -1023,7 +1032,7 @@ int32_t adn_chain_f64(const adn_chain_t* c, const double* src, int64_t n_src, in
             int64_t no = b - a - nb;
             if (no > n_filt - o0) no = n_filt - o0;
             if (no < 0) no = 0;
-            double* zout = k + 1 == nchunks ? nullptr : d_state[k & 1];
+            double* zout = b == n_src ? nullptr : d_state[k & 1];
             if (no > 0 || zout) {
                 if ((rc = sosfilt_dev(c->sos, c->S, din + a * C, b - a, C, nb, no > 0 ? dfilt + o0 * C : nullptr, no,
                                       zin, zout, cx.stream)))
@@ -1034,6 +1043,7 @@ int32_t adn_chain_f64(const adn_chain_t* c, const double* src, int64_t n_src, in
                 if ((rc = chain(cx.stream, g_d2h))) return rc;
                 ADN_CK(d2h(filtered + o0 * C, dfilt + o0 * C, (size_t)no * C * 8, g_d2h));
             }
+            a = b;
         }
         dsrc = din;
     }
