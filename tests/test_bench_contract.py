@@ -34,6 +34,21 @@ def test_reference_arm_line():
     assert 'workload' in d['config']
 
 
+def test_stdout_carries_the_json_line_only():
+    """Whatever libraries print on file descriptor 1 while the bench runs goes to stderr (NCCL's
+    version banner used to land in front of the JSON line): stdout is exactly one line."""
+    code = ('import os, sys; sys.argv = ["bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1"];'
+            'import bench; real = bench.run_reference;'
+            'bench.run_reference = lambda a: (os.write(1, b"banner from a library\\n"), real(a));'
+            'bench.main()')
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = out.stdout.splitlines()
+    assert len(lines) == 1 and lines[0].startswith('{'), out.stdout[:300]
+    assert json.loads(lines[0])['impl'] == 'reference'
+    assert 'banner from a library' in out.stderr
+
+
 def test_reference_arm_other_ranks_stay_silent():
     env = dict(os.environ, RANK='1', WORLD_SIZE='2', LOCAL_RANK='1')
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference',
