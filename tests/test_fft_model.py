@@ -74,3 +74,47 @@ def test_fft_model(N):
                           detrend='constant', scaling='density', mode='psd')
     P = model_frame(x, 1000.)
     assert np.allclose(P, S[:, 0], rtol=1e-9, atol=1e-22*np.max(S))
+
+
+# ---- the exchange-buffer layouts of the ring kernel's second pass (spectrogram.cu, T < 32)
+
+def _groups(addrs):
+    """16-byte bank groups (a 128-byte wavefront has eight) of complex-element addresses."""
+    return [a % 8 for a in addrs]
+
+
+def test_exchange_rows_of_nfft_256_are_conflict_free():
+    """T = 8 (nfft 256): rows of 8 padded to 9, lane t owns rows t and t + 8.  A 128-bit access is
+    served a quarter warp (= the 8 lanes of one frame) at a time: the eight lanes must hit eight
+    different bank groups in the first-pass stores and in the second-pass loads.  The layout it
+    replaced (rows 2 t + r at stride 17, results written back in natural order) had two-way
+    conflicts in the natural-order stores."""
+    for k1 in range(16):                                  # first pass: element (k1, t) of the frame
+        assert sorted(_groups([k1*9 + t for t in range(8)])) == list(range(8))
+    for i in range(16):                                   # second pass: a[i] of lane t
+        assert sorted(_groups([(t + 8*(i >> 3))*9 + (i & 7) for t in range(8)])) == list(range(8))
+    for r in range(2):                                    # the old natural-order stores, for the record
+        for k2 in range(8):
+            old = _groups([2*t + r + 16*k2 for t in range(8)])
+            assert len(set(old)) == 4
+
+
+def test_exchange_rows_of_nfft_128_are_conflict_free():
+    """T = 4 (nfft 128): rows of 4 rotated by the row index, lane t owns rows t + 4 r; a quarter warp
+    holds the lanes of two frames whose buffers sit FS = 68 (== 4 mod 8) elements apart."""
+    FS = 68
+    for k1 in range(16):
+        a = [s*FS + k1*4 + ((t + k1) & 3) for s in range(2) for t in range(4)]
+        assert sorted(_groups(a)) == list(range(8))
+    for i in range(16):
+        a = [s*FS + (t + 4*(i >> 2))*4 + ((t + i) & 3) for s in range(2) for t in range(4)]
+        assert sorted(_groups(a)) == list(range(8))
+    # every element of a frame has exactly one place
+    places = sorted(k1*4 + ((t + k1) & 3) for k1 in range(16) for t in range(4))
+    assert places == list(range(64))
+    # what lane t loads as a[4 r + j] is element j of row t + 4 r
+    for t in range(4):
+        for i in range(16):
+            r, j = i >> 2, i & 3
+            row = t + 4*r
+            assert (t + 4*(i >> 2))*4 + ((t + i) & 3) == row*4 + ((j + row) & 3)
