@@ -118,3 +118,34 @@ def test_exchange_rows_of_nfft_128_are_conflict_free():
             r, j = i >> 2, i & 3
             row = t + 4*r
             assert (t + 4*(i >> 2))*4 + ((t + i) & 3) == row*4 + ((j + row) & 3)
+
+
+def test_register_split_step_partners():
+    """Split step in registers (all ring sizes): lane t of a frame holds Z[t + T m], m < 16, in register
+    RG(m); the partner Z[M - k] of k = t + T m (m < 8) sits in lane (T - t) % T at m' = 15 - m, for
+    lane 0 in its own register m' = 16 - m; the twiddle W_N^(t + T m) is W_N^t W_32^m."""
+    def RG(T, m):
+        return m if T >= 16 else (8*(m & 1) + (m >> 1) if T == 8 else 4*(m & 3) + (m >> 2))
+    for T in (4, 8, 16, 32):
+        M, N = 16*T, 32*T
+        Q = max(1, 16//T)                              # rows per lane in the second pass
+        # register i of lane t = output k2 of the DFT of row t + T r:  Z[(t + T r) + 16 k2]
+        for t in range(T):
+            held = {}
+            for i in range(16):
+                r, k2 = (i // (16//Q), i % (16//Q)) if T < 32 else (0, i)
+                k = (t + T*r) + 16*k2 if T < 32 else t + 32*i
+                held[i] = k
+            assert sorted(held.values()) == [t + T*m for m in range(16)]
+            for m in range(16):
+                assert held[RG(T, m)] == t + T*m
+        for t in range(T):
+            for m in range(8):
+                k = t + T*m
+                if t > 0:
+                    assert ((T - t) % T) + T*(15 - m) == M - k
+                elif m > 0:
+                    assert T*(16 - m) == M - k
+                w = np.exp(-2j*np.pi*k/N)
+                assert abs(w - np.exp(-2j*np.pi*t/N)*np.exp(-2j*np.pi*m/32)) < 1e-15
+        assert T*8 == M//2                              # the self-paired bin is lane 0, m = 8
